@@ -1,0 +1,207 @@
+/*
+ * svimasm_b200.h -- C ABI of libsvimasm_b200.so: the B200 (sm_100a) drop-in for the
+ * alignment-scan + haplotype-pairing hot path of SVIM-asm.
+ *
+ * The reference (eldariont/svim-asm v1.0.3) is pure Python and has no FFI of its own; the
+ * seams this library sits behind are the Python call sites listed in SURVEY.md section 8(b).
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * tree, src/svim_asm/...).  The ctypes binding a maintainer would add is in INTEGRATION.md and
+ * in svim_asm_b200/_lib.py.
+ *
+ * Conventions: plain C, pointers + sizes, no torch types.  Every function returns 0 on success
+ * or a negative svb_status; nothing throws across the boundary.  Input host buffers are borrowed
+ * for the duration of the call.  The library owns all device memory.  One svb_ctx per device; a
+ * ctx is not thread-safe (the reference is single threaded); different ctxs may run concurrently.
+ * There is NO CPU fallback: without a CUDA device svb_create() fails with SVB_ERR_CUDA.
+ */
+#ifndef SVIMASM_B200_H
+#define SVIMASM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_ABI_VERSION 1
+
+typedef enum {
+    SVB_OK = 0,
+    SVB_ERR_ARG = -1,       /* bad argument */
+    SVB_ERR_CUDA = -2,      /* CUDA runtime error / no device */
+    SVB_ERR_NOMEM = -3,
+    SVB_ERR_IO = -4,        /* file missing / truncated / not BGZF-BAM */
+    SVB_ERR_FORMAT = -5,    /* malformed record / SA tag (reference would raise) */
+    SVB_ERR_CAPACITY = -6,  /* internal per-read scratch limit exceeded */
+    SVB_ERR_ASSERT = -7     /* a reference `assert end >= start` would have fired (SVCandidate.py:40,83,130,181,266) */
+} svb_status;
+
+/* candidate types, in the fixed order of pair_candidates (SVIM_COMBINE.py:180-365) */
+enum { SVB_DEL = 0, SVB_INV = 1, SVB_INS = 2, SVB_DUP_TAN = 3, SVB_DUP_INT = 4, SVB_BND = 5 };
+/* svb_row.flags */
+enum {
+    SVB_F_COMPLETE = 1,       /* CandidateInversion.complete            (SVCandidate.py:93)  */
+    SVB_F_FULLY_COVERED = 2,  /* CandidateDuplicationTandem.fully_covered (SVCandidate.py:194) */
+    SVB_F_CUTPASTE = 4,       /* CandidateDuplicationInterspersed.cutpaste (SVCandidate.py:282) */
+    SVB_F_SRC_FWD = 8,        /* CandidateBreakend.source_direction == 'fwd' (SVCandidate.py:357) */
+    SVB_F_DST_FWD = 16        /* CandidateBreakend.dest_direction == 'fwd' */
+};
+/* svb_row.genotype */
+enum { SVB_GT_HOM = 0 /* "1/1" */, SVB_GT_HAP1 = 1 /* "1/0" */, SVB_GT_HAP2 = 2 /* "0/1" */ };
+
+/* The nine integer options the hot path reads (SVIM_input_parsing.py:45-95,221,229). */
+typedef struct {
+    int32_t min_mapq;
+    int32_t min_sv_size;
+    int32_t max_sv_size;
+    int32_t query_gap_tolerance;
+    int32_t query_overlap_tolerance;
+    int32_t reference_gap_tolerance;
+    int32_t reference_overlap_tolerance;
+    int32_t partition_max_distance;
+    int32_t max_edit_distance;
+} svb_params;
+
+/* One BAM record, 32 bytes.  Everything CIGAR-derived is computed on the device. */
+typedef struct {
+    int32_t tid;           /* AlignedSegment.reference_id */
+    int32_t pos;           /* AlignedSegment.reference_start (0-based) */
+    uint16_t flag;
+    uint8_t mapq;
+    uint8_t reserved0;
+    uint32_t n_cigar;      /* real op count (after CG:B,I restore), may exceed 65535 */
+    uint64_t cigar_off;    /* index of the first op in cigar[]; multiple of 4 (16-byte aligned run) */
+    uint32_t l_seq;        /* stored query length */
+    uint32_t sa_first;     /* first entry of this record in seg[]; its count is sa_count */
+} svb_aln_hdr;
+
+/* One entry of an SA:Z tag after retrieve_other_alignments (SVIM_COLLECT.py:18-55): the pseudo
+ * AlignedSegment reduced to the integers analyze_read_segments reads (SVIM_inter.py:68-80). */
+typedef struct {
+    int32_t tid;           /* bam.get_tid(rname), -1 if unknown */
+    int32_t pos;           /* pos - 1 */
+    uint8_t is_reverse;    /* strand != '+'  (flag 2064 vs 2048) */
+    uint8_t mapq;          /* 0 if the text value is outside 0..255 (SVIM_COLLECT.py:42-45) */
+    uint16_t reserved0;
+    int32_t ref_end;       /* pysam reference_end: pos + sum(M,D,N,=,X), pos+1 if that sum is 0 */
+    int32_t q_astart;      /* pysam query_alignment_start */
+    int32_t q_aend;        /* pysam query_alignment_end for l_qseq == 0 */
+    int32_t read_len;      /* pysam infer_read_length(): sum(M,I,S,=,X,H) */
+    int32_t reserved1;
+} svb_segment;
+
+/* One structural-variant candidate (the Candidate* classes of SVCandidate.py), 64 bytes. */
+typedef struct {
+    uint8_t type;          /* SVB_DEL ... SVB_BND */
+    uint8_t flags;         /* SVB_F_* */
+    uint8_t genotype;      /* SVB_GT_* */
+    uint8_t hap;           /* haplotype of the (first) supporting record: 1 or 2, 0 in haploid runs */
+    int32_t src_tid;       /* source_contig  (-1 when the class has none: INS) */
+    int32_t src_start;
+    int32_t src_end;
+    int32_t dst_tid;       /* dest_contig    (-1 when the class has none: DEL/INV/DUP_TAN) */
+    int32_t dst_start;
+    int32_t dst_end;
+    int32_t copies;        /* DUP_TAN */
+    uint32_t aln_idx;      /* record that produced it: reads[0] = its query_name; INS sequence source */
+    uint32_t seq_pos;      /* INS: start of the inserted bases in that record's query_sequence */
+    uint32_t seq_len;      /* INS: number of bases the python slice yields */
+    uint32_t mate_aln;     /* paired ("1/1") rows: record index in the OTHER haplotype, else 0xFFFFFFFF */
+    uint64_t ordinal;      /* total order = the reference's list-append order within one collect */
+    uint64_t reserved0;
+} svb_row;
+
+/* Kernel timings accumulated since svb_timing_reset(): CUDA events on the library's stream. */
+enum { SVB_K_CIGAR_SCAN = 0, SVB_K_SEGMENT_WALK = 1, SVB_K_MERGE = 2, SVB_K_SORT = 3, SVB_K_EDIT_DISTANCE = 4,
+       SVB_K_CLUSTER = 5, SVB_K_COUNT = 8 };
+typedef struct {
+    double ms[SVB_K_COUNT];
+    uint64_t launches[SVB_K_COUNT];
+} svb_timing;
+
+typedef struct svb_ctx svb_ctx;
+typedef struct svb_records svb_records;   /* one BAM file (one haplotype) resident in HBM */
+typedef struct svb_table svb_table;       /* candidate table resident in HBM */
+typedef struct svb_ref svb_ref;           /* reference genome resident in HBM */
+typedef struct svb_bam svb_bam;           /* host image of a BAM file produced by the ingest */
+
+/* ---- context ------------------------------------------------------------------------------ */
+int svb_abi_version(void);
+int svb_create(int device, svb_ctx** out);
+void svb_destroy(svb_ctx* ctx);
+const char* svb_last_error(const svb_ctx* ctx);          /* valid until the next call on ctx */
+int svb_synchronize(svb_ctx* ctx);
+int svb_timing_reset(svb_ctx* ctx);
+int svb_timing_get(svb_ctx* ctx, svb_timing* out);       /* synchronises the stream first */
+int svb_set_scan_variant(svb_ctx* ctx, int variant);      /* 0 = TMA bulk-copy staging (default), 1 = LDG.128 */
+
+/* ---- host ingest: replaces pysam.AlignmentFile / bam.fetch (svim-asm:63,85-86; SVIM_COLLECT.py:62-65)
+ * and retrieve_other_alignments (SVIM_COLLECT.py:8-58). Pure host code (zlib inflate, thread pool). */
+int svb_bam_open(const char* path, int n_threads, svb_bam** out, char* err, int err_len);
+void svb_bam_close(svb_bam* bam);
+int64_t svb_bam_n_records(const svb_bam* bam);
+int64_t svb_bam_n_ops_padded(const svb_bam* bam);
+int64_t svb_bam_n_segments(const svb_bam* bam);
+int32_t svb_bam_n_contigs(const svb_bam* bam);
+const char* svb_bam_contig_name(const svb_bam* bam, int32_t tid);
+const int32_t* svb_bam_contig_lengths(const svb_bam* bam);
+const char* svb_bam_sort_order(const svb_bam* bam);      /* @HD SO value or "" (svim-asm:65) */
+const svb_aln_hdr* svb_bam_headers(const svb_bam* bam);
+const uint32_t* svb_bam_cigar(const svb_bam* bam);
+const svb_segment* svb_bam_segments(const svb_bam* bam);
+const uint32_t* svb_bam_sa_count(const svb_bam* bam);
+const uint8_t* svb_bam_seq4(const svb_bam* bam);         /* 4-bit packed query bases */
+const uint64_t* svb_bam_seq_offsets(const svb_bam* bam); /* n_records + 1 byte offsets */
+const char* svb_bam_query_name(const svb_bam* bam, int64_t record);
+/* SA:Z text -> segments for callers that hold records in memory (same rules as the ingest).
+ * names/n_contig resolve rname -> tid.  Returns the number of segments written or a negative status. */
+int svb_parse_sa(const char* sa_text, const char* const* contig_names, int32_t n_contig,
+                 svb_segment* out, int32_t cap);
+
+/* ---- device: replaces analyze_alignment_file_coordsorted (SVIM_COLLECT.py:61-83) and below ---- */
+int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar,
+                     uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,
+                     const int32_t* contig_len, const int32_t* contig_lexrank, int32_t n_contig,
+                     svb_records** out);
+void svb_records_free(svb_records* rec);
+/* Attach the 4-bit query sequences (needed only when the table is paired: INS edit distances,
+ * SVIM_COMBINE.py:65-76).  seq_off has n_aln + 1 byte offsets. */
+int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq4, const uint64_t* seq_off);
+
+/* K2 cigar_scan + K4 segment_walk + K5 ordered merge.  hap = 0 (haploid), 1 or 2.
+ * Rows come out in the reference's emission order (SVIM_COLLECT.py:74,79-80). */
+int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_table** out);
+
+/* analyze_cigar_indel (SVIM_intra.py:8-30) on one op list: rows of (pos_ref, pos_read, length, is_del). */
+int svb_cigar_indel(svb_ctx* ctx, const uint32_t* packed_ops, uint32_t n_ops, int32_t min_length,
+                    int64_t* out4, uint32_t cap, uint32_t* n_out);
+
+/* Reference genome: upper-cased bases, 1 byte each, contigs concatenated; contig_off has n_contig + 1 entries. */
+int svb_ref_load(svb_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, int32_t n_contig, svb_ref** out);
+void svb_ref_free(svb_ref* ref);
+
+/* pair_candidates (SVIM_COMBINE.py:164-366): form_partitions + compute_distance + pair_haplotypes(_breakends).
+ * rec1/rec2 supply the INS sequences of the two haplotypes. Rows come out in the reference's order. */
+int svb_pair(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
+             const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);
+
+/* compute_distance for explicit strings (edlib.align(a,b)["editDistance"], SVIM_COMBINE.py:50): test hook of K8. */
+int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
+                      uint32_t n_pairs, int64_t* out);
+/* scipy linkage(method="complete") + fcluster(t, "distance") labels for n <= 32 points given condensed
+ * distances (SVIM_COMBINE.py:134-135, SVIM_inter.py:47-48): test hook of K9. */
+int svb_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,
+                       double threshold, int32_t* labels_out /* 32 per problem */);
+
+int64_t svb_table_size(const svb_table* t);
+int svb_table_to_host(svb_ctx* ctx, const svb_table* t, svb_row* dst, uint64_t cap, uint64_t* n);
+int svb_table_from_host(svb_ctx* ctx, const svb_row* rows, uint64_t n, svb_table** out);
+/* device-to-device export / import: the all-gatherv of the candidate table between ranks runs on these. */
+int svb_table_export(svb_ctx* ctx, const svb_table* t, void* device_dst, uint64_t cap_rows);
+int svb_table_import(svb_ctx* ctx, const void* device_src, uint64_t n_rows, svb_table** out);
+void svb_table_free(svb_table* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVIMASM_B200_H */

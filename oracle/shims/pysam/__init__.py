@@ -11,6 +11,7 @@ Nothing in the product (`svim_asm_b200/`) may import this file.
 """
 import gzip
 import os
+import re
 import struct
 
 __version__ = "0.0-shim"
@@ -23,25 +24,18 @@ _Q_OPS = (0, 1, 4, 7, 8)
 _R_OPS = (0, 2, 3, 7, 8)
 
 
+_CIGAR_RE = re.compile(r"(\d+)([MIDNSHP=XB])")
+
+
 def _parse_cigar_string(text):
+    # pysam: CIGAR_REGEX.findall(text) -- anything that is not "<digits><op>" is silently ignored;
+    # a length that does not fit 28 bits overflows the packed uint32 -> OverflowError
     ops = []
-    num = 0
-    seen_digit = False
-    for ch in text:
-        if ch.isdigit():
-            num = num * 10 + ord(ch) - 48
-            seen_digit = True
-        else:
-            code = _CIGAR_LETTERS.find(ch)
-            if code < 0 or not seen_digit:
-                raise ValueError("invalid CIGAR string: %r" % text)
-            if num >= (1 << 28):
-                raise OverflowError("CIGAR operation length too large")
-            ops.append((code, num))
-            num = 0
-            seen_digit = False
-    if seen_digit:
-        raise ValueError("invalid CIGAR string: %r" % text)
+    for num, letter in _CIGAR_RE.findall(text):
+        n = int(num)
+        if n >= (1 << 28):
+            raise OverflowError("value too large to convert to uint32_t")
+        ops.append((_CIGAR_LETTERS.index(letter), n))
     return ops
 
 

@@ -1,0 +1,545 @@
+// C-ABI glue of libsvimasm_b200.so (include/svimasm_b200.h): context, uploads, collect, tables.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+int svb_fail(svb_ctx* ctx, int code, const char* what, cudaError_t e) {
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+KernelTimer::KernelTimer(svb_ctx* c, int kernel_id) : ctx(c), live(false) {
+    if (!c->timing_enabled) return;
+    auto take = [&](cudaEvent_t* ev) {
+        if (!c->free_events.empty()) {
+            *ev = c->free_events.back();
+            c->free_events.pop_back();
+            return true;
+        }
+        return cudaEventCreate(ev) == cudaSuccess;
+    };
+    span.kernel = kernel_id;
+    if (!take(&span.start)) return;
+    if (!take(&span.stop)) {
+        c->free_events.push_back(span.start);
+        return;
+    }
+    cudaEventRecord(span.start, c->stream);
+    live = true;
+}
+
+KernelTimer::~KernelTimer() {
+    if (!live) return;
+    cudaEventRecord(span.stop, ctx->stream);
+    ctx->spans.push_back(span);
+}
+
+void* svb_scratch(svb_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return ctx->d_scratch;
+    if (ctx->d_scratch) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_scratch);
+        ctx->d_scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    size_t want = std::max(bytes, static_cast<size_t>(1) << 20);
+    want = (want + 0xFFFFF) & ~static_cast<size_t>(0xFFFFF);
+    if (cudaMalloc(&ctx->d_scratch, want) != cudaSuccess) return nullptr;
+    ctx->scratch_bytes = want;
+    return ctx->d_scratch;
+}
+
+static int check_device_status(svb_ctx* ctx) {
+    // one 4-byte readback; called where the host synchronises anyway
+    uint32_t st = 0;
+    SVB_CUDA(ctx, cudaMemcpyAsync(&st, ctx->d_status, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!st) return SVB_OK;
+    cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
+    if (st & DEV_ERR_BAD_TID)
+        return svb_fail(ctx, SVB_ERR_FORMAT, "reference_id out of range (pysam get_reference_name would raise ValueError)");
+    if (st & DEV_ERR_ASSERT)
+        return svb_fail(ctx, SVB_ERR_ASSERT, "candidate end is smaller than its start (reference assertion, SVCandidate.py)");
+    return svb_fail(ctx, SVB_ERR_CAPACITY, "per-read scratch capacity exceeded");
+}
+
+extern "C" {
+
+int svb_abi_version(void) { return SVB_ABI_VERSION; }
+
+int svb_create(int device, svb_ctx** out) {
+    if (!out) return SVB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SVB_ERR_CUDA;
+    svb_ctx* ctx = new (std::nothrow) svb_ctx();
+    if (!ctx) return SVB_ERR_NOMEM;
+    ctx->device = device;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, 64 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, 64 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;      // keep freed blocks cached: tables are re-allocated every step
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    if (e != cudaSuccess) {
+        svb_destroy(ctx);
+        return SVB_ERR_CUDA;
+    }
+    *out = ctx;
+    return SVB_OK;
+}
+
+void svb_destroy(svb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->spans) {
+        cudaEventDestroy(s.start);
+        cudaEventDestroy(s.stop);
+    }
+    for (auto e : ctx->free_events) cudaEventDestroy(e);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* svb_last_error(const svb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int svb_synchronize(svb_ctx* ctx) {
+    if (!ctx) return SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
+static int fold_spans(svb_ctx* ctx) {
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& s : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.start, s.stop) == cudaSuccess && s.kernel >= 0 && s.kernel < SVB_K_COUNT) {
+            ctx->timing.ms[s.kernel] += ms;
+            ctx->timing.launches[s.kernel] += 1;
+        }
+        ctx->free_events.push_back(s.start);
+        ctx->free_events.push_back(s.stop);
+    }
+    ctx->spans.clear();
+    return SVB_OK;
+}
+
+int svb_timing_reset(svb_ctx* ctx) {
+    if (!ctx) return SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = fold_spans(ctx);
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    return rc;
+}
+
+int svb_timing_get(svb_ctx* ctx, svb_timing* out) {
+    if (!ctx || !out) return SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = fold_spans(ctx);
+    *out = ctx->timing;
+    return rc;
+}
+
+int svb_set_scan_variant(svb_ctx* ctx, int variant) {
+    if (!ctx || variant < 0 || variant > 1) return SVB_ERR_ARG;
+    ctx->scan_variant = variant;
+    return SVB_OK;
+}
+
+// ---- records ---------------------------------------------------------------------------------
+
+void svb_records_free(svb_records* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaFree(r->d_hdr);
+    cudaFree(r->d_cigar);
+    cudaFree(r->d_off4);
+    cudaFree(r->d_chunk_first);
+    cudaFree(r->d_seg);
+    cudaFree(r->d_sa_count);
+    cudaFree(r->d_contig_len);
+    cudaFree(r->d_contig_lexrank);
+    cudaFree(r->d_aln_sum);
+    cudaFree(r->d_prim_list);
+    cudaFree(r->d_seq4);
+    cudaFree(r->d_seq_off);
+    delete r;
+}
+
+int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar,
+                     uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,
+                     const int32_t* contig_len, const int32_t* contig_lexrank, int32_t n_contig,
+                     svb_records** out) {
+    if (!ctx || !out || (n_aln && !hdr) || (n_ops_padded && !cigar) || n_contig < 0 || (n_contig && (!contig_len || !contig_lexrank)))
+        return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: null argument") : SVB_ERR_ARG;
+    if (n_ops_padded % 4) return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: n_ops_padded must be a multiple of 4");
+    if (n_ops_padded / 4 >= 0xFFFFFFFFull) return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: more than 2^34 ops");
+    if (n_seg && (!seg || !sa_count)) return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: segments without counts");
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    svb_records* r = new (std::nothrow) svb_records();
+    if (!r) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_load_records");
+    r->device = ctx->device;
+    r->n_aln = n_aln;
+    r->n_seg = n_seg;
+    r->n_contig = n_contig;
+    r->n4 = n_ops_padded / 4;
+
+    // host-side derived index: off4[] and the list of records that carry SA segments
+    std::vector<uint32_t> off4(static_cast<size_t>(n_aln) + 1), prim;
+    uint64_t expect = 0;
+    uint64_t seg_seen = 0;
+    for (uint32_t i = 0; i < n_aln; ++i) {
+        if (hdr[i].cigar_off % 4 || hdr[i].cigar_off != expect) {
+            delete r;
+            return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: CIGAR runs must be contiguous, in record order and 4-op aligned");
+        }
+        off4[i] = static_cast<uint32_t>(hdr[i].cigar_off / 4);
+        expect += (static_cast<uint64_t>(hdr[i].n_cigar) + 3) / 4 * 4;
+        r->n_ops += hdr[i].n_cigar;
+        const uint32_t cnt = sa_count ? sa_count[i] : 0;
+        if (cnt) {
+            if (hdr[i].sa_first != seg_seen) {
+                delete r;
+                return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: sa_first must index seg[] in record order");
+            }
+            prim.push_back(i);
+            seg_seen += cnt;
+        }
+    }
+    if (expect != n_ops_padded || seg_seen != n_seg) {
+        delete r;
+        return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: totals do not match the per-record counts");
+    }
+    off4[n_aln] = static_cast<uint32_t>(r->n4);
+    r->n_prim = static_cast<uint32_t>(prim.size());
+
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        *dst = nullptr;
+        if (!bytes) return cudaSuccess;
+        cudaError_t e = cudaMalloc(dst, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_hdr), hdr, sizeof(svb_aln_hdr) * n_aln);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_cigar), cigar, sizeof(uint32_t) * n_ops_padded);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_off4), off4.data(), sizeof(uint32_t) * off4.size());
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_seg), seg, sizeof(svb_segment) * n_seg);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_sa_count), sa_count, sa_count ? sizeof(uint32_t) * n_aln : 0);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_contig_len), contig_len, sizeof(int32_t) * n_contig);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_contig_lexrank), contig_lexrank, sizeof(int32_t) * n_contig);
+    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_prim_list), prim.data(), sizeof(uint32_t) * prim.size());
+    if (e == cudaSuccess && n_aln) e = cudaMalloc(&r->d_aln_sum, sizeof(uint4) * n_aln);
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(ctx->stream);
+        svb_records_free(r);
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_load_records upload", e);
+    }
+    int rc = launch_build_chunk_index(ctx, r);
+    if (rc == SVB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_load_records sync");
+    if (rc != SVB_OK) {
+        svb_records_free(r);
+        return rc;
+    }
+    *out = r;
+    return SVB_OK;
+}
+
+int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq4, const uint64_t* seq_off) {
+    if (!ctx || !rec || !seq_off) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_records_set_sequences") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const uint64_t bytes = seq_off[rec->n_aln];
+    cudaFree(rec->d_seq4);
+    cudaFree(rec->d_seq_off);
+    rec->d_seq4 = nullptr;
+    rec->d_seq_off = nullptr;
+    SVB_CUDA(ctx, cudaMalloc(&rec->d_seq_off, sizeof(uint64_t) * (static_cast<size_t>(rec->n_aln) + 1)));
+    SVB_CUDA(ctx, cudaMemcpyAsync(rec->d_seq_off, seq_off, sizeof(uint64_t) * (static_cast<size_t>(rec->n_aln) + 1),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) {
+        SVB_CUDA(ctx, cudaMalloc(&rec->d_seq4, bytes));
+        SVB_CUDA(ctx, cudaMemcpyAsync(rec->d_seq4, seq4, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rec->seq_bytes = bytes;
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
+// ---- tables ----------------------------------------------------------------------------------
+
+static svb_table* table_alloc(svb_ctx* ctx, uint64_t cap) {
+    svb_table* t = new (std::nothrow) svb_table();
+    if (!t) return nullptr;
+    t->device = ctx->device;
+    t->cap = std::max<uint64_t>(cap, 1);
+    if (cudaMallocAsync(&t->d_rows, sizeof(svb_row) * t->cap, ctx->stream) != cudaSuccess) {
+        delete t;
+        return nullptr;
+    }
+    return t;
+}
+
+void svb_table_free(svb_table* t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->d_rows) cudaFree(t->d_rows);      // cudaFree accepts pool allocations and synchronises
+    delete t;
+}
+
+int64_t svb_table_size(const svb_table* t) { return t ? static_cast<int64_t>(t->n) : -1; }
+
+int svb_table_to_host(svb_ctx* ctx, const svb_table* t, svb_row* dst, uint64_t cap, uint64_t* n) {
+    if (!ctx || !t || !n) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_to_host") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    *n = t->n;
+    const uint64_t m = std::min(cap, t->n);
+    if (m && !dst) return svb_fail(ctx, SVB_ERR_ARG, "svb_table_to_host: null destination");
+    if (m) SVB_CUDA(ctx, cudaMemcpyAsync(dst, t->d_rows, sizeof(svb_row) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
+int svb_table_from_host(svb_ctx* ctx, const svb_row* rows, uint64_t n, svb_table** out) {
+    if (!ctx || !out || (n && !rows)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_from_host") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    svb_table* t = table_alloc(ctx, n);
+    if (!t) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_table_from_host");
+    t->n = n;
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(t->d_rows, rows, sizeof(svb_row) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            svb_table_free(t);
+            return svb_fail(ctx, SVB_ERR_CUDA, "svb_table_from_host", e);
+        }
+    }
+    *out = t;
+    return SVB_OK;
+}
+
+int svb_table_export(svb_ctx* ctx, const svb_table* t, void* device_dst, uint64_t cap_rows) {
+    if (!ctx || !t || (t->n && !device_dst)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_export") : SVB_ERR_ARG;
+    if (t->n > cap_rows) return svb_fail(ctx, SVB_ERR_ARG, "svb_table_export: destination too small");
+    cudaSetDevice(ctx->device);
+    if (t->n) SVB_CUDA(ctx, cudaMemcpyAsync(device_dst, t->d_rows, sizeof(svb_row) * t->n, cudaMemcpyDeviceToDevice, ctx->stream));
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
+int svb_table_import(svb_ctx* ctx, const void* device_src, uint64_t n_rows, svb_table** out) {
+    if (!ctx || !out || (n_rows && !device_src)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_import") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    svb_table* t = table_alloc(ctx, n_rows);
+    if (!t) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_table_import");
+    t->n = n_rows;
+    if (n_rows) {
+        cudaError_t e = cudaMemcpyAsync(t->d_rows, device_src, sizeof(svb_row) * n_rows, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            svb_table_free(t);
+            return svb_fail(ctx, SVB_ERR_CUDA, "svb_table_import", e);
+        }
+    }
+    *out = t;
+    return SVB_OK;
+}
+
+// ---- collect -----------------------------------------------------------------------------------
+
+int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_table** out) {
+    if (!ctx || !rec || !p || !out || hap < 0 || hap > 2) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_collect") : SVB_ERR_ARG;
+    if (rec->device != ctx->device) return svb_fail(ctx, SVB_ERR_ARG, "svb_collect: records live on another device");
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+
+    // K2: indel rows.  Capacity is a guess (1 row per 64 ops, far above real SV density); an
+    // overflow is detected from the exact count and the scan is repeated once with the right size.
+    uint64_t cap = std::max<uint64_t>(4096, rec->n_ops / 64);
+    svb_table* indel = nullptr;
+    unsigned long long n_indel = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        indel = table_alloc(ctx, cap);
+        if (!indel) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: indel table");
+        ScanOutput so{indel->d_rows, indel->cap, ctx->d_counters};
+        int rc = launch_cigar_scan(ctx, rec, p, hap, so);
+        if (rc != SVB_OK) {
+            svb_table_free(indel);
+            return rc;
+        }
+        cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            svb_table_free(indel);
+            return svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: cigar_scan", e);
+        }
+        n_indel = ctx->h_pinned[0];
+        if (n_indel <= indel->cap) break;
+        svb_table_free(indel);
+        indel = nullptr;
+        cap = n_indel;
+    }
+    if (!indel) return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_collect: indel table overflow");
+    indel->n = n_indel;
+
+    // K4: split-alignment walk rows (own table, emission order per primary)
+    svb_row* d_walk = nullptr;
+    uint64_t n_walk = 0;
+    int rc = launch_segment_walk(ctx, rec, p, hap, &d_walk, &n_walk);
+    if (rc != SVB_OK) {
+        svb_table_free(indel);
+        return rc;
+    }
+    rc = check_device_status(ctx);
+    if (rc != SVB_OK) {
+        svb_table_free(indel);
+        if (d_walk) cudaFree(d_walk);
+        return rc;
+    }
+    if (n_walk == 0) {
+        *out = indel;
+        return SVB_OK;
+    }
+    // K5: order-preserving merge by ordinal (record order; indels of a record before its walk rows)
+    svb_table* merged = table_alloc(ctx, n_indel + n_walk);
+    if (!merged) {
+        svb_table_free(indel);
+        cudaFree(d_walk);
+        return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: merged table");
+    }
+    rc = launch_merge_tables(ctx, indel->d_rows, n_indel, d_walk, n_walk, merged->d_rows);
+    if (rc == SVB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: merge");
+    svb_table_free(indel);
+    cudaFree(d_walk);
+    if (rc != SVB_OK) {
+        svb_table_free(merged);
+        return rc;
+    }
+    merged->n = n_indel + n_walk;
+    *out = merged;
+    return SVB_OK;
+}
+
+int svb_cigar_indel(svb_ctx* ctx, const uint32_t* packed_ops, uint32_t n_ops, int32_t min_length, int64_t* out4,
+                    uint32_t cap, uint32_t* n_out) {
+    if (!ctx || !n_out || (n_ops && !packed_ops)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_cigar_indel") : SVB_ERR_ARG;
+    // one mapped, forward, mapq-255 record at position 0 of a contig as long as a BAM coordinate can be
+    std::vector<uint32_t> ops((static_cast<size_t>(n_ops) + 3) / 4 * 4, 15u);
+    std::copy(packed_ops, packed_ops + n_ops, ops.begin());
+    svb_aln_hdr h;
+    memset(&h, 0, sizeof h);
+    h.mapq = 255;
+    h.n_cigar = n_ops;
+    h.l_seq = 0xFFFFFFFFu;
+    const int32_t clen = 0x7FFFFFFF, lex = 0;
+    svb_records* rec = nullptr;
+    int rc = svb_load_records(ctx, &h, 1, ops.data(), ops.size(), nullptr, nullptr, 0, &clen, &lex, 1, &rec);
+    if (rc != SVB_OK) return rc;
+    svb_params p;
+    memset(&p, 0, sizeof p);
+    p.min_sv_size = min_length;
+    svb_table* t = nullptr;
+    rc = svb_collect(ctx, rec, &p, 0, &t);
+    svb_records_free(rec);
+    if (rc != SVB_OK) return rc;
+    std::vector<svb_row> rows(t->n);
+    uint64_t n = 0;
+    rc = svb_table_to_host(ctx, t, rows.data(), rows.size(), &n);
+    svb_table_free(t);
+    if (rc != SVB_OK) return rc;
+    *n_out = static_cast<uint32_t>(n);
+    for (uint64_t i = 0; i < n && i < cap; ++i) {
+        const svb_row& r = rows[i];
+        const bool del = r.type == SVB_DEL;
+        // with pos = 0 and an unbounded contig the clamps are the identity: start == pos_ref
+        out4[4 * i + 0] = del ? r.src_start : r.dst_start;
+        out4[4 * i + 1] = del ? -1 : static_cast<int64_t>(r.seq_pos);
+        out4[4 * i + 2] = del ? static_cast<int64_t>(r.src_end) - r.src_start : static_cast<int64_t>(r.dst_end) - r.dst_start;
+        out4[4 * i + 3] = del ? 1 : 0;
+    }
+    return SVB_OK;
+}
+
+// ---- reference genome ------------------------------------------------------------------------
+
+int svb_ref_load(svb_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, int32_t n_contig, svb_ref** out) {
+    if (!ctx || !out || n_contig < 0 || !contig_off) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_ref_load") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    svb_ref* r = new (std::nothrow) svb_ref();
+    if (!r) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_ref_load");
+    r->device = ctx->device;
+    r->n_contig = n_contig;
+    r->n_bases = contig_off[n_contig];
+    cudaError_t e = cudaMalloc(&r->d_contig_off, sizeof(uint64_t) * (static_cast<size_t>(n_contig) + 1));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(r->d_contig_off, contig_off, sizeof(uint64_t) * (static_cast<size_t>(n_contig) + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && r->n_bases) e = cudaMalloc(&r->d_bases, r->n_bases);
+    if (e == cudaSuccess && r->n_bases) e = cudaMemcpyAsync(r->d_bases, bases, r->n_bases, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        svb_ref_free(r);
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_ref_load", e);
+    }
+    *out = r;
+    return SVB_OK;
+}
+
+void svb_ref_free(svb_ref* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaFree(r->d_bases);
+    cudaFree(r->d_contig_off);
+    delete r;
+}
+
+int svb_pair(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1, const svb_records* rec2,
+             const svb_ref* ref, const svb_params* p, svb_table** out) {
+    if (!ctx || !h1 || !h2 || !ref || !p || !out) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_pair") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = run_pairing(ctx, h1, h2, rec1, rec2, ref, p, out);
+    if (rc != SVB_OK) return rc;
+    return check_device_status(ctx);
+}
+
+int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
+                      uint32_t n_pairs, int64_t* out) {
+    if (!ctx || !a_off || !b_off || (n_pairs && !out)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_edit_distance") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return run_edit_distance_strings(ctx, a, a_off, b, b_off, n_pairs, out);
+}
+
+int svb_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,
+                       double threshold, int32_t* labels_out) {
+    if (!ctx || !n_points || !labels_out) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_cluster_labels") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return run_cluster_labels(ctx, condensed, n_points, n_problems, threshold, labels_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Shared declarations of libsvimasm_b200 (device layouts, context, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/svimasm_b200.h"
+
+// ---- device image of one BAM file -----------------------------------------------------------
+// cigar: BAM-packed ops (len << 4 | op) as uint4 (4 ops = 16 B); every alignment's run starts on
+// a uint4 boundary and is padded with op 15.  off4[a] is the run start in uint4 units.
+struct svb_records {
+    int device = 0;
+    uint32_t n_aln = 0;
+    uint32_t n_seg = 0;
+    int32_t n_contig = 0;
+    uint64_t n4 = 0;                  // number of uint4 in cigar
+    uint64_t n_ops = 0;               // sum of n_cigar (real ops)
+    svb_aln_hdr* d_hdr = nullptr;     // [n_aln]
+    uint4* d_cigar = nullptr;         // [n4]
+    uint32_t* d_off4 = nullptr;       // [n_aln + 1]
+    uint32_t* d_chunk_first = nullptr;// [ceil(n4 / 256)] alignment that owns the first uint4 of each 1024-op chunk
+    svb_segment* d_seg = nullptr;     // [n_seg]
+    uint32_t* d_sa_count = nullptr;   // [n_aln]
+    int32_t* d_contig_len = nullptr;  // [n_contig]
+    int32_t* d_contig_lexrank = nullptr;
+    uint4* d_aln_sum = nullptr;       // [n_aln] x: sum(M,D,=,X) y: sum(M,I,S,=,X) z: sum(N) w: sum(H); written by cigar_scan
+    uint32_t* d_prim_list = nullptr;  // [n_prim] record indices that carry SA segments
+    uint32_t n_prim = 0;
+    uint8_t* d_seq4 = nullptr;        // optional 4-bit query sequences
+    uint64_t* d_seq_off = nullptr;    // [n_aln + 1]
+    uint64_t seq_bytes = 0;
+};
+
+struct svb_table {
+    int device = 0;
+    svb_row* d_rows = nullptr;
+    uint64_t n = 0;
+    uint64_t cap = 0;
+};
+
+struct svb_ref {
+    int device = 0;
+    uint8_t* d_bases = nullptr;       // upper-cased ASCII, contigs concatenated
+    uint64_t* d_contig_off = nullptr; // [n_contig + 1]
+    int32_t n_contig = 0;
+    uint64_t n_bases = 0;
+};
+
+struct TimedSpan {
+    int kernel;
+    cudaEvent_t start, stop;
+};
+
+struct svb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int scan_variant = 0;             // 0 TMA bulk-copy staging, 1 LDG.128
+    int sm_count = 148;
+    bool timing_enabled = true;
+    std::vector<TimedSpan> spans;     // recorded, not yet folded into `timing`
+    std::vector<cudaEvent_t> free_events;
+    svb_timing timing;
+    void* d_scratch = nullptr;        // grow-only device scratch
+    size_t scratch_bytes = 0;
+    uint32_t* d_status = nullptr;     // device error word (atomicOr of DEV_ERR_*)
+    unsigned long long* d_counters = nullptr;   // 64 device counters
+    unsigned long long* h_pinned = nullptr;     // 64-word pinned readback area
+};
+
+enum : uint32_t {
+    DEV_ERR_BAD_TID = 1u,        // a name lookup on tid < 0 or >= n_contig (pysam would raise ValueError)
+    DEV_ERR_ASSERT = 2u,         // reference assert end >= start would fire
+    DEV_ERR_CAPACITY = 4u,       // per-read scratch exceeded (inversion run > 32, ...)
+};
+
+int svb_fail(svb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess);
+
+#define SVB_CUDA(ctx, call)                                                         \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) return svb_fail((ctx), SVB_ERR_CUDA, #call, e__);   \
+    } while (0)
+
+// scoped kernel timer: records start/stop events on ctx->stream for kernel class `k`
+struct KernelTimer {
+    svb_ctx* ctx;
+    TimedSpan span;
+    bool live;
+    KernelTimer(svb_ctx* c, int kernel_id);
+    ~KernelTimer();
+};
+
+void* svb_scratch(svb_ctx* ctx, size_t bytes);   // grow-only device scratch (nullptr on failure)
+
+// ---- kernels (host launchers) -----------------------------------------------------------------
+struct ScanOutput {
+    svb_row* rows;            // capacity `cap`
+    uint64_t cap;
+    unsigned long long* d_count;   // total number of emitted rows (may exceed cap)
+};
+int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec);
+int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out);
+int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_row** d_rows_out,
+                        uint64_t* n_out);
+int launch_merge_tables(svb_ctx* ctx, const svb_row* a, uint64_t na, const svb_row* b, uint64_t nb, svb_row* out);
+int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
+                const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);
+int run_edit_distance_strings(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b,
+                              const uint64_t* b_off, uint32_t n_pairs, int64_t* out);
+int run_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,
+                       double threshold, int32_t* labels_out);

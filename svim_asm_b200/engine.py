@@ -1,0 +1,363 @@
+"""Python face of the C ABI: device context, uploaded BAM images, candidate tables.
+
+`HostBatch` is the host-side record image (what pysam.AlignmentFile + fetch() are to the
+reference, svim-asm:63, SVIM_COLLECT.py:62-65): built either from a BAM file by the C++ ingest or
+from a synthetic `synth.RecordBatch`.  `Engine` owns one GPU context.  Every failure of the
+library surfaces as `RuntimeError(svb_last_error())`, which lands in the same top-level handler as
+the reference's exceptions (svim-asm:182-185).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib
+
+NT16 = "=ACMGRSVTWYHKDBN"
+_NT16_LUT = np.frombuffer(NT16.encode("ascii"), dtype=np.uint8)
+
+DEFAULT_PARAMS = dict(min_mapq=20, min_sv_size=40, max_sv_size=100000, query_gap_tolerance=50,
+                      query_overlap_tolerance=50, reference_gap_tolerance=50, reference_overlap_tolerance=50,
+                      partition_max_distance=1000, max_edit_distance=200)
+
+
+def make_params(options=None, **overrides):
+    """svb_params from an argparse namespace (SVIM_input_parsing.py) and/or keyword overrides."""
+    p = np.zeros(1, dtype=_lib.PARAMS_DTYPE)
+    for name, default in DEFAULT_PARAMS.items():
+        value = overrides.get(name, getattr(options, name, default) if options is not None else default)
+        p[name] = int(value)
+    return p
+
+
+def lexrank(names):
+    """Rank of each contig name under python str ordering (SVCandidate.py:352, SVIM_COMBINE.py:17)."""
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    rank = np.zeros(len(names), dtype=np.int32)
+    rank[order] = np.arange(len(names), dtype=np.int32)
+    return rank
+
+
+class HostBatch(object):
+    """Flat host image of one BAM file."""
+
+    def __init__(self):
+        self.contig_names = []
+        self.contig_lengths = np.zeros(0, dtype=np.int32)
+        self.sort_order = ""
+        self.hdr = np.zeros(0, dtype=_lib.HDR_DTYPE)
+        self.cigar = np.zeros(0, dtype=np.uint32)
+        self.seg = np.zeros(0, dtype=_lib.SEG_DTYPE)
+        self.sa_count = np.zeros(0, dtype=np.uint32)
+        self.seq4 = np.zeros(0, dtype=np.uint8)
+        self.seq_off = np.zeros(1, dtype=np.uint64)
+        self._names = None
+        self._bam = None                 # svb_bam* keeping the C++ buffers alive
+        self.path = None
+
+    # ---- construction
+    @classmethod
+    def from_bam(cls, path, threads=0):
+        handle = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(512)
+        rc = lib.svb_bam_open(str(path).encode(), int(threads), ctypes.byref(handle), err, len(err))
+        if rc != 0:
+            if rc == -4:
+                raise IOError(err.value.decode() or "cannot read %s" % path)
+            raise RuntimeError(err.value.decode() or "svb_bam_open failed (%d)" % rc)
+        self = cls()
+        self._bam = handle
+        self.path = str(path)
+        n = lib.svb_bam_n_records(handle)
+        n_contig = lib.svb_bam_n_contigs(handle)
+        self.contig_names = [lib.svb_bam_contig_name(handle, t).decode() for t in range(n_contig)]
+
+        def view(address, dtype, count):
+            if count == 0 or not address:
+                return np.zeros(0, dtype=dtype)
+            buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(address)
+            return np.frombuffer(buf, dtype=dtype, count=count)
+
+        self.contig_lengths = view(lib.svb_bam_contig_lengths(handle), np.int32, n_contig)
+        self.sort_order = lib.svb_bam_sort_order(handle).decode()
+        self.hdr = view(lib.svb_bam_headers(handle), _lib.HDR_DTYPE, n)
+        self.cigar = view(lib.svb_bam_cigar(handle), np.uint32, lib.svb_bam_n_ops_padded(handle))
+        self.seg = view(lib.svb_bam_segments(handle), _lib.SEG_DTYPE, lib.svb_bam_n_segments(handle))
+        self.sa_count = view(lib.svb_bam_sa_count(handle), np.uint32, n)
+        self.seq_off = view(lib.svb_bam_seq_offsets(handle), np.uint64, n + 1)
+        self.seq4 = view(lib.svb_bam_seq4(handle), np.uint8, int(self.seq_off[-1]) if n else 0)
+        return self
+
+    @classmethod
+    def from_record_batch(cls, rb):
+        """From a synth.RecordBatch (SA text goes through the same parser as the ingest)."""
+        self = cls()
+        n = rb.n_aln
+        self.contig_names = list(rb.contig_names)
+        self.contig_lengths = np.ascontiguousarray(rb.contig_lengths, dtype=np.int32)
+        self.sort_order = "coordinate"
+        hdr = np.zeros(n, dtype=_lib.HDR_DTYPE)
+        hdr["tid"], hdr["pos"], hdr["flag"], hdr["mapq"] = rb.tid, rb.pos, rb.flag, rb.mapq
+        hdr["n_cigar"], hdr["cigar_off"], hdr["l_seq"] = rb.n_cigar, rb.cigar_off[:-1], rb.l_seq
+        self.cigar = np.ascontiguousarray(rb.cigar, dtype=np.uint32)
+        self.seq4 = np.ascontiguousarray(rb.seq4, dtype=np.uint8)
+        self.seq_off = np.ascontiguousarray(rb.seq_off, dtype=np.uint64)
+        self.sa_count = np.zeros(n, dtype=np.uint32)
+        names_c = (ctypes.c_char_p * len(self.contig_names))(*[s.encode() for s in self.contig_names])
+        segs = []
+        total = 0
+        tmp = np.zeros(64, dtype=_lib.SEG_DTYPE)
+        first = np.zeros(n, dtype=np.uint32)
+        for i in sorted(rb.sa):
+            text = rb.sa[i].encode()
+            cnt = lib.svb_parse_sa(text, names_c, len(self.contig_names), tmp.ctypes.data, tmp.shape[0])
+            if cnt > tmp.shape[0]:
+                tmp = np.zeros(cnt, dtype=_lib.SEG_DTYPE)
+                cnt = lib.svb_parse_sa(text, names_c, len(self.contig_names), tmp.ctypes.data, tmp.shape[0])
+            if cnt < 0:
+                raise ValueError("invalid literal in SA tag: %r" % rb.sa[i])
+            first[i] = total
+            self.sa_count[i] = cnt
+            segs.append(tmp[:cnt].copy())
+            total += cnt
+        # sa_first of records without SA: running total (never dereferenced)
+        running = np.concatenate(([0], np.cumsum(self.sa_count)[:-1])).astype(np.uint32) if n else first
+        hdr["sa_first"] = running
+        self.hdr = hdr
+        self.seg = np.concatenate(segs) if segs else np.zeros(0, dtype=_lib.SEG_DTYPE)
+        self._names = list(rb.names)
+        return self
+
+    # ---- access
+    @property
+    def n_aln(self):
+        return int(self.hdr.shape[0])
+
+    @property
+    def n_ops(self):
+        return int(self.hdr["n_cigar"].sum(dtype=np.uint64))
+
+    def query_name(self, i):
+        if self._names is not None:
+            return self._names[int(i)]
+        return lib.svb_bam_query_name(self._bam, int(i)).decode()
+
+    def sequence_slice(self, i, start, length):
+        """query_sequence[start:start+length] of record i (start/length already python-slice normalised)."""
+        if length <= 0:
+            return ""
+        nib0 = 2 * int(self.seq_off[i]) + int(start)
+        b0, b1 = nib0 // 2, (nib0 + int(length) + 1) // 2
+        raw = self.seq4[b0:b1]
+        nib = np.empty(raw.shape[0] * 2, dtype=np.uint8)
+        nib[0::2] = raw >> 4
+        nib[1::2] = raw & 15
+        s = nib0 - 2 * b0
+        return _NT16_LUT[nib[s:s + int(length)]].tobytes().decode("ascii")
+
+    def close(self):
+        if self._bam is not None:
+            for name in ("hdr", "cigar", "seg", "sa_count", "seq4", "seq_off", "contig_lengths"):
+                setattr(self, name, np.zeros(0, dtype=getattr(self, name).dtype))
+            lib.svb_bam_close(self._bam)
+            self._bam = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Table(object):
+    """Device-resident candidate table (svb_table*)."""
+
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self.handle = handle
+
+    def __len__(self):
+        return int(lib.svb_table_size(self.handle))
+
+    def to_numpy(self):
+        n = len(self)
+        rows = np.zeros(n, dtype=_lib.ROW_DTYPE)
+        got = ctypes.c_uint64()
+        self.engine._check(lib.svb_table_to_host(self.engine.handle, self.handle, _lib.ptr(rows), n, ctypes.byref(got)))
+        return rows
+
+    def free(self):
+        if self.handle:
+            lib.svb_table_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Records(object):
+    """Device-resident BAM image (svb_records*)."""
+
+    def __init__(self, engine, handle, host):
+        self.engine = engine
+        self.handle = handle
+        self.host = host
+        self.has_sequences = False
+
+    def free(self):
+        if self.handle:
+            lib.svb_records_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Reference(object):
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self.handle = handle
+
+    def free(self):
+        if self.handle:
+            lib.svb_ref_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine(object):
+    """One GPU context (svb_ctx*).  Not thread-safe, like the reference."""
+
+    def __init__(self, device=0):
+        handle = ctypes.c_void_p()
+        rc = lib.svb_create(int(device), ctypes.byref(handle))
+        if rc != 0:
+            raise RuntimeError("svb_create(device=%d) failed (%d): no usable CUDA device -- this package has no "
+                               "CPU fallback" % (device, rc))
+        self.handle = handle
+        self.device = int(device)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("libsvimasm_b200 error %d: %s" % (rc, lib.svb_last_error(self.handle).decode()))
+
+    def close(self):
+        if self.handle:
+            lib.svb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- uploads
+    def load_records(self, host, with_sequences=False):
+        out = ctypes.c_void_p()
+        rank = lexrank(host.contig_names)
+        self._check(lib.svb_load_records(self.handle, _lib.ptr(host.hdr), host.n_aln, _lib.ptr(host.cigar),
+                                         int(host.cigar.shape[0]), _lib.ptr(host.seg), _lib.ptr(host.sa_count),
+                                         int(host.seg.shape[0]), _lib.ptr(host.contig_lengths), _lib.ptr(rank),
+                                         len(host.contig_names), ctypes.byref(out)))
+        rec = Records(self, out, host)
+        if with_sequences:
+            self.set_sequences(rec)
+        return rec
+
+    def set_sequences(self, rec):
+        host = rec.host
+        self._check(lib.svb_records_set_sequences(self.handle, rec.handle, _lib.ptr(host.seq4), _lib.ptr(host.seq_off)))
+        rec.has_sequences = True
+
+    def load_reference(self, bases, contig_off):
+        """bases: uint8 upper-cased ASCII, contigs concatenated in BAM header order; contig_off: uint64[n+1]."""
+        out = ctypes.c_void_p()
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.uint64)
+        self._check(lib.svb_ref_load(self.handle, _lib.ptr(bases), _lib.ptr(contig_off), contig_off.shape[0] - 1,
+                                     ctypes.byref(out)))
+        return Reference(self, out)
+
+    # ---- hot path
+    def collect(self, rec, params, hap=0):
+        out = ctypes.c_void_p()
+        self._check(lib.svb_collect(self.handle, rec.handle, _lib.ptr(params), int(hap), ctypes.byref(out)))
+        return Table(self, out)
+
+    def pair(self, table1, table2, rec1, rec2, reference, params):
+        out = ctypes.c_void_p()
+        self._check(lib.svb_pair(self.handle, table1.handle, table2.handle, rec1.handle, rec2.handle,
+                                 reference.handle, _lib.ptr(params), ctypes.byref(out)))
+        return Table(self, out)
+
+    def table_from_numpy(self, rows):
+        out = ctypes.c_void_p()
+        rows = np.ascontiguousarray(rows, dtype=_lib.ROW_DTYPE)
+        self._check(lib.svb_table_from_host(self.handle, _lib.ptr(rows), rows.shape[0], ctypes.byref(out)))
+        return Table(self, out)
+
+    def cigar_indel(self, tuples, min_length):
+        """analyze_cigar_indel (SVIM_intra.py:8-30) on the GPU."""
+        ops = np.array([(int(n) << 4) | int(op) for op, n in tuples], dtype=np.uint32)
+        cap = max(1, ops.shape[0])
+        out = np.zeros((cap, 4), dtype=np.int64)
+        n = ctypes.c_uint32()
+        self._check(lib.svb_cigar_indel(self.handle, _lib.ptr(ops), ops.shape[0], int(min_length), _lib.ptr(out), cap,
+                                        ctypes.byref(n)))
+        return [(int(r[0]), int(r[1]), int(r[2]), "DEL" if r[3] else "INS") for r in out[:n.value]]
+
+    def edit_distance(self, pairs):
+        """Unit-cost global edit distance of each (a, b) byte-string pair (edlib.align(a, b)['editDistance'])."""
+        a = b"".join(p[0] for p in pairs)
+        b = b"".join(p[1] for p in pairs)
+        a_off = np.cumsum([0] + [len(p[0]) for p in pairs]).astype(np.uint64)
+        b_off = np.cumsum([0] + [len(p[1]) for p in pairs]).astype(np.uint64)
+        av = np.frombuffer(a, dtype=np.uint8) if a else np.zeros(0, dtype=np.uint8)
+        bv = np.frombuffer(b, dtype=np.uint8) if b else np.zeros(0, dtype=np.uint8)
+        out = np.zeros(len(pairs), dtype=np.int64)
+        self._check(lib.svb_edit_distance(self.handle, _lib.ptr(av), _lib.ptr(a_off), _lib.ptr(bv), _lib.ptr(b_off),
+                                          len(pairs), _lib.ptr(out)))
+        return out
+
+    def cluster_labels(self, condensed_list, threshold):
+        n_points = []
+        for d in condensed_list:
+            m = len(d)
+            n = int(round((1 + (1 + 8 * m) ** 0.5) / 2))
+            assert n * (n - 1) // 2 == m
+            n_points.append(n)
+        flat = np.concatenate([np.asarray(d, dtype=np.float64) for d in condensed_list]) if condensed_list else np.zeros(0)
+        npts = np.asarray(n_points, dtype=np.uint32)
+        out = np.zeros((len(n_points), 32), dtype=np.int32)
+        self._check(lib.svb_cluster_labels(self.handle, _lib.ptr(flat), _lib.ptr(npts), len(n_points), float(threshold),
+                                           _lib.ptr(out)))
+        return [out[i, :n].tolist() for i, n in enumerate(n_points)]
+
+    # ---- timing
+    def timing_reset(self):
+        self._check(lib.svb_timing_reset(self.handle))
+
+    def timing(self):
+        buf = np.zeros(2 * _lib.SVB_K_COUNT, dtype=np.uint64)
+        self._check(lib.svb_timing_get(self.handle, _lib.ptr(buf)))
+        ms = buf[:_lib.SVB_K_COUNT].view(np.float64)
+        launches = buf[_lib.SVB_K_COUNT:]
+        return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(_lib.KERNEL_NAMES)}
+
+    def set_scan_variant(self, variant):
+        self._check(lib.svb_set_scan_variant(self.handle, int(variant)))
+
+    def synchronize(self):
+        self._check(lib.svb_synchronize(self.handle))

@@ -13,6 +13,7 @@ two haplotypes of a diploid sample) are merged in by coordinate, so that the
 same SV gets the same reference position in both haplotypes.
 All randomness comes from numpy.random.Generator(PCG64(seed)).
 """
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -22,6 +23,10 @@ OP_PAD = 15                      # filler used to pad every CIGAR run to 4 ops (
 NT16 = "=ACMGRSVTWYHKDBN"
 _ACGT_CODE = np.array([1, 2, 4, 8], dtype=np.uint8)
 _ACGT_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+_GAP_LUT = (1 + np.floor(np.log1p(-(np.arange(65536) + 0.5) / 65536.0) / np.log(1.0 - 1.0 / 12.0))).astype(np.uint16)
+_KIND_LUT = np.where(np.arange(256) < 154, 8, np.where(np.arange(256) < 205, 1, 2)).astype(np.int8)      # X / I / D
+_LEN_LUT = np.array([1 + (bin(b ^ (b + 1)).count("1") - 1 if b != 255 else 8) for b in range(256)], dtype=np.uint8)
 
 HG38_LENGTHS = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
                 138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
@@ -265,20 +270,73 @@ def _write_nibbles(seq4, nib_off, codes):
 # one haplotype
 
 
-def make_haplotype(cfg, layout, truth, hap_seed, name_prefix="ctg"):
+N_GROUPS = 16          # fixed, so that the data do not depend on the number of worker processes
+
+
+def make_haplotype(cfg, layout, truth, hap_seed, name_prefix="ctg", workers=None):
+    """One haplotype.  Large configurations are generated as N_GROUPS independent slices of the alignment
+    list (own PCG64 stream each) in a process pool and concatenated."""
+    n = layout.tid.shape[0]
+    if cfg.target_ops < 2e7 or n < 16 * N_GROUPS:
+        batch, supp, rng = _make_group((cfg, layout, truth, hap_seed, name_prefix, 0))
+        return _append_records(batch, supp, rng) if supp else batch
+    cuts = np.searchsorted(layout.bound, np.linspace(0, layout.bound[-1], N_GROUPS + 1)[1:-1])
+    cuts = np.unique(np.concatenate(([0], cuts, [n])))
+    jobs = []
+    for g in range(cuts.shape[0] - 1):
+        a, b = int(cuts[g]), int(cuts[g + 1])
+        base = layout.bound[a]
+        sub = Layout(layout.tid[a:b], layout.pos[a:b], layout.span[a:b], layout.bound[a:b + 1] - base)
+        sel = (truth.gpos >= base) & (truth.gpos < layout.bound[b])
+        sub_truth = SVTruth(truth.gpos[sel] - base, truth.kind[sel], truth.length[sel], truth.sv_id[sel], truth.edit[sel])
+        jobs.append((cfg, sub, sub_truth, hap_seed + 1000003 * (g + 1), name_prefix, a))
+    if workers is None:
+        workers = min(len(jobs), os.cpu_count() or 1)
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_make_group, jobs)
+    else:
+        parts = [_make_group(j) for j in jobs]
+    batches = [p[0] for p in parts]
+    supp = [r for p in parts for r in p[1]]
+    n_c = np.concatenate([b.n_cigar for b in batches])
+    l_seq = np.concatenate([b.l_seq for b in batches])
+    c_off = np.zeros(n + 1, dtype=np.uint64)
+    c_off[1:] = np.cumsum((n_c.astype(np.int64) + 3) // 4 * 4)
+    s_off = np.zeros(n + 1, dtype=np.uint64)
+    s_off[1:] = np.cumsum((l_seq.astype(np.int64) + 1) // 2)
+    sa = {}
+    names = []
+    for (cfg_, sub, tr, seed, pre, first), b in zip(jobs, batches):
+        sa.update({i + first: t for i, t in b.sa.items()})
+        names.extend(b.names)
+    whole = RecordBatch(list(cfg.contig_names), np.asarray(cfg.contig_lengths, dtype=np.int32),
+                        np.concatenate([b.tid for b in batches]), np.concatenate([b.pos for b in batches]),
+                        np.concatenate([b.flag for b in batches]), np.concatenate([b.mapq for b in batches]), n_c, c_off,
+                        l_seq, s_off, np.concatenate([b.cigar for b in batches]),
+                        np.concatenate([b.seq4 for b in batches]), names, sa)
+    rng = np.random.Generator(np.random.PCG64(hap_seed ^ 0xABCDEF))
+    return _append_records(whole, supp, rng) if supp else whole
+
+
+def _make_group(job):
+    cfg, layout, truth, hap_seed, name_prefix, first_index = job
     rng = np.random.Generator(np.random.PCG64(hap_seed))
     n = layout.tid.shape[0]
     bound = layout.bound
     total = int(bound[-1])
 
-    # ---- noise events as a renewal process over alignment space
+    # ---- noise events as a renewal process over alignment space.  One 32-bit draw per event feeds three
+    # inverse-CDF tables: gap ~ geometric(1/12) (16 bits), kind X/I/D = 60/20/20 % (8 bits), short indel
+    # length ~ geometric(1/2) (8 bits)
     n_guess = int(total / 13.0 * 1.02) + 1024
-    gaps = rng.geometric(1.0 / 12.0, n_guess).astype(np.int64)
-    u = rng.random(n_guess)
-    kind = np.where(u < 0.6, OP_X, np.where(u < 0.8, OP_I, OP_D)).astype(np.int8)
-    length = np.minimum(rng.geometric(0.5, n_guess), 39).astype(np.int64)
+    raw = rng.integers(0, 2 ** 32, n_guess, dtype=np.uint32)
+    gaps = _GAP_LUT[raw & 0xFFFF].astype(np.int64)
+    kind = _KIND_LUT[(raw >> 16) & 0xFF]
+    length = _LEN_LUT[raw >> 24].astype(np.int64)
+    del raw
     length[kind == OP_X] = 1
-    del u
     rspan = np.where(kind == OP_I, 0, length)
     start = np.cumsum(gaps + rspan) - rspan           # event start = previous end + gap
     del gaps
@@ -297,9 +355,7 @@ def make_haplotype(cfg, layout, truth, hap_seed, name_prefix="ctg"):
     tid_sv, tedit = truth.sv_id[ok], truth.edit[ok]
     lo = np.searchsorted(start, tpos - 42, side="left")
     hi = np.searchsorted(start, tpos + tspan + 2, side="right")
-    marks = np.zeros(start.shape[0] + 1, dtype=np.int32)
-    np.add.at(marks, lo, 1)
-    np.add.at(marks, hi, -1)
+    marks = (np.bincount(lo, minlength=start.shape[0] + 1) - np.bincount(hi, minlength=start.shape[0] + 1)).astype(np.int32)
     keep &= np.cumsum(marks[:-1]) == 0
     del marks
     start, kind, length, rspan = start[keep], kind[keep], length[keep], rspan[keep]
@@ -407,14 +463,12 @@ def make_haplotype(cfg, layout, truth, hap_seed, name_prefix="ctg"):
     else:
         seq4 = np.zeros(int(seq_off[-1]), dtype=np.uint8)
 
-    names = ["%s%06d" % (name_prefix, i) for i in range(n)]
+    names = ["%s%06d" % (name_prefix, first_index + i) for i in range(n)]
     batch = RecordBatch(list(cfg.contig_names), np.asarray(cfg.contig_lengths, dtype=np.int32),
                         layout.tid.astype(np.int32), layout.pos.astype(np.int32), flag, mapq,
                         n_cigar.astype(np.uint32), cigar_off.astype(np.uint64), l_seq.astype(np.uint32),
                         seq_off.astype(np.uint64), cigar, seq4, names, sa_text)
-    if supp:
-        batch = _append_records(batch, supp, rng)
-    return batch
+    return batch, supp, rng
 
 
 # ----------------------------------------------------------------------------------------------
@@ -561,52 +615,62 @@ def _split_read(rng, cfg, lengths, tid, pos, span, rev, q_body):
 
 
 def _append_records(batch, extra, rng):
-    """Add supplementary records and restore coordinate order (stable on (tid, pos))."""
+    """Insert supplementary records at their coordinate-sorted places (stable on (tid, pos))."""
     n0 = batch.n_aln
     m = len(extra)
-    tid = np.concatenate([batch.tid, np.array([r["tid"] for r in extra], dtype=np.int32)])
-    pos = np.concatenate([batch.pos, np.array([r["pos"] for r in extra], dtype=np.int32)])
-    flag = np.concatenate([batch.flag, np.array([r["flag"] for r in extra], dtype=np.uint16)])
-    mapq = np.concatenate([batch.mapq, np.array([r["mapq"] for r in extra], dtype=np.uint8)])
-    n_c = np.concatenate([batch.n_cigar, np.array([len(r["ops"]) for r in extra], dtype=np.uint32)])
-    l_seq = np.concatenate([batch.l_seq, np.array([r["l_seq"] for r in extra], dtype=np.uint32)])
-    add_ops = int(sum((len(r["ops"]) + 3) // 4 * 4 for r in extra))
-    add_seq = int(sum((r["l_seq"] + 1) // 2 for r in extra))
-    cigar = np.concatenate([batch.cigar, np.full(add_ops, OP_PAD, dtype=np.uint32)])
-    raw = np.frombuffer(rng.bytes(add_seq), dtype=np.uint8)
-    seq4 = np.concatenate([batch.seq4, (_ACGT_CODE[raw & 3] << 4) | _ACGT_CODE[(raw >> 2) & 3]])
-    c_off = np.concatenate([batch.cigar_off[:-1], np.zeros(m, dtype=np.uint64)])
-    s_off = np.concatenate([batch.seq_off[:-1], np.zeros(m, dtype=np.uint64)])
-    co, so = int(batch.cigar_off[-1]), int(batch.seq_off[-1])
+    e_tid = np.array([r["tid"] for r in extra], dtype=np.int64)
+    e_pos = np.array([r["pos"] for r in extra], dtype=np.int64)
+    e_order = np.lexsort((e_pos, e_tid))
+    extra = [extra[int(i)] for i in e_order]
+    e_key = e_tid[e_order] * (1 << 32) + e_pos[e_order]
+    o_key = batch.tid.astype(np.int64) * (1 << 32) + batch.pos.astype(np.int64)
+    where = np.searchsorted(o_key, e_key, side="right")          # originals first on ties
+    # per-record tables
+    def ins(arr, vals, dtype):
+        return np.insert(arr, where, np.asarray(vals, dtype=dtype))
+    tid = ins(batch.tid, [r["tid"] for r in extra], np.int32)
+    pos = ins(batch.pos, [r["pos"] for r in extra], np.int32)
+    flag = ins(batch.flag, [r["flag"] for r in extra], np.uint16)
+    mapq = ins(batch.mapq, [r["mapq"] for r in extra], np.uint8)
+    n_c = ins(batch.n_cigar, [len(r["ops"]) for r in extra], np.uint32)
+    l_seq = ins(batch.l_seq, [r["l_seq"] for r in extra], np.uint32)
+    # flat arrays: slices of the original interleaved with the new runs
+    c_parts, s_parts = [], []
+    prev = 0
     for k, r in enumerate(extra):
-        c_off[n0 + k], s_off[n0 + k] = co, so
-        vals = np.array([(ln << 4) | op for op, ln in r["ops"]], dtype=np.uint32)
-        cigar[co:co + vals.shape[0]] = vals
-        co += (len(r["ops"]) + 3) // 4 * 4
-        so += (r["l_seq"] + 1) // 2
-    names = batch.names + ["supp%06d" % k for k in range(m)]
-    order = np.lexsort((np.arange(n0 + m), pos, tid))
-    # the flat arrays keep their physical order; only the per-record tables are permuted, then offsets rebuilt
-    n_c_o = n_c[order].astype(np.int64)
-    padded = (n_c_o + 3) // 4 * 4
+        w = int(where[k])
+        if w > prev:
+            c_parts.append(batch.cigar[int(batch.cigar_off[prev]):int(batch.cigar_off[w])])
+            s_parts.append(batch.seq4[int(batch.seq_off[prev]):int(batch.seq_off[w])])
+            prev = w
+        run = np.full((len(r["ops"]) + 3) // 4 * 4, OP_PAD, dtype=np.uint32)
+        run[:len(r["ops"])] = [(ln << 4) | op for op, ln in r["ops"]]
+        c_parts.append(run)
+        raw = np.frombuffer(rng.bytes((r["l_seq"] + 1) // 2), dtype=np.uint8)
+        s_parts.append((_ACGT_CODE[raw & 3] << 4) | _ACGT_CODE[(raw >> 2) & 3])
+    c_parts.append(batch.cigar[int(batch.cigar_off[prev]):])
+    s_parts.append(batch.seq4[int(batch.seq_off[prev]):])
+    cigar = np.concatenate(c_parts)
+    seq4 = np.concatenate(s_parts)
+    padded = (n_c.astype(np.int64) + 3) // 4 * 4
     new_off = np.zeros(n0 + m + 1, dtype=np.uint64)
     new_off[1:] = np.cumsum(padded)
-    new_cigar = np.full(int(new_off[-1]), OP_PAD, dtype=np.uint32)
-    nb = (l_seq[order].astype(np.int64) + 1) // 2
     new_soff = np.zeros(n0 + m + 1, dtype=np.uint64)
-    new_soff[1:] = np.cumsum(nb)
-    new_seq = np.empty(int(new_soff[-1]), dtype=np.uint8)
-    # vectorised gather through a per-op source index
-    src_c = np.repeat(c_off[order].astype(np.int64) - new_off[:-1].astype(np.int64), padded) + np.arange(int(new_off[-1]))
-    new_cigar[:] = cigar[src_c]
-    src_s = np.repeat(s_off[order].astype(np.int64) - new_soff[:-1].astype(np.int64), nb) + np.arange(int(new_soff[-1]))
-    new_seq[:] = seq4[src_s]
-    inv = np.empty(n0 + m, dtype=np.int64)
-    inv[order] = np.arange(n0 + m)
-    sa = {int(inv[i]): s for i, s in batch.sa.items()}
-    return RecordBatch(batch.contig_names, batch.contig_lengths, tid[order], pos[order], flag[order], mapq[order],
-                       n_c[order], new_off, l_seq[order], new_soff, new_cigar, new_seq,
-                       [names[int(i)] for i in order], sa)
+    new_soff[1:] = np.cumsum((l_seq.astype(np.int64) + 1) // 2)
+    # new index of every original record = old index + number of inserts before it
+    shift = np.searchsorted(where, np.arange(n0), side="right")
+    new_index = np.arange(n0) + shift
+    names = [None] * (n0 + m)
+    for i, nm in enumerate(batch.names):
+        names[int(new_index[i])] = nm
+    k = 0
+    for i in range(n0 + m):
+        if names[i] is None:
+            names[i] = "supp%06d" % k
+            k += 1
+    sa = {int(new_index[i]): t for i, t in batch.sa.items()}
+    return RecordBatch(batch.contig_names, batch.contig_lengths, tid, pos, flag, mapq, n_c, new_off, l_seq, new_soff,
+                       cigar, seq4, names, sa)
 
 
 # ----------------------------------------------------------------------------------------------

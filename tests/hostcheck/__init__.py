@@ -1,0 +1,23 @@
+"""TEST INFRASTRUCTURE: builds tests/hostcheck/hostcheck.cpp (host compile of the kernels' cores)."""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "hostcheck.so")
+
+
+def load():
+    src = os.path.join(_HERE, "hostcheck.cpp")
+    deps = [src] + [os.path.join(_HERE, "..", "..", "svim_asm_b200", "csrc", f) for f in ("linkage.cuh", "walk.cuh")]
+    if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _SO, src])
+    lib = ctypes.CDLL(_SO)
+    vp = ctypes.c_void_p
+    lib.hc_cluster_labels.restype = ctypes.c_int
+    lib.hc_cluster_labels.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp]
+    lib.hc_walk.restype = ctypes.c_int
+    lib.hc_walk.argtypes = [vp, ctypes.c_int, ctypes.c_int32, ctypes.c_uint32, vp, vp, vp, ctypes.c_int32,
+                            ctypes.c_uint32, ctypes.c_uint32, vp, ctypes.c_int]
+    return lib

@@ -1,0 +1,35 @@
+// TEST INFRASTRUCTURE: compiles the __host__ __device__ cores of the kernels (linkage, segment walk)
+// with g++ so that their logic is checked on a CPU-only box.  Never shipped, never loaded by the
+// product: the product path is the CUDA library only.
+#include <stdint.h>
+#include <vector>
+#include "../../svim_asm_b200/csrc/linkage.cuh"
+#include "../../svim_asm_b200/csrc/walk.cuh"
+
+extern "C" int hc_cluster_labels(const double* condensed, int n, double threshold, int* labels) {
+    double work[LINK_MAXN * (LINK_MAXN - 1) / 2];
+    for (int i = 0; i < n * (n - 1) / 2; ++i) work[i] = condensed[i];
+    return link_complete_fcluster(n, work, threshold, labels);
+}
+
+// segs: k rows of (q_start, q_end, tid, ref_start, ref_end, rev), primary first.  params: min_mapq,
+// min_sv, max_sv, qgt, qot, rgt, rot.  Returns the number of rows, or -(error bits) on a reference abort.
+extern "C" int hc_walk(const int32_t* segs, int k, int32_t read_len, uint32_t l_seq, const int32_t* params,
+                       const int32_t* contig_len, const int32_t* lexrank, int32_t n_contig, uint32_t aln_idx,
+                       uint32_t hap, svb_row* rows_out, int cap) {
+    std::vector<WalkScratch> sc(static_cast<size_t>(k) + 1);
+    for (int i = 0; i < k; ++i) {
+        WalkSeg s;
+        s.q_start = segs[6 * i]; s.q_end = segs[6 * i + 1]; s.tid = segs[6 * i + 2];
+        s.ref_start = segs[6 * i + 3]; s.ref_end = segs[6 * i + 4]; s.rev = segs[6 * i + 5];
+        sc[i].seg = s;
+    }
+    WalkParams p{params[0], params[1], params[2], params[3], params[4], params[5], params[6]};
+    WalkRead rd{aln_idx, hap, read_len, l_seq, contig_len, lexrank, n_contig};
+    std::vector<svb_row> rows(static_cast<size_t>(k) * k + 8);
+    WalkOut o{rows.data(), 0, 0};
+    walk_read(rd, p, sc.data(), static_cast<uint32_t>(k), o);
+    if (o.err) return -static_cast<int>(o.err);
+    for (uint32_t i = 0; i < o.n && static_cast<int>(i) < cap; ++i) rows_out[i] = rows[i];
+    return static_cast<int>(o.n);
+}

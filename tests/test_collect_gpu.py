@@ -1,0 +1,105 @@
+"""GPU parity of svb_collect (K2 cigar_scan + K4 segment_walk + K5 merge) against the CPU oracle.
+
+Reference path under test: SVIM_COLLECT.py:61-83 -> SVIM_intra.py:8-44 + SVIM_inter.py:62-340.
+Bit-exact: every integer field of every row, and the row order."""
+import numpy as np
+import pytest
+
+from oracle import port
+from svim_asm_b200 import synth
+from svim_asm_b200.engine import HostBatch, make_params
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+KATS = [  # reference src/tests/test_intra.py:8-22
+    ([(5, 10), (4, 20), (0, 10), (7, 10), (8, 5), (0, 5), (1, 50), (0, 30), (4, 25), (5, 15)], [(30, 50, 50, "INS")]),
+    ([(5, 10), (4, 20), (0, 30), (2, 50), (0, 30), (4, 25), (5, 15)], [(30, 50, 50, "DEL")]),
+    ([(5, 10), (4, 20), (0, 30), (2, 40), (1, 50), (0, 30), (4, 25), (5, 15)], [(30, 50, 40, "DEL"), (70, 50, 50, "INS")]),
+    ([(5, 10), (4, 20), (0, 30), (1, 40), (2, 50), (0, 30), (4, 25), (5, 15)], [(30, 50, 40, "INS"), (30, 90, 50, "DEL")]),
+]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_reference_known_answers(engine, variant):
+    engine.set_scan_variant(variant)
+    for tuples, want in KATS:
+        assert engine.cigar_indel(tuples, 30) == want
+    assert engine.cigar_indel([], 30) == []
+    assert engine.cigar_indel([(3, 100), (2, 40)], 40) == [(0, 0, 40, "DEL")]      # N does not advance (App. B#1)
+    engine.set_scan_variant(0)
+
+
+def _compare(engine, rb, variants=(0, 1), **params):
+    host = HostBatch.from_record_batch(rb)
+    want = port.collect(host, port.Params(**params))
+    rec = engine.load_records(host)
+    for v in variants:
+        engine.set_scan_variant(v)
+        got = engine.collect(rec, make_params(**params)).to_numpy()
+        diff = util.rows_equal(got, want)
+        assert diff is None, (v, diff)
+        assert np.all(np.diff(got["ordinal"].astype(np.uint64)) > 0) if got.shape[0] > 1 else True
+    engine.set_scan_variant(0)
+    rec.free()
+    return want
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_small_random_batches(engine, seed):
+    multi = seed % 2 == 0
+    cfg = synth.SynthConfig(["chr1", "chr10", "chr2"] if multi else ["chrA"],
+                            [400000, 300000, 350000] if multi else [900000], 60, 4e4, seed,
+                            sv_per_event=5e-3, split_fraction=0.5)
+    want = _compare(engine, synth.make_haploid(cfg))
+    assert want.shape[0] > 20
+
+
+def test_many_tiny_alignments(engine):
+    # several alignment heads per 1024-op chunk: the generic per-piece path of the scan
+    rng = np.random.default_rng(9)
+    recs = []
+    pos = 10
+    for i in range(3000):
+        k = int(rng.integers(0, 9))
+        cig = []
+        for _ in range(k):
+            op = int(rng.choice([0, 1, 2, 3, 4, 5, 7, 8]))
+            cig.append((op, int(rng.choice([1, 5, 39, 40, 41, 300]))))
+        flag = int(rng.choice([0, 16, 4, 256, 2048]))
+        recs.append(dict(tid=int(i >= 1500), pos=pos % 400000, flag=flag, mapq=int(rng.choice([60, 19, 20])), cigar=cig,
+                         l_seq=100000))
+        pos += 97
+    recs.sort(key=lambda r: (r["tid"], r["pos"]))
+    rb = util.batch_from_records(["c1", "c2"], [500000, 500000], recs)
+    want = _compare(engine, rb)
+    assert want.shape[0] > 500
+
+
+def test_dense_events_and_capacity_retry(engine):
+    # every op emits: the output is far larger than the first capacity guess
+    cig = [(1 if i % 2 else 2, 50) for i in range(20000)]
+    recs = [dict(tid=0, pos=100, cigar=cig, l_seq=2_000_000), dict(tid=0, pos=200, cigar=cig[:777], l_seq=100000)]
+    rb = util.batch_from_records(["c1"], [3_000_000], recs)
+    want = _compare(engine, rb)
+    assert want.shape[0] == 20777
+
+
+def test_contig_end_clamp_and_min_size(engine):
+    recs = [dict(tid=0, pos=990, cigar=[(0, 5), (1, 100), (2, 60), (0, 5)], l_seq=110),     # INS/DEL ends clamp to 1000
+            dict(tid=0, pos=0, cigar=[(2, 40), (0, 10), (1, 39), (0, 1)], l_seq=50)]
+    rb = util.batch_from_records(["c1"], [1000], recs)
+    _compare(engine, rb)
+    _compare(engine, rb, min_sv_size=1)
+    _compare(engine, rb, min_sv_size=0)
+    _compare(engine, rb, min_mapq=61)
+
+
+def test_chr20_scale_with_giant_alignment(engine):
+    cfg = synth.config_c2()
+    cfg.target_ops = 3.0e6
+    cfg.n_aln = 600
+    cfg.giant_ops = 200_000                     # > 65535 ops and > 24 tiles: long look-back chains
+    rb = synth.make_haploid(cfg)
+    want = _compare(engine, rb)
+    assert int(rb.n_cigar.max()) > 150_000 and want.shape[0] > 100
