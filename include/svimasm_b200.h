@@ -153,6 +153,7 @@ const uint32_t* svb_bam_sa_count(const svb_bam* bam);
 const uint8_t* svb_bam_seq4(const svb_bam* bam);         /* 4-bit packed query bases */
 const uint64_t* svb_bam_seq_offsets(const svb_bam* bam); /* n_records + 1 byte offsets */
 const char* svb_bam_query_name(const svb_bam* bam, int64_t record);
+const char* svb_bam_sa_text(const svb_bam* bam, int64_t record);   /* raw SA:Z value or NULL (AlignedSegment.get_tag("SA")) */
 /* SA:Z text -> segments for callers that hold records in memory (same rules as the ingest).
  * names/n_contig resolve rname -> tid.  Returns the number of segments written or a negative status. */
 int svb_parse_sa(const char* sa_text, const char* const* contig_names, int32_t n_contig,

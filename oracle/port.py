@@ -429,7 +429,9 @@ def collect(host, p, hap=0, scan=None):
         for k, (pr, pq, ln, kind) in enumerate(scan(ops, p.min_sv_size)):
             # ordinal: the GPU derives it from the op index; only the ORDER matters for comparisons
             if kind == "DEL":
-                rows.append(_span_row(DEL, tid, pos + pr, pos + pr + ln, clen, hap, i, (int(i) << 32) | k))
+                r = _span_row(DEL, tid, pos + pr, pos + pr + ln, clen, hap, i, (int(i) << 32) | k)
+                r["seq_pos"] = pq                    # pos_read travels with the row (no sequence: seq_len 0)
+                rows.append(r)
             else:
                 if l_seq == 0:
                     raise OracleAbort("query_sequence is None")

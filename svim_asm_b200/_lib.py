@@ -66,6 +66,7 @@ SIGNATURES = {
     "svb_bam_seq4": (c_void_p, [c_void_p]),
     "svb_bam_seq_offsets": (c_void_p, [c_void_p]),
     "svb_bam_query_name": (c_char_p, [c_void_p, c_i64]),
+    "svb_bam_sa_text": (c_char_p, [c_void_p, c_i64]),
     "svb_parse_sa": (c_int, [c_char_p, P(c_char_p), c_i32, c_void_p, c_i32]),
     "svb_load_records": (c_int, [c_void_p, c_void_p, c_u32, c_void_p, c_u64, c_void_p, c_void_p, c_u32, c_void_p,
                                  c_void_p, c_i32, P(c_void_p)]),

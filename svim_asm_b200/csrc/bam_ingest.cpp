@@ -31,6 +31,8 @@ struct svb_bam {
     std::vector<uint64_t> seq_off;
     std::vector<char> names;
     std::vector<uint64_t> name_off;
+    std::vector<char> sa_text;            // raw SA:Z values, NUL separated (get_tag("SA") of the seam-level API)
+    std::vector<int64_t> sa_text_off;     // per record: offset into sa_text or -1
 };
 
 namespace {
@@ -329,6 +331,7 @@ int svb_bam_open(const char* path, int n_threads, svb_bam** out, char* err, int 
     bam->seq_off.resize(n + 1);
     bam->names.resize(name_bytes);
     bam->name_off.resize(n + 1);
+    bam->sa_text_off.assign(n, -1);
     uint64_t co = 0, so = 0, no = 0;
     for (size_t i = 0; i < n; ++i) {
         const Rec& r = recs[i];
@@ -361,6 +364,8 @@ int svb_bam_open(const char* path, int n_threads, svb_bam** out, char* err, int 
         no += l_name;
         h.sa_first = static_cast<uint32_t>(bam->seg.size());
         if (r.sa) {
+            bam->sa_text_off[i] = static_cast<int64_t>(bam->sa_text.size());
+            bam->sa_text.insert(bam->sa_text.end(), r.sa, r.sa + strlen(r.sa) + 1);
             const int cnt = svb_parse_sa(r.sa, name_ptrs.data(), n_ref, nullptr, 0);
             if (cnt < 0) {
                 delete bam;
@@ -394,6 +399,10 @@ const svb_segment* svb_bam_segments(const svb_bam* b) { return b ? b->seg.data()
 const uint32_t* svb_bam_sa_count(const svb_bam* b) { return b ? b->sa_count.data() : nullptr; }
 const uint8_t* svb_bam_seq4(const svb_bam* b) { return b ? b->seq4.data() : nullptr; }
 const uint64_t* svb_bam_seq_offsets(const svb_bam* b) { return b ? b->seq_off.data() : nullptr; }
+const char* svb_bam_sa_text(const svb_bam* b, int64_t record) {
+    if (!b || record < 0 || static_cast<size_t>(record) >= b->hdr.size() || b->sa_text_off[static_cast<size_t>(record)] < 0) return nullptr;
+    return b->sa_text.data() + b->sa_text_off[static_cast<size_t>(record)];
+}
 const char* svb_bam_query_name(const svb_bam* b, int64_t record) {
     return (b && record >= 0 && static_cast<size_t>(record) < b->hdr.size()) ? b->names.data() + b->name_off[static_cast<size_t>(record)] : nullptr;
 }

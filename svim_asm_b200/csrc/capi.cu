@@ -5,6 +5,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "pairing.cuh"
 
 int svb_fail(svb_ctx* ctx, int code, const char* what, cudaError_t e) {
     if (ctx) {
@@ -70,6 +71,8 @@ static int check_device_status(svb_ctx* ctx) {
         return svb_fail(ctx, SVB_ERR_FORMAT, "reference_id out of range (pysam get_reference_name would raise ValueError)");
     if (st & DEV_ERR_ASSERT)
         return svb_fail(ctx, SVB_ERR_ASSERT, "candidate end is smaller than its start (reference assertion, SVCandidate.py)");
+    if (st & DEV_ERR_NOSEQ)
+        return svb_fail(ctx, SVB_ERR_ARG, "insertion candidates need the query sequences: call svb_records_set_sequences first");
     return svb_fail(ctx, SVB_ERR_CAPACITY, "per-read scratch capacity exceeded");
 }
 
@@ -480,7 +483,7 @@ int svb_cigar_indel(svb_ctx* ctx, const uint32_t* packed_ops, uint32_t n_ops, in
         const bool del = r.type == SVB_DEL;
         // with pos = 0 and an unbounded contig the clamps are the identity: start == pos_ref
         out4[4 * i + 0] = del ? r.src_start : r.dst_start;
-        out4[4 * i + 1] = del ? -1 : static_cast<int64_t>(r.seq_pos);
+        out4[4 * i + 1] = static_cast<int64_t>(r.seq_pos);      // pos_read is kept for deletions too
         out4[4 * i + 2] = del ? static_cast<int64_t>(r.src_end) - r.src_start : static_cast<int64_t>(r.dst_end) - r.dst_start;
         out4[4 * i + 3] = del ? 1 : 0;
     }
@@ -502,6 +505,15 @@ int svb_ref_load(svb_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
         e = cudaMemcpyAsync(r->d_contig_off, contig_off, sizeof(uint64_t) * (static_cast<size_t>(n_contig) + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && r->n_bases) e = cudaMalloc(&r->d_bases, r->n_bases);
     if (e == cudaSuccess && r->n_bases) e = cudaMemcpyAsync(r->d_bases, bases, r->n_bases, cudaMemcpyHostToDevice, ctx->stream);
+    uint8_t map[256];
+    std::string why;
+    if (build_class_map(bases, r->n_bases, map, &why) != SVB_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        svb_ref_free(r);
+        return svb_fail(ctx, SVB_ERR_FORMAT, why.c_str());
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_class_map, 256);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_class_map, map, 256, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         svb_ref_free(r);
@@ -516,6 +528,7 @@ void svb_ref_free(svb_ref* r) {
     cudaSetDevice(r->device);
     cudaFree(r->d_bases);
     cudaFree(r->d_contig_off);
+    cudaFree(r->d_class_map);
     delete r;
 }
 

@@ -105,11 +105,37 @@ __device__ __forceinline__ bool record_passes(const svb_aln_hdr& h, int32_t min_
 }
 
 template <bool USE_TMA>
-__global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a) {
+__device__ __forceinline__ uint4 reload_row_fn(const uint4* s_tile, const uint4* cigar, uint64_t tile4, uint32_t here4, uint32_t i4) {
+    if (i4 >= here4) return make_uint4(15u, 15u, 15u, 15u);
+    if (USE_TMA) return s_tile[i4];
+    return cigar[tile4 + i4];
+}
+
+// fast path of one uint4 (4 ops): packed advance sums and the rare flag
+__device__ __forceinline__ void fast_row_fn(const uint4 d, const uint2* lut, bool in_head, uint32_t& totR, uint32_t& totQ,
+                                            uint32_t& headR, uint32_t& headQ, bool& rare) {
+    const uint2 e0 = lut[d.x & 15u], e1 = lut[d.y & 15u], e2 = lut[d.z & 15u], e3 = lut[d.w & 15u];
+    unsigned long long acc = static_cast<unsigned long long>(d.x >> 4) * e0.x;
+    acc += static_cast<unsigned long long>(d.y >> 4) * e1.x;
+    acc += static_cast<unsigned long long>(d.z >> 4) * e2.x;
+    acc += static_cast<unsigned long long>(d.w >> 4) * e3.x;
+    rare = rare || d.x >= e0.y || d.y >= e1.y || d.z >= e2.y || d.w >= e3.y;
+    const uint32_t rr = static_cast<uint32_t>(acc >> 31), qq = static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
+    totR += rr;
+    totQ += qq;
+    if (in_head) {
+        headR += rr;
+        headQ += qq;
+    }
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(THREADS, 5) cigar_scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_tile = reinterpret_cast<uint4*>(smem_raw);       // TILE4 uint4 when USE_TMA
     __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ uint32_t s_tile_id;
+    __shared__ uint2 s_lut[16];      // per op code: x = multiplier (bit 0 read advance, bit 31 reference advance), y = rare threshold
     __shared__ uint32_t s_wR[WARPS], s_wQ[WARPS], s_wCnt[WARPS], s_wHead[WARPS];
     __shared__ uint32_t s_cR[WARPS], s_cQ[WARPS], s_cResolved[WARPS], s_cBase[WARPS];
     __shared__ uint32_t s_tileR, s_tileQ;
@@ -117,6 +143,13 @@ __global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
+    if (tid >= 32u && tid < 48u) {
+        const uint32_t op = tid - 32u;
+        uint2 e;
+        e.x = (((REF_MASK >> op) & 1u) << 31) | ((READ_MASK >> op) & 1u);
+        e.y = ((INDEL_MASK >> op) & 1u) ? a.min16 : (((NH_MASK >> op) & 1u) ? 16u : 0xFFFFFFFFu);
+        s_lut[op] = e;
+    }
     if (tid == 0) {
         s_tile_id = atomicAdd(a.ticket, 1u);      // tiles are claimed in scheduling order: look-back cannot deadlock
         if (USE_TMA) {
@@ -158,16 +191,11 @@ __global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a
     }
 
     // ---- load + per-lane decode, phase 1: totals and emit counts of the chunk's alignment pieces.
-    // Common case: at most one alignment head inside the chunk -> one decode pass feeds two accumulator
-    // sets (before / after the head).  Chunks with several heads take the generic per-piece loop.
-    uint4 v[ROWS];
-    if (!USE_TMA) {
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const uint64_t g4 = g4base + static_cast<uint64_t>(r) * 32u + lane;
-            v[r] = (g4 < a.n4) ? ldg_stream(a.cigar + g4) : make_uint4(15u, 15u, 15u, 15u);
-        }
-    } else {
+    // Fast path per op (no branches, three pipes): one 8-byte table entry {multiplier, threshold} from
+    // shared memory; IMAD.WIDE adds len * multiplier to a packed accumulator (read sum in bits 0..30,
+    // reference sum from bit 31 up); one compare-OR flags the rare ops (I/D with len >= min_sv_size,
+    // N/H with len > 0).  Exact event bits are only recomputed when the flag fires somewhere in the warp.
+    if (USE_TMA) {
         uint32_t ready = 0;
         while (!ready) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -175,52 +203,58 @@ __global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a
         }
     }
     // re-read of a row for the rare paths (shared memory, or L2 for the LDG variant)
-    auto reload_row = [&](int r) -> uint4 {
-        const uint32_t i4 = warp * CHUNK4 + static_cast<uint32_t>(r) * 32u + lane;
-        if (i4 >= here4) return make_uint4(15u, 15u, 15u, 15u);
-        if (USE_TMA) return s_tile[i4];
-        return a.cigar[tile4 + i4];
-    };
+    const uint32_t lane4 = warp * CHUNK4 + lane;            // this lane's uint4 index inside the tile, row 0
+#define reload_row(r) reload_row_fn<USE_TMA>(s_tile, a.cigar, tile4, here4, lane4 + static_cast<uint32_t>(r) * 32u)
 
-    uint32_t evbits = 0, nhbits = 0;
+    uint32_t evbits = 0;
     uint32_t tailR = 0, tailQ = 0, warp_cnt = 0;
     if (chunk_live) {
         const uint32_t n_pieces = a_hi - a_lo + 1u;
-        // rows of this lane that lie before the (single) head: g4base + 32 r + lane < split4
+        // rows of this lane that lie before the first head inside the chunk: g4base + 32 r + lane < split4
         const uint64_t split4 = (n_pieces >= 2u) ? static_cast<uint64_t>(a.off4[a_lo + 1u]) : g4end;
-        uint32_t headR = 0, headQ = 0, restR = 0, restQ = 0;
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            uint4 d;
-            if (USE_TMA) {
-                const uint32_t i4 = warp * CHUNK4 + static_cast<uint32_t>(r) * 32u + lane;
-                d = (i4 < here4) ? s_tile[i4] : make_uint4(15u, 15u, 15u, 15u);
-            } else {
-                d = v[r];
-            }
-            uint32_t rr = 0, qq = 0;
-            decode_op(d.x, a.min16, rr, qq, evbits, nhbits, 1u << (4 * r + 0));
-            decode_op(d.y, a.min16, rr, qq, evbits, nhbits, 1u << (4 * r + 1));
-            decode_op(d.z, a.min16, rr, qq, evbits, nhbits, 1u << (4 * r + 2));
-            decode_op(d.w, a.min16, rr, qq, evbits, nhbits, 1u << (4 * r + 3));
-            const bool before = g4base + static_cast<uint64_t>(r) * 32u + lane < split4;
-            headR += before ? rr : 0u;
-            headQ += before ? qq : 0u;
-            restR += before ? 0u : rr;
-            restQ += before ? 0u : qq;
-        }
-        // bit mask of this lane's rows before the head
         const long long rows_before = (static_cast<long long>(split4) - static_cast<long long>(g4base) - lane + 31) / 32;
-        const uint32_t nb = rows_before <= 0 ? 0u : (rows_before >= ROWS ? static_cast<uint32_t>(ROWS) : static_cast<uint32_t>(rows_before));
-        const uint32_t first_mask = nb >= 8u ? 0xFFFFFFFFu : ((1u << (4u * nb)) - 1u);
+        const int nb = rows_before <= 0 ? 0 : (rows_before >= ROWS ? ROWS : static_cast<int>(rows_before));
+        uint32_t headR = 0, headQ = 0, totR = 0, totQ = 0;
+        bool rare = false;
+        if (USE_TMA) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const uint32_t i4 = warp * CHUNK4 + static_cast<uint32_t>(r) * 32u + lane;
+                fast_row_fn((i4 < here4) ? s_tile[i4] : make_uint4(15u, 15u, 15u, 15u), s_lut, r < nb, totR, totQ, headR, headQ, rare);
+            }
+        } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {         // two batches of four 128-bit loads in flight per lane
+                uint4 v[ROWS / 2];
+#pragma unroll
+                for (int k = 0; k < ROWS / 2; ++k) {
+                    const uint64_t g4 = g4base + static_cast<uint64_t>(half * (ROWS / 2) + k) * 32u + lane;
+                    v[k] = (g4 < a.n4) ? ldg_stream(a.cigar + g4) : make_uint4(15u, 15u, 15u, 15u);
+                }
+#pragma unroll
+                for (int k = 0; k < ROWS / 2; ++k) fast_row_fn(v[k], s_lut, half * (ROWS / 2) + k < nb, totR, totQ, headR, headQ, rare);
+            }
+        }
+        const uint32_t first_mask = nb >= 8 ? 0xFFFFFFFFu : ((1u << (4u * static_cast<uint32_t>(nb))) - 1u);
+        const bool any_rare = __ballot_sync(0xffffffffu, rare) != 0u;
+
+        // exact bits of the rare ops, only when the warp saw one (about 1 chunk in 8 for human assemblies)
+        uint32_t nhbits = 0;
+        if (any_rare) {
+#pragma unroll 1
+            for (int r = 0; r < ROWS; ++r) {
+                const uint4 d = reload_row(r);
+                uint32_t r0 = 0, q0 = 0;
+                decode_op(d.x, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 0));
+                decode_op(d.y, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 1));
+                decode_op(d.z, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 2));
+                decode_op(d.w, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 3));
+            }
+        }
 
         if (n_pieces <= 2u) {
-            const bool pass0 = record_passes(a.hdr[a_lo], a.min_mapq);
-            const bool pass1 = n_pieces == 2u ? record_passes(a.hdr[a_hi], a.min_mapq) : false;
-            evbits &= (pass0 ? first_mask : 0u) | (pass1 ? ~first_mask : 0u);      // SVIM_COLLECT.py:71
             headR = __reduce_add_sync(0xffffffffu, headR);
             headQ = __reduce_add_sync(0xffffffffu, headQ);
-            warp_cnt = __reduce_add_sync(0xffffffffu, __popc(evbits));
             if (lane == 0 && (headR | headQ)) {
                 atomicAdd(&a.aln_sum[a_lo].x, headR);
                 atomicAdd(&a.aln_sum[a_lo].y, headQ);
@@ -228,14 +262,20 @@ __global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a
             tailR = headR;
             tailQ = headQ;
             if (n_pieces == 2u) {
-                restR = __reduce_add_sync(0xffffffffu, restR);
-                restQ = __reduce_add_sync(0xffffffffu, restQ);
+                const uint32_t restR = __reduce_add_sync(0xffffffffu, totR) - headR;
+                const uint32_t restQ = __reduce_add_sync(0xffffffffu, totQ) - headQ;
                 if (lane == 0 && (restR | restQ)) {
                     atomicAdd(&a.aln_sum[a_hi].x, restR);
                     atomicAdd(&a.aln_sum[a_hi].y, restQ);
                 }
                 tailR = restR;
                 tailQ = restQ;
+            }
+            if (any_rare) {
+                const bool pass0 = record_passes(a.hdr[a_lo], a.min_mapq);
+                const bool pass1 = n_pieces == 2u ? record_passes(a.hdr[a_hi], a.min_mapq) : false;
+                evbits &= (pass0 ? first_mask : 0u) | (pass1 ? ~first_mask : 0u);      // SVIM_COLLECT.py:71
+                warp_cnt = __reduce_add_sync(0xffffffffu, __popc(evbits));
             }
         } else {
             // generic: several alignment heads inside one 1024-op chunk (short alignments)
@@ -268,10 +308,10 @@ __global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a
                 tailQ = sQ;
             }
             evbits &= keep;
-            warp_cnt = __reduce_add_sync(0xffffffffu, __popc(evbits));
+            if (any_rare) warp_cnt = __reduce_add_sync(0xffffffffu, __popc(evbits));
         }
         // rare: N / H ops feed reference_end / infer_read_length of the split-alignment walk
-        if (__ballot_sync(0xffffffffu, nhbits != 0u)) {
+        if (any_rare && __ballot_sync(0xffffffffu, nhbits != 0u)) {
             uint32_t bits = nhbits;
             while (bits) {
                 const int b = __ffs(bits) - 1;
@@ -480,6 +520,8 @@ __global__ void __launch_bounds__(THREADS, 4) cigar_scan_kernel(const ScanArgs a
         }
     }
 }
+
+#undef reload_row
 
 // chunk_first[c] = last alignment whose run starts at or before uint4 index c * CHUNK4
 __global__ void chunk_index_kernel(const uint32_t* __restrict__ off4, uint32_t n_aln, uint64_t n_chunks,

@@ -44,6 +44,7 @@ struct svb_ref {
     int device = 0;
     uint8_t* d_bases = nullptr;       // upper-cased ASCII, contigs concatenated
     uint64_t* d_contig_off = nullptr; // [n_contig + 1]
+    uint8_t* d_class_map = nullptr;   // [256] byte -> symbol class of the edit-distance kernel (255 = none)
     int32_t n_contig = 0;
     uint64_t n_bases = 0;
 };
@@ -74,6 +75,7 @@ enum : uint32_t {
     DEV_ERR_BAD_TID = 1u,        // a name lookup on tid < 0 or >= n_contig (pysam would raise ValueError)
     DEV_ERR_ASSERT = 2u,         // reference assert end >= start would fire
     DEV_ERR_CAPACITY = 4u,       // per-read scratch exceeded (inversion run > 32, ...)
+    DEV_ERR_NOSEQ = 8u,          // an insertion needs query bases that were not uploaded
 };
 
 int svb_fail(svb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess);

@@ -1,0 +1,88 @@
+// K8 core -- bit-parallel global edit distance (Myers 1999 / Hyyro 2003 block recurrence).
+//
+// The reference computes edlib.align(h1, h2)["editDistance"] (SVIM_COMBINE.py:50,64,76,88,100):
+// edlib's default is mode="NW", task="distance", i.e. the unit-cost global Levenshtein distance
+// [ext: edlib is an un-vendored dependency, setup.py:38].  That number is unique, so any exact
+// algorithm reproduces it.  This header holds the 64-row block step and the virtual haplotype
+// strings of compute_distance (SVIM_COMBINE.py:35-102); edit_distance.cu pipelines the blocks of
+// one pattern across the 32 lanes of a warp.  The block step also compiles for the host
+// (tests/hostcheck) where it is checked against a plain DP.
+#pragma once
+#include <stdint.h>
+
+#include "linkage.cuh"   // SVB_HD
+
+// One column step of a 64-row block.  pv/mv: vertical +1/-1 delta bit vectors (in/out).
+// eq: rows whose pattern char equals the text char.  hin: horizontal delta entering at the top
+// row (-1, 0, +1).  hibit: the row whose horizontal delta is returned.
+SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_t hibit) {
+    const uint64_t xv = eq | mv;
+    if (hin < 0) eq |= 1ull;
+    const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
+    uint64_t ph = mv | ~(xh | pv);
+    uint64_t mh = pv & xh;
+    int hout = 0;
+    if (ph & hibit) hout = 1;
+    if (mh & hibit) hout = -1;
+    ph <<= 1;
+    mh <<= 1;
+    if (hin < 0) mh |= 1ull;
+    else if (hin > 0) ph |= 1ull;
+    pv = mh | ~(xv | ph);
+    mv = ph & xv;
+    return hout;
+}
+
+// ---- virtual haplotype strings --------------------------------------------------------------------
+// compute_distance builds  ref[lo:s] + MIDDLE + ref[e:hi]  for both candidates; MIDDLE depends on the
+// type.  Nothing is materialised: a descriptor addresses the bases in HBM.
+enum : uint32_t {
+    HAP_MID_NONE = 0,      // DEL  (SVIM_COMBINE.py:48-49)
+    HAP_MID_REVCOMP = 1,   // INV: reverse complement of ref[s:e], non-ACGT unchanged (:56-63)
+    HAP_MID_REPEAT = 2,    // DUP_TAN: ref[s:e] * (copies + 1) (:82-87)
+    HAP_MID_SEQ4 = 3,      // INS: the candidate's own sequence, 4-bit packed query bases (:70-75)
+    HAP_MID_REF = 4        // DUP_INT: ref[source_start:source_end] of the source contig (:94-99)
+};
+
+struct HapDesc {
+    uint64_t l_base;       // absolute index into the concatenated reference of ref[lo]
+    uint64_t r_base;       // ... of ref[e]
+    uint64_t m_base;       // reference index of the unit start, or NIBBLE index into seq4
+    uint32_t l_len, r_len, m_len;
+    uint32_t m_kind;
+    uint32_t m_unit;       // HAP_MID_REPEAT: length of one copy
+    uint32_t seq_sel;      // HAP_MID_SEQ4: 0 = haplotype-1 sequences, 1 = haplotype-2 sequences
+};
+
+SVB_HD uint32_t hap_length(const HapDesc& d) { return d.l_len + d.m_len + d.r_len; }
+
+SVB_HD uint8_t hap_complement(uint8_t c) {
+    switch (c) {
+        case 'A': return 'T';
+        case 'C': return 'G';
+        case 'G': return 'C';
+        case 'T': return 'A';
+        default: return c;
+    }
+}
+
+SVB_HD uint8_t hap_char(const HapDesc& d, uint32_t i, const uint8_t* ref, const uint8_t* seq4_a, const uint8_t* seq4_b) {
+    if (i < d.l_len) return ref[d.l_base + i];
+    i -= d.l_len;
+    if (i < d.m_len) {
+        switch (d.m_kind) {
+            case HAP_MID_REVCOMP: return hap_complement(ref[d.m_base + (d.m_len - 1u - i)]);
+            case HAP_MID_REPEAT: return ref[d.m_base + (i % d.m_unit)];
+            case HAP_MID_SEQ4: {
+                const uint8_t* s = d.seq_sel ? seq4_b : seq4_a;
+                const uint64_t nib = d.m_base + i;
+                const uint8_t byte = s[nib >> 1];
+                const uint32_t code = (nib & 1ull) ? (byte & 15u) : (byte >> 4);
+                return static_cast<uint8_t>("=ACMGRSVTWYHKDBN"[code]);
+            }
+            default: return ref[d.m_base + i];
+        }
+    }
+    i -= d.m_len;
+    return ref[d.r_base + i];
+}

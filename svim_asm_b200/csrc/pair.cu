@@ -1,7 +1,477 @@
-// K6-K9 haplotype pairing (placeholder until the pairing kernels land).
-#include "common.cuh"
-#include "linkage.cuh"
+// K6-K9 diploid haplotype pairing on the device.
+//
+// Replaces pair_candidates (reference src/svim_asm/SVIM_COMBINE.py:164-366):
+//   K6  form_partitions' sorted(key=get_key)  (:17; keys SVCandidate.py:17-19,147-148,292-293,386-387)
+//       -> stable LSD radix sort (8-bit digits, warp match_any ranking) of both haplotypes' rows on
+//          (type, contig rank under python string order, position); hap 1 precedes hap 2 on ties.
+//   K7  the linear split into partitions (:20-31) -> head flags + exclusive scan.
+//   K8  compute_distance (:35-102) for every cross-haplotype pair of a partition with 2..10 members
+//       -> edit_distance.cu (job list built here); span_position_distance_breakends (:105-117) inline.
+//   K9  pair_haplotypes / pair_haplotypes_breakends (:120-161): complete linkage, cut, clusters in scipy's
+//       label order -> linkage.cuh, one thread per partition; then the genotype / merge rules of :184-365.
+// Output rows appear in the reference's order: type by type, partition by partition, label by label.
+#include <algorithm>
 
+#include "pairing.cuh"
+#include "walk.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROUNDS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+
+struct PairArgs {
+    const svb_row* rows;            // concatenated h1 ++ h2 (hap set)
+    const uint32_t* order;          // sorted position -> index into rows
+    const uint32_t* part_start;     // [n_parts + 1]
+    uint32_t n_parts;
+    const int32_t* contig_len;      // BAM header lengths (constructor clamps)
+    const int32_t* contig_lexrank;
+    int32_t n_contig;
+    const uint64_t* ref_off;        // reference contig offsets (get_reference_length of the FASTA)
+    int32_t ref_n_contig;
+    const uint64_t* seq_off_a;
+    const uint64_t* seq_off_b;
+    double max_edit_distance;
+    double* dist;                   // [n_parts * PAIR_DIST_STRIDE]
+    EditJob* jobs;
+    unsigned long long* job_count;
+    unsigned long long* max_multi;
+    uint32_t* counts;               // [n_parts + 1]
+    svb_row* out;
+    uint32_t* dev_status;
+};
+
+__device__ __forceinline__ void key_of(const svb_row& r, int32_t& tid, int32_t& pos) {
+    switch (r.type) {
+        case SVB_DEL: case SVB_INV: case SVB_DUP_TAN:
+            tid = r.src_tid;
+            pos = static_cast<int32_t>((static_cast<long long>(r.src_start) + r.src_end) >> 1);   // (start + end) // 2
+            break;
+        case SVB_INS: case SVB_DUP_INT:
+            tid = r.dst_tid; pos = r.dst_start; break;
+        default:
+            tid = r.src_tid; pos = r.src_start; break;
+    }
+}
+
+__global__ void concat_keys_kernel(const svb_row* __restrict__ h1, uint32_t n1, const svb_row* __restrict__ h2, uint32_t n2,
+                                   const int32_t* __restrict__ lexrank, int32_t n_contig, uint32_t rank_bits,
+                                   svb_row* __restrict__ rows, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                   uint32_t* dev_status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1 + n2) return;
+    svb_row r = i < n1 ? h1[i] : h2[i - n1];
+    r.hap = i < n1 ? 1 : 2;
+    rows[i] = r;
+    int32_t tid, pos;
+    key_of(r, tid, pos);
+    uint32_t rank = 0;
+    if (tid < 0 || tid >= n_contig) atomicOr(dev_status, DEV_ERR_BAD_TID);
+    else rank = static_cast<uint32_t>(lexrank[tid]);
+    keys[i] = (static_cast<unsigned long long>(r.type) << (32u + rank_bits)) | (static_cast<unsigned long long>(rank) << 32) |
+              static_cast<uint32_t>(pos);
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t shift,
+                                                                uint32_t* __restrict__ hist, uint32_t n_blocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in,
+                                                                   const uint32_t* __restrict__ vals_in,
+                                                                   unsigned long long* __restrict__ keys_out,
+                                                                   uint32_t* __restrict__ vals_out, uint32_t n, uint32_t shift,
+                                                                   const uint32_t* __restrict__ hist_scanned, uint32_t n_blocks) {
+    __shared__ uint32_t s_base[256], s_running[256];
+    __shared__ uint32_t s_wc[RS_THREADS / 32][256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    s_base[tid] = hist_scanned[tid * n_blocks + blockIdx.x];
+    s_running[tid] = 0;
+    const uint32_t base = blockIdx.x * RS_TILE;
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) s_wc[w][tid] = 0;
+        __syncthreads();
+        const uint32_t i = base + r * RS_THREADS + tid;
+        const bool valid = i < n;
+        unsigned long long key = 0;
+        uint32_t val = 0, d = 0x100u | lane;                 // invalid lanes match nobody
+        if (valid) {
+            key = keys_in[i];
+            val = vals_in[i];
+            d = static_cast<uint32_t>(key >> shift) & 255u;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank_in_warp == 0u) s_wc[warp][d] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; ++w) before += s_wc[w][d];
+            const uint32_t dst = s_base[d] + s_running[d] + before + rank_in_warp;     // stable: round, warp, lane order
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+        __syncthreads();
+        uint32_t add = 0;
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) add += s_wc[w][tid];
+        s_running[tid] += add;
+        __syncthreads();
+    }
+}
+
+// form_partitions' split (SVIM_COMBINE.py:20-31): a new partition starts when type or contig differ or the
+// key positions of CONSECUTIVE items are more than max_distance apart
+__global__ void heads_kernel(const unsigned long long* __restrict__ keys, uint32_t n, long long max_distance,
+                             uint32_t* __restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = 1;
+    if (i > 0) {
+        const unsigned long long a = keys[i - 1], b = keys[i];
+        const long long pa = static_cast<int32_t>(static_cast<uint32_t>(a)), pb = static_cast<int32_t>(static_cast<uint32_t>(b));
+        const long long gap = pa > pb ? pa - pb : pb - pa;
+        h = ((a >> 32) != (b >> 32) || gap > max_distance) ? 1u : 0u;
+    }
+    head[i] = h;
+}
+
+__global__ void part_start_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ excl, uint32_t n,
+                                  long long max_distance, uint32_t* __restrict__ part_start, uint32_t n_parts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) part_start[n_parts] = n;
+    if (i >= n) return;
+    bool h = true;
+    if (i > 0) {
+        const unsigned long long a = keys[i - 1], b = keys[i];
+        const long long pa = static_cast<int32_t>(static_cast<uint32_t>(a)), pb = static_cast<int32_t>(static_cast<uint32_t>(b));
+        const long long gap = pa > pb ? pa - pb : pb - pa;
+        h = (a >> 32) != (b >> 32) || gap > max_distance;
+    }
+    if (h) part_start[excl[i]] = i;
+}
+
+__device__ void make_desc(const svb_row& r, long long lo, long long hi, const PairArgs& a, HapDesc& d) {
+    d.m_kind = HAP_MID_NONE; d.m_len = 0; d.m_base = 0; d.m_unit = 1; d.seq_sel = 0;
+    if (r.type == SVB_DEL || r.type == SVB_INV || r.type == SVB_DUP_TAN) {
+        const uint64_t base = a.ref_off[r.src_tid];
+        const long long s = r.src_start, e = r.src_end;
+        d.l_base = base + static_cast<uint64_t>(lo);
+        d.l_len = static_cast<uint32_t>(s > lo ? s - lo : 0);
+        d.r_base = base + static_cast<uint64_t>(e);
+        d.r_len = static_cast<uint32_t>(hi > e ? hi - e : 0);
+        if (r.type == SVB_INV) {
+            d.m_kind = HAP_MID_REVCOMP; d.m_base = base + static_cast<uint64_t>(s); d.m_len = static_cast<uint32_t>(e > s ? e - s : 0);
+        } else if (r.type == SVB_DUP_TAN) {
+            const uint32_t unit = static_cast<uint32_t>(e > s ? e - s : 0);
+            d.m_kind = HAP_MID_REPEAT; d.m_base = base + static_cast<uint64_t>(s); d.m_unit = unit ? unit : 1u;
+            d.m_len = unit * static_cast<uint32_t>(r.copies + 1 > 0 ? r.copies + 1 : 0);
+        }
+    } else {   // INS, DUP_INT: the window is anchored on dest_start (SVIM_COMBINE.py:68-69,92-93)
+        const uint64_t base = a.ref_off[r.dst_tid];
+        const long long s = r.dst_start;
+        d.l_base = base + static_cast<uint64_t>(lo);
+        d.l_len = static_cast<uint32_t>(s > lo ? s - lo : 0);
+        d.r_base = base + static_cast<uint64_t>(s);
+        d.r_len = static_cast<uint32_t>(hi > s ? hi - s : 0);
+        if (r.type == SVB_INS) {
+            const uint64_t* so = r.hap == 2 ? a.seq_off_b : a.seq_off_a;
+            d.m_kind = HAP_MID_SEQ4; d.seq_sel = r.hap == 2 ? 1u : 0u;
+            if (so) {
+                d.m_base = so[r.aln_idx] * 2ull + r.seq_pos;
+                d.m_len = r.seq_len;
+            } else {
+                atomicOr(a.dev_status, DEV_ERR_NOSEQ);         // svb_records_set_sequences was not called
+            }
+        } else {
+            const long long ss = r.src_start, se = r.src_end;
+            d.m_kind = HAP_MID_REF; d.m_base = a.ref_off[r.src_tid] + static_cast<uint64_t>(ss);
+            d.m_len = static_cast<uint32_t>(se > ss ? se - ss : 0);
+        }
+    }
+}
+
+// one thread per partition: the cross-haplotype pairs that need an edit distance
+__global__ void enumerate_jobs_kernel(const PairArgs a) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_parts) return;
+    const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
+    if (n < 2u || n > static_cast<uint32_t>(PAIR_MAX)) return;
+    const svb_row r0 = a.rows[a.order[first]];
+    if (r0.type == SVB_BND) return;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        const svb_row ri = a.rows[a.order[first + i]];
+        for (uint32_t j = i + 1; j < n; ++j) {
+            const svb_row rj = a.rows[a.order[first + j]];
+            if (ri.hap == rj.hap) continue;
+            const bool by_source = ri.type == SVB_DEL || ri.type == SVB_INV || ri.type == SVB_DUP_TAN;
+            const int32_t tid = by_source ? ri.src_tid : ri.dst_tid;
+            if (tid < 0 || tid >= a.ref_n_contig) { atomicOr(a.dev_status, DEV_ERR_BAD_TID); continue; }
+            const long long clen = static_cast<long long>(a.ref_off[tid + 1] - a.ref_off[tid]);   // reference.get_reference_length
+            long long lo, hi;
+            if (by_source) {
+                lo = max(0ll, static_cast<long long>(min(ri.src_start, rj.src_start)) - 100);
+                hi = min(clen, static_cast<long long>(max(ri.src_end, rj.src_end)) + 100);
+            } else {
+                lo = max(0ll, static_cast<long long>(min(ri.dst_start, rj.dst_start)) - 100);
+                hi = min(clen, static_cast<long long>(max(ri.dst_start, rj.dst_start)) + 100);
+            }
+            EditJob job;
+            make_desc(ri, lo, hi, a, job.a);
+            make_desc(rj, lo, hi, a, job.b);
+            job.out_index = p * PAIR_DIST_STRIDE + static_cast<uint32_t>(link_cidx(static_cast<int>(n), static_cast<int>(i), static_cast<int>(j)));
+            job.pad = 0;
+            const unsigned long long slot = atomicAdd(a.job_count, 1ull);
+            a.jobs[slot] = job;
+            const uint32_t la = hap_length(job.a), lb = hap_length(job.b);
+            if (min(la, lb) > 2048u) atomicMax(a.max_multi, static_cast<unsigned long long>(max(la, lb)));
+        }
+    }
+}
+
+// pair_candidates' per-cluster rules (SVIM_COMBINE.py:184-365) for one cluster of 1 or 2 members
+__device__ void emit_cluster(const svb_row& first, const svb_row* second, const PairArgs& a, svb_row* out, uint32_t slot) {
+    svb_row r = first;
+    r.mate_aln = 0xFFFFFFFFu;
+    if (!second) {
+        r.genotype = first.hap == 1 ? SVB_GT_HAP1 : SVB_GT_HAP2;                          // "1/0" / "0/1"
+    } else {
+        r.genotype = SVB_GT_HOM;
+        r.mate_aln = second->aln_idx;                                                      // reads = c0.reads + c1.reads
+        if (r.type != SVB_BND) r.flags = first.flags | (second->flags & (SVB_F_COMPLETE | SVB_F_FULLY_COVERED | SVB_F_CUTPASTE));
+        if (r.type == SVB_DUP_TAN) {                                                       // round(mean([c0, c1])): half to even (:290)
+            const long long s = static_cast<long long>(first.copies) + second->copies;
+            long long k = s >> 1;
+            if (s & 1) k += (k & 1);
+            r.copies = static_cast<int32_t>(k);
+        }
+    }
+    if (r.type == SVB_BND)       // the constructor runs again on the stored fields (:342-363)
+        wk_fill_bnd(r, a.contig_len, a.contig_lexrank, first.src_tid, first.src_start, (first.flags & SVB_F_SRC_FWD) != 0,
+                    first.dst_tid, first.dst_start, (first.flags & SVB_F_DST_FWD) != 0);
+    r.ordinal = slot;
+    out[slot] = r;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(64) cluster_kernel(const PairArgs a) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_parts) return;
+    const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
+    uint32_t slot = WRITE ? a.counts[p] : 0u;
+    uint32_t produced = 0;
+    if (n == 1u) {
+        if (WRITE) emit_cluster(a.rows[a.order[first]], nullptr, a, a.out, slot);
+        produced = 1;
+    } else if (n <= static_cast<uint32_t>(PAIR_MAX)) {
+        double D[PAIR_DIST_STRIDE];
+        int labels[PAIR_MAX];
+        const bool bnd = a.rows[a.order[first]].type == SVB_BND;
+        int m = 0;
+        for (uint32_t i = 0; i + 1 < n; ++i) {
+            const svb_row& ri = a.rows[a.order[first + i]];
+            for (uint32_t j = i + 1; j < n; ++j, ++m) {
+                const svb_row& rj = a.rows[a.order[first + j]];
+                double d;
+                if (bnd) {                                                                 // :105-117 (dest contig never compared)
+                    const bool same_dirs = ((ri.flags ^ rj.flags) & (SVB_F_SRC_FWD | SVB_F_DST_FWD)) == 0;
+                    if (ri.hap != rj.hap && same_dirs) {
+                        const long long d1 = static_cast<long long>(ri.src_start) - rj.src_start;
+                        const long long d2 = static_cast<long long>(ri.dst_start) - rj.dst_start;
+                        d = static_cast<double>((d1 < 0 ? -d1 : d1) + (d2 < 0 ? -d2 : d2)) / 3000.0;
+                    } else {
+                        d = 99999.0;
+                    }
+                } else if (ri.hap == rj.hap) {
+                    d = 1000000000.0;                                                      // :40-41
+                } else {
+                    d = a.dist[static_cast<size_t>(p) * PAIR_DIST_STRIDE + m];
+                }
+                D[m] = d;
+            }
+        }
+        const int n_clusters = link_complete_fcluster(static_cast<int>(n), D, bnd ? 0.3 : a.max_edit_distance, labels);
+        for (int c = 1; c <= n_clusters; ++c) {
+            int members = 0, i0 = -1, i1 = -1;
+            for (uint32_t i = 0; i < n; ++i)
+                if (labels[i] == c) {
+                    if (members == 0) i0 = static_cast<int>(i);
+                    else if (members == 1) i1 = static_cast<int>(i);
+                    ++members;
+                }
+            if (members == 1 || members == 2) {                                            // other sizes: logged, skipped (:204-205)
+                if (WRITE) {
+                    const svb_row f = a.rows[a.order[first + i0]];
+                    if (members == 2) {
+                        const svb_row s = a.rows[a.order[first + i1]];
+                        emit_cluster(f, &s, a, a.out, slot + produced);
+                    } else {
+                        emit_cluster(f, nullptr, a, a.out, slot + produced);
+                    }
+                }
+                ++produced;
+            }
+        }
+    }
+    if (!WRITE) a.counts[p] = produced;
+}
+
+}  // namespace
+
+int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1, const svb_records* rec2,
+                const svb_ref* ref, const svb_params* p, svb_table** out) {
+    *out = nullptr;
+    const uint64_t n64 = h1->n + h2->n;
+    if (n64 >= 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "svb_pair: too many candidates");
+    const uint32_t n1 = static_cast<uint32_t>(h1->n), n2 = static_cast<uint32_t>(h2->n), n = n1 + n2;
+    svb_table* result = new (std::nothrow) svb_table();
+    if (!result) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_pair");
+    result->device = ctx->device;
+    if (n == 0) {
+        SVB_CUDA(ctx, cudaMallocAsync(&result->d_rows, sizeof(svb_row), ctx->stream));
+        result->cap = 1;
+        *out = result;
+        return SVB_OK;
+    }
+    if (!rec1 || !rec2) { delete result; return svb_fail(ctx, SVB_ERR_ARG, "svb_pair: records of both haplotypes are required"); }
+    const svb_records* rec = rec1;
+    uint32_t rank_bits = 1;
+    while ((1u << rank_bits) < static_cast<uint32_t>(std::max(rec->n_contig, 1))) ++rank_bits;
+    const uint32_t key_bits = 32u + rank_bits + 3u;
+    const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+
+    // one slab for everything that lives only during this call
+    auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    const size_t sz_rows = align(sizeof(svb_row) * n), sz_keys = align(sizeof(unsigned long long) * n), sz_vals = align(sizeof(uint32_t) * n);
+    const size_t sz_hist = align(sizeof(uint32_t) * (256ull * n_blocks + 1)), sz_head = align(sizeof(uint32_t) * (static_cast<size_t>(n) + 1));
+    const size_t sz_dist = align(sizeof(double) * PAIR_DIST_STRIDE * n), sz_jobs = align(sizeof(EditJob) * (static_cast<size_t>(n) * 5 / 2 + 1));
+    const size_t total = sz_rows + 2 * sz_keys + 2 * sz_vals + sz_hist + 3 * sz_head + sz_dist + sz_jobs;
+    unsigned char* slab = nullptr;
+    if (cudaMallocAsync(&slab, total, ctx->stream) != cudaSuccess) { delete result; return svb_fail(ctx, SVB_ERR_NOMEM, "svb_pair: scratch"); }
+    unsigned char* cur = slab;
+    auto carve = [&](size_t bytes) { unsigned char* q = cur; cur += bytes; return q; };
+    svb_row* rows = reinterpret_cast<svb_row*>(carve(sz_rows));
+    unsigned long long* keys[2] = {reinterpret_cast<unsigned long long*>(carve(sz_keys)), reinterpret_cast<unsigned long long*>(carve(sz_keys))};
+    uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(carve(sz_vals)), reinterpret_cast<uint32_t*>(carve(sz_vals))};
+    uint32_t* hist = reinterpret_cast<uint32_t*>(carve(sz_hist));
+    uint32_t* head = reinterpret_cast<uint32_t*>(carve(sz_head));
+    uint32_t* part_start = reinterpret_cast<uint32_t*>(carve(sz_head));
+    uint32_t* counts = reinterpret_cast<uint32_t*>(carve(sz_head));
+    double* dist = reinterpret_cast<double*>(carve(sz_dist));
+    EditJob* jobs = reinterpret_cast<EditJob*>(carve(sz_jobs));
+
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeAsync(slab, ctx->stream);
+        if (result->d_rows) cudaFree(result->d_rows);
+        delete result;
+        return rc;
+    };
+#define PAIR_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) return fail(svb_fail(ctx, SVB_ERR_CUDA, #call, e__));     \
+    } while (0)
+
+    int cur_buf = 0;
+    uint32_t n_parts = 0;
+    {
+        KernelTimer timer(ctx, SVB_K_SORT);
+        concat_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h1->d_rows, n1, h2->d_rows, n2, rec->d_contig_lexrank, rec->n_contig,
+                                                                     rank_bits, rows, keys[0], vals[0], ctx->d_status);
+        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+            radix_hist_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], n, shift, hist, n_blocks);
+            int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, ctx->d_counters + 9);
+            if (rc != SVB_OK) return fail(rc);
+            radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], vals[cur_buf], keys[cur_buf ^ 1], vals[cur_buf ^ 1], n,
+                                                                           shift, hist, n_blocks);
+            cur_buf ^= 1;
+        }
+        heads_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], n, p->partition_max_distance, head);
+        int rc = launch_scan_u32(ctx, head, n, ctx->d_counters + 2);
+        if (rc != SVB_OK) return fail(rc);
+    }
+    PAIR_CUDA(cudaGetLastError());
+    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
+    n_parts = static_cast<uint32_t>(ctx->h_pinned[2]);
+
+    PairArgs a;
+    a.rows = rows;
+    a.order = vals[cur_buf];
+    a.part_start = part_start;
+    a.n_parts = n_parts;
+    a.contig_len = rec->d_contig_len;
+    a.contig_lexrank = rec->d_contig_lexrank;
+    a.n_contig = rec->n_contig;
+    a.ref_off = ref->d_contig_off;
+    a.ref_n_contig = ref->n_contig;
+    a.seq_off_a = rec1->d_seq_off;
+    a.seq_off_b = rec2->d_seq_off;
+    a.max_edit_distance = static_cast<double>(p->max_edit_distance);
+    a.dist = dist;
+    a.jobs = jobs;
+    a.job_count = ctx->d_counters + 3;
+    a.max_multi = ctx->d_counters + 4;
+    a.counts = counts;
+    a.out = nullptr;
+    a.dev_status = ctx->d_status;
+    PAIR_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    {
+        KernelTimer timer(ctx, SVB_K_SORT);
+        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start, n_parts);
+        enumerate_jobs_kernel<<<(n_parts + 127) / 128, 128, 0, ctx->stream>>>(a);
+    }
+    PAIR_CUDA(cudaGetLastError());
+    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_jobs = static_cast<uint32_t>(ctx->h_pinned[3]);
+    const uint64_t max_multi = ctx->h_pinned[4];
+    if (n_jobs) {
+        // INS pairs read the 4-bit query bases of both haplotypes
+        int rc = launch_edit_distance(ctx, jobs, n_jobs, max_multi, ref->d_bases, rec1->d_seq4, rec2->d_seq4, ref->d_class_map, dist);
+        if (rc != SVB_OK) return fail(rc);
+    }
+    {
+        KernelTimer timer(ctx, SVB_K_CLUSTER);
+        cluster_kernel<false><<<(n_parts + 63) / 64, 64, 0, ctx->stream>>>(a);
+        int rc = launch_scan_u32(ctx, counts, n_parts, ctx->d_counters + 5);
+        if (rc != SVB_OK) return fail(rc);
+    }
+    PAIR_CUDA(cudaGetLastError());
+    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 5, ctx->d_counters + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint64_t n_out = ctx->h_pinned[5];
+    result->cap = std::max<uint64_t>(n_out, 1);
+    PAIR_CUDA(cudaMallocAsync(&result->d_rows, sizeof(svb_row) * result->cap, ctx->stream));
+    result->n = n_out;
+    a.out = result->d_rows;
+    {
+        KernelTimer timer(ctx, SVB_K_CLUSTER);
+        cluster_kernel<true><<<(n_parts + 63) / 64, 64, 0, ctx->stream>>>(a);
+    }
+    PAIR_CUDA(cudaGetLastError());
+    PAIR_CUDA(cudaFreeAsync(slab, ctx->stream));
+    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef PAIR_CUDA
+    *out = result;
+    return SVB_OK;
+}
+
+// ---- test hook: scipy-compatible flat cluster labels (svb_cluster_labels) ------------------------------
 namespace {
 __global__ void cluster_labels_kernel(const double* __restrict__ condensed, const uint32_t* __restrict__ n_points,
                                       const uint64_t* __restrict__ offsets, uint32_t n_problems, double threshold,
@@ -50,12 +520,4 @@ int run_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_
     cudaFreeAsync(d_o, ctx->stream);
     cudaFreeAsync(d_l, ctx->stream);
     return SVB_OK;
-}
-
-int run_pairing(svb_ctx* ctx, const svb_table*, const svb_table*, const svb_records*, const svb_records*, const svb_ref*,
-                const svb_params*, svb_table**) {
-    return svb_fail(ctx, SVB_ERR_ARG, "svb_pair: not built yet");
-}
-int run_edit_distance_strings(svb_ctx* ctx, const uint8_t*, const uint64_t*, const uint8_t*, const uint64_t*, uint32_t, int64_t*) {
-    return svb_fail(ctx, SVB_ERR_ARG, "svb_edit_distance: not built yet");
 }

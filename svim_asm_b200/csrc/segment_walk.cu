@@ -12,6 +12,7 @@
 // per record, its indels first, then its walk candidates (SVIM_COLLECT.py:79-80).
 #include "common.cuh"
 #include "walk.cuh"
+#include "pairing.cuh"
 
 namespace {
 
@@ -253,6 +254,12 @@ int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* 
         *n_out = n_rows;
     }
     cudaFreeAsync(base, ctx->stream);
+    return SVB_OK;
+}
+
+int launch_scan_u32(svb_ctx* ctx, uint32_t* v, uint32_t n, unsigned long long* d_total) {
+    scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(v, n, d_total);
+    SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;
 }
 

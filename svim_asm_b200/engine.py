@@ -126,6 +126,7 @@ class HostBatch(object):
         self.hdr = hdr
         self.seg = np.concatenate(segs) if segs else np.zeros(0, dtype=_lib.SEG_DTYPE)
         self._names = list(rb.names)
+        self._sa_text = dict(rb.sa)
         return self
 
     # ---- access
@@ -141,6 +142,13 @@ class HostBatch(object):
         if self._names is not None:
             return self._names[int(i)]
         return lib.svb_bam_query_name(self._bam, int(i)).decode()
+
+    def sa_text(self, i):
+        """Raw SA:Z value of record i or None."""
+        if self._bam is not None:
+            raw = lib.svb_bam_sa_text(self._bam, int(i))
+            return raw.decode() if raw is not None else None
+        return getattr(self, "_sa_text", {}).get(int(i))
 
     def sequence_slice(self, i, start, length):
         """query_sequence[start:start+length] of record i (start/length already python-slice normalised)."""

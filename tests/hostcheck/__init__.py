@@ -9,7 +9,7 @@ _SO = os.path.join(_HERE, "_build", "hostcheck.so")
 
 def load():
     src = os.path.join(_HERE, "hostcheck.cpp")
-    deps = [src] + [os.path.join(_HERE, "..", "..", "svim_asm_b200", "csrc", f) for f in ("linkage.cuh", "walk.cuh")]
+    deps = [src] + [os.path.join(_HERE, "..", "..", "svim_asm_b200", "csrc", f) for f in ("linkage.cuh", "walk.cuh", "edit_core.cuh")]
     if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _SO, src])
@@ -20,4 +20,6 @@ def load():
     lib.hc_walk.restype = ctypes.c_int
     lib.hc_walk.argtypes = [vp, ctypes.c_int, ctypes.c_int32, ctypes.c_uint32, vp, vp, vp, ctypes.c_int32,
                             ctypes.c_uint32, ctypes.c_uint32, vp, ctypes.c_int]
+    lib.hc_myers.restype = ctypes.c_longlong
+    lib.hc_myers.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_int]
     return lib

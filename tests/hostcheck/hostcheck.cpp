@@ -33,3 +33,34 @@ extern "C" int hc_walk(const int32_t* segs, int k, int32_t read_len, uint32_t l_
     for (uint32_t i = 0; i < o.n && static_cast<int>(i) < cap; ++i) rows_out[i] = rows[i];
     return static_cast<int>(o.n);
 }
+
+#include "../../svim_asm_b200/csrc/edit_core.cuh"
+#include <string.h>
+// Sequential use of the 64-row block step (what the GPU pipelines across the lanes of a warp):
+// pattern = a (rows), text = b (columns); stripes of `blocks_per_stripe` blocks with the horizontal
+// deltas of the stripe's last row carried in hbuf, exactly like edit_distance.cu.
+extern "C" long long hc_myers(const uint8_t* a, long long m, const uint8_t* b, long long n, int blocks_per_stripe) {
+    if (m == 0) return n;
+    if (n == 0) return m;
+    std::vector<signed char> hbuf(static_cast<size_t>(n), 1);
+    long long total = 0;
+    const long long stripe_rows = 64ll * blocks_per_stripe;
+    for (long long row0 = 0; row0 < m; row0 += stripe_rows) {
+        const long long rows = (m - row0 < stripe_rows) ? (m - row0) : stripe_rows;
+        const bool final_stripe = row0 + rows == m;
+        const int nblk = static_cast<int>((rows + 63) / 64);
+        std::vector<uint64_t> pv(nblk, ~0ull), mv(nblk, 0ull);
+        std::vector<uint64_t> peq(static_cast<size_t>(nblk) * 256, 0ull);
+        for (long long r = 0; r < rows; ++r) peq[static_cast<size_t>(r / 64) * 256 + a[row0 + r]] |= 1ull << (r & 63);
+        for (long long j = 0; j < n; ++j) {
+            int h = hbuf[static_cast<size_t>(j)];
+            for (int k = 0; k < nblk; ++k) {
+                const bool last = k == nblk - 1;
+                const uint64_t hibit = (last && final_stripe) ? (1ull << ((rows - 1) & 63)) : (1ull << 63);
+                h = myers_block(pv[k], mv[k], peq[static_cast<size_t>(k) * 256 + b[j]], h, hibit);
+            }
+            if (final_stripe) total += h; else hbuf[static_cast<size_t>(j)] = static_cast<signed char>(h);
+        }
+    }
+    return m + total;
+}

@@ -1,0 +1,107 @@
+"""GPU parity of the pairing stage (K6 sort, K7 partitions, K8 edit distance, K9 clustering) vs the CPU oracle.
+
+Reference path: SVIM_COMBINE.py:15-366 (form_partitions, compute_distance, pair_haplotypes[_breakends],
+pair_candidates).  Bit-exact rows in the reference's order."""
+import numpy as np
+import pytest
+
+from oracle import port
+from svim_asm_b200 import synth
+from svim_asm_b200.engine import HostBatch, make_params
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _mutate(rng, s, n_edits, alphabet):
+    b = list(s)
+    for _ in range(n_edits):
+        kind = int(rng.integers(0, 3))
+        pos = int(rng.integers(0, max(1, len(b))))
+        if kind == 0 and b:
+            b[pos % len(b)] = int(rng.choice(alphabet))
+        elif kind == 1:
+            b.insert(pos, int(rng.choice(alphabet)))
+        elif b:
+            del b[pos % len(b)]
+    return bytes(b)
+
+
+def test_edit_distance_matches_plain_dp(engine, oracle_clib):
+    rng = np.random.default_rng(21)
+    alphabet = list(b"ACGT")
+    pairs = [(b"", b""), (b"", b"ACGT"), (b"ACGT", b""), (b"kitten", b"sitting"), (b"A" * 64, b"A" * 64), (b"A" * 65, b"C" * 63)]
+    for _ in range(300):
+        m = int(rng.integers(1, 700))
+        a = bytes(rng.choice(alphabet, m).tolist())
+        if rng.random() < 0.6:
+            b = _mutate(rng, a, int(rng.integers(0, 40)), alphabet)
+        else:
+            b = bytes(rng.choice(alphabet, int(rng.integers(1, 700))).tolist())
+        pairs.append((a, b))
+    # several 2048-row stripes (horizontal deltas parked in HBM between stripes)
+    for m, n in ((2048, 2048), (2049, 2500), (5000, 4100), (6200, 9000)):
+        a = bytes(rng.choice(alphabet + list(b"N"), m).tolist())
+        pairs.append((a, _mutate(rng, a, 150, alphabet) if n == 4100 else bytes(rng.choice(alphabet, n).tolist())))
+    got = engine.edit_distance(pairs)
+    want = [port.edit_distance(a, b) for a, b in pairs]
+    assert got.tolist() == want
+
+
+def test_cluster_labels_match_scipy(engine):
+    rng = np.random.default_rng(22)
+    problems = []
+    for _ in range(3000):
+        n = int(rng.integers(2, 11))
+        m = n * (n - 1) // 2
+        if rng.random() < 0.7:
+            problems.append(rng.choice([1e9, 200.0, 300.0, 150.0, 0.0, 201.0, 99999.0], size=m))
+        else:
+            problems.append(np.round(rng.uniform(0, 400, m)))
+    got = engine.cluster_labels(problems, 200.0)
+    for d, g in zip(problems, got):
+        assert g == [int(x) for x in port.cluster_labels(d, 200.0)]
+
+
+def _reference_arrays(cfg):
+    ref = synth.random_reference(cfg)
+    off = np.zeros(len(cfg.contig_names) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([ref[n].shape[0] for n in cfg.contig_names])
+    return np.concatenate([ref[n] for n in cfg.contig_names]), off
+
+
+def _pair_both(engine, cfg, **params):
+    rb1, rb2 = synth.make_diploid(cfg)
+    h1, h2 = HostBatch.from_record_batch(rb1), HostBatch.from_record_batch(rb2)
+    bases, off = _reference_arrays(cfg)
+    p = port.Params(**params)
+    w1, w2 = port.collect(h1, p, hap=1), port.collect(h2, p, hap=2)
+
+    def fetch(tid, s, e):
+        return bases[int(off[tid]) + s:int(off[tid]) + e].tobytes()
+    want = port.pair(w1, w2, h1, h2, fetch, p)
+    r1, r2 = engine.load_records(h1, with_sequences=True), engine.load_records(h2, with_sequences=True)
+    ref = engine.load_reference(bases, off)
+    dp = make_params(**params)
+    t1, t2 = engine.collect(r1, dp, hap=1), engine.collect(r2, dp, hap=2)
+    assert util.rows_equal(t1.to_numpy(), w1) is None and util.rows_equal(t2.to_numpy(), w2) is None
+    got = engine.pair(t1, t2, r1, r2, ref, dp).to_numpy()
+    return got, want
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_diploid_pairing_small(engine, oracle_clib, seed):
+    cfg = synth.SynthConfig(["chr1", "chr10", "chr2"], [400000, 300000, 350000], 90, 6e4, seed, sv_per_event=6e-3,
+                            split_fraction=0.5, sv_max=3000)
+    got, want = _pair_both(engine, cfg)
+    diff = util.rows_equal(got, want)
+    assert diff is None, diff
+    assert {0, 1, 2} <= set(int(g) for g in got["genotype"])        # 1/1, 1/0 and 0/1 all occur
+    assert want.shape[0] > 60
+
+
+def test_diploid_pairing_tight_partitions(engine, oracle_clib):
+    # many candidates close together: large partitions (some > 10 are dropped), chains, label order
+    cfg = synth.SynthConfig(["chrA"], [120000], 12, 1.5e4, 77, sv_per_event=6e-2, split_fraction=0.3, sv_max=300)
+    got, want = _pair_both(engine, cfg, partition_max_distance=3000, max_edit_distance=150)
+    assert util.rows_equal(got, want) is None, util.rows_equal(got, want)
