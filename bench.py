@@ -1,0 +1,303 @@
+#!/usr/bin/env python3
+"""bench.py -- the hot path of SVIM-asm on B200, measured the way BASELINE.json asks.
+
+Workload (N=1): BASELINE.json configs[3] "diploid: two synthetic haplotype BAMs, whole-genome, SVIM_COMBINE pairing
+on 1xB200" -- 24 contigs with hg38 lengths, 2 x 40,000 alignments, 2 x 2.0e8 CIGAR ops (svim_asm_b200/synth.py,
+seed 1004).  One STEP = collect(hap1) + collect(hap2) + pair: cigar_scan, segment_walk, merge, radix sort, partition,
+edit distances, clustering -> the paired candidate table (what write_final_vcf consumes).
+  value : alignments/s with the record images resident in HBM, timed with CUDA events on the library's stream.
+  e2e   : the same step through the C ABI with HOST buffers: every step uploads both record images from pinned
+          memory (svb_load_records + sequences) and reads the paired table back.
+  N>1   : the records are sharded by reference contig over the ranks (strong scaling, total work fixed); the
+          candidate tables are all-gathered (NCCL) and every rank pairs the contigs it owns.
+`--impl reference` times the reference's own algorithm on the host CPU (1 core: the reference is single threaded)
+through the oracle port on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench] " + msg, file=sys.stderr, flush=True)
+
+
+def build_workload(scale, seed=1004):
+    from svim_asm_b200 import synth
+    cfg = synth.config_c3(seed=seed, scale=scale)
+    t0 = time.time()
+    rb1, rb2 = synth.make_diploid(cfg)
+    log("generated 2 x %d alignments, %d + %d CIGAR ops in %.1fs" % (rb1.n_aln, rb1.n_ops, rb2.n_ops, time.time() - t0))
+    t0 = time.time()
+    ref = synth.random_reference(cfg)
+    off = np.zeros(len(cfg.contig_names) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([ref[n].shape[0] for n in cfg.contig_names])
+    bases = np.concatenate([ref[n] for n in cfg.contig_names])
+    log("reference %.2f Gb in %.1fs" % (bases.shape[0] / 1e9, time.time() - t0))
+    return cfg, rb1, rb2, bases, off
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.tmp.name) if ln.strip()]
+        os.unlink(self.tmp.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on a bounded sample
+
+
+def cpu_sample(rb1, rb2, bases, off, cfg, n_contigs_in_sample=4):
+    """The records of the last few contigs of both haplotypes + the matching reference slices."""
+    tids = list(range(len(cfg.contig_names) - n_contigs_in_sample, len(cfg.contig_names)))
+    idx1 = np.nonzero(np.isin(rb1.tid, tids))[0]
+    idx2 = np.nonzero(np.isin(rb2.tid, tids))[0]
+    return rb1.subset(idx1), rb2.subset(idx2), tids
+
+
+def run_cpu_pipeline(s1, s2, bases, off):
+    """collect x2 + pair with the oracle port: one interpreter iteration per CIGAR op, like the reference."""
+    from oracle import port
+    from svim_asm_b200.engine import HostBatch
+    h1, h2 = HostBatch.from_record_batch(s1), HostBatch.from_record_batch(s2)
+    p = port.Params()
+
+    def scan(ops, min_length):
+        return port.scan_python(ops.tolist(), min_length)
+
+    def fetch(tid, s, e):
+        return bases[int(off[tid]) + s:int(off[tid]) + e].tobytes()
+    t0 = time.perf_counter()
+    r1 = port.collect(h1, p, hap=1, scan=scan)
+    r2 = port.collect(h2, p, hap=2, scan=scan)
+    paired = port.pair(r1, r2, h1, h2, fetch, p)
+    return time.perf_counter() - t0, h1.n_aln + h2.n_aln, h1.n_ops + h2.n_ops, paired.shape[0]
+
+
+def cpu_baseline_block(rb1, rb2, bases, off, cfg, steps=1):
+    subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    s1, s2, tids = cpu_sample(rb1, rb2, bases, off, cfg)
+    best = None
+    for _ in range(steps):
+        dt, n_aln, n_ops, n_out = run_cpu_pipeline(s1, s2, bases, off)
+        best = dt if best is None else min(best, dt)
+    return {"value": n_aln / best, "unit": "alignments/s", "cores": 1, "kind": "port",
+            "cigar_ops_per_sec": n_ops / best,
+            "sample": "records of contigs %s of both haplotypes: %d alignments, %d CIGAR ops, %d paired rows, %.1f s per pass "
+                      "(oracle/port.py: per-op python loop like SVIM_intra.py:13-29, scipy linkage, C edit distance)"
+                      % (",".join(cfg.contig_names[t] for t in tids), n_aln, n_ops, n_out, best)}, (s1, s2)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, rb1, rb2, bases, off = build_workload(args.scale)
+    subprocess.call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    s1, s2, tids = cpu_sample(rb1, rb2, bases, off, cfg)
+    del rb1, rb2
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_pipeline(s1, s2, bases, off)
+    times = []
+    n_aln = n_ops = 0
+    for _ in range(args.steps):
+        dt, n_aln, n_ops, _n = run_cpu_pipeline(s1, s2, bases, off)
+        times.append(dt)
+    per = float(np.mean(times))
+    value = n_aln / per
+    sample = "records of contigs %s of both haplotypes: %d alignments, %d CIGAR ops per step" % (
+        ",".join(cfg.contig_names[t] for t in tids), n_aln, n_ops)
+    print(json.dumps({
+        "impl": "reference", "metric": "alignments_per_sec", "value": value, "unit": "alignments/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic", "cigar_ops_per_sec": n_ops / per,
+        "config": workload_config(cfg, args, sample=sample),
+        "cpu_baseline": {"value": value, "unit": "alignments/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(cfg, args, **extra):
+    c = {"workload": "diploid whole-genome: 2 synthetic haplotype BAM images, %d contigs (hg38 lengths), 2 x %d alignments, "
+                     "2 x %.3g CIGAR ops; step = collect(h1) + collect(h2) + pair" % (len(cfg.contig_names), cfg.n_aln, cfg.target_ops),
+         "baseline_config": "BASELINE.json configs[3] (configs[4] for n_gpus > 1)", "seed": cfg.seed, "scale": args.scale,
+         "l2": "inputs (2 x 0.8 GB of CIGAR ops) are far larger than the 126 MB L2; no explicit flush",
+         "reference_genome": "resident in HBM, uploaded once before the timed region (like an index)",
+         "parallelism": "1 GPU" if args.gpus == 1 else "records sharded by contig over %d GPUs, all-gather of candidate tables" % args.gpus}
+    c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+
+
+def b200_arm(args):
+    import torch
+    from svim_asm_b200.bench_util import pin, pinned_host
+    from svim_asm_b200.engine import Engine, HostBatch, make_params
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from svim_asm_b200 import sharded
+        return sharded.bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block)
+    torch.cuda.set_device(local)
+    cfg, rb1, rb2, bases, off = build_workload(args.scale)
+    h1, h2 = pinned_host(HostBatch.from_record_batch(rb1)), pinned_host(HostBatch.from_record_batch(rb2))
+    n_aln, n_ops = h1.n_aln + h2.n_aln, h1.n_ops + h2.n_ops
+    eng = Engine(local)
+    params = make_params()
+    bases_p, keep_ref = pin(bases)
+    ref = eng.load_reference(bases_p, off)
+
+    # ---- value: record images resident in HBM
+    rec1, rec2 = eng.load_records(h1, with_sequences=True), eng.load_records(h2, with_sequences=True)
+
+    def step_resident():
+        t1 = eng.collect(rec1, params, hap=1)
+        t2 = eng.collect(rec2, params, hap=2)
+        paired = eng.pair(t1, t2, rec1, rec2, ref, params)
+        n = len(paired), len(t1), len(t2)
+        t1.free(), t2.free(), paired.free()
+        return n
+
+    for _ in range(max(args.warmup, 3)):
+        n_out = step_resident()
+    eng.synchronize()
+    eng.timing_reset()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    eng.mark(0)
+    for _ in range(args.steps):
+        step_resident()
+    eng.mark(1)
+    ms_total = eng.elapsed_ms(0, 1)
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    timing = eng.timing()
+    ms_step = ms_total / args.steps
+    value = n_aln / (ms_step / 1e3)
+
+    scan_ms, scan_launches = timing["cigar_scan"]
+    scan_avg = scan_ms / max(scan_launches, 1)
+    # algorithmic bytes of one cigar_scan launch: 4 B per op + 32 B per alignment + 64 B per emitted row
+    alg_bytes = (4.0 * n_ops + 32.0 * n_aln + 64.0 * (n_out[1] + n_out[2])) / 2.0
+    peak, peak_src = peak_hbm()
+    achieved = alg_bytes / (scan_avg * 1e-3) / 1e9
+    roofline = {"kernel": "cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "launch_ms": scan_avg, "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items()}}
+    rec1.free(), rec2.free()
+
+    # ---- e2e: host buffers in, paired table out, every step
+    def step_e2e():
+        r1, r2 = eng.load_records(h1), eng.load_records(h2)
+        t1 = eng.collect(r1, params, hap=1)
+        t2 = eng.collect(r2, params, hap=2)
+        t1.attach_sequences_host(h1)          # only the inserted bases cross PCIe, not the 2 x 0.65 GB of query sequence
+        t2.attach_sequences_host(h2)
+        paired = eng.pair(t1, t2, r1, r2, ref, params)
+        rows = paired.to_numpy()
+        for obj in (t1, t2, paired, r1, r2):
+            obj.free()
+        return rows
+
+    for _ in range(max(args.warmup, 3)):
+        rows = step_e2e()
+    eng.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rows = step_e2e()
+    eng.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    h2d = sum(getattr(h, n).nbytes for h in (h1, h2) for n in ("hdr", "cigar", "seg", "sa_count"))
+    e2e = {"value": n_aln / e2e_s, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(rows.nbytes),
+           "ms_per_step": e2e_s * 1e3, "cigar_ops_per_sec": n_ops / e2e_s}
+
+    cpu, _ = cpu_baseline_block(rb1, rb2, bases, off, cfg)
+    print(json.dumps({
+        "metric": "alignments_per_sec", "value": value, "unit": "alignments/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic", "cigar_ops_per_sec": n_ops / (ms_step / 1e3),
+        "config": workload_config(cfg, args, paired_rows=int(n_out[0]), candidates=[int(n_out[1]), int(n_out[2])]),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the whole-genome workload (testing only)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,11 @@ int svb_synchronize(svb_ctx* ctx);
 int svb_timing_reset(svb_ctx* ctx);
 int svb_timing_get(svb_ctx* ctx, svb_timing* out);       /* synchronises the stream first */
 int svb_set_scan_variant(svb_ctx* ctx, int variant);      /* 0 = TMA bulk-copy staging (default), 1 = LDG.128 */
+/* Step timing on the library's own stream: record marker `slot` (0..15) now; elapsed ms between two markers
+ * (synchronises on the later one).  bench.py brackets its timed region with these. */
+int svb_launch_count(svb_ctx* ctx, uint64_t* out);       /* kernels this context has launched so far */
+int svb_mark(svb_ctx* ctx, int slot);
+int svb_elapsed_ms(svb_ctx* ctx, int slot_begin, int slot_end, double* ms);
 
 /* ---- host ingest: replaces pysam.AlignmentFile / bam.fetch (svim-asm:63,85-86; SVIM_COLLECT.py:62-65)
  * and retrieve_other_alignments (SVIM_COLLECT.py:8-58). Pure host code (zlib inflate, thread pool). */
@@ -201,6 +206,14 @@ int svb_table_from_host(svb_ctx* ctx, const svb_row* rows, uint64_t n, svb_table
 int svb_table_export(svb_ctx* ctx, const svb_table* t, void* device_dst, uint64_t cap_rows);
 int svb_table_import(svb_ctx* ctx, const void* device_src, uint64_t n_rows, svb_table** out);
 void svb_table_free(svb_table* t);
+
+/* Sequence pools: the inserted bases of the INS rows (candidate.sequence, SVIM_intra.py:42, SVIM_inter.py:117,120)
+ * copied next to the table so that it can be paired -- or sent to another rank -- without the record image. */
+int svb_table_gather_sequences(svb_ctx* ctx, svb_table* t, const svb_records* rec);          /* device gather */
+int svb_table_attach_sequences_host(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off);
+int svb_table_pool_to_host(svb_ctx* ctx, const svb_table* t, uint8_t* pool_dst, uint64_t cap_bytes, uint64_t* off_dst,
+                           uint64_t* pool_bytes);
+int svb_table_set_pool_from_host(svb_ctx* ctx, svb_table* t, const uint8_t* pool, const uint64_t* pool_off);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,9 @@ def run_cli(argv):
     before = list(root.handlers)
     try:
         sys.argv = [script] + list(argv)
+        # parse_arguments() binds sys.argv[1:] as a default argument when its module is imported
+        # (SVIM_input_parsing.py:7), so a second CLI run in this process needs a fresh import
+        sys.modules.pop("svim_asm.SVIM_input_parsing", None)
         try:
             runpy.run_path(script, run_name="__main__")
         except SystemExit:

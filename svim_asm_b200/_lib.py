@@ -50,6 +50,9 @@ SIGNATURES = {
     "svb_timing_reset": (c_int, [c_void_p]),
     "svb_timing_get": (c_int, [c_void_p, c_void_p]),
     "svb_set_scan_variant": (c_int, [c_void_p, c_int]),
+    "svb_launch_count": (c_int, [c_void_p, P(c_u64)]),
+    "svb_mark": (c_int, [c_void_p, c_int]),
+    "svb_elapsed_ms": (c_int, [c_void_p, c_int, c_int, P(c_double)]),
     "svb_bam_open": (c_int, [c_char_p, c_int, P(c_void_p), c_char_p, c_int]),
     "svb_bam_close": (None, [c_void_p]),
     "svb_bam_n_records": (c_i64, [c_void_p]),
@@ -85,6 +88,10 @@ SIGNATURES = {
     "svb_table_export": (c_int, [c_void_p, c_void_p, c_void_p, c_u64]),
     "svb_table_import": (c_int, [c_void_p, c_void_p, c_u64, P(c_void_p)]),
     "svb_table_free": (None, [c_void_p]),
+    "svb_table_gather_sequences": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_table_attach_sequences_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "svb_table_pool_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_void_p, P(c_u64)]),
+    "svb_table_set_pool_from_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

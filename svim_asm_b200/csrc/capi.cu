@@ -122,6 +122,8 @@ void svb_destroy(svb_ctx* ctx) {
         cudaEventDestroy(s.stop);
     }
     for (auto e : ctx->free_events) cudaEventDestroy(e);
+    for (auto e : ctx->marks)
+        if (e) cudaEventDestroy(e);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -170,6 +172,32 @@ int svb_timing_get(svb_ctx* ctx, svb_timing* out) {
     return rc;
 }
 
+int svb_mark(svb_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (!ctx->marks[slot]) SVB_CUDA(ctx, cudaEventCreate(&ctx->marks[slot]));
+    SVB_CUDA(ctx, cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return SVB_OK;
+}
+
+int svb_elapsed_ms(svb_ctx* ctx, int slot_begin, int slot_end, double* ms) {
+    if (!ctx || !ms || slot_begin < 0 || slot_begin >= 16 || slot_end < 0 || slot_end >= 16 || !ctx->marks[slot_begin] ||
+        !ctx->marks[slot_end])
+        return SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    SVB_CUDA(ctx, cudaEventSynchronize(ctx->marks[slot_end]));
+    float f = 0.f;
+    SVB_CUDA(ctx, cudaEventElapsedTime(&f, ctx->marks[slot_begin], ctx->marks[slot_end]));
+    *ms = f;
+    return SVB_OK;
+}
+
+int svb_launch_count(svb_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return SVB_ERR_ARG;
+    *out = ctx->launches;
+    return SVB_OK;
+}
+
 int svb_set_scan_variant(svb_ctx* ctx, int variant) {
     if (!ctx || variant < 0 || variant > 1) return SVB_ERR_ARG;
     ctx->scan_variant = variant;
@@ -178,21 +206,16 @@ int svb_set_scan_variant(svb_ctx* ctx, int variant) {
 
 // ---- records ---------------------------------------------------------------------------------
 
+static void free_async(void* p, cudaStream_t st) {
+    if (p) cudaFreeAsync(p, st);
+}
+
 void svb_records_free(svb_records* r) {
     if (!r) return;
     cudaSetDevice(r->device);
-    cudaFree(r->d_hdr);
-    cudaFree(r->d_cigar);
-    cudaFree(r->d_off4);
-    cudaFree(r->d_chunk_first);
-    cudaFree(r->d_seg);
-    cudaFree(r->d_sa_count);
-    cudaFree(r->d_contig_len);
-    cudaFree(r->d_contig_lexrank);
-    cudaFree(r->d_aln_sum);
-    cudaFree(r->d_prim_list);
-    cudaFree(r->d_seq4);
-    cudaFree(r->d_seq_off);
+    void* ptrs[] = {r->d_hdr, r->d_cigar, r->d_off4, r->d_chunk_first, r->d_seg, r->d_sa_count, r->d_contig_len,
+                    r->d_contig_lexrank, r->d_aln_sum, r->d_prim_list, r->d_seq4, r->d_seq_off};
+    for (void* q : ptrs) free_async(q, r->stream);
     delete r;
 }
 
@@ -210,6 +233,7 @@ int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const
     svb_records* r = new (std::nothrow) svb_records();
     if (!r) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_load_records");
     r->device = ctx->device;
+    r->stream = ctx->stream;
     r->n_aln = n_aln;
     r->n_seg = n_seg;
     r->n_contig = n_contig;
@@ -247,7 +271,7 @@ int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         *dst = nullptr;
         if (!bytes) return cudaSuccess;
-        cudaError_t e = cudaMalloc(dst, bytes);
+        cudaError_t e = cudaMallocAsync(dst, bytes, ctx->stream);      // stream-ordered pool: no device-wide sync per step
         if (e != cudaSuccess) return e;
         return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
@@ -260,7 +284,7 @@ int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_contig_len), contig_len, sizeof(int32_t) * n_contig);
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_contig_lexrank), contig_lexrank, sizeof(int32_t) * n_contig);
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_prim_list), prim.data(), sizeof(uint32_t) * prim.size());
-    if (e == cudaSuccess && n_aln) e = cudaMalloc(&r->d_aln_sum, sizeof(uint4) * n_aln);
+    if (e == cudaSuccess && n_aln) e = cudaMallocAsync(&r->d_aln_sum, sizeof(uint4) * n_aln, ctx->stream);
     if (e != cudaSuccess) {
         cudaStreamSynchronize(ctx->stream);
         svb_records_free(r);
@@ -280,15 +304,15 @@ int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq
     if (!ctx || !rec || !seq_off) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_records_set_sequences") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
     const uint64_t bytes = seq_off[rec->n_aln];
-    cudaFree(rec->d_seq4);
-    cudaFree(rec->d_seq_off);
+    free_async(rec->d_seq4, ctx->stream);
+    free_async(rec->d_seq_off, ctx->stream);
     rec->d_seq4 = nullptr;
     rec->d_seq_off = nullptr;
-    SVB_CUDA(ctx, cudaMalloc(&rec->d_seq_off, sizeof(uint64_t) * (static_cast<size_t>(rec->n_aln) + 1)));
+    SVB_CUDA(ctx, cudaMallocAsync(&rec->d_seq_off, sizeof(uint64_t) * (static_cast<size_t>(rec->n_aln) + 1), ctx->stream));
     SVB_CUDA(ctx, cudaMemcpyAsync(rec->d_seq_off, seq_off, sizeof(uint64_t) * (static_cast<size_t>(rec->n_aln) + 1),
                                   cudaMemcpyHostToDevice, ctx->stream));
     if (bytes) {
-        SVB_CUDA(ctx, cudaMalloc(&rec->d_seq4, bytes));
+        SVB_CUDA(ctx, cudaMallocAsync(&rec->d_seq4, bytes, ctx->stream));
         SVB_CUDA(ctx, cudaMemcpyAsync(rec->d_seq4, seq4, bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     rec->seq_bytes = bytes;
@@ -302,6 +326,7 @@ static svb_table* table_alloc(svb_ctx* ctx, uint64_t cap) {
     svb_table* t = new (std::nothrow) svb_table();
     if (!t) return nullptr;
     t->device = ctx->device;
+    t->stream = ctx->stream;
     t->cap = std::max<uint64_t>(cap, 1);
     if (cudaMallocAsync(&t->d_rows, sizeof(svb_row) * t->cap, ctx->stream) != cudaSuccess) {
         delete t;
@@ -313,7 +338,8 @@ static svb_table* table_alloc(svb_ctx* ctx, uint64_t cap) {
 void svb_table_free(svb_table* t) {
     if (!t) return;
     cudaSetDevice(t->device);
-    if (t->d_rows) cudaFree(t->d_rows);      // cudaFree accepts pool allocations and synchronises
+    free_async(t->d_rows, t->stream);
+    table_drop_pool(t);
     delete t;
 }
 
@@ -423,7 +449,7 @@ int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int h
     rc = check_device_status(ctx);
     if (rc != SVB_OK) {
         svb_table_free(indel);
-        if (d_walk) cudaFree(d_walk);
+        free_async(d_walk, ctx->stream);
         return rc;
     }
     if (n_walk == 0) {
@@ -434,13 +460,13 @@ int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int h
     svb_table* merged = table_alloc(ctx, n_indel + n_walk);
     if (!merged) {
         svb_table_free(indel);
-        cudaFree(d_walk);
+        free_async(d_walk, ctx->stream);
         return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: merged table");
     }
     rc = launch_merge_tables(ctx, indel->d_rows, n_indel, d_walk, n_walk, merged->d_rows);
     if (rc == SVB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: merge");
     svb_table_free(indel);
-    cudaFree(d_walk);
+    free_async(d_walk, ctx->stream);
     if (rc != SVB_OK) {
         svb_table_free(merged);
         return rc;

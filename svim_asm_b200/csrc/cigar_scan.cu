@@ -545,6 +545,7 @@ int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec) {
     SVB_CUDA(ctx, cudaMalloc(&rec->d_chunk_first, n_chunks * sizeof(uint32_t)));
     const unsigned blocks = static_cast<unsigned>((n_chunks + 255) / 256);
     chunk_index_kernel<<<blocks, 256, 0, ctx->stream>>>(rec->d_off4, rec->n_aln, n_chunks, rec->d_chunk_first);
+    ctx->launches += 1;
     SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;
 }
@@ -596,6 +597,7 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     } else {
         cigar_scan_kernel<false><<<n_tiles, THREADS, 16, ctx->stream>>>(a);
     }
+    ctx->launches += 1;
     SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;
 }

@@ -12,6 +12,7 @@
 // a uint4 boundary and is padded with op 15.  off4[a] is the run start in uint4 units.
 struct svb_records {
     int device = 0;
+    cudaStream_t stream = nullptr;    // stream of the owning context (stream-ordered frees)
     uint32_t n_aln = 0;
     uint32_t n_seg = 0;
     int32_t n_contig = 0;
@@ -35,10 +36,15 @@ struct svb_records {
 
 struct svb_table {
     int device = 0;
+    cudaStream_t stream = nullptr;
     svb_row* d_rows = nullptr;
     uint64_t n = 0;
     uint64_t cap = 0;
+    uint8_t* d_pool = nullptr;        // optional: 4-bit inserted sequences of the INS rows (seqpool.cu)
+    uint64_t* d_pool_off = nullptr;   // [n + 1] byte offset of each row's run in d_pool
+    uint64_t pool_bytes = 0;
 };
+int table_drop_pool(svb_table* t);
 
 struct svb_ref {
     int device = 0;
@@ -64,6 +70,8 @@ struct svb_ctx {
     std::vector<TimedSpan> spans;     // recorded, not yet folded into `timing`
     std::vector<cudaEvent_t> free_events;
     svb_timing timing;
+    cudaEvent_t marks[16] = {};
+    uint64_t launches = 0;            // kernels launched by this context (svb_launch_count)
     void* d_scratch = nullptr;        // grow-only device scratch
     size_t scratch_bytes = 0;
     uint32_t* d_status = nullptr;     // device error word (atomicOr of DEV_ERR_*)

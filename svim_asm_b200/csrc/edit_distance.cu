@@ -153,6 +153,7 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
         KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
         edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, reinterpret_cast<unsigned int*>(ctx->d_counters + 8),
                                                                        d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out);
+        ctx->launches += 1;
     }
     SVB_CUDA(ctx, cudaGetLastError());
     if (hbuf) SVB_CUDA(ctx, cudaFreeAsync(hbuf, ctx->stream));
@@ -199,6 +200,7 @@ int run_edit_distance_strings(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_
     SVB_CUDA(ctx, cudaMemcpyAsync(d_aoff, a_off, sizeof(uint64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
     SVB_CUDA(ctx, cudaMemcpyAsync(d_boff, b_off, sizeof(uint64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
     make_string_jobs<<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(d_aoff, d_boff, na, n_pairs, d_jobs);
+    ctx->launches += 1;
     SVB_CUDA(ctx, cudaGetLastError());
     int rc = launch_edit_distance(ctx, d_jobs, n_pairs, max_multi, d_bytes, nullptr, nullptr, d_map, d_out);
     if (rc != SVB_OK) return rc;

@@ -31,8 +31,6 @@ struct PairArgs {
     int32_t n_contig;
     const uint64_t* ref_off;        // reference contig offsets (get_reference_length of the FASTA)
     int32_t ref_n_contig;
-    const uint64_t* seq_off_a;
-    const uint64_t* seq_off_b;
     double max_edit_distance;
     double* dist;                   // [n_parts * PAIR_DIST_STRIDE]
     EditJob* jobs;
@@ -57,6 +55,8 @@ __device__ __forceinline__ void key_of(const svb_row& r, int32_t& tid, int32_t& 
 }
 
 __global__ void concat_keys_kernel(const svb_row* __restrict__ h1, uint32_t n1, const svb_row* __restrict__ h2, uint32_t n2,
+                                   const uint64_t* __restrict__ pool_off1, const uint64_t* __restrict__ pool_off2,
+                                   const uint64_t* __restrict__ seq_off1, const uint64_t* __restrict__ seq_off2,
                                    const int32_t* __restrict__ lexrank, int32_t n_contig, uint32_t rank_bits,
                                    svb_row* __restrict__ rows, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
                                    uint32_t* dev_status) {
@@ -64,6 +64,16 @@ __global__ void concat_keys_kernel(const svb_row* __restrict__ h1, uint32_t n1, 
     if (i >= n1 + n2) return;
     svb_row r = i < n1 ? h1[i] : h2[i - n1];
     r.hap = i < n1 ? 1 : 2;
+    // where this row's inserted sequence starts, as a nibble index: in the table's pool if it has one, else in
+    // the haplotype's full 4-bit query sequences
+    r.reserved0 = ~0ull;
+    if (r.type == SVB_INS) {
+        const uint64_t* pool_off = i < n1 ? pool_off1 : pool_off2;
+        const uint64_t* seq_off = i < n1 ? seq_off1 : seq_off2;
+        if (pool_off) r.reserved0 = pool_off[i < n1 ? i : i - n1] * 2ull;
+        else if (seq_off) r.reserved0 = seq_off[r.aln_idx] * 2ull + r.seq_pos;
+        else atomicOr(dev_status, DEV_ERR_NOSEQ);
+    }
     rows[i] = r;
     int32_t tid, pos;
     key_of(r, tid, pos);
@@ -188,13 +198,10 @@ __device__ void make_desc(const svb_row& r, long long lo, long long hi, const Pa
         d.r_base = base + static_cast<uint64_t>(s);
         d.r_len = static_cast<uint32_t>(hi > s ? hi - s : 0);
         if (r.type == SVB_INS) {
-            const uint64_t* so = r.hap == 2 ? a.seq_off_b : a.seq_off_a;
             d.m_kind = HAP_MID_SEQ4; d.seq_sel = r.hap == 2 ? 1u : 0u;
-            if (so) {
-                d.m_base = so[r.aln_idx] * 2ull + r.seq_pos;
+            if (r.reserved0 != ~0ull) {
+                d.m_base = r.reserved0;
                 d.m_len = r.seq_len;
-            } else {
-                atomicOr(a.dev_status, DEV_ERR_NOSEQ);         // svb_records_set_sequences was not called
             }
         } else {
             const long long ss = r.src_start, se = r.src_end;
@@ -263,6 +270,7 @@ __device__ void emit_cluster(const svb_row& first, const svb_row* second, const 
         wk_fill_bnd(r, a.contig_len, a.contig_lexrank, first.src_tid, first.src_start, (first.flags & SVB_F_SRC_FWD) != 0,
                     first.dst_tid, first.dst_start, (first.flags & SVB_F_DST_FWD) != 0);
     r.ordinal = slot;
+    r.reserved0 = 0;
     out[slot] = r;
 }
 
@@ -340,6 +348,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     svb_table* result = new (std::nothrow) svb_table();
     if (!result) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_pair");
     result->device = ctx->device;
+    result->stream = ctx->stream;
     if (n == 0) {
         SVB_CUDA(ctx, cudaMallocAsync(&result->d_rows, sizeof(svb_row), ctx->stream));
         result->cap = 1;
@@ -376,7 +385,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     auto fail = [&](int rc) {
         cudaStreamSynchronize(ctx->stream);
         cudaFreeAsync(slab, ctx->stream);
-        if (result->d_rows) cudaFree(result->d_rows);
+        if (result->d_rows) cudaFreeAsync(result->d_rows, ctx->stream);
         delete result;
         return rc;
     };
@@ -390,8 +399,11 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     uint32_t n_parts = 0;
     {
         KernelTimer timer(ctx, SVB_K_SORT);
-        concat_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h1->d_rows, n1, h2->d_rows, n2, rec->d_contig_lexrank, rec->n_contig,
+        concat_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h1->d_rows, n1, h2->d_rows, n2, h1->d_pool_off, h2->d_pool_off,
+                                                                     h1->d_pool_off ? nullptr : rec1->d_seq_off,
+                                                                     h2->d_pool_off ? nullptr : rec2->d_seq_off, rec->d_contig_lexrank, rec->n_contig,
                                                                      rank_bits, rows, keys[0], vals[0], ctx->d_status);
+        ctx->launches += 1;
         for (uint32_t shift = 0; shift < key_bits; shift += 8) {
             radix_hist_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], n, shift, hist, n_blocks);
             int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, ctx->d_counters + 9);
@@ -399,8 +411,10 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
             radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], vals[cur_buf], keys[cur_buf ^ 1], vals[cur_buf ^ 1], n,
                                                                            shift, hist, n_blocks);
             cur_buf ^= 1;
+            ctx->launches += 2;
         }
         heads_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], n, p->partition_max_distance, head);
+        ctx->launches += 1;
         int rc = launch_scan_u32(ctx, head, n, ctx->d_counters + 2);
         if (rc != SVB_OK) return fail(rc);
     }
@@ -419,8 +433,6 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     a.n_contig = rec->n_contig;
     a.ref_off = ref->d_contig_off;
     a.ref_n_contig = ref->n_contig;
-    a.seq_off_a = rec1->d_seq_off;
-    a.seq_off_b = rec2->d_seq_off;
     a.max_edit_distance = static_cast<double>(p->max_edit_distance);
     a.dist = dist;
     a.jobs = jobs;
@@ -434,6 +446,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         KernelTimer timer(ctx, SVB_K_SORT);
         part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start, n_parts);
         enumerate_jobs_kernel<<<(n_parts + 127) / 128, 128, 0, ctx->stream>>>(a);
+        ctx->launches += 2;
     }
     PAIR_CUDA(cudaGetLastError());
     PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -442,12 +455,14 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     const uint64_t max_multi = ctx->h_pinned[4];
     if (n_jobs) {
         // INS pairs read the 4-bit query bases of both haplotypes
-        int rc = launch_edit_distance(ctx, jobs, n_jobs, max_multi, ref->d_bases, rec1->d_seq4, rec2->d_seq4, ref->d_class_map, dist);
+        int rc = launch_edit_distance(ctx, jobs, n_jobs, max_multi, ref->d_bases, h1->d_pool_off ? h1->d_pool : rec1->d_seq4,
+                                      h2->d_pool_off ? h2->d_pool : rec2->d_seq4, ref->d_class_map, dist);
         if (rc != SVB_OK) return fail(rc);
     }
     {
         KernelTimer timer(ctx, SVB_K_CLUSTER);
         cluster_kernel<false><<<(n_parts + 63) / 64, 64, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
         int rc = launch_scan_u32(ctx, counts, n_parts, ctx->d_counters + 5);
         if (rc != SVB_OK) return fail(rc);
     }
@@ -462,6 +477,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     {
         KernelTimer timer(ctx, SVB_K_CLUSTER);
         cluster_kernel<true><<<(n_parts + 63) / 64, 64, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
     }
     PAIR_CUDA(cudaGetLastError());
     PAIR_CUDA(cudaFreeAsync(slab, ctx->stream));
@@ -511,6 +527,7 @@ int run_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_
     {
         KernelTimer timer(ctx, SVB_K_CLUSTER);
         cluster_labels_kernel<<<(n_problems + 63) / 64, 64, 0, ctx->stream>>>(d_c, d_n, d_o, n_problems, threshold, d_l);
+        ctx->launches += 1;
     }
     SVB_CUDA(ctx, cudaGetLastError());
     SVB_CUDA(ctx, cudaMemcpyAsync(labels_out, d_l, sizeof(int32_t) * LINK_MAXN * n_problems, cudaMemcpyDeviceToHost, ctx->stream));

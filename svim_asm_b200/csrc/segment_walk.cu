@@ -223,6 +223,7 @@ int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* 
         KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
         walk_kernel<false><<<blocks, 128, 0, ctx->stream>>>(a);
         scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(a.counts, rec->n_prim, ctx->d_counters + 1);
+        ctx->launches += 2;
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -243,6 +244,7 @@ int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* 
         {
             KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
             walk_kernel<true><<<blocks, 128, 0, ctx->stream>>>(a);
+            ctx->launches += 1;
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) {
@@ -259,6 +261,7 @@ int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* 
 
 int launch_scan_u32(svb_ctx* ctx, uint32_t* v, uint32_t n, unsigned long long* d_total) {
     scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(v, n, d_total);
+    ctx->launches += 1;
     SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;
 }
@@ -268,6 +271,7 @@ int launch_merge_tables(svb_ctx* ctx, const svb_row* a, uint64_t na, const svb_r
     if (!n) return SVB_OK;
     KernelTimer timer(ctx, SVB_K_MERGE);
     merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(a, na, b, nb, out);
+    ctx->launches += 1;
     SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;
 }

@@ -194,6 +194,33 @@ class Table(object):
         self.engine._check(lib.svb_table_to_host(self.engine.handle, self.handle, _lib.ptr(rows), n, ctypes.byref(got)))
         return rows
 
+    # ---- sequence pool (inserted bases of the INS rows travelling with the table)
+    def gather_sequences(self, rec):
+        """Device-side gather from the record image's resident query sequences."""
+        self.engine._check(lib.svb_table_gather_sequences(self.engine.handle, self.handle, rec.handle))
+
+    def attach_sequences_host(self, host):
+        """Host-side gather from a HostBatch: only the inserted bases cross PCIe, not the whole assembly."""
+        self.engine._check(lib.svb_table_attach_sequences_host(self.engine.handle, self.handle, _lib.ptr(host.seq4),
+                                                               _lib.ptr(host.seq_off)))
+
+    def pool_to_numpy(self):
+        n = len(self)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        size = ctypes.c_uint64()
+        self.engine._check(lib.svb_table_pool_to_host(self.engine.handle, self.handle, None, 0, _lib.ptr(off), ctypes.byref(size)))
+        pool = np.zeros(int(size.value), dtype=np.uint8)
+        if pool.shape[0]:
+            self.engine._check(lib.svb_table_pool_to_host(self.engine.handle, self.handle, _lib.ptr(pool), pool.shape[0], None,
+                                                          ctypes.byref(size)))
+        return pool, off
+
+    def set_pool(self, pool, off):
+        pool = np.ascontiguousarray(pool, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        assert off.shape[0] == len(self) + 1
+        self.engine._check(lib.svb_table_set_pool_from_host(self.engine.handle, self.handle, _lib.ptr(pool), _lib.ptr(off)))
+
     def free(self):
         if self.handle:
             lib.svb_table_free(self.handle)
@@ -363,6 +390,20 @@ class Engine(object):
         ms = buf[:_lib.SVB_K_COUNT].view(np.float64)
         launches = buf[_lib.SVB_K_COUNT:]
         return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(_lib.KERNEL_NAMES)}
+
+    def launch_count(self):
+        n = ctypes.c_uint64()
+        self._check(lib.svb_launch_count(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def mark(self, slot):
+        """Record a timing marker on the library's stream."""
+        self._check(lib.svb_mark(self.handle, int(slot)))
+
+    def elapsed_ms(self, slot_begin, slot_end):
+        ms = ctypes.c_double()
+        self._check(lib.svb_elapsed_ms(self.handle, int(slot_begin), int(slot_end), ctypes.byref(ms)))
+        return ms.value
 
     def set_scan_variant(self, variant):
         self._check(lib.svb_set_scan_variant(self.handle, int(variant)))

@@ -1,0 +1,284 @@
+"""Multi-GPU layout of the hot path: one process per GPU, records sharded by reference contig.
+
+COLLECT needs no communication: every BAM record lives on one contig and the split-alignment walk of a primary
+only reads that record's own SA tag.  The one exchange step is an all-gatherv of the
+candidate tables (rows + the sequence pools of their INS rows): walk-derived candidates can land on a contig owned
+by another rank, both haplotypes' rows of a key contig must meet for pairing, and the writer needs the global order.
+After the exchange every rank pairs the key contigs it owns; the paired rows are gathered and put into the
+reference's order (type, then contig by python string order, then partition order).
+
+Everything here is host logic on numpy arrays plus torch.distributed collectives (NCCL on the GPU box, gloo in the
+CPU tests); the compute stages are passed in, so the same code is exercised with world_size 2 on a CPU-only box.
+"""
+import os
+import time
+
+import numpy as np
+
+HEADER_WORDS = 4
+
+
+def lpt_assign(weights, n_ranks):
+    """Longest-processing-time bin packing of contigs onto ranks by CIGAR-op count.  Returns owner[contig]."""
+    order = np.argsort(-np.asarray(weights, dtype=np.float64), kind="stable")
+    load = np.zeros(n_ranks)
+    owner = np.zeros(len(weights), dtype=np.int32)
+    for c in order:
+        r = int(np.argmin(load))
+        owner[c] = r
+        load[r] += weights[c]
+    return owner
+
+
+def contig_weights(rb, n_contigs):
+    return np.bincount(rb.tid[rb.tid >= 0], weights=rb.n_cigar[rb.tid >= 0].astype(np.float64), minlength=n_contigs)
+
+
+def shard_records(rb, owner, rank):
+    """(sub-batch of the records on this rank's contigs, their indices in the full batch)."""
+    mine = np.nonzero((rb.tid >= 0) & (owner[np.maximum(rb.tid, 0)] == rank))[0]
+    return rb.subset(mine), mine.astype(np.uint32)
+
+
+def key_contig(rows):
+    """tid of Candidate.get_key() (SVCandidate.py:17-19,147-148,292-293,386-387)."""
+    by_dest = (rows["type"] == 2) | (rows["type"] == 4)
+    return np.where(by_dest, rows["dst_tid"], rows["src_tid"])
+
+
+def remap_to_global(rows, global_idx):
+    """Local record indices -> indices in the full (unsharded) batch, in aln_idx and in the ordering key."""
+    rows = rows.copy()
+    g = global_idx[rows["aln_idx"]].astype(np.uint64)
+    rows["aln_idx"] = g
+    rows["ordinal"] = (g << np.uint64(32)) | (rows["ordinal"] & np.uint64(0xFFFFFFFF))
+    return rows
+
+
+def repack_pool(pool, off, order):
+    """Pool and offsets of rows[order] (vectorised gather of variable-length runs)."""
+    lens = (off[1:] - off[:-1]).astype(np.int64)[order]
+    new_off = np.zeros(order.shape[0] + 1, dtype=np.uint64)
+    new_off[1:] = np.cumsum(lens)
+    total = int(new_off[-1])
+    if total == 0:
+        return np.zeros(0, dtype=np.uint8), new_off
+    src = np.repeat(off[:-1].astype(np.int64)[order] - new_off[:-1].astype(np.int64), lens) + np.arange(total, dtype=np.int64)
+    return pool[src], new_off
+
+
+def pack_payload(parts):
+    """[(rows, pool, off), ...] -> one uint8 buffer (header: counts per part)."""
+    header = np.zeros(HEADER_WORDS * len(parts), dtype=np.uint64)
+    chunks = []
+    for k, (rows, pool, off) in enumerate(parts):
+        header[HEADER_WORDS * k:HEADER_WORDS * k + 2] = (rows.shape[0], pool.shape[0])
+        chunks += [rows.view(np.uint8).reshape(-1), off.view(np.uint8).reshape(-1), pool]
+    return np.concatenate([header.view(np.uint8)] + chunks)
+
+
+def unpack_payload(buf, n_parts, row_dtype):
+    header = buf[:8 * HEADER_WORDS * n_parts].view(np.uint64)
+    pos = 8 * HEADER_WORDS * n_parts
+    out = []
+    for k in range(n_parts):
+        n_rows, n_pool = int(header[HEADER_WORDS * k]), int(header[HEADER_WORDS * k + 1])
+        rows = buf[pos:pos + n_rows * row_dtype.itemsize].view(row_dtype)
+        pos += n_rows * row_dtype.itemsize
+        off = buf[pos:pos + 8 * (n_rows + 1)].view(np.uint64)
+        pos += 8 * (n_rows + 1)
+        pool = buf[pos:pos + n_pool]
+        pos += n_pool
+        out.append((rows, pool, off))
+    return out
+
+
+def all_gather_bytes(buf, device):
+    """Variable-length all-gather of a uint8 numpy buffer: sizes first, then one padded all_gather."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    size = torch.tensor([buf.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    sizes = [int(s.item()) for s in sizes]
+    width = max(max(sizes), 1)
+    mine = torch.zeros(width, dtype=torch.uint8, device=device)
+    if buf.shape[0]:
+        mine[:buf.shape[0]] = torch.from_numpy(np.ascontiguousarray(buf)).to(device)
+    outs = [torch.empty(width, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    return [o[:s].cpu().numpy() for o, s in zip(outs, sizes)]
+
+
+def merge_gathered(parts_by_rank, part):
+    """Concatenate one haplotype's (rows, pool, off) of all ranks and restore the global append order (ordinal)."""
+    rows = np.concatenate([p[part][0] for p in parts_by_rank])
+    pools, offs, base = [], [], 0
+    for p in parts_by_rank:
+        pools.append(p[part][1])
+        offs.append(p[part][2][:-1].astype(np.uint64) + np.uint64(base))
+        base += int(p[part][2][-1])
+    pool = np.concatenate(pools) if pools else np.zeros(0, dtype=np.uint8)
+    off = np.concatenate(offs + [np.array([base], dtype=np.uint64)])
+    order = np.argsort(rows["ordinal"], kind="stable")
+    new_pool, new_off = repack_pool(pool, off, order)
+    return rows[order], new_pool, new_off
+
+
+def select_owned(rows, pool, off, owner, rank):
+    keep = np.nonzero(owner[key_contig(rows)] == rank)[0]
+    new_pool, new_off = repack_pool(pool, off, keep)
+    return rows[keep], new_pool, new_off
+
+
+def order_paired(rows_by_rank, lexrank):
+    """Final order of pair_candidates' output: type, then key contig in python string order; inside one
+    (type, contig) every row comes from the owning rank, already in partition / label order."""
+    rows = np.concatenate(rows_by_rank)
+    if rows.shape[0] == 0:
+        return rows
+    key = rows["type"].astype(np.int64) * (1 << 32) + np.asarray(lexrank, dtype=np.int64)[key_contig(rows)]
+    out = rows[np.argsort(key, kind="stable")]
+    out["ordinal"] = np.arange(out.shape[0], dtype=np.uint64)
+    return out
+
+
+def sharded_step(stage, rank, owner, lexrank, device, row_dtype):
+    """One step on one rank.  `stage` supplies the compute:
+         stage.collect(hap) -> (rows, pool, off) with GLOBAL record indices
+         stage.pair(part1, part2) -> paired rows (numpy)
+       Returns the complete paired table (identical on every rank)."""
+    mine = [stage.collect(1), stage.collect(2)]
+    gathered = [unpack_payload(b, 2, row_dtype) for b in all_gather_bytes(pack_payload(mine), device)]
+    parts = []
+    for hap in (0, 1):
+        rows, pool, off = merge_gathered(gathered, hap)
+        parts.append(select_owned(rows, pool, off, owner, rank))
+    paired = stage.pair(parts[0], parts[1])
+    empty = (np.zeros(0, dtype=np.uint8), np.zeros(paired.shape[0] + 1, dtype=np.uint64))
+    back = [unpack_payload(b, 1, row_dtype)[0][0] for b in all_gather_bytes(pack_payload([(paired, empty[0], empty[1])]), device)]
+    return order_paired(back, lexrank)
+
+
+class EngineStage(object):
+    """The compute stages of one rank on its GPU (libsvimasm_b200 through the ctypes engine)."""
+
+    def __init__(self, eng, hosts, global_idx, ref, params, resident):
+        self.eng, self.hosts, self.global_idx, self.ref, self.params = eng, hosts, global_idx, ref, params
+        self.resident = resident                       # record images (with sequences) kept in HBM, or None: upload per step
+        self.records = list(resident) if resident else [None, None]
+        self.h2d = 0
+
+    def collect(self, hap):
+        k = hap - 1
+        if self.resident is None:
+            self.records[k] = self.eng.load_records(self.hosts[k])
+            h = self.hosts[k]
+            self.h2d += sum(getattr(h, n).nbytes for n in ("hdr", "cigar", "seg", "sa_count"))
+        table = self.eng.collect(self.records[k], self.params, hap=hap)
+        if self.resident is None:
+            table.attach_sequences_host(self.hosts[k])
+        else:
+            table.gather_sequences(self.records[k])
+        rows = remap_to_global(table.to_numpy(), self.global_idx[k])
+        pool, off = table.pool_to_numpy()
+        table.free()
+        return rows, pool, off
+
+    def pair(self, part1, part2):
+        tables = []
+        for rows, pool, off in (part1, part2):
+            t = self.eng.table_from_numpy(rows)
+            t.set_pool(pool, off)
+            tables.append(t)
+        paired = self.eng.pair(tables[0], tables[1], self.records[0], self.records[1], self.ref, self.params)
+        out = paired.to_numpy()
+        for t in tables + [paired]:
+            t.free()
+        if self.resident is None:
+            for r in self.records:
+                r.free()
+        return out
+
+
+def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block):
+    """bench.py for WORLD_SIZE > 1 (launched by torchrun): strong scaling, max over ranks."""
+    import json
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .engine import Engine, HostBatch, lexrank, make_params
+    from .bench_util import pinned_host, pin
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    cfg, rb1, rb2, bases, off = build_workload(args.scale)
+    n_contigs = len(cfg.contig_names)
+    owner = lpt_assign(contig_weights(rb1, n_contigs) + contig_weights(rb2, n_contigs), world)
+    s1, g1 = shard_records(rb1, owner, rank)
+    s2, g2 = shard_records(rb2, owner, rank)
+    n_aln_total, n_ops_total = rb1.n_aln + rb2.n_aln, rb1.n_ops + rb2.n_ops
+    hosts = [pinned_host(HostBatch.from_record_batch(s1)), pinned_host(HostBatch.from_record_batch(s2))]
+    ranks = lexrank(cfg.contig_names)
+    eng = Engine(local)
+    params = make_params()
+    bases_p, _keep = pin(bases)
+    ref = eng.load_reference(bases_p, off)                 # every rank keeps the whole reference (3.1 GB of 180 GB)
+    resident = [eng.load_records(h, with_sequences=True) for h in hosts]
+
+    def timed(stage_factory, steps, warmup):
+        for _ in range(warmup):
+            table = sharded_step(stage_factory(), rank, owner, ranks, device, _lib.ROW_DTYPE)
+        dist.barrier()
+        torch.cuda.synchronize()
+        eng.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            table = sharded_step(stage_factory(), rank, owner, ranks, device, _lib.ROW_DTYPE)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()) / steps, table
+
+    warm = max(args.warmup, 3)
+    eng.timing_reset()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    sec, table = timed(lambda: EngineStage(eng, hosts, [g1, g2], ref, params, resident), args.steps, warm)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - launches0
+    timing = eng.timing()
+    scan_ms, scan_launches = timing["cigar_scan"]
+    stages = []
+
+    def e2e_factory():
+        st = EngineStage(eng, hosts, [g1, g2], ref, params, None)
+        stages.append(st)
+        return st
+    e2e_sec, table2 = timed(e2e_factory, args.steps, warm)
+    h2d = torch.tensor([float(stages[-1].h2d)], dtype=torch.float64, device=device)
+    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    assert table.shape[0] == table2.shape[0]
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        local_ops, local_aln = hosts[0].n_ops + hosts[1].n_ops, hosts[0].n_aln + hosts[1].n_aln
+        scan_avg = scan_ms / max(scan_launches, 1)
+        alg = (4.0 * local_ops + 32.0 * local_aln) / 2.0
+        achieved = alg / (scan_avg * 1e-3) / 1e9 if scan_avg > 0 else 0.0
+        print(json.dumps({
+            "metric": "alignments_per_sec", "value": n_aln_total / sec, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "cigar_ops_per_sec": n_ops_total / sec,
+            "config": workload_config(cfg, args, paired_rows=int(table.shape[0]),
+                                      shard="rank 0 holds %d of %d alignments" % (local_aln, n_aln_total)),
+            "roofline": {"kernel": "cigar_scan (rank 0 shard)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launch_ms": scan_avg},
+            "e2e": {"value": n_aln_total / e2e_sec, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d.item()),
+                    "d2h_bytes_per_step": int(table.nbytes), "ms_per_step": e2e_sec * 1e3},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }), flush=True)
+    dist.destroy_process_group()

@@ -133,13 +133,16 @@ def config_c3(seed=1003, scale=1.0):
                        giant_ops=int(1_000_000 * min(1.0, scale * 4)))
 
 
+_ACGT_QUADS = np.array([[_ACGT_ASCII[(b >> s) & 3] for s in (0, 2, 4, 6)] for b in range(256)], dtype=np.uint8).view(np.uint32).reshape(256)
+
+
 def random_reference(cfg, seed=None):
-    """dict name -> uint8 ASCII array (uniform ACGT)."""
+    """dict name -> uint8 ASCII array (uniform ACGT); one random byte yields four bases."""
     rng = np.random.Generator(np.random.PCG64((cfg.seed if seed is None else seed) ^ 0x5EED))
     ref = {}
     for name, length in zip(cfg.contig_names, cfg.contig_lengths):
-        raw = np.frombuffer(rng.bytes(int(length)), dtype=np.uint8)
-        ref[name] = _ACGT_ASCII[raw & 3]
+        raw = np.frombuffer(rng.bytes((int(length) + 3) // 4), dtype=np.uint8)
+        ref[name] = _ACGT_QUADS[raw].view(np.uint8)[:int(length)]
     return ref
 
 
