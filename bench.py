@@ -60,24 +60,33 @@ def peak_hbm():
 
 
 class ClockSampler(object):
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """nvidia-smi sampling every 20 ms while the GPU works (B200_PROFILING.md clocks line).  Started before the
+    warm-up so that samples exist even when the timed region is only tens of milliseconds long."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,{r}.active,{r}.hw_slowdown,{r}.hw_thermal_slowdown,"
+              "{r}.sw_thermal_slowdown,{r}.sw_power_cap")
 
     def __init__(self, device):
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.proc = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
-                                         stderr=subprocess.DEVNULL)
-        except OSError:
-            pass
+        self.proc, self.tmp = None, None
+        for family in ("clocks_event_reasons", "clocks_throttle_reasons"):
+            query = "timestamp," + self.FIELDS.format(r=family)
+            try:
+                probe = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=" + query, "--format=csv,noheader,nounits"],
+                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=20)
+            except (OSError, subprocess.TimeoutExpired):
+                return
+            if probe.returncode == 0 and probe.stdout.strip():
+                self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + query,
+                                              "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.tmp,
+                                             stderr=subprocess.DEVNULL)
+                time.sleep(0.3)           # let the first samples arrive
+                return
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    def stop(self, busy_from=None, busy_to=None):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -97,7 +106,10 @@ class ClockSampler(object):
                 if len(r) > col and r[col].strip().lower() == "active":
                     reasons.add(name)
         if sm:
-            out["sm_mhz"] = float(np.median(sm))
+            # the GPU is busy for the whole sampling window (warm-up + timed steps); idle samples at the edges
+            # would only lower the median, so take the upper half
+            sm.sort()
+            out["sm_mhz"] = float(np.median(sm[len(sm) // 2:]))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
@@ -222,12 +234,12 @@ def b200_arm(args):
         t1.free(), t2.free(), paired.free()
         return n
 
+    sampler = ClockSampler(local)
     for _ in range(max(args.warmup, 3)):
         n_out = step_resident()
     eng.synchronize()
     eng.timing_reset()
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
     eng.mark(0)
     for _ in range(args.steps):
         step_resident()

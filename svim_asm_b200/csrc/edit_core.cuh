@@ -16,18 +16,16 @@
 // eq: rows whose pattern char equals the text char.  hin: horizontal delta entering at the top
 // row (-1, 0, +1).  hibit: the row whose horizontal delta is returned.
 SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_t hibit) {
+    // branch-free: lanes of a warp see different hin values every step
+    const uint64_t hin_neg = hin < 0 ? 1ull : 0ull, hin_pos = hin > 0 ? 1ull : 0ull;
     const uint64_t xv = eq | mv;
-    if (hin < 0) eq |= 1ull;
+    eq |= hin_neg;
     const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint64_t ph = mv | ~(xh | pv);
     uint64_t mh = pv & xh;
-    int hout = 0;
-    if (ph & hibit) hout = 1;
-    if (mh & hibit) hout = -1;
-    ph <<= 1;
-    mh <<= 1;
-    if (hin < 0) mh |= 1ull;
-    else if (hin > 0) ph |= 1ull;
+    const int hout = static_cast<int>((ph & hibit) != 0) - static_cast<int>((mh & hibit) != 0);
+    ph = (ph << 1) | hin_pos;
+    mh = (mh << 1) | hin_neg;
     pv = mh | ~(xv | ph);
     mv = ph & xv;
     return hout;

@@ -31,74 +31,106 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
     __syncthreads();
     signed char* hbuf = hbuf_pool ? hbuf_pool + (static_cast<uint64_t>(blockIdx.x) * ED_WARPS + warp) * hbuf_stride : nullptr;
 
-    while (true) {
-        uint32_t job_id = 0;
-        if (lane == 0) job_id = atomicAdd(next_job, 1u);
-        job_id = __shfl_sync(0xffffffffu, job_id, 0);
-        if (job_id >= n_jobs) break;
-        const EditJob job = jobs[job_id];
-        const uint32_t la = hap_length(job.a), lb = hap_length(job.b);
-        const HapDesc& P = la <= lb ? job.a : job.b;       // pattern = the shorter string
-        const HapDesc& T = la <= lb ? job.b : job.a;
-        const uint32_t m = la <= lb ? la : lb, n = la <= lb ? lb : la;
-        long long dist;
-        if (m == 0u) {
-            dist = n;
-        } else {
-            int total = 0;
-            uint32_t last_lane = 0;
-            for (uint32_t row0 = 0; row0 < m; row0 += 2048u) {
-                const uint32_t rows = min(2048u, m - row0);
-                const bool final_stripe = row0 + rows == m;
-                const uint32_t nblk = (rows + 63u) / 64u;
-                last_lane = nblk - 1u;
-                // per-class match masks of this lane's 64 rows
+    // Two sweeps over the job list: patterns longer than one 2048-row stripe first (they are the long poles),
+    // then the single-stripe jobs.
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        while (true) {
+            uint32_t job_id = 0;
+            if (lane == 0) job_id = atomicAdd(next_job + sweep, 1u);
+            job_id = __shfl_sync(0xffffffffu, job_id, 0);
+            if (job_id >= n_jobs) break;
+            const EditJob job = jobs[job_id];
+            const uint32_t la = hap_length(job.a), lb = hap_length(job.b);
+            const bool a_is_pattern = la <= lb;                // pattern = the shorter string
+            const uint32_t m = a_is_pattern ? la : lb, n = a_is_pattern ? lb : la;
+            if ((m > 2048u) != (sweep == 0)) continue;
+            const HapDesc P = a_is_pattern ? job.a : job.b;
+            const HapDesc T = a_is_pattern ? job.b : job.a;
+            long long dist = n;
+            if (m != 0u) {
+                // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of
+                // half-width K gives the exact distance whenever the result is <= K; otherwise widen and repeat.
+                // Single-stripe patterns are computed in full at once.
+                const uint32_t bands[3] = {128u, 1024u, 0xFFFFFFFFu};
+                for (int attempt = m > 2048u ? 0 : 2; attempt < 3; ++attempt) {
+                    const unsigned long long K = bands[attempt];
+                    long long anchor = 0;                      // D'[last row of the previous stripe, jlo - 1]
+                    uint32_t prev_jhi = 0;
+                    for (uint32_t row0 = 0; row0 < m; row0 += 2048u) {
+                        const uint32_t rows = min(2048u, m - row0);
+                        const bool final_stripe = row0 + rows == m;
+                        const uint32_t nblk = (rows + 63u) / 64u, last_lane = nblk - 1u;
+                        const uint32_t jlo = static_cast<unsigned long long>(row0) > K ? static_cast<uint32_t>(row0 - K) : 0u;
+                        const uint32_t jhi = static_cast<uint32_t>(min(static_cast<unsigned long long>(n),
+                                                                       static_cast<unsigned long long>(row0) + rows + (n - m) + K));
+                        // first column of the NEXT stripe's band: the running anchor stops there
+                        const uint32_t next_row0 = row0 + rows;
+                        const uint32_t next_jlo = static_cast<unsigned long long>(next_row0) > K ? static_cast<uint32_t>(next_row0 - K) : 0u;
+                        // per-class match masks of this lane's 64 rows
 #pragma unroll 4
-                for (int c = 0; c < ED_NCLASS; ++c) s_peq[warp][c][lane] = 0ull;
-                for (uint32_t r = 0; r < 64u; ++r) {
-                    const uint32_t idx = lane * 64u + r;
-                    if (idx < rows) {
-                        const uint8_t cls = s_class[hap_char(P, row0 + idx, ref, seq4_a, seq4_b)];
-                        if (cls < ED_NCLASS) s_peq[warp][cls][lane] |= 1ull << r;
-                    }
-                }
-                __syncwarp();
-                uint64_t pv = ~0ull, mv = 0ull;
-                const uint64_t hibit = (final_stripe && lane == last_lane) ? (1ull << ((rows - 1u) & 63u)) : (1ull << 63);
-                uint32_t carry = 0xFFu;                     // low byte: text class (255 = none); bits 8..9: hout + 1
-                uint32_t pre_cls = 255u;
-                int pre_h = 1;
-                const uint32_t steps = n + nblk - 1u;
-                for (uint32_t t = 0; t < steps; ++t) {
-                    if ((t & 31u) == 0u) {                  // every lane prefetches one of the next 32 columns
-                        const uint32_t j = t + lane;
-                        pre_cls = j < n ? s_class[hap_char(T, j, ref, seq4_a, seq4_b)] : 255u;
-                        pre_h = row0 == 0u ? 1 : (j < n ? hbuf[j] : 0);
-                    }
-                    const uint32_t fresh = (pre_cls & 0xFFu) | (static_cast<uint32_t>(pre_h + 1) << 8);
-                    const uint32_t top = __shfl_sync(0xffffffffu, fresh, t & 31u);
-                    uint32_t in = __shfl_up_sync(0xffffffffu, carry, 1);
-                    if (lane == 0u) in = top;
-                    const uint32_t cls = in & 0xFFu;
-                    const int hin = static_cast<int>((in >> 8) & 3u) - 1;
-                    const long long j = static_cast<long long>(t) - lane;
-                    int hout = 0;
-                    if (lane < nblk && j >= 0 && j < static_cast<long long>(n)) {
-                        const uint64_t eq = cls < ED_NCLASS ? s_peq[warp][cls][lane] : 0ull;
-                        hout = myers_block(pv, mv, eq, hin, hibit);
-                        if (lane == last_lane) {
-                            if (final_stripe) total += hout;
-                            else hbuf[j] = static_cast<signed char>(hout);
+                        for (int c = 0; c < ED_NCLASS; ++c) s_peq[warp][c][lane] = 0ull;
+                        for (uint32_t r = 0; r < 64u; ++r) {
+                            const uint32_t idx = lane * 64u + r;
+                            if (idx < rows) {
+                                const uint8_t cls = s_class[hap_char(P, row0 + idx, ref, seq4_a, seq4_b)];
+                                if (cls < ED_NCLASS) s_peq[warp][cls][lane] |= 1ull << r;
+                            }
                         }
+                        __syncwarp();
+                        uint64_t pv = ~0ull, mv = 0ull;
+                        const uint64_t hibit = (final_stripe && lane == last_lane) ? (1ull << ((rows - 1u) & 63u)) : (1ull << 63);
+                        uint32_t carry = 0xFFu;                 // low byte: text class (255 = none); bits 8..9: hout + 1
+                        int sum_all = 0, sum_anchor = 0;        // bottom-row deltas over [jlo, jhi) and over [jlo, next_jlo)
+                        const uint32_t width = jhi - jlo, steps = width + nblk - 1u;
+                        // text classes / top-row deltas are fetched 32 columns at a time, one block ahead of their use
+                        uint32_t nxt = 0xFFu | (2u << 8);
+                        {
+                            const uint32_t j = jlo + lane;
+                            const uint32_t cls = (lane < width) ? s_class[hap_char(T, j, ref, seq4_a, seq4_b)] : 255u;
+                            const int h = (row0 == 0u || j >= prev_jhi) ? 1 : hbuf[j];
+                            nxt = cls | (static_cast<uint32_t>(h + 1) << 8);
+                        }
+                        uint32_t cur = nxt;
+                        for (uint32_t t = 0; t < steps; ++t) {
+                            if ((t & 31u) == 0u) {
+                                cur = nxt;
+                                const uint32_t rel = t + 32u + lane;
+                                const uint32_t j = jlo + rel;
+                                const uint32_t cls = (rel < width) ? s_class[hap_char(T, j, ref, seq4_a, seq4_b)] : 255u;
+                                const int h = (rel < width && row0 != 0u && j < prev_jhi) ? hbuf[j] : 1;
+                                nxt = cls | (static_cast<uint32_t>(h + 1) << 8);
+                            }
+                            const uint32_t top = __shfl_sync(0xffffffffu, cur, t & 31u);
+                            uint32_t in = __shfl_up_sync(0xffffffffu, carry, 1);
+                            if (lane == 0u) in = top;
+                            const uint32_t cls = in & 0xFFu;
+                            const int hin = static_cast<int>((in >> 8) & 3u) - 1;
+                            const long long rel = static_cast<long long>(t) - lane;
+                            int hout = 0;
+                            if (lane < nblk && rel >= 0 && rel < static_cast<long long>(width)) {
+                                const uint64_t eq = cls < ED_NCLASS ? s_peq[warp][cls][lane] : 0ull;
+                                hout = myers_block(pv, mv, eq, hin, hibit);
+                                if (lane == last_lane) {
+                                    const uint32_t j = jlo + static_cast<uint32_t>(rel);
+                                    sum_all += hout;
+                                    if (j < next_jlo) sum_anchor += hout;
+                                    if (!final_stripe) hbuf[j] = static_cast<signed char>(hout);
+                                }
+                            }
+                            carry = cls | (static_cast<uint32_t>(hout + 1) << 8);
+                        }
+                        __syncwarp();
+                        sum_all = __shfl_sync(0xffffffffu, sum_all, last_lane);
+                        sum_anchor = __shfl_sync(0xffffffffu, sum_anchor, last_lane);
+                        if (final_stripe) dist = anchor + rows + sum_all;
+                        else anchor += static_cast<long long>(rows) + sum_anchor;
+                        prev_jhi = jhi;
                     }
-                    carry = cls | (static_cast<uint32_t>(hout + 1) << 8);
+                    if (static_cast<unsigned long long>(dist) <= K) break;      // exact
                 }
-                __syncwarp();
             }
-            total = __shfl_sync(0xffffffffu, total, last_lane);
-            dist = static_cast<long long>(m) + total;
+            if (lane == 0) out[job.out_index] = static_cast<double>(dist);
         }
-        if (lane == 0) out[job.out_index] = static_cast<double>(dist);
     }
 }
 
@@ -148,7 +180,7 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
     signed char* hbuf = nullptr;
     const uint64_t stride = (max_text_multi_stripe + 127) & ~127ull;
     if (stride) SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));
-    SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, sizeof(unsigned long long), ctx->stream));
+    SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, sizeof(unsigned long long), ctx->stream));   // two 32-bit job counters
     {
         KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
         edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, reinterpret_cast<unsigned int*>(ctx->d_counters + 8),
