@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvimasm_b200.so")
+LIB_PATH = os.environ.get("SVIM_ASM_B200_LIB", os.path.join(_HERE, "libsvimasm_b200.so"))   # override: tuning builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError("libsvimasm_b200.so is missing at %s -- build it with `python -m svim_asm_b200.build`; "

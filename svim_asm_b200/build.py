@@ -19,31 +19,33 @@ def _stale():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    """Compile every CUDA/C++ source of the package into one shared library.  Returns its path."""
-    if not force and not _stale():
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every CUDA/C++ source of the package into one shared library.  Returns its path.
+    `extra_flags` / `out` build tuning variants (e.g. -DK2_CHUNKS_PER_WARP=8) next to the default library."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, proc in procs:
-        out, _ = proc.communicate()
+        text, _ = proc.communicate()
         if verbose or proc.returncode:
-            sys.stderr.write(out)
+            sys.stderr.write(text)
         if proc.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    link = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread"]
+    target = LIB if out is None else out
+    link = [nvcc, "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lz", "-lpthread"]
     subprocess.check_call(link)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

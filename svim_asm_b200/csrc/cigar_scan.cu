@@ -36,12 +36,10 @@ constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int ROWS = 8;                    // uint4 per lane per chunk
 constexpr int CHUNK4 = 32 * ROWS;          // 256 uint4  = 1024 ops = 4 KB per chunk
-#ifndef K2_CHUNKS_PER_WARP
-#define K2_CHUNKS_PER_WARP 4
-#endif
-constexpr int G = K2_CHUNKS_PER_WARP;      // chunks per warp per run
-constexpr int RUN4 = WARPS * G * CHUNK4;   // uint4 per run (G = 4: 8192 uint4 = 32768 ops = 128 KB)
 constexpr int STAGES = 2;                  // TMA ring depth per warp
+// G = chunks per warp per run (template parameter): a run is WARPS * G * CHUNK4 uint4 (G = 16: 512 KB).  Bigger runs
+// amortise the run-end barrier + look-back (measured on B200, 2.0e8 ops: G=4 2.5 TB/s, G=8 3.0 TB/s, G=16 3.1 TB/s
+// with the LDG variant); smaller ones keep all SMs busy on small inputs.
 
 constexpr uint32_t REF_MASK = (1u << 0) | (1u << 2) | (1u << 7) | (1u << 8);              // M D = X  (SVIM_intra.py:15,23,28)
 constexpr uint32_t READ_MASK = (1u << 0) | (1u << 1) | (1u << 4) | (1u << 7) | (1u << 8); // M I S = X (SVIM_intra.py:16,20,26,29)
@@ -382,8 +380,9 @@ struct Snap {
     uint32_t R, Q, head, cnt;
 };
 
-template <bool USE_TMA>
+template <bool USE_TMA, int G>
 __global__ void __launch_bounds__(THREADS, USE_TMA ? 3 : 4) cigar_scan_kernel(const ScanArgs a) {
+    constexpr int RUN4 = WARPS * G * CHUNK4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_ring = reinterpret_cast<uint4*>(smem_raw);       // [WARPS][STAGES][CHUNK4] when USE_TMA
     __shared__ __align__(8) unsigned long long s_mbar[WARPS][STAGES];
@@ -635,10 +634,9 @@ int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec) {
     return SVB_OK;
 }
 
-int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out) {
-    SVB_CUDA(ctx, cudaMemsetAsync(out.d_count, 0, sizeof(unsigned long long), ctx->stream));
-    if (rec->n_aln) SVB_CUDA(ctx, cudaMemsetAsync(rec->d_aln_sum, 0, sizeof(uint4) * rec->n_aln, ctx->stream));
-    if (rec->n4 == 0) return SVB_OK;
+template <int G>
+static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a) {
+    constexpr int RUN4 = WARPS * G * CHUNK4;
     const uint64_t n_runs64 = (rec->n4 + RUN4 - 1) / RUN4;
     if (n_runs64 > 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "too many CIGAR ops for one launch");
     const uint32_t n_runs = static_cast<uint32_t>(n_runs64);
@@ -646,7 +644,31 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     unsigned char* scratch = static_cast<unsigned char*>(svb_scratch(ctx, need));
     if (!scratch) return svb_fail(ctx, SVB_ERR_NOMEM, "run status scratch");
     SVB_CUDA(ctx, cudaMemsetAsync(scratch, 0, need, ctx->stream));
+    a.n_runs = n_runs;
+    a.ticket = reinterpret_cast<unsigned int*>(scratch);
+    a.status = reinterpret_cast<RunStatus*>(scratch + 256);
+    KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);
+    if (ctx->scan_variant == 0) {
+        const size_t smem = static_cast<size_t>(WARPS) * STAGES * CHUNK4 * sizeof(uint4);
+        static bool attr_set = false;
+        if (!attr_set) {
+            SVB_CUDA(ctx, cudaFuncSetAttribute(cigar_scan_kernel<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)));
+            attr_set = true;
+        }
+        cigar_scan_kernel<true, G><<<n_runs, THREADS, smem, ctx->stream>>>(a);
+    } else {
+        cigar_scan_kernel<false, G><<<n_runs, THREADS, 16, ctx->stream>>>(a);
+    }
+    ctx->launches += 1;
+    SVB_CUDA(ctx, cudaGetLastError());
+    return SVB_OK;
+}
 
+int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out) {
+    SVB_CUDA(ctx, cudaMemsetAsync(out.d_count, 0, sizeof(unsigned long long), ctx->stream));
+    if (rec->n_aln) SVB_CUDA(ctx, cudaMemsetAsync(rec->d_aln_sum, 0, sizeof(uint4) * rec->n_aln, ctx->stream));
+    if (rec->n4 == 0) return SVB_OK;
     ScanArgs a;
     a.cigar = rec->d_cigar;
     a.n4 = rec->n4;
@@ -656,33 +678,23 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     a.contig_len = rec->d_contig_len;
     a.n_aln = rec->n_aln;
     a.n_contig = rec->n_contig;
-    a.n_runs = n_runs;
+    a.n_runs = 0;
     a.min_mapq = p->min_mapq;
     const long long m = p->min_sv_size < 0 ? 0 : p->min_sv_size;
     a.min16 = m >= (1ll << 28) ? 0xFFFFFFFFu : static_cast<uint32_t>(m << 4);
     a.hap = static_cast<uint32_t>(hap);
     a.aln_sum = rec->d_aln_sum;
-    a.ticket = reinterpret_cast<unsigned int*>(scratch);
-    a.status = reinterpret_cast<RunStatus*>(scratch + 256);
+    a.ticket = nullptr;
+    a.status = nullptr;
     a.rows = out.rows;
     a.cap = out.cap;
     a.total = out.d_count;
     a.dev_status = ctx->d_status;
-
-    KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);
-    if (ctx->scan_variant == 0) {
-        const size_t smem = static_cast<size_t>(WARPS) * STAGES * CHUNK4 * sizeof(uint4);
-        static bool attr_set = false;
-        if (!attr_set) {
-            SVB_CUDA(ctx, cudaFuncSetAttribute(cigar_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(smem)));
-            attr_set = true;
-        }
-        cigar_scan_kernel<true><<<n_runs, THREADS, smem, ctx->stream>>>(a);
-    } else {
-        cigar_scan_kernel<false><<<n_runs, THREADS, 16, ctx->stream>>>(a);
-    }
-    ctx->launches += 1;
-    SVB_CUDA(ctx, cudaGetLastError());
-    return SVB_OK;
+    // run length: as long as possible while at least two full waves of CTAs (4 per SM) remain
+    const uint64_t two_waves = 2ull * 4ull * static_cast<uint64_t>(ctx->sm_count);
+    const uint64_t chunks = (rec->n4 + CHUNK4 - 1) / CHUNK4;
+    if (chunks / (WARPS * 16) >= two_waves) return launch_scan_g<16>(ctx, rec, a);
+    if (chunks / (WARPS * 8) >= two_waves) return launch_scan_g<8>(ctx, rec, a);
+    if (chunks / (WARPS * 4) >= two_waves) return launch_scan_g<4>(ctx, rec, a);
+    return launch_scan_g<2>(ctx, rec, a);
 }
