@@ -257,8 +257,15 @@ def b200_arm(args):
     alg_bytes = (4.0 * n_ops + 32.0 * n_aln + 64.0 * (n_out[1] + n_out[2])) / 2.0
     peak, peak_src = peak_hbm()
     achieved = alg_bytes / (scan_avg * 1e-3) / 1e9
+    traffic = None
+    try:      # DRAM bytes of one launch from the committed ncu capture (profiles/), valid for the full-size workload only
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_cigar_scan_traffic.json")))
+        if abs(cap["n_ops"] - n_ops / 2.0) < 0.02 * cap["n_ops"]:
+            traffic = cap["cigar_scan_dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"kernel": "cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "launch_ms": scan_avg, "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": traffic, "peak_source": peak_src, "launch_ms": scan_avg, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items()}}
     rec1.free(), rec2.free()
 

@@ -40,10 +40,33 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             job_id = __shfl_sync(0xffffffffu, job_id, 0);
             if (job_id >= n_jobs) break;
             const EditJob job = jobs[job_id];
-            const uint32_t la = hap_length(job.a), lb = hap_length(job.b);
+            const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
+            if ((min(la0, lb0) > 2048u) != (sweep == 0)) continue;
+            // The edit distance does not change when the common prefix and suffix are removed; the two haplotypes of
+            // a shared variant are mostly identical, so this alone finishes most pairs (warp-parallel compare).
+            const uint32_t lim = min(la0, lb0);
+            uint32_t pre = 0;
+            while (pre < lim) {
+                const uint32_t i = pre + lane;
+                const bool same = i < lim && hap_char(job.a, i, ref, seq4_a, seq4_b) == hap_char(job.b, i, ref, seq4_a, seq4_b);
+                const uint32_t mask = __ballot_sync(0xffffffffu, same);
+                if (mask != 0xffffffffu) { pre += static_cast<uint32_t>(__ffs(~mask) - 1); break; }
+                pre += 32u;
+            }
+            pre = min(pre, lim);
+            const uint32_t lim2 = lim - pre;
+            uint32_t suf = 0;
+            while (suf < lim2) {
+                const uint32_t i = suf + lane;
+                const bool same = i < lim2 && hap_char(job.a, la0 - 1u - i, ref, seq4_a, seq4_b) == hap_char(job.b, lb0 - 1u - i, ref, seq4_a, seq4_b);
+                const uint32_t mask = __ballot_sync(0xffffffffu, same);
+                if (mask != 0xffffffffu) { suf += static_cast<uint32_t>(__ffs(~mask) - 1); break; }
+                suf += 32u;
+            }
+            suf = min(suf, lim2);
+            const uint32_t la = la0 - pre - suf, lb = lb0 - pre - suf;
             const bool a_is_pattern = la <= lb;                // pattern = the shorter string
             const uint32_t m = a_is_pattern ? la : lb, n = a_is_pattern ? lb : la;
-            if ((m > 2048u) != (sweep == 0)) continue;
             const HapDesc P = a_is_pattern ? job.a : job.b;
             const HapDesc T = a_is_pattern ? job.b : job.a;
             long long dist = n;
@@ -51,7 +74,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                 // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of
                 // half-width K gives the exact distance whenever the result is <= K; otherwise widen and repeat.
                 // Single-stripe patterns are computed in full at once.
-                const uint32_t bands[3] = {128u, 1024u, 0xFFFFFFFFu};
+                const uint32_t bands[3] = {max(128u, m / 16u), max(1024u, m / 4u), 0xFFFFFFFFu};
                 for (int attempt = m > 2048u ? 0 : 2; attempt < 3; ++attempt) {
                     const unsigned long long K = bands[attempt];
                     long long anchor = 0;                      // D'[last row of the previous stripe, jlo - 1]
@@ -72,7 +95,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         for (uint32_t r = 0; r < 64u; ++r) {
                             const uint32_t idx = lane * 64u + r;
                             if (idx < rows) {
-                                const uint8_t cls = s_class[hap_char(P, row0 + idx, ref, seq4_a, seq4_b)];
+                                const uint8_t cls = s_class[hap_char(P, pre + row0 + idx, ref, seq4_a, seq4_b)];
                                 if (cls < ED_NCLASS) s_peq[warp][cls][lane] |= 1ull << r;
                             }
                         }
@@ -86,7 +109,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         uint32_t nxt = 0xFFu | (2u << 8);
                         {
                             const uint32_t j = jlo + lane;
-                            const uint32_t cls = (lane < width) ? s_class[hap_char(T, j, ref, seq4_a, seq4_b)] : 255u;
+                            const uint32_t cls = (lane < width) ? s_class[hap_char(T, pre + j, ref, seq4_a, seq4_b)] : 255u;
                             const int h = (row0 == 0u || j >= prev_jhi) ? 1 : hbuf[j];
                             nxt = cls | (static_cast<uint32_t>(h + 1) << 8);
                         }
@@ -96,7 +119,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                 cur = nxt;
                                 const uint32_t rel = t + 32u + lane;
                                 const uint32_t j = jlo + rel;
-                                const uint32_t cls = (rel < width) ? s_class[hap_char(T, j, ref, seq4_a, seq4_b)] : 255u;
+                                const uint32_t cls = (rel < width) ? s_class[hap_char(T, pre + j, ref, seq4_a, seq4_b)] : 255u;
                                 const int h = (rel < width && row0 != 0u && j < prev_jhi) ? hbuf[j] : 1;
                                 nxt = cls | (static_cast<uint32_t>(h + 1) << 8);
                             }
