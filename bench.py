@@ -36,6 +36,9 @@ def log(msg):
 
 def build_workload(scale, seed=1004):
     from svim_asm_b200 import synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:        # every rank generates the (deterministic) workload: share the host cores
+        os.environ.setdefault("SVIM_SYNTH_WORKERS", str(max(1, (os.cpu_count() or 1) // world)))
     cfg = synth.config_c3(seed=seed, scale=scale)
     t0 = time.time()
     rb1, rb2 = synth.make_diploid(cfg)

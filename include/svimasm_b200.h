@@ -133,7 +133,7 @@ const char* svb_last_error(const svb_ctx* ctx);          /* valid until the next
 int svb_synchronize(svb_ctx* ctx);
 int svb_timing_reset(svb_ctx* ctx);
 int svb_timing_get(svb_ctx* ctx, svb_timing* out);       /* synchronises the stream first */
-int svb_set_scan_variant(svb_ctx* ctx, int variant);      /* cigar_scan loads: 0 = per-warp TMA bulk-copy ring, 1 = LDG.128.nc (default) */
+int svb_set_scan_variant(svb_ctx* ctx, int variant);      /* cigar_scan loads: 0 = per-warp TMA bulk-copy ring (default), 1 = LDG.128.nc */
 /* Step timing on the library's own stream: record marker `slot` (0..15) now; elapsed ms between two markers
  * (synchronises on the later one).  bench.py brackets its timed region with these. */
 int svb_launch_count(svb_ctx* ctx, uint64_t* out);       /* kernels this context has launched so far */

@@ -409,9 +409,9 @@ int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int h
     cudaSetDevice(ctx->device);
     *out = nullptr;
 
-    // K2: indel rows.  Capacity is a guess (1 row per 64 ops, far above real SV density); an
+    // K2: indel rows.  Capacity is a guess (1 row per 512 ops; human assemblies have about 1 per 20,000); an
     // overflow is detected from the exact count and the scan is repeated once with the right size.
-    uint64_t cap = std::max<uint64_t>(4096, rec->n_ops / 64);
+    uint64_t cap = std::max<uint64_t>(4096, rec->n_ops / 512);
     svb_table* indel = nullptr;
     unsigned long long n_indel = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {

@@ -10,24 +10,29 @@
 // a BAM file sit in one flat array of BAM-packed ops, and the walk becomes a segmented exclusive
 // scan (segments = alignments) fused with an order-preserving stream compaction of the rare
 // emitting ops, done in ONE pass over HBM:
-//   * a CTA claims a RUN of 8 warps x G chunks x 1024 ops with a ticket; warp w owns G consecutive
-//     chunks (4 KB each), so its running "sum since the last alignment head" stays in registers;
-//   * a chunk is staged to shared memory by a per-warp ring of TMA bulk copies (cp.async.bulk +
-//     mbarrier, two 4 KB stages per warp, the next chunk is in flight while this one is decoded);
-//     variant 1 reads the chunk with coalesced 128-bit LDG.nc straight into registers instead;
+//   * the array is cut into UNITS of G chunks x 1024 ops (G = 16: 64 KB); one warp owns one unit, so its
+//     running "sum since the last alignment head" stays in registers and warps never wait for each other:
+//     no block barrier, no inter-block look-back in the streaming kernel;
+//   * a chunk (4 KB) is staged to shared memory by a per-warp ring of TMA bulk copies (cp.async.bulk +
+//     mbarrier, two stages: the next chunk is in flight while this one is decoded; default), or, variant 1,
+//     read with coalesced 128-bit LDG.nc into registers;
 //   * per op: one 8-byte table entry {multiplier, threshold} from shared memory, one IMAD.WIDE into a
 //     packed accumulator (read advance in bits 0..30, reference advance from bit 31 up), one compare
 //     that flags the rare ops (I/D with len >= min_sv_size, N/H).  Exact event bits are recomputed
-//     only when the flag fires somewhere in the warp (about 1 chunk in 8 for human assemblies);
-//   * the run's aggregate and emit count go to a run-status array; ALL 8 warps look back together
-//     (256 predecessors per round trip) once per run, so the look-back latency is paid per 128 KB;
-//   * only chunks that hold an emitting op are re-read (from L2) to compute the exclusive prefix of
-//     that op (two warp reductions per event) and to write the finished 64-byte candidate row at its
-//     final, stable position.
+//     only for the rows where the flag fired (about 1 chunk in 8 holds one for human assemblies);
+//   * a chunk that holds an emitting op writes its finished 64-byte rows at once, into a staging area at an
+//     atomically reserved slot, tagged with (unit, index inside the unit).  Rows of the alignment that was
+//     already running when the unit began (about 15 % of the rows) cannot know their offset yet: they are
+//     flagged and carry their raw partial sums;
+//   * two tiny kernels finish the job: a segmented scan over the per-unit aggregates (carry-in and row
+//     base of every unit) and a per-row pass that moves each row to its final, stable position and
+//     completes the flagged ones (clamps of SVCandidate.py:44-46,134-136 applied then).
 // Per-alignment totals (reference span, read span, N and H bases), needed by the split-alignment
 // walk for reference_end / infer_read_length (SVIM_inter.py:68-80), fall out as atomics.
 //
 // Bound: HBM bandwidth.  Algorithmic bytes: 4 B/op + 32 B/alignment + 64 B/emitted row.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -37,24 +42,16 @@ constexpr int WARPS = THREADS / 32;
 constexpr int ROWS = 8;                    // uint4 per lane per chunk
 constexpr int CHUNK4 = 32 * ROWS;          // 256 uint4  = 1024 ops = 4 KB per chunk
 constexpr int STAGES = 2;                  // TMA ring depth per warp
-// G = chunks per warp per run (template parameter): a run is WARPS * G * CHUNK4 uint4 (G = 16: 512 KB).  Bigger runs
-// amortise the run-end barrier + look-back (measured on B200, 2.0e8 ops: G=4 2.5 TB/s, G=8 3.0 TB/s, G=16 3.1 TB/s
-// with the LDG variant); smaller ones keep all SMs busy on small inputs.
+#ifndef K2_LDG_CTAS
+#define K2_LDG_CTAS 4                      // resident CTAs per SM the LDG variant is compiled for (64 registers)
+#endif
+// G = chunks per unit (template parameter, picked at launch): one warp walks G chunks of 4 KB with its carry in
+// registers.  Long units amortise the per-unit work; short ones keep every SM busy on small inputs.
 
 constexpr uint32_t REF_MASK = (1u << 0) | (1u << 2) | (1u << 7) | (1u << 8);              // M D = X  (SVIM_intra.py:15,23,28)
 constexpr uint32_t READ_MASK = (1u << 0) | (1u << 1) | (1u << 4) | (1u << 7) | (1u << 8); // M I S = X (SVIM_intra.py:16,20,26,29)
 constexpr uint32_t INDEL_MASK = (1u << 1) | (1u << 2);
 constexpr uint32_t NH_MASK = (1u << 3) | (1u << 5);
-
-// run status: three 64-bit words, each tagged with its own state in the top 2 bits so that a reader
-// can validate a snapshot without fences (values are self-describing).
-constexpr unsigned long long ST_INVALID = 0ull, ST_AGG = 1ull, ST_PREFIX = 2ull;
-struct RunStatus {
-    unsigned long long w_ref;    // [63:62] state  [32] has_head  [31:0] ref sum since last head
-    unsigned long long w_read;   // [63:62] state               [31:0] read sum since last head
-    unsigned long long w_cnt;    // [63:62] state  [61:0] emitted rows
-    unsigned long long pad;
-};
 
 // geometry of one 1024-op chunk, precomputed when the record image is loaded
 struct ChunkGeom {
@@ -73,18 +70,19 @@ struct ScanArgs {
     const int32_t* contig_len;
     uint32_t n_aln;
     int32_t n_contig;
-    uint32_t n_runs;
+    uint32_t n_units;
     int32_t min_mapq;
     uint32_t min16;           // min_sv_size << 4 : (x >= min16) <=> (len >= min_sv_size)
     uint32_t hap;
     uint4* aln_sum;
-    RunStatus* status;
-    unsigned int* ticket;
-    svb_row* rows;
+    uint4* unit_agg;          // [n_units] x: ref sum since last head, y: read sum, z: head seen, w: rows emitted
+    svb_row* rows;            // staging rows (slots reserved with atomics)
     unsigned long long cap;
-    unsigned long long* total;
+    unsigned long long* total;     // number of staged rows (may exceed cap)
     uint32_t* dev_status;
 };
+
+constexpr uint8_t ROW_NEEDS_CARRY = 0x80;     // staging flag: offsets are relative to the unit start
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -93,14 +91,6 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     uint32_t ready = 0;
@@ -134,13 +124,13 @@ __device__ __forceinline__ bool record_passes(const svb_aln_hdr& h, int32_t min_
 
 // fast path of one uint4 (4 ops): packed advance sums and the rare flag
 __device__ __forceinline__ void fast_row(const uint4 d, const uint2* lut, bool in_head, uint32_t& totR, uint32_t& totQ,
-                                         uint32_t& headR, uint32_t& headQ, bool& rare) {
+                                         uint32_t& headR, uint32_t& headQ, uint32_t& rare_rows, uint32_t row_bit) {
     const uint2 e0 = lut[d.x & 15u], e1 = lut[d.y & 15u], e2 = lut[d.z & 15u], e3 = lut[d.w & 15u];
     unsigned long long acc = static_cast<unsigned long long>(d.x >> 4) * e0.x;
     acc += static_cast<unsigned long long>(d.y >> 4) * e1.x;
     acc += static_cast<unsigned long long>(d.z >> 4) * e2.x;
     acc += static_cast<unsigned long long>(d.w >> 4) * e3.x;
-    rare = rare || d.x >= e0.y || d.y >= e1.y || d.z >= e2.y || d.w >= e3.y;
+    if (d.x >= e0.y || d.y >= e1.y || d.z >= e2.y || d.w >= e3.y) rare_rows |= row_bit;
     const uint32_t rr = static_cast<uint32_t>(acc >> 31), qq = static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
     totR += rr;
     totQ += qq;
@@ -174,16 +164,18 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uin
     const int rows_before = (static_cast<int>(g.split_rel) - static_cast<int>(lane) + 31) / 32;
     const int nb = rows_before <= 0 ? 0 : (rows_before >= ROWS ? ROWS : rows_before);
     uint32_t headR = 0, headQ = 0, totR = 0, totQ = 0;
-    bool rare = false;
+    uint32_t rare_rows = 0;               // bit r: this lane's uint4 of row r holds a rare op
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) fast_row(rowsrc(r), lut, r < nb, totR, totQ, headR, headQ, rare);
+    for (int r = 0; r < ROWS; ++r) fast_row(rowsrc(r), lut, r < nb, totR, totQ, headR, headQ, rare_rows, 1u << r);
     const uint32_t first_mask = nb >= 8 ? 0xFFFFFFFFu : ((1u << (4u * static_cast<uint32_t>(nb))) - 1u);
-    const bool any_rare = __ballot_sync(0xffffffffu, rare) != 0u;
+    uint32_t warp_rows = __reduce_or_sync(0xffffffffu, rare_rows);      // rows that need the exact classification
+    const bool any_rare = warp_rows != 0u;
 
     uint32_t nhbits = 0, evbits = 0;
-    if (any_rare) {                        // exact bits of the rare ops
-#pragma unroll 1
-        for (int r = 0; r < ROWS; ++r) {
+    while (warp_rows) {                    // exact bits, only for the rows (usually one) that hold a rare op
+        const int r = __ffs(warp_rows) - 1;
+        warp_rows &= warp_rows - 1u;
+        if ((rare_rows >> r) & 1u) {
             const uint4 d = raresrc(r);
             uint32_t r0 = 0, q0 = 0;
             decode_op(d.x, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 0));
@@ -273,13 +265,17 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uin
     return out;
 }
 
-// Phase 3 of one chunk that holds emitting ops: exclusive prefixes and the finished rows.
-// carryR/carryQ: advance sums from the start of alignment g.a_lo up to the chunk start (used only if that
-// alignment began before the chunk).  `out` is the slot of the chunk's first row.
-__device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g, uint64_t c4, uint32_t lane, uint32_t evbits,
-                                        uint32_t carryR, uint32_t carryQ, unsigned long long out) {
+// Rows of one chunk that holds emitting ops.  carryR/carryQ: advance sums since the last alignment head inside
+// the unit (or since the unit start when `resolved` is false: then rows of the alignment that spans the chunk
+// start are flagged ROW_NEEDS_CARRY and finished by finalize_rows_kernel).  Rows go to staging slots
+// base, base+1, ...; `local0` is the index of the chunk's first row inside its unit.  `rows4` = the chunk in
+// shared memory (ring stage or spill buffer), 256 uint4.
+__device__ __forceinline__ void chunk_emit(const ScanArgs& a, const uint2* lut, const ChunkGeom g, uint64_t c4, uint32_t lane,
+                                           uint32_t evbits, const uint4* rows4, uint32_t here4, uint32_t carryR, uint32_t carryQ,
+                                           bool resolved, uint32_t unit, uint32_t local0, unsigned long long base) {
     const uint64_t c4end = min(c4 + CHUNK4, a.n4);
     const uint32_t a_lo = g.a_lo, a_hi = g.a_lo + g.n_heads;
+    uint32_t emitted = 0;
     for (uint32_t al = a_lo; al <= a_hi; ++al) {
         const uint64_t lo = max(static_cast<uint64_t>(a.off4[al]), c4);
         const uint64_t hi = min(static_cast<uint64_t>(a.off4[al + 1]), c4end);
@@ -296,6 +292,7 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
         const bool continued = static_cast<uint64_t>(a.off4[al]) < c4;
         const uint32_t baseR = continued ? carryR : 0u;
         const uint32_t baseQ = continued ? carryQ : 0u;
+        const bool needs_carry = continued && !resolved;
         int32_t clen = 0;
         if (h.tid < 0 || h.tid >= a.n_contig) {
             if (lane == 0) atomicOr(a.dev_status, DEV_ERR_BAD_TID);       // bam.getrname(tid) would raise (SVIM_intra.py:35)
@@ -306,13 +303,11 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
 #pragma unroll 1
         for (int r = 0; r < ROWS; ++r) {
             const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
+            const uint32_t i4 = static_cast<uint32_t>(r) * 32u + lane;
             const bool in = ((in_mask >> (4 * r)) & 1u) != 0u;
-            const uint4 d = in ? reload_row(a.cigar, a.n4, c4, r, lane) : make_uint4(15u, 15u, 15u, 15u);
-            uint32_t rr = 0, qq = 0, e0 = 0, n0 = 0;
-            decode_op(d.x, a.min16, rr, qq, e0, n0, 1u);
-            decode_op(d.y, a.min16, rr, qq, e0, n0, 1u);
-            decode_op(d.z, a.min16, rr, qq, e0, n0, 1u);
-            decode_op(d.w, a.min16, rr, qq, e0, n0, 1u);
+            const uint4 d = (in && i4 < here4) ? rows4[i4] : make_uint4(15u, 15u, 15u, 15u);
+            uint32_t rr = 0, qq = 0, h0 = 0, h1 = 0, rare0 = 0;
+            fast_row(d, lut, false, rr, qq, h0, h1, rare0, 1u);
             const uint32_t rowbits = in ? ((evbits >> (4 * r)) & 0xFu) : 0u;
             uint32_t bal = __ballot_sync(0xffffffffu, rowbits != 0u);
             while (bal) {
@@ -324,12 +319,13 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
                 const uint32_t n_emit = __popc(__shfl_sync(0xffffffffu, rowbits, L));
                 if (static_cast<int>(lane) == L) {
                     uint32_t pr = baseR + preR, pq = baseQ + preQ;
-                    unsigned long long slot = out;
+                    uint32_t idx = emitted;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t x = k == 0 ? d.x : k == 1 ? d.y : k == 2 ? d.z : d.w;
                         const uint32_t op = x & 15u, len = x >> 4;
                         if ((rowbits >> k) & 1u) {
+                            const unsigned long long slot = base + idx;
                             if (slot < a.cap) {
                                 // SVIM_intra.py:38-43 + the clamps of SVCandidate.py:44-46,134-136
                                 const long long start = static_cast<long long>(h.pos) + pr;
@@ -341,34 +337,36 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
                                 const uint32_t seq_len = (del || pq >= h.l_seq) ? 0u : min(len, h.l_seq - pq);
                                 const unsigned long long ordinal = (static_cast<unsigned long long>(al) << 32) |
                                                                    static_cast<unsigned long long>((g4 - a.off4[al]) * 4u + k);
-                                // svb_row as four 16-byte stores (field order of include/svimasm_b200.h)
+                                // svb_row as four 16-byte stores (field order of include/svimasm_b200.h); staging uses
+                                // copies = index inside the unit, mate_aln = unit, reserved0 = (len << 32) | raw pos_ref
                                 uint4 w0, w1, w2, w3;
-                                w0.x = (del ? SVB_DEL : SVB_INS) | (static_cast<uint32_t>(SVB_GT_HOM) << 16) | (a.hap << 24);
+                                w0.x = (del ? SVB_DEL : SVB_INS) | (needs_carry ? (static_cast<uint32_t>(ROW_NEEDS_CARRY) << 8) : 0u) |
+                                       (static_cast<uint32_t>(SVB_GT_HOM) << 16) | (a.hap << 24);
                                 w0.y = del ? static_cast<uint32_t>(h.tid) : 0xFFFFFFFFu;     // src_tid
                                 w0.z = del ? static_cast<uint32_t>(cs) : 0u;                   // src_start
                                 w0.w = del ? static_cast<uint32_t>(ce) : 0u;                   // src_end
                                 w1.x = del ? 0xFFFFFFFFu : static_cast<uint32_t>(h.tid);     // dst_tid
                                 w1.y = del ? 0u : static_cast<uint32_t>(cs);                   // dst_start
                                 w1.z = del ? 0u : static_cast<uint32_t>(ce);                   // dst_end
-                                w1.w = 0u;                                                      // copies
+                                w1.w = local0 + idx;                                            // (staging) index inside the unit
                                 w2.x = al;                                                      // aln_idx
                                 w2.y = pq;                                                      // seq_pos (= pos_read)
                                 w2.z = seq_len;
-                                w2.w = 0xFFFFFFFFu;                                             // mate_aln
+                                w2.w = unit;                                                    // (staging) unit
                                 w3.x = static_cast<uint32_t>(ordinal);
                                 w3.y = static_cast<uint32_t>(ordinal >> 32);
-                                w3.z = 0u;
-                                w3.w = 0u;
+                                w3.z = pr;                                                      // (staging) raw pos_ref
+                                w3.w = len;                                                     // (staging) op length
                                 uint4* dst = reinterpret_cast<uint4*>(a.rows + slot);
                                 dst[0] = w0; dst[1] = w1; dst[2] = w2; dst[3] = w3;
                             }
-                            ++slot;
+                            ++idx;
                         }
                         if ((REF_MASK >> op) & 1u) pr += len;
                         if ((READ_MASK >> op) & 1u) pq += len;
                     }
                 }
-                out += n_emit;
+                emitted += n_emit;
             }
             accR += rr;                                   // rr, qq are 0 for rows outside the piece (pad ops)
             accQ += qq;
@@ -376,24 +374,13 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
     }
 }
 
-struct Snap {
-    uint32_t R, Q, head, cnt;
-};
-
 template <bool USE_TMA, int G>
-__global__ void __launch_bounds__(THREADS, USE_TMA ? 3 : 4) cigar_scan_kernel(const ScanArgs a) {
-    constexpr int RUN4 = WARPS * G * CHUNK4;
+__global__ void __launch_bounds__(THREADS, USE_TMA ? 3 : K2_LDG_CTAS) cigar_scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* s_ring = reinterpret_cast<uint4*>(smem_raw);       // [WARPS][STAGES][CHUNK4] when USE_TMA
+    // USE_TMA: [WARPS][STAGES][CHUNK4] ring.  LDG: [WARPS][CHUNK4] spill buffer, written only for chunks with events
+    uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
     __shared__ __align__(8) unsigned long long s_mbar[WARPS][STAGES];
     __shared__ uint2 s_lut[16];      // per op code: x = multiplier (bit 0 read advance, bit 31 reference advance), y = rare threshold
-    __shared__ uint32_t s_run_id;
-    __shared__ uint32_t s_ev[WARPS][G][32];
-    __shared__ Snap s_snap[WARPS][G];          // carry of each chunk relative to the warp's first chunk
-    __shared__ Snap s_warp[WARPS];             // aggregate of each warp's G chunks
-    __shared__ Snap s_wcarry[WARPS];           // carry of each warp relative to the run start
-    __shared__ uint32_t s_lbR[WARPS], s_lbQ[WARPS], s_lbFlags[WARPS];
-    __shared__ unsigned long long s_lbCnt[WARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid >= 32u && tid < 48u) {
@@ -403,17 +390,17 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? 3 : 4) cigar_scan_kernel(co
         e.y = ((INDEL_MASK >> op) & 1u) ? a.min16 : (((NH_MASK >> op) & 1u) ? 16u : 0xFFFFFFFFu);
         s_lut[op] = e;
     }
-    if (tid == 0) s_run_id = atomicAdd(a.ticket, 1u);       // runs are claimed in scheduling order: look-back cannot deadlock
     if (USE_TMA && lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_mbar[warp][s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();
-    const uint32_t run = s_run_id;
-    const uint64_t w4 = static_cast<uint64_t>(run) * RUN4 + static_cast<uint64_t>(warp) * (G * CHUNK4);   // this warp's first uint4
-    uint4* my_ring = s_ring + static_cast<size_t>(warp) * STAGES * CHUNK4;
+    __syncthreads();                 // the only block-wide barrier: the decode table
+    const uint32_t unit = blockIdx.x * WARPS + warp;
+    if (unit >= a.n_units) return;
+    const uint64_t w4 = static_cast<uint64_t>(unit) * (G * CHUNK4);      // this warp's first uint4
+    uint4* my_buf = s_buf + static_cast<size_t>(warp) * (USE_TMA ? STAGES : 1) * CHUNK4;
 
     auto chunk_bytes = [&](int j) -> uint32_t {
         const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
@@ -423,175 +410,162 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? 3 : 4) cigar_scan_kernel(co
 #pragma unroll
         for (int j = 0; j < STAGES && j < G; ++j) {
             const uint32_t bytes = chunk_bytes(j);
-            if (bytes) tma_chunk(my_ring + j * CHUNK4, a.cigar + w4 + static_cast<uint64_t>(j) * CHUNK4, bytes, &s_mbar[warp][j]);
+            if (bytes) tma_chunk(my_buf + j * CHUNK4, a.cigar + w4 + static_cast<uint64_t>(j) * CHUNK4, bytes, &s_mbar[warp][j]);
         }
     }
 
-    // ---- phase 1: this warp's G chunks, carry in registers
-    uint32_t accR = 0, accQ = 0, accHead = 0, accCnt = 0;
+    uint32_t accR = 0, accQ = 0, accHead = 0, accCnt = 0;     // since the last head inside the unit / rows so far
     ChunkGeom g_next;
     g_next.a_lo = 0; g_next.n_heads = 0; g_next.split_rel = 0; g_next.head_at_start = 0;
     if (w4 < a.n4) g_next = a.geom[w4 / CHUNK4];
 #pragma unroll 1
     for (int j = 0; j < G; ++j) {
         const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
-        const bool live = c4 < a.n4;
+        if (c4 >= a.n4) break;
         const ChunkGeom g = g_next;
         if (j + 1 < G && c4 + CHUNK4 < a.n4) g_next = a.geom[c4 / CHUNK4 + 1];        // prefetch next chunk's geometry
-        if (lane == 0) {
-            Snap s;
-            s.R = accR; s.Q = accQ; s.head = accHead; s.cnt = accCnt;
-            s_snap[warp][j] = s;
-        }
-        uint32_t evbits = 0;
-        if (live) {
-            ChunkResult res;
-            if (USE_TMA) {
-                mbar_wait(&s_mbar[warp][j % STAGES], static_cast<uint32_t>(j / STAGES) & 1u);
-                const uint4* buf = my_ring + (j % STAGES) * CHUNK4;
-                const uint32_t here = chunk_bytes(j) / 16u;
-                auto from_ring = [&](int r) -> uint4 {
-                    const uint32_t i4 = static_cast<uint32_t>(r) * 32u + lane;
-                    return i4 < here ? buf[i4] : make_uint4(15u, 15u, 15u, 15u);
-                };
-                res = chunk_phase1(a, s_lut, g, c4, lane, from_ring, from_ring);
-            } else {
-                uint4 v[ROWS];
+        const uint32_t here = chunk_bytes(j) / 16u;
+        ChunkResult res;
+        const uint4* rows4;
+        if (USE_TMA) {
+            mbar_wait(&s_mbar[warp][j % STAGES], static_cast<uint32_t>(j / STAGES) & 1u);
+            const uint4* buf = my_buf + (j % STAGES) * CHUNK4;
+            auto from_ring = [&](int r) -> uint4 {
+                const uint32_t i4 = static_cast<uint32_t>(r) * 32u + lane;
+                return i4 < here ? buf[i4] : make_uint4(15u, 15u, 15u, 15u);
+            };
+            res = chunk_phase1(a, s_lut, g, c4, lane, from_ring, from_ring);
+            rows4 = buf;
+        } else {
+            uint4 v[ROWS];
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
-                    v[r] = g4 < a.n4 ? ldg_stream(a.cigar + g4) : make_uint4(15u, 15u, 15u, 15u);
-                }
-                res = chunk_phase1(a, s_lut, g, c4, lane, [&](int r) -> uint4 { return v[r]; },
-                                   [&](int r) -> uint4 { return reload_row(a.cigar, a.n4, c4, r, lane); });
+            for (int r = 0; r < ROWS; ++r) {
+                const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
+                v[r] = g4 < a.n4 ? ldg_stream(a.cigar + g4) : make_uint4(15u, 15u, 15u, 15u);
             }
-            evbits = res.evbits;
-            if (res.head) { accR = res.tailR; accQ = res.tailQ; accHead = 1u; }
-            else { accR += res.tailR; accQ += res.tailQ; }
-            accCnt += res.cnt;
+            res = chunk_phase1(a, s_lut, g, c4, lane, [&](int r) -> uint4 { return v[r]; },
+                               [&](int r) -> uint4 { return reload_row(a.cigar, a.n4, c4, r, lane); });
+            if (res.cnt) {                                 // rare: park the chunk in shared memory for the row writer
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) my_buf[r * 32 + lane] = v[r];
+                __syncwarp();
+            }
+            rows4 = my_buf;
         }
-        s_ev[warp][j][lane] = evbits;
+        if (res.cnt) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.total, static_cast<unsigned long long>(res.cnt));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            chunk_emit(a, s_lut, g, c4, lane, res.evbits, rows4, here, accR, accQ, accHead != 0u, unit, accCnt, base);
+        }
+        if (res.head) { accR = res.tailR; accQ = res.tailQ; accHead = 1u; }
+        else { accR += res.tailR; accQ += res.tailQ; }
+        accCnt += res.cnt;
         if (USE_TMA) {
             __syncwarp();                                  // every lane is done with this stage
             if (lane == 0 && j + STAGES < G) {
                 const uint32_t bytes = chunk_bytes(j + STAGES);
                 if (bytes) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    tma_chunk(my_ring + (j % STAGES) * CHUNK4, a.cigar + c4 + static_cast<uint64_t>(STAGES) * CHUNK4, bytes,
+                    tma_chunk(my_buf + (j % STAGES) * CHUNK4, a.cigar + c4 + static_cast<uint64_t>(STAGES) * CHUNK4, bytes,
                               &s_mbar[warp][j % STAGES]);
                 }
             }
+        } else {
+            __syncwarp();                                  // the spill buffer is reused by the next chunk with events
         }
     }
-    if (lane == 0) {
-        Snap s;
-        s.R = accR; s.Q = accQ; s.head = accHead; s.cnt = accCnt;
-        s_warp[warp] = s;
+    if (lane == 0) a.unit_agg[unit] = make_uint4(accR, accQ, accHead, accCnt);
+}
+
+// ---- finalize 1: segmented exclusive scan of the unit aggregates (one CTA) ---------------------------------
+// carry[u] = advance sums since the last alignment head before unit u (x: ref, y: read); base[u] = rows before u.
+struct UnitPrefix {
+    uint32_t R, Q;
+    unsigned long long base;
+};
+
+__global__ void __launch_bounds__(1024) unit_scan_kernel(const uint4* __restrict__ agg, uint32_t n_units, UnitPrefix* __restrict__ prefix) {
+    __shared__ uint32_t s_R[1024], s_Q[1024], s_H[1024];
+    __shared__ unsigned long long s_C[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_units + 1023u) / 1024u;
+    const uint32_t lo = min(t * per, n_units), hi = min(lo + per, n_units);
+    uint32_t R = 0, Q = 0, H = 0;
+    unsigned long long C = 0;
+    for (uint32_t u = lo; u < hi; ++u) {               // aggregate of this thread's block of units
+        const uint4 x = agg[u];
+        if (x.z) { R = x.x; Q = x.y; H = 1u; } else { R += x.x; Q += x.y; }
+        C += x.w;
+    }
+    s_R[t] = R; s_Q[t] = Q; s_H[t] = H; s_C[t] = C;
+    __syncthreads();
+    if (t < 32u) {                                      // exclusive segmented scan over the 1024 block aggregates
+        uint32_t bR = 0, bQ = 0, bH = 0;
+        unsigned long long bC = 0;
+        for (uint32_t k = t * 32u; k < t * 32u + 32u; ++k) {       // lane aggregate over its 32 entries
+            if (s_H[k]) { bR = s_R[k]; bQ = s_Q[k]; bH = 1u; } else { bR += s_R[k]; bQ += s_Q[k]; }
+            bC += s_C[k];
+        }
+        // exclusive scan across the 32 lanes (serial in lane order through shuffles: 32 steps, trivial)
+        uint32_t eR = 0, eQ = 0;
+        unsigned long long eC = 0;
+        for (uint32_t l = 0; l < 32u; ++l) {
+            const uint32_t lR = __shfl_sync(0xffffffffu, bR, l), lQ = __shfl_sync(0xffffffffu, bQ, l), lH = __shfl_sync(0xffffffffu, bH, l);
+            const unsigned long long lC = __shfl_sync(0xffffffffu, bC, l);
+            if (l < t) {
+                if (lH) { eR = lR; eQ = lQ; } else { eR += lR; eQ += lQ; }
+                eC += lC;
+            }
+        }
+        for (uint32_t k = t * 32u; k < t * 32u + 32u; ++k) {       // turn the entries into exclusive prefixes
+            const uint32_t r = s_R[k], q = s_Q[k], h = s_H[k];
+            const unsigned long long c = s_C[k];
+            s_R[k] = eR; s_Q[k] = eQ; s_C[k] = eC;
+            if (h) { eR = r; eQ = q; } else { eR += r; eQ += q; }
+            eC += c;
+        }
     }
     __syncthreads();
+    R = s_R[t]; Q = s_Q[t]; C = s_C[t];
+    for (uint32_t u = lo; u < hi; ++u) {
+        UnitPrefix p;
+        p.R = R; p.Q = Q; p.base = C;
+        prefix[u] = p;
+        const uint4 x = agg[u];
+        if (x.z) { R = x.x; Q = x.y; } else { R += x.x; Q += x.y; }
+        C += x.w;
+    }
+}
 
-    // ---- phase 2: run aggregate, publish, look-back by all 8 warps (256 predecessors per round), publish prefix
-    uint32_t runR = 0, runQ = 0, runHead = 0, runCnt = 0;
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) {                      // every thread computes the same serial combine
-        if (tid == 0) {
-            Snap c;
-            c.R = runR; c.Q = runQ; c.head = runHead; c.cnt = runCnt;
-            s_wcarry[w] = c;
-        }
-        const Snap s = s_warp[w];
-        if (s.head) { runR = s.R; runQ = s.Q; runHead = 1u; }
-        else { runR += s.R; runQ += s.Q; }
-        runCnt += s.cnt;
+// ---- finalize 2: every staged row moves to its final slot; flagged rows get their carry and their clamps --
+__global__ void finalize_rows_kernel(const svb_row* __restrict__ staged, const unsigned long long* __restrict__ n_staged,
+                                     unsigned long long cap, const UnitPrefix* __restrict__ prefix,
+                                     const svb_aln_hdr* __restrict__ hdr, const int32_t* __restrict__ contig_len, int32_t n_contig,
+                                     svb_row* __restrict__ out) {
+    const unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned long long n = min(*n_staged, cap);
+    if (i >= n) return;
+    svb_row r = staged[i];
+    const UnitPrefix p = prefix[r.mate_aln];
+    const unsigned long long dst = p.base + static_cast<uint32_t>(r.copies);
+    if (r.flags & ROW_NEEDS_CARRY) {
+        const svb_aln_hdr h = hdr[r.aln_idx];
+        const uint32_t pr = static_cast<uint32_t>(r.reserved0) + p.R, len = static_cast<uint32_t>(r.reserved0 >> 32);
+        const uint32_t pq = r.seq_pos + p.Q;
+        const int32_t clen = (h.tid >= 0 && h.tid < n_contig) ? contig_len[h.tid] : 0;
+        const long long start = static_cast<long long>(h.pos) + pr, end = start + len;
+        const int32_t cs = static_cast<int32_t>(max(0ll, start));
+        const int32_t ce = static_cast<int32_t>(min(static_cast<long long>(clen), end));
+        if (r.type == SVB_DEL) { r.src_start = cs; r.src_end = ce; r.seq_len = 0; }
+        else { r.dst_start = cs; r.dst_end = ce; r.seq_len = pq >= h.l_seq ? 0u : min(len, h.l_seq - pq); }
+        r.seq_pos = pq;
     }
-    __syncthreads();                                       // s_wcarry is read by every warp in phase 3
-    RunStatus* mine = a.status + run;
-    if (run != 0 && tid == 0) {
-        st_relaxed(&mine->w_ref, (ST_AGG << 62) | (static_cast<unsigned long long>(runHead) << 32) | runR);
-        st_relaxed(&mine->w_read, (ST_AGG << 62) | runQ);
-        st_relaxed(&mine->w_cnt, (ST_AGG << 62) | runCnt);
-    }
-    uint32_t carryR = 0, carryQ = 0;
-    unsigned long long excl = 0;
-    if (run != 0) {
-        bool sums_done = false;
-        int64_t look = static_cast<int64_t>(run) - 1;
-        while (true) {
-            const int64_t t = look - static_cast<int64_t>(warp * 32u + lane);
-            unsigned long long wr = (ST_PREFIX << 62), wq = (ST_PREFIX << 62), wc = (ST_PREFIX << 62);   // virtual run -1
-            if (t >= 0) {
-                const RunStatus* ts = a.status + t;
-                while (true) {
-                    wr = ld_relaxed(&ts->w_ref);
-                    wq = ld_relaxed(&ts->w_read);
-                    wc = ld_relaxed(&ts->w_cnt);
-                    const unsigned long long s = wr >> 62;
-                    if (s != ST_INVALID && s == (wq >> 62) && s == (wc >> 62)) break;
-                }
-            }
-            const bool is_prefix = (wr >> 62) == ST_PREFIX;
-            const bool stops_sum = is_prefix || ((wr >> 32) & 1ull);
-            const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
-            const uint32_t smask = __ballot_sync(0xffffffffu, stops_sum);
-            const int k_cnt = pmask ? (__ffs(pmask) - 1) : 31;
-            const int k_sum = smask ? (__ffs(smask) - 1) : 31;
-            unsigned long long csum = (static_cast<int>(lane) <= k_cnt) ? (wc & ((1ull << 62) - 1ull)) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
-            const bool take = static_cast<int>(lane) <= k_sum;
-            const uint32_t sR = __reduce_add_sync(0xffffffffu, take ? static_cast<uint32_t>(wr) : 0u);
-            const uint32_t sQ = __reduce_add_sync(0xffffffffu, take ? static_cast<uint32_t>(wq) : 0u);
-            if (lane == 0) {
-                s_lbCnt[warp] = csum;
-                s_lbR[warp] = sR;
-                s_lbQ[warp] = sQ;
-                s_lbFlags[warp] = (pmask ? 1u : 0u) | (smask ? 2u : 0u);
-            }
-            __syncthreads();
-            bool cnt_done = false;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {                // nearest window first; every thread computes the same
-                if (!cnt_done) {
-                    excl += s_lbCnt[w];
-                    if (!sums_done) {
-                        carryR += s_lbR[w];
-                        carryQ += s_lbQ[w];
-                        if (s_lbFlags[w] & 2u) sums_done = true;
-                    }
-                    if (s_lbFlags[w] & 1u) cnt_done = true;
-                }
-            }
-            __syncthreads();                                 // s_lb* are rewritten in the next round
-            if (cnt_done) break;
-            look -= WARPS * 32;
-        }
-    }
-    if (tid == 0) {
-        const uint32_t incR = runHead ? runR : carryR + runR;
-        const uint32_t incQ = runHead ? runQ : carryQ + runQ;
-        st_relaxed(&mine->w_ref, (ST_PREFIX << 62) | (1ull << 32) | incR);
-        st_relaxed(&mine->w_read, (ST_PREFIX << 62) | incQ);
-        st_relaxed(&mine->w_cnt, (ST_PREFIX << 62) | (excl + runCnt));
-        if (run == a.n_runs - 1u) *a.total = excl + runCnt;
-    }
-
-    // ---- phase 3: chunks that hold an emitting op
-    const Snap wc = s_wcarry[warp];
-#pragma unroll 1
-    for (int j = 0; j < G; ++j) {
-        const uint32_t evbits = s_ev[warp][j][lane];
-        if (__ballot_sync(0xffffffffu, evbits != 0u) == 0u) continue;
-        const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
-        const Snap sn = s_snap[warp][j];
-        // advance sums since the start of the alignment that spans the chunk start: chunk snapshot, then the
-        // warp's carry inside the run, then the run's carry-in -- each level only if no head occurred closer
-        uint32_t cR = sn.R, cQ = sn.Q;
-        if (!sn.head) {
-            cR += wc.R; cQ += wc.Q;
-            if (!wc.head) { cR += carryR; cQ += carryQ; }
-        }
-        chunk_emit(a, a.geom[c4 / CHUNK4], c4, lane, evbits, cR, cQ, excl + wc.cnt + sn.cnt);
-    }
+    r.flags = 0;
+    r.copies = 0;
+    r.mate_aln = 0xFFFFFFFFu;
+    r.reserved0 = 0;
+    if (dst < cap) out[dst] = r;
 }
 
 // geometry of every chunk (one thread per chunk, two binary searches over off4)
@@ -635,18 +609,21 @@ int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec) {
 }
 
 template <int G>
-static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a) {
-    constexpr int RUN4 = WARPS * G * CHUNK4;
-    const uint64_t n_runs64 = (rec->n4 + RUN4 - 1) / RUN4;
-    if (n_runs64 > 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "too many CIGAR ops for one launch");
-    const uint32_t n_runs = static_cast<uint32_t>(n_runs64);
-    const size_t need = sizeof(RunStatus) * n_runs + 256;
-    unsigned char* scratch = static_cast<unsigned char*>(svb_scratch(ctx, need));
-    if (!scratch) return svb_fail(ctx, SVB_ERR_NOMEM, "run status scratch");
-    SVB_CUDA(ctx, cudaMemsetAsync(scratch, 0, need, ctx->stream));
-    a.n_runs = n_runs;
-    a.ticket = reinterpret_cast<unsigned int*>(scratch);
-    a.status = reinterpret_cast<RunStatus*>(scratch + 256);
+static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_row* final_rows) {
+    const uint64_t unit4 = static_cast<uint64_t>(G) * CHUNK4;
+    const uint64_t n_units64 = (rec->n4 + unit4 - 1) / unit4;
+    if (n_units64 > 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "too many CIGAR ops for one launch");
+    const uint32_t n_units = static_cast<uint32_t>(n_units64);
+    // scratch: unit aggregates, unit prefixes, staging rows
+    const size_t agg_bytes = (sizeof(uint4) * n_units + 255) & ~static_cast<size_t>(255);
+    const size_t pre_bytes = (sizeof(UnitPrefix) * n_units + 255) & ~static_cast<size_t>(255);
+    unsigned char* scratch = static_cast<unsigned char*>(svb_scratch(ctx, agg_bytes + pre_bytes + sizeof(svb_row) * a.cap));
+    if (!scratch) return svb_fail(ctx, SVB_ERR_NOMEM, "cigar_scan scratch");
+    a.n_units = n_units;
+    a.unit_agg = reinterpret_cast<uint4*>(scratch);
+    UnitPrefix* prefix = reinterpret_cast<UnitPrefix*>(scratch + agg_bytes);
+    a.rows = reinterpret_cast<svb_row*>(scratch + agg_bytes + pre_bytes);
+    const unsigned blocks = (n_units + WARPS - 1) / WARPS;
     KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);
     if (ctx->scan_variant == 0) {
         const size_t smem = static_cast<size_t>(WARPS) * STAGES * CHUNK4 * sizeof(uint4);
@@ -656,11 +633,16 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a) {
                                                static_cast<int>(smem)));
             attr_set = true;
         }
-        cigar_scan_kernel<true, G><<<n_runs, THREADS, smem, ctx->stream>>>(a);
+        cigar_scan_kernel<true, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
     } else {
-        cigar_scan_kernel<false, G><<<n_runs, THREADS, 16, ctx->stream>>>(a);
+        const size_t smem = static_cast<size_t>(WARPS) * CHUNK4 * sizeof(uint4);
+        cigar_scan_kernel<false, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
     }
-    ctx->launches += 1;
+    unit_scan_kernel<<<1, 1024, 0, ctx->stream>>>(a.unit_agg, n_units, prefix);
+    const unsigned long long fin_blocks = (a.cap + 255) / 256;
+    finalize_rows_kernel<<<static_cast<unsigned>(std::min<unsigned long long>(fin_blocks, 0x7fffffffull)), 256, 0, ctx->stream>>>(
+        a.rows, a.total, a.cap, prefix, rec->d_hdr, rec->d_contig_len, rec->n_contig, final_rows);
+    ctx->launches += 3;
     SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;
 }
@@ -678,23 +660,22 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     a.contig_len = rec->d_contig_len;
     a.n_aln = rec->n_aln;
     a.n_contig = rec->n_contig;
-    a.n_runs = 0;
+    a.n_units = 0;
     a.min_mapq = p->min_mapq;
     const long long m = p->min_sv_size < 0 ? 0 : p->min_sv_size;
     a.min16 = m >= (1ll << 28) ? 0xFFFFFFFFu : static_cast<uint32_t>(m << 4);
     a.hap = static_cast<uint32_t>(hap);
     a.aln_sum = rec->d_aln_sum;
-    a.ticket = nullptr;
-    a.status = nullptr;
-    a.rows = out.rows;
+    a.unit_agg = nullptr;
+    a.rows = nullptr;
     a.cap = out.cap;
     a.total = out.d_count;
     a.dev_status = ctx->d_status;
-    // run length: as long as possible while at least two full waves of CTAs (4 per SM) remain
-    const uint64_t two_waves = 2ull * 4ull * static_cast<uint64_t>(ctx->sm_count);
+    // unit length: as long as possible while at least four full waves of warps (32 per SM) remain
+    const uint64_t four_waves = 4ull * 32ull * static_cast<uint64_t>(ctx->sm_count);
     const uint64_t chunks = (rec->n4 + CHUNK4 - 1) / CHUNK4;
-    if (chunks / (WARPS * 16) >= two_waves) return launch_scan_g<16>(ctx, rec, a);
-    if (chunks / (WARPS * 8) >= two_waves) return launch_scan_g<8>(ctx, rec, a);
-    if (chunks / (WARPS * 4) >= two_waves) return launch_scan_g<4>(ctx, rec, a);
-    return launch_scan_g<2>(ctx, rec, a);
+    if (chunks / 16 >= four_waves) return launch_scan_g<16>(ctx, rec, a, out.rows);
+    if (chunks / 8 >= four_waves) return launch_scan_g<8>(ctx, rec, a, out.rows);
+    if (chunks / 4 >= four_waves) return launch_scan_g<4>(ctx, rec, a, out.rows);
+    return launch_scan_g<2>(ctx, rec, a, out.rows);
 }

@@ -64,7 +64,7 @@ struct svb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    int scan_variant = 1;             // 0 TMA bulk-copy ring, 1 LDG.128.nc (default: measured faster, profiles/)
+    int scan_variant = 0;             // 0 per-warp TMA bulk-copy ring (default: measured faster, profiles/), 1 LDG.128.nc
     int sm_count = 148;
     bool timing_enabled = true;
     std::vector<TimedSpan> spans;     // recorded, not yet folded into `timing`

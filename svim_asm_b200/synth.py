@@ -294,7 +294,7 @@ def make_haplotype(cfg, layout, truth, hap_seed, name_prefix="ctg", workers=None
         sub_truth = SVTruth(truth.gpos[sel] - base, truth.kind[sel], truth.length[sel], truth.sv_id[sel], truth.edit[sel])
         jobs.append((cfg, sub, sub_truth, hap_seed + 1000003 * (g + 1), name_prefix, a))
     if workers is None:
-        workers = min(len(jobs), os.cpu_count() or 1)
+        workers = min(len(jobs), int(os.environ.get("SVIM_SYNTH_WORKERS", os.cpu_count() or 1)))
     if workers > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(workers) as pool:
