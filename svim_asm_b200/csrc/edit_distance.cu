@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                                                        double* __restrict__ out) {
     __shared__ unsigned long long s_peq[ED_WARPS][ED_NCLASS][32];
     __shared__ uint8_t s_class[256];
+    __shared__ uint8_t s_tcls[ED_WARPS][64];        // ring: symbol class of the band's columns
+    __shared__ signed char s_th[ED_WARPS][64];       // ring: horizontal delta entering the stripe's top row
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) s_class[i] = class_map[i];
     __syncthreads();
@@ -102,36 +104,40 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         __syncwarp();
                         uint64_t pv = ~0ull, mv = 0ull;
                         const uint64_t hibit = (final_stripe && lane == last_lane) ? (1ull << ((rows - 1u) & 63u)) : (1ull << 63);
-                        uint32_t carry = 0xFFu;                 // low byte: text class (255 = none); bits 8..9: hout + 1
                         int sum_all = 0, sum_anchor = 0;        // bottom-row deltas over [jlo, jhi) and over [jlo, next_jlo)
                         const uint32_t width = jhi - jlo, steps = width + nblk - 1u;
-                        // text classes / top-row deltas are fetched 32 columns at a time, one block ahead of their use
-                        uint32_t nxt = 0xFFu | (2u << 8);
+                        // Text classes and top-row deltas of the band's columns live in a 64-entry ring in shared memory,
+                        // refilled 32 columns at a time one block ahead of their use.  Every lane reads the class of ITS
+                        // column (t - lane) from the ring, so the match mask of step t+1 is fetched while step t computes
+                        // and only the 2-bit horizontal delta travels lane to lane: the loop-carried path is one shuffle
+                        // plus the block recurrence.
+                        auto fetch = [&](uint32_t rel) -> uint32_t {           // (class, top delta + 1) of band column `rel`
+                            const uint32_t j = jlo + rel;
+                            const uint32_t cls = (rel < width) ? s_class[hap_char(T, pre + j, ref, seq4_a, seq4_b)] : 255u;
+                            const int h = (rel < width && row0 != 0u && j < prev_jhi) ? hbuf[j] : 1;
+                            return cls | (static_cast<uint32_t>(h + 1) << 8);
+                        };
                         {
-                            const uint32_t j = jlo + lane;
-                            const uint32_t cls = (lane < width) ? s_class[hap_char(T, pre + j, ref, seq4_a, seq4_b)] : 255u;
-                            const int h = (row0 == 0u || j >= prev_jhi) ? 1 : hbuf[j];
-                            nxt = cls | (static_cast<uint32_t>(h + 1) << 8);
+                            const uint32_t first = fetch(lane);
+                            s_tcls[warp][lane] = static_cast<uint8_t>(first & 0xFFu);
+                            s_th[warp][lane] = static_cast<signed char>(static_cast<int>(first >> 8) - 1);
                         }
-                        uint32_t cur = nxt;
-                        for (uint32_t t = 0; t < steps; ++t) {
-                            if ((t & 31u) == 0u) {
-                                cur = nxt;
-                                const uint32_t rel = t + 32u + lane;
-                                const uint32_t j = jlo + rel;
-                                const uint32_t cls = (rel < width) ? s_class[hap_char(T, pre + j, ref, seq4_a, seq4_b)] : 255u;
-                                const int h = (rel < width && row0 != 0u && j < prev_jhi) ? hbuf[j] : 1;
-                                nxt = cls | (static_cast<uint32_t>(h + 1) << 8);
-                            }
-                            const uint32_t top = __shfl_sync(0xffffffffu, cur, t & 31u);
-                            uint32_t in = __shfl_up_sync(0xffffffffu, carry, 1);
-                            if (lane == 0u) in = top;
-                            const uint32_t cls = in & 0xFFu;
-                            const int hin = static_cast<int>((in >> 8) & 3u) - 1;
+                        uint32_t nxt = fetch(32u + lane);
+                        __syncwarp();
+                        auto lookup = [&](uint32_t t) -> uint64_t {            // match mask of this lane's block at step t
                             const long long rel = static_cast<long long>(t) - lane;
-                            int hout = 0;
+                            if (rel < 0 || rel >= static_cast<long long>(width)) return 0ull;
+                            const uint32_t cls = s_tcls[warp][static_cast<uint32_t>(rel) & 63u];
+                            return cls < ED_NCLASS ? s_peq[warp][cls][lane] : 0ull;
+                        };
+                        uint64_t eq = lookup(0u);
+                        int hout = 0;
+                        for (uint32_t t = 0; t < steps; ++t) {
+                            int hin = __shfl_up_sync(0xffffffffu, hout, 1);
+                            if (lane == 0u) hin = s_th[warp][t & 63u];
+                            const long long rel = static_cast<long long>(t) - lane;
+                            hout = 0;
                             if (lane < nblk && rel >= 0 && rel < static_cast<long long>(width)) {
-                                const uint64_t eq = cls < ED_NCLASS ? s_peq[warp][cls][lane] : 0ull;
                                 hout = myers_block(pv, mv, eq, hin, hibit);
                                 if (lane == last_lane) {
                                     const uint32_t j = jlo + static_cast<uint32_t>(rel);
@@ -140,7 +146,14 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                     if (!final_stripe) hbuf[j] = static_cast<signed char>(hout);
                                 }
                             }
-                            carry = cls | (static_cast<uint32_t>(hout + 1) << 8);
+                            if (((t + 1u) & 31u) == 0u) {              // columns t+1 .. t+32 enter the ring, t+33 .. t+64 are fetched
+                                const uint32_t slot = (t + 1u + lane) & 63u;
+                                s_tcls[warp][slot] = static_cast<uint8_t>(nxt & 0xFFu);
+                                s_th[warp][slot] = static_cast<signed char>(static_cast<int>(nxt >> 8) - 1);
+                                nxt = fetch(t + 33u + lane);
+                                __syncwarp();
+                            }
+                            eq = lookup(t + 1u);
                         }
                         __syncwarp();
                         sum_all = __shfl_sync(0xffffffffu, sum_all, last_lane);
