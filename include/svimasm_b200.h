@@ -207,13 +207,37 @@ int svb_table_export(svb_ctx* ctx, const svb_table* t, void* device_dst, uint64_
 int svb_table_import(svb_ctx* ctx, const void* device_src, uint64_t n_rows, svb_table** out);
 void svb_table_free(svb_table* t);
 
+/* ---- Multi-GPU exchange (one process per GPU, records sharded by contig) --------------------
+ * The reference is one process with one candidate list per type (SVIM_COLLECT.py:67-91, svim-asm:70-76), so every
+ * candidate is visible to pair_candidates (SVIM_COMBINE.py:164).  These calls restore that across ranks without host
+ * staging: pack both haplotype tables of a rank into one device buffer, all-gather it (NCCL, by the caller), unpack
+ * the gathered buffers into "all ranks' rows in append order, restricted to the key contigs this rank owns". */
+void* svb_stream(svb_ctx* ctx);                                   /* cudaStream_t the context works on */
+int svb_device_alloc(svb_ctx* ctx, uint64_t bytes, void** out);   /* stream-ordered scratch for the collective */
+void svb_device_free(svb_ctx* ctx, void* p);
+/* index of every record of a shard in the unsharded batch: aln_idx / ordinal of a table become global with
+ * svb_table_remap_records (the reference's append order is the BAM order of the whole file, SVIM_COLLECT.py:65) */
+int svb_records_set_global_index(svb_ctx* ctx, svb_records* rec, const uint32_t* global_idx);
+int svb_table_remap_records(svb_ctx* ctx, svb_table* t, const svb_records* rec);
+/* sizes = {rows of table 1, pool bytes 1, rows 2, pool bytes 2}; svb_exchange_bytes = packed size of such a pair */
+int svb_exchange_sizes(const svb_table* t1, const svb_table* t2, uint64_t sizes[4]);
+uint64_t svb_exchange_bytes(const uint64_t sizes[4]);
+int svb_exchange_pack(svb_ctx* ctx, const svb_table* t1, const svb_table* t2, void* d_buf, uint64_t cap_bytes);
+/* d_gathered: world buffers of `stride` bytes each, sizes: world x 4 (host), owner[n_contig]: rank owning each contig
+ * (host).  The result keeps the rows whose key contig (Candidate.get_key, SVCandidate.py:17-19) belongs to `rank`. */
+int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, const uint64_t* sizes, int world, int hap,
+                        const int32_t* owner, int n_contig, int rank, svb_table** out);
+const void* svb_table_device_rows(const svb_table* t);            /* device pointer of the rows (all-gather of paired rows) */
+
 /* Sequence pools: the inserted bases of the INS rows (candidate.sequence, SVIM_intra.py:42, SVIM_inter.py:117,120)
  * copied next to the table so that it can be paired -- or sent to another rank -- without the record image. */
 int svb_table_gather_sequences(svb_ctx* ctx, svb_table* t, const svb_records* rec);          /* device gather */
 int svb_table_attach_sequences_host(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off);
 int svb_table_pool_to_host(svb_ctx* ctx, const svb_table* t, uint8_t* pool_dst, uint64_t cap_bytes, uint64_t* off_dst,
                            uint64_t* pool_bytes);
-int svb_table_set_pool_from_host(svb_ctx* ctx, svb_table* t, const uint8_t* pool, const uint64_t* pool_off);
+/* row_off[i] = byte offset of row i's run in `pool` (runs need not be contiguous or in row order: a gathered pool of
+ * several ranks is uploaded as is, only the per-row offsets are permuted) */
+int svb_table_set_pool_from_host(svb_ctx* ctx, svb_table* t, const uint8_t* pool, uint64_t pool_bytes, const uint64_t* row_off);
 
 #ifdef __cplusplus
 }

@@ -91,7 +91,17 @@ SIGNATURES = {
     "svb_table_gather_sequences": (c_int, [c_void_p, c_void_p, c_void_p]),
     "svb_table_attach_sequences_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "svb_table_pool_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_void_p, P(c_u64)]),
-    "svb_table_set_pool_from_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "svb_stream": (c_void_p, [c_void_p]),
+    "svb_device_alloc": (c_int, [c_void_p, c_u64, c_void_p]),
+    "svb_device_free": (None, [c_void_p, c_void_p]),
+    "svb_records_set_global_index": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_table_remap_records": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_exchange_sizes": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_exchange_bytes": (c_u64, [c_void_p]),
+    "svb_exchange_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u64]),
+    "svb_exchange_unpack": (c_int, [c_void_p, c_void_p, c_u64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "svb_table_device_rows": (c_void_p, [c_void_p]),
+    "svb_table_set_pool_from_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -214,7 +214,7 @@ void svb_records_free(svb_records* r) {
     if (!r) return;
     cudaSetDevice(r->device);
     void* ptrs[] = {r->d_hdr, r->d_cigar, r->d_off4, r->d_chunk_first, r->d_seg, r->d_sa_count, r->d_contig_len,
-                    r->d_contig_lexrank, r->d_aln_sum, r->d_prim_list, r->d_seq4, r->d_seq_off};
+                    r->d_contig_lexrank, r->d_aln_sum, r->d_prim_list, r->d_seq4, r->d_seq_off, r->d_global_idx};
     for (void* q : ptrs) free_async(q, r->stream);
     delete r;
 }

@@ -39,9 +39,15 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int ROWS = 8;                    // uint4 per lane per chunk
+#ifndef K2_ROWS
+#define K2_ROWS 8
+#endif
+constexpr int ROWS = K2_ROWS;              // uint4 per lane per chunk (8: 4 KB chunks, 4: 2 KB chunks)
 constexpr int CHUNK4 = 32 * ROWS;          // 256 uint4  = 1024 ops = 4 KB per chunk
 constexpr int STAGES = 2;                  // TMA ring depth per warp
+#ifndef K2_TMA_CTAS
+#define K2_TMA_CTAS 3                      // resident CTAs per SM the TMA variant is compiled for (64 KB ring each)
+#endif
 #ifndef K2_LDG_CTAS
 #define K2_LDG_CTAS 4                      // resident CTAs per SM the LDG variant is compiled for (64 registers)
 #endif
@@ -167,7 +173,7 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uin
     uint32_t rare_rows = 0;               // bit r: this lane's uint4 of row r holds a rare op
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) fast_row(rowsrc(r), lut, r < nb, totR, totQ, headR, headQ, rare_rows, 1u << r);
-    const uint32_t first_mask = nb >= 8 ? 0xFFFFFFFFu : ((1u << (4u * static_cast<uint32_t>(nb))) - 1u);
+    const uint32_t first_mask = nb >= 8 ? 0xFFFFFFFFu : ((1u << (4u * static_cast<uint32_t>(nb))) - 1u);   // ROWS <= 8
     uint32_t warp_rows = __reduce_or_sync(0xffffffffu, rare_rows);      // rows that need the exact classification
     const bool any_rare = warp_rows != 0u;
 
@@ -375,7 +381,7 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const uint2* lut, 
 }
 
 template <bool USE_TMA, int G>
-__global__ void __launch_bounds__(THREADS, USE_TMA ? 3 : K2_LDG_CTAS) cigar_scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) cigar_scan_kernel(const ScanArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // USE_TMA: [WARPS][STAGES][CHUNK4] ring.  LDG: [WARPS][CHUNK4] spill buffer, written only for chunks with events
     uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
@@ -674,8 +680,9 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     // unit length: as long as possible while at least four full waves of warps (32 per SM) remain
     const uint64_t four_waves = 4ull * 32ull * static_cast<uint64_t>(ctx->sm_count);
     const uint64_t chunks = (rec->n4 + CHUNK4 - 1) / CHUNK4;
-    if (chunks / 16 >= four_waves) return launch_scan_g<16>(ctx, rec, a, out.rows);
-    if (chunks / 8 >= four_waves) return launch_scan_g<8>(ctx, rec, a, out.rows);
-    if (chunks / 4 >= four_waves) return launch_scan_g<4>(ctx, rec, a, out.rows);
-    return launch_scan_g<2>(ctx, rec, a, out.rows);
+    constexpr int S = 8 / ROWS;                      // keep the unit length in ops when chunks are smaller
+    if (chunks / (16 * S) >= four_waves) return launch_scan_g<16 * S>(ctx, rec, a, out.rows);
+    if (chunks / (8 * S) >= four_waves) return launch_scan_g<8 * S>(ctx, rec, a, out.rows);
+    if (chunks / (4 * S) >= four_waves) return launch_scan_g<4 * S>(ctx, rec, a, out.rows);
+    return launch_scan_g<2 * S>(ctx, rec, a, out.rows);
 }

@@ -31,6 +31,7 @@ struct svb_records {
     uint32_t n_prim = 0;
     uint8_t* d_seq4 = nullptr;        // optional 4-bit query sequences
     uint64_t* d_seq_off = nullptr;    // [n_aln + 1]
+    uint32_t* d_global_idx = nullptr; // optional [n_aln]: index of each record in the unsharded batch (exchange.cu)
     uint64_t seq_bytes = 0;
 };
 

@@ -12,23 +12,31 @@
 
 #include "linkage.cuh"   // SVB_HD
 
-// One column step of a 64-row block.  pv/mv: vertical +1/-1 delta bit vectors (in/out).
-// eq: rows whose pattern char equals the text char.  hin: horizontal delta entering at the top
-// row (-1, 0, +1).  hibit: the row whose horizontal delta is returned.
-SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_t hibit) {
-    // branch-free: lanes of a warp see different hin values every step
-    const uint64_t hin_neg = hin < 0 ? 1ull : 0ull, hin_pos = hin > 0 ? 1ull : 0ull;
+// One column step of a 64-row block.  pv/mv: vertical +1/-1 delta bit vectors (in/out).  eq: rows whose
+// pattern char equals the text char.  Horizontal deltas travel as 2-bit codes (bit 0: +1, bit 1: -1): `hin`
+// enters at the top row, the code of row `hshift` is returned.  Branch-free; the path hin -> return value is
+// the loop-carried dependency of the lane pipeline (or, and, 64-bit add, xor, or, one LOP3, shift).
+SVB_HD uint32_t myers_step(uint64_t& pv, uint64_t& mv, uint64_t eq, uint32_t hin, uint32_t hshift) {
+    const uint64_t hin_neg = hin >> 1, hin_pos = hin & 1u;
     const uint64_t xv = eq | mv;
     eq |= hin_neg;
     const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
     uint64_t ph = mv | ~(xh | pv);
     uint64_t mh = pv & xh;
-    const int hout = static_cast<int>((ph & hibit) != 0) - static_cast<int>((mh & hibit) != 0);
+    const uint32_t hout = static_cast<uint32_t>((ph >> hshift) & 1ull) | (static_cast<uint32_t>((mh >> hshift) & 1ull) << 1);
     ph = (ph << 1) | hin_pos;
     mh = (mh << 1) | hin_neg;
     pv = mh | ~(xv | ph);
     mv = ph & xv;
     return hout;
+}
+
+// Same step with signed deltas (-1, 0, +1) and a one-hot output row; used by the host check against a plain DP.
+SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_t hibit) {
+    uint32_t shift = 0;
+    while (!((hibit >> shift) & 1ull)) ++shift;
+    const uint32_t out = myers_step(pv, mv, eq, hin > 0 ? 1u : (hin < 0 ? 2u : 0u), shift);
+    return static_cast<int>(out & 1u) - static_cast<int>(out >> 1);
 }
 
 // ---- virtual haplotype strings --------------------------------------------------------------------
@@ -83,4 +91,37 @@ SVB_HD uint8_t hap_char(const HapDesc& d, uint32_t i, const uint8_t* ref, const 
     }
     i -= d.m_len;
     return ref[d.r_base + i];
+}
+
+// Split form of hap_char for latency hiding: hap_fetch computes the address and issues ONE load whose result is not
+// touched; `mode` says how to turn the byte into a symbol later (0: reference byte, 1: complemented reference byte,
+// 2 / 3: high / low nibble of a packed query byte).
+enum : uint32_t { TOK_REF = 0, TOK_REF_COMP = 1, TOK_NIB_HI = 2, TOK_NIB_LO = 3, TOK_NONE = 4 };
+
+SVB_HD uint32_t hap_fetch(const HapDesc& d, uint32_t i, const uint8_t* ref, const uint8_t* seq4_a, const uint8_t* seq4_b,
+                          uint32_t& mode) {
+    const uint8_t* p;
+    mode = TOK_REF;
+    if (i < d.l_len) {
+        p = ref + d.l_base + i;
+    } else {
+        i -= d.l_len;
+        if (i < d.m_len) {
+            if (d.m_kind == HAP_MID_SEQ4) {
+                const uint64_t nib = d.m_base + i;
+                p = (d.seq_sel ? seq4_b : seq4_a) + (nib >> 1);
+                mode = TOK_NIB_HI + static_cast<uint32_t>(nib & 1ull);
+            } else if (d.m_kind == HAP_MID_REVCOMP) {
+                p = ref + d.m_base + (d.m_len - 1u - i);
+                mode = TOK_REF_COMP;
+            } else if (d.m_kind == HAP_MID_REPEAT) {
+                p = ref + d.m_base + (i % d.m_unit);
+            } else {
+                p = ref + d.m_base + i;
+            }
+        } else {
+            p = ref + d.r_base + (i - d.m_len);
+        }
+    }
+    return *p;
 }

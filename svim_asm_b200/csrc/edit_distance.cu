@@ -3,11 +3,20 @@
 // Replaces compute_distance's edlib.align(h1, h2)["editDistance"] (reference SVIM_COMBINE.py:35-102).
 // The shorter string is the pattern: its rows are cut into 64-row blocks (edit_core.cuh), block b of a
 // 2048-row stripe lives in lane b, and the columns of the text stream through the lanes as a software
-// pipeline -- lane b works on column t-b at step t and hands (text class, horizontal delta) to lane b+1
-// with one shuffle.  Patterns longer than 2048 rows take several stripes; the horizontal deltas of a
-// stripe's last row are parked in a per-warp byte buffer in HBM.  Strings are never materialised:
-// bases are read through HapDesc (reference bytes / 4-bit query bases resident in HBM).
-// Bound: integer issue rate (about 60 instructions per column step per warp), not bandwidth.
+// pipeline -- lane b works on column t-b at step t and hands its 2-bit horizontal delta to lane b+1 with one
+// shuffle.  Patterns longer than 2048 rows take several stripes; the horizontal deltas of a stripe's last row
+// are parked in a per-warp byte buffer in HBM.  Strings are never materialised: bases are read through HapDesc
+// (reference bytes / 4-bit query bases resident in HBM).
+//
+// Bound: the latency of ONE warp's dependency chain (the longest pair is the critical path of the launch), so
+// the step loop is written for latency: shuffle + block recurrence are the only loop-carried work; the match
+// mask of step t+1 and the symbol class of step t+2 are loaded while step t computes, the steady state runs
+// without masks or divergent branches, and the global loads that feed the column ring are issued 32..64 steps
+// before their first use and only decoded (class lookup) when they enter the ring.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 #include "edit_core.cuh"
 #include "pairing.cuh"
@@ -15,6 +24,60 @@
 namespace {
 
 constexpr int ED_WARPS = 4;
+constexpr uint32_t ED_NOCLASS = ED_NCLASS;      // extra all-zero row of the match-mask table: "matches nothing"
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct EdShared {
+    unsigned long long peq[ED_WARPS][ED_NCLASS + 1][32];   // [class][lane]: match mask of the lane's 64 rows
+    uint8_t cls2[512];                                     // byte -> class, complemented byte -> class
+    uint8_t tcls[ED_WARPS][64];                            // ring: symbol class of the band's columns
+    uint8_t th[ED_WARPS][64];                              // ring: delta code entering the stripe's top row
+};
+
+__device__ __forceinline__ uint32_t tok_class(const uint8_t* cls2, uint32_t byte, uint32_t mode) {
+    uint32_t c;
+    if (mode >= TOK_NIB_HI) c = (mode == TOK_NIB_HI) ? (byte >> 4) : (byte & 15u);      // class i == nt16 code i
+    else c = cls2[mode * 256u + byte];
+    return min(c, ED_NOCLASS);
+}
+
+// Length of the common prefix (REVERSED = false) or suffix of the two strings, at most `lim`; 128 positions per round so
+// that four loads per string are in flight.
+template <bool REVERSED>
+__device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& B, uint32_t la, uint32_t lb, uint32_t lim,
+                                               const uint8_t* ref, const uint8_t* sa, const uint8_t* sb, const uint8_t* cls2,
+                                               uint32_t lane) {
+    uint32_t run = 0;
+    bool done = false;
+    while (run < lim && !done) {
+        uint32_t ba[4], ma[4], bb[4], mb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = run + 32u * k + lane;
+            ma[k] = mb[k] = TOK_NONE;
+            ba[k] = bb[k] = 0u;
+            if (i < lim) {
+                ba[k] = hap_fetch(A, REVERSED ? la - 1u - i : i, ref, sa, sb, ma[k]);
+                bb[k] = hap_fetch(B, REVERSED ? lb - 1u - i : i, ref, sa, sb, mb[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool same = false;
+            if (ma[k] != TOK_NONE) {
+                const uint32_t ca = tok_class(cls2, ba[k], ma[k]);
+                same = ca < ED_NOCLASS && ca == tok_class(cls2, bb[k], mb[k]);
+            }
+            const uint32_t mask = __ballot_sync(FULL, same);
+            if (!done && mask != FULL) {
+                run += 32u * k + static_cast<uint32_t>(__ffs(~mask) - 1);
+                done = true;
+            }
+        }
+        if (!done) run += 128u;
+    }
+    return min(run, lim);
+}
 
 __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const EditJob* __restrict__ jobs, uint32_t n_jobs,
                                                                        unsigned int* next_job,
@@ -22,16 +85,22 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                                                        const uint8_t* __restrict__ seq4_a,
                                                                        const uint8_t* __restrict__ seq4_b,
                                                                        const uint8_t* __restrict__ class_map,
-                                                                       signed char* hbuf_pool, uint64_t hbuf_stride,
-                                                                       double* __restrict__ out) {
-    __shared__ unsigned long long s_peq[ED_WARPS][ED_NCLASS][32];
-    __shared__ uint8_t s_class[256];
-    __shared__ uint8_t s_tcls[ED_WARPS][64];        // ring: symbol class of the band's columns
-    __shared__ signed char s_th[ED_WARPS][64];       // ring: horizontal delta entering the stripe's top row
+                                                                       uint8_t* hbuf_pool, uint64_t hbuf_stride,
+                                                                       double* __restrict__ out, uint4* __restrict__ profile) {
+    __shared__ EdShared sh;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) s_class[i] = class_map[i];
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+        sh.cls2[i] = class_map[i];
+        sh.cls2[256u + i] = class_map[hap_complement(static_cast<uint8_t>(i))];
+    }
+    // the maskless steady state lets lanes without a block read ring slots no refill has written yet: any class <= 32 is fine
+    for (uint32_t i = threadIdx.x; i < ED_WARPS * 64u; i += blockDim.x) (&sh.tcls[0][0])[i] = static_cast<uint8_t>(ED_NOCLASS);
     __syncthreads();
-    signed char* hbuf = hbuf_pool ? hbuf_pool + (static_cast<uint64_t>(blockIdx.x) * ED_WARPS + warp) * hbuf_stride : nullptr;
+    uint8_t* hbuf = hbuf_pool ? hbuf_pool + (static_cast<uint64_t>(blockIdx.x) * ED_WARPS + warp) * hbuf_stride : nullptr;
+    unsigned long long (*peq)[32] = sh.peq[warp];
+    uint32_t* peq32 = reinterpret_cast<uint32_t*>(&sh.peq[warp][0][0]);       // [class][lane][half]
+    uint8_t* tcls = sh.tcls[warp];
+    uint8_t* th = sh.th[warp];
 
     // Two sweeps over the job list: patterns longer than one 2048-row stripe first (they are the long poles),
     // then the single-stripe jobs.
@@ -39,33 +108,18 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
         while (true) {
             uint32_t job_id = 0;
             if (lane == 0) job_id = atomicAdd(next_job + sweep, 1u);
-            job_id = __shfl_sync(0xffffffffu, job_id, 0);
+            job_id = __shfl_sync(FULL, job_id, 0);
             if (job_id >= n_jobs) break;
             const EditJob job = jobs[job_id];
             const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
             if ((min(la0, lb0) > 2048u) != (sweep == 0)) continue;
+            const long long clock_begin = profile ? clock64() : 0ll;
+            uint32_t steps_total = 0;
             // The edit distance does not change when the common prefix and suffix are removed; the two haplotypes of
             // a shared variant are mostly identical, so this alone finishes most pairs (warp-parallel compare).
             const uint32_t lim = min(la0, lb0);
-            uint32_t pre = 0;
-            while (pre < lim) {
-                const uint32_t i = pre + lane;
-                const bool same = i < lim && hap_char(job.a, i, ref, seq4_a, seq4_b) == hap_char(job.b, i, ref, seq4_a, seq4_b);
-                const uint32_t mask = __ballot_sync(0xffffffffu, same);
-                if (mask != 0xffffffffu) { pre += static_cast<uint32_t>(__ffs(~mask) - 1); break; }
-                pre += 32u;
-            }
-            pre = min(pre, lim);
-            const uint32_t lim2 = lim - pre;
-            uint32_t suf = 0;
-            while (suf < lim2) {
-                const uint32_t i = suf + lane;
-                const bool same = i < lim2 && hap_char(job.a, la0 - 1u - i, ref, seq4_a, seq4_b) == hap_char(job.b, lb0 - 1u - i, ref, seq4_a, seq4_b);
-                const uint32_t mask = __ballot_sync(0xffffffffu, same);
-                if (mask != 0xffffffffu) { suf += static_cast<uint32_t>(__ffs(~mask) - 1); break; }
-                suf += 32u;
-            }
-            suf = min(suf, lim2);
+            const uint32_t pre = common_run<false>(job.a, job.b, la0, lb0, lim, ref, seq4_a, seq4_b, sh.cls2, lane);
+            const uint32_t suf = common_run<true>(job.a, job.b, la0, lb0, lim - pre, ref, seq4_a, seq4_b, sh.cls2, lane);
             const uint32_t la = la0 - pre - suf, lb = lb0 - pre - suf;
             const bool a_is_pattern = la <= lb;                // pattern = the shorter string
             const uint32_t m = a_is_pattern ? la : lb, n = a_is_pattern ? lb : la;
@@ -74,11 +128,12 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             long long dist = n;
             if (m != 0u) {
                 // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of
-                // half-width K gives the exact distance whenever the result is <= K; otherwise widen and repeat.
+                // half-width K gives the exact distance whenever the result is <= K; otherwise widen (x4) and repeat.
                 // Single-stripe patterns are computed in full at once.
-                const uint32_t bands[3] = {max(128u, m / 16u), max(1024u, m / 4u), 0xFFFFFFFFu};
-                for (int attempt = m > 2048u ? 0 : 2; attempt < 3; ++attempt) {
-                    const unsigned long long K = bands[attempt];
+                for (int attempt = 0;; ++attempt) {
+                    unsigned long long K = 256ull << (2 * attempt);
+                    const bool full_table = m <= 2048u || K >= m;
+                    if (full_table) K = ~0ull >> 1;
                     long long anchor = 0;                      // D'[last row of the previous stripe, jlo - 1]
                     uint32_t prev_jhi = 0;
                     for (uint32_t row0 = 0; row0 < m; row0 += 2048u) {
@@ -91,81 +146,133 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         // first column of the NEXT stripe's band: the running anchor stops there
                         const uint32_t next_row0 = row0 + rows;
                         const uint32_t next_jlo = static_cast<unsigned long long>(next_row0) > K ? static_cast<uint32_t>(next_row0 - K) : 0u;
-                        // per-class match masks of this lane's 64 rows
-#pragma unroll 4
-                        for (int c = 0; c < ED_NCLASS; ++c) s_peq[warp][c][lane] = 0ull;
-                        for (uint32_t r = 0; r < 64u; ++r) {
-                            const uint32_t idx = lane * 64u + r;
-                            if (idx < rows) {
-                                const uint8_t cls = s_class[hap_char(P, pre + row0 + idx, ref, seq4_a, seq4_b)];
-                                if (cls < ED_NCLASS) s_peq[warp][cls][lane] |= 1ull << r;
+                        const int width = static_cast<int>(jhi - jlo);
+                        const int steps = width + static_cast<int>(nblk) - 1;
+                        const int anchor_rel = static_cast<int>(min(next_jlo, jhi) - jlo);
+
+                        // ---- match masks: 32 rows per round, the lanes holding the same class form one 32-bit mask
+                        __syncwarp();
+                        for (uint32_t i = lane; i < (ED_NCLASS + 1) * 64u; i += 32u) peq32[i] = 0u;
+                        __syncwarp();
+                        const uint32_t ngroups = (rows + 31u) / 32u;
+                        for (uint32_t g0 = 0; g0 < ngroups; g0 += 4u) {
+                            uint32_t byte[4], mode[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t idx = (g0 + k) * 32u + lane;
+                                mode[k] = TOK_NONE;
+                                byte[k] = 0u;
+                                if (idx < rows) byte[k] = hap_fetch(P, pre + row0 + idx, ref, seq4_a, seq4_b, mode[k]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t cls = mode[k] == TOK_NONE ? ED_NOCLASS + 1u : tok_class(sh.cls2, byte[k], mode[k]);
+                                const uint32_t peers = __match_any_sync(FULL, cls);
+                                if (cls < ED_NOCLASS && static_cast<uint32_t>(__ffs(peers) - 1) == lane)
+                                    peq32[cls * 64u + (g0 + k)] = peers;            // word (g0+k): block (g0+k)/2, half (g0+k)&1
                             }
                         }
+
+                        // ---- column ring: classes and top-row delta codes, 32 columns per refill
+                        uint32_t nxt_byte = 0, nxt_mode = TOK_NONE, nxt_h = 1;
+                        auto fetch = [&](int rel) {                                 // issue the loads of band column `rel`
+                            nxt_mode = TOK_NONE;
+                            nxt_byte = 0u;
+                            nxt_h = 1u;                                             // outside the previous band: +1
+                            if (rel < width) {
+                                const uint32_t j = jlo + static_cast<uint32_t>(rel);
+                                nxt_byte = hap_fetch(T, pre + j, ref, seq4_a, seq4_b, nxt_mode);
+                                if (row0 != 0u && j < prev_jhi) nxt_h = __ldcg(hbuf + j);
+                            }
+                        };
+                        auto insert = [&](int first_rel) {                          // decode the pending loads into the ring
+                            const uint32_t slot = static_cast<uint32_t>(first_rel + static_cast<int>(lane)) & 63u;
+                            tcls[slot] = static_cast<uint8_t>(nxt_mode == TOK_NONE ? ED_NOCLASS : tok_class(sh.cls2, nxt_byte, nxt_mode));
+                            th[slot] = static_cast<uint8_t>(nxt_h);
+                        };
+                        fetch(static_cast<int>(lane));
+                        insert(0);
+                        fetch(32 + static_cast<int>(lane));
                         __syncwarp();
+
                         uint64_t pv = ~0ull, mv = 0ull;
-                        const uint64_t hibit = (final_stripe && lane == last_lane) ? (1ull << ((rows - 1u) & 63u)) : (1ull << 63);
+                        const uint32_t hshift = (final_stripe && lane == last_lane) ? ((rows - 1u) & 63u) : 63u;
+                        const bool park = !final_stripe && lane == last_lane;
                         int sum_all = 0, sum_anchor = 0;        // bottom-row deltas over [jlo, jhi) and over [jlo, next_jlo)
-                        const uint32_t width = jhi - jlo, steps = width + nblk - 1u;
-                        // Text classes and top-row deltas of the band's columns live in a 64-entry ring in shared memory,
-                        // refilled 32 columns at a time one block ahead of their use.  Every lane reads the class of ITS
-                        // column (t - lane) from the ring, so the match mask of step t+1 is fetched while step t computes
-                        // and only the 2-bit horizontal delta travels lane to lane: the loop-carried path is one shuffle
-                        // plus the block recurrence.
-                        auto fetch = [&](uint32_t rel) -> uint32_t {           // (class, top delta + 1) of band column `rel`
-                            const uint32_t j = jlo + rel;
-                            const uint32_t cls = (rel < width) ? s_class[hap_char(T, pre + j, ref, seq4_a, seq4_b)] : 255u;
-                            const int h = (rel < width && row0 != 0u && j < prev_jhi) ? hbuf[j] : 1;
-                            return cls | (static_cast<uint32_t>(h + 1) << 8);
+                        const int ilane = static_cast<int>(lane);
+                        auto ring_class = [&](int rel) -> uint32_t {
+                            return (rel >= 0 && rel < width) ? tcls[static_cast<uint32_t>(rel) & 63u] : ED_NOCLASS;
                         };
-                        {
-                            const uint32_t first = fetch(lane);
-                            s_tcls[warp][lane] = static_cast<uint8_t>(first & 0xFFu);
-                            s_th[warp][lane] = static_cast<signed char>(static_cast<int>(first >> 8) - 1);
-                        }
-                        uint32_t nxt = fetch(32u + lane);
-                        __syncwarp();
-                        auto lookup = [&](uint32_t t) -> uint64_t {            // match mask of this lane's block at step t
-                            const long long rel = static_cast<long long>(t) - lane;
-                            if (rel < 0 || rel >= static_cast<long long>(width)) return 0ull;
-                            const uint32_t cls = s_tcls[warp][static_cast<uint32_t>(rel) & 63u];
-                            return cls < ED_NCLASS ? s_peq[warp][cls][lane] : 0ull;
-                        };
-                        uint64_t eq = lookup(0u);
-                        int hout = 0;
-                        for (uint32_t t = 0; t < steps; ++t) {
-                            int hin = __shfl_up_sync(0xffffffffu, hout, 1);
-                            if (lane == 0u) hin = s_th[warp][t & 63u];
-                            const long long rel = static_cast<long long>(t) - lane;
-                            hout = 0;
-                            if (lane < nblk && rel >= 0 && rel < static_cast<long long>(width)) {
-                                hout = myers_block(pv, mv, eq, hin, hibit);
-                                if (lane == last_lane) {
-                                    const uint32_t j = jlo + static_cast<uint32_t>(rel);
-                                    sum_all += hout;
-                                    if (j < next_jlo) sum_anchor += hout;
-                                    if (!final_stripe) hbuf[j] = static_cast<signed char>(hout);
+                        // pipeline registers: eq0 = match mask of step t, cls1 = class of step t+1, th0 = top code of step t
+                        uint64_t eq0 = peq[ring_class(-ilane)][lane];
+                        uint32_t cls1 = ring_class(1 - ilane);
+                        uint32_t th0 = th[0];
+                        uint32_t hout = 0;
+
+                        auto run = [&](auto masked_tag, int t, const int t_end) {
+                            constexpr bool MASKED = decltype(masked_tag)::value;
+#pragma unroll 2
+                            for (; t < t_end; ++t) {
+                                uint32_t hin = __shfl_up_sync(FULL, hout, 1);
+                                hin = lane == 0u ? th0 : hin;
+                                const int rel = t - ilane;
+                                // loads for the next steps (independent of the recurrence)
+                                const uint64_t eq1 = peq[cls1][lane];
+                                uint32_t cls2;
+                                if (MASKED) cls2 = ring_class(rel + 2);
+                                else cls2 = tcls[static_cast<uint32_t>(rel + 2) & 63u];
+                                const uint32_t th1 = th[static_cast<uint32_t>(t + 1) & 63u];
+                                uint64_t npv = pv, nmv = mv;
+                                uint32_t ho = myers_step(npv, nmv, eq0, hin, hshift);
+                                if (MASKED) {
+                                    const bool active = lane < nblk && rel >= 0 && rel < width;
+                                    pv = active ? npv : pv;
+                                    mv = active ? nmv : mv;
+                                    ho = active ? ho : 0u;
+                                    if (park && active) hbuf[jlo + static_cast<uint32_t>(rel)] = static_cast<uint8_t>(ho);
+                                } else {
+                                    pv = npv;
+                                    mv = nmv;
+                                    if (park) hbuf[jlo + static_cast<uint32_t>(rel)] = static_cast<uint8_t>(ho);
                                 }
+                                if (rel == anchor_rel) sum_anchor = sum_all;
+                                sum_all += static_cast<int>(ho & 1u) - static_cast<int>(ho >> 1);
+                                hout = ho;
+                                eq0 = eq1;
+                                cls1 = cls2;
+                                th0 = th1;
                             }
-                            if (((t + 1u) & 31u) == 0u) {              // columns t+1 .. t+32 enter the ring, t+33 .. t+64 are fetched
-                                const uint32_t slot = (t + 1u + lane) & 63u;
-                                s_tcls[warp][slot] = static_cast<uint8_t>(nxt & 0xFFu);
-                                s_th[warp][slot] = static_cast<signed char>(static_cast<int>(nxt >> 8) - 1);
-                                nxt = fetch(t + 33u + lane);
+                        };
+                        // The ring is refilled before the steps t = 30 (mod 32): columns t+2 .. t+33 enter, t+34 .. t+65 are
+                        // requested.  Chunks that lie inside [nblk-1, width) need no masks: every block lane is on a column.
+                        int t = 0, next_refill = 30;
+                        steps_total += static_cast<uint32_t>(steps);
+                        while (t < steps) {
+                            if (t == next_refill) {
+                                insert(t + 2);
+                                fetch(t + 34 + ilane);
                                 __syncwarp();
+                                next_refill += 32;
                             }
-                            eq = lookup(t + 1u);
+                            const int t_end = min(steps, next_refill);
+                            if (t >= static_cast<int>(nblk) - 1 && t_end <= width) run(std::false_type(), t, t_end);
+                            else run(std::true_type(), t, t_end);
+                            t = t_end;
                         }
                         __syncwarp();
-                        sum_all = __shfl_sync(0xffffffffu, sum_all, last_lane);
-                        sum_anchor = __shfl_sync(0xffffffffu, sum_anchor, last_lane);
+                        if (anchor_rel >= width) sum_anchor = sum_all;
+                        sum_all = __shfl_sync(FULL, sum_all, last_lane);
+                        sum_anchor = __shfl_sync(FULL, sum_anchor, last_lane);
                         if (final_stripe) dist = anchor + rows + sum_all;
                         else anchor += static_cast<long long>(rows) + sum_anchor;
                         prev_jhi = jhi;
                     }
-                    if (static_cast<unsigned long long>(dist) <= K) break;      // exact
+                    if (full_table || static_cast<unsigned long long>(dist) <= K) break;      // exact
                 }
             }
             if (lane == 0) out[job.out_index] = static_cast<double>(dist);
+            if (profile && lane == 0)      // SVB_ED_PROFILE: {trimmed pattern rows, trimmed text columns, column steps, cycles}
+                profile[job_id] = make_uint4(m, n, steps_total, static_cast<uint32_t>(clock64() - clock_begin));
         }
     }
 }
@@ -213,17 +320,34 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
     if (!n_jobs) return SVB_OK;
     const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n_jobs + ED_WARPS - 1) / ED_WARPS,
                                                                      static_cast<uint64_t>(ctx->sm_count) * 8));
-    signed char* hbuf = nullptr;
+    uint8_t* hbuf = nullptr;
     const uint64_t stride = (max_text_multi_stripe + 127) & ~127ull;
     if (stride) SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));
     SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, sizeof(unsigned long long), ctx->stream));   // two 32-bit job counters
+    // profiling aid: SVB_ED_PROFILE=<file> dumps one uint4 per job {rows, columns, column steps, SM cycles} of the launch
+    const char* profile_path = getenv("SVB_ED_PROFILE");
+    uint4* d_profile = nullptr;
+    if (profile_path) {
+        SVB_CUDA(ctx, cudaMallocAsync(&d_profile, sizeof(uint4) * n_jobs, ctx->stream));
+        SVB_CUDA(ctx, cudaMemsetAsync(d_profile, 0, sizeof(uint4) * n_jobs, ctx->stream));
+    }
     {
         KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
         edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, reinterpret_cast<unsigned int*>(ctx->d_counters + 8),
-                                                                       d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out);
+                                                                       d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out, d_profile);
         ctx->launches += 1;
     }
     SVB_CUDA(ctx, cudaGetLastError());
+    if (d_profile) {
+        std::vector<uint4> h(n_jobs);
+        SVB_CUDA(ctx, cudaMemcpyAsync(h.data(), d_profile, sizeof(uint4) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+        SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (FILE* f = fopen(profile_path, "wb")) {
+            fwrite(h.data(), sizeof(uint4), n_jobs, f);
+            fclose(f);
+        }
+        cudaFreeAsync(d_profile, ctx->stream);
+    }
     if (hbuf) SVB_CUDA(ctx, cudaFreeAsync(hbuf, ctx->stream));
     return SVB_OK;
 }

@@ -135,15 +135,15 @@ int svb_table_pool_to_host(svb_ctx* ctx, const svb_table* t, uint8_t* pool_dst, 
     return SVB_OK;
 }
 
-int svb_table_set_pool_from_host(svb_ctx* ctx, svb_table* t, const uint8_t* pool, const uint64_t* pool_off) {
-    if (!ctx || !t || !pool_off) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_set_pool_from_host") : SVB_ERR_ARG;
+int svb_table_set_pool_from_host(svb_ctx* ctx, svb_table* t, const uint8_t* pool, uint64_t pool_bytes, const uint64_t* row_off) {
+    if (!ctx || !t || (t->n && !row_off) || (pool_bytes && !pool)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_set_pool_from_host") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
     table_drop_pool(t);
-    t->pool_bytes = pool_off[t->n];
+    t->pool_bytes = pool_bytes;
     SVB_CUDA(ctx, cudaMallocAsync(&t->d_pool, std::max<uint64_t>(t->pool_bytes, 1), ctx->stream));
     SVB_CUDA(ctx, cudaMallocAsync(&t->d_pool_off, sizeof(uint64_t) * (t->n + 1), ctx->stream));
     if (t->pool_bytes) SVB_CUDA(ctx, cudaMemcpyAsync(t->d_pool, pool, t->pool_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    SVB_CUDA(ctx, cudaMemcpyAsync(t->d_pool_off, pool_off, sizeof(uint64_t) * (t->n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (t->n) SVB_CUDA(ctx, cudaMemcpyAsync(t->d_pool_off, row_off, sizeof(uint64_t) * t->n, cudaMemcpyHostToDevice, ctx->stream));
     SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SVB_OK;
 }

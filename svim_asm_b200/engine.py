@@ -205,6 +205,7 @@ class Table(object):
                                                                _lib.ptr(host.seq_off)))
 
     def pool_to_numpy(self):
+        """(pool bytes, start offset of every row's run)."""
         n = len(self)
         off = np.zeros(n + 1, dtype=np.uint64)
         size = ctypes.c_uint64()
@@ -213,13 +214,23 @@ class Table(object):
         if pool.shape[0]:
             self.engine._check(lib.svb_table_pool_to_host(self.engine.handle, self.handle, _lib.ptr(pool), pool.shape[0], None,
                                                           ctypes.byref(size)))
-        return pool, off
+        return pool, off[:-1].copy()
 
-    def set_pool(self, pool, off):
+    def remap_records(self, rec):
+        """aln_idx / ordinal -> indices in the unsharded batch (Records.set_global_index)."""
+        self.engine._check(lib.svb_table_remap_records(self.engine.handle, self.handle, rec.handle))
+
+    def device_rows(self):
+        """(device pointer, bytes) of the rows."""
+        return int(lib.svb_table_device_rows(self.handle) or 0), len(self) * _lib.ROW_DTYPE.itemsize
+
+    def set_pool(self, pool, starts):
+        """Attach a pool given the start offset of every row's run (any order, gaps allowed)."""
         pool = np.ascontiguousarray(pool, dtype=np.uint8)
-        off = np.ascontiguousarray(off, dtype=np.uint64)
-        assert off.shape[0] == len(self) + 1
-        self.engine._check(lib.svb_table_set_pool_from_host(self.engine.handle, self.handle, _lib.ptr(pool), _lib.ptr(off)))
+        starts = np.ascontiguousarray(starts, dtype=np.uint64)
+        assert starts.shape[0] == len(self)
+        self.engine._check(lib.svb_table_set_pool_from_host(self.engine.handle, self.handle, _lib.ptr(pool), pool.shape[0],
+                                                            _lib.ptr(starts)))
 
     def free(self):
         if self.handle:
@@ -269,6 +280,33 @@ class Reference(object):
             self.free()
         except Exception:
             pass
+
+
+class DeviceView(object):
+    """A span of device memory owned by someone else, visible to torch (`torch.as_tensor(view, device=...)`) through
+    __cuda_array_interface__: the collectives of the multi-GPU exchange read and write the library's buffers in place."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = int(ptr), int(nbytes)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+
+class DeviceBuffer(DeviceView):
+    """Stream-ordered scratch of the engine's context."""
+
+    def __init__(self, engine, nbytes):
+        out = ctypes.c_void_p()
+        engine._check(lib.svb_device_alloc(engine.handle, int(nbytes), ctypes.byref(out)))
+        DeviceView.__init__(self, out.value, nbytes)
+        self.engine = engine
+
+    def free(self):
+        if self.ptr:
+            lib.svb_device_free(self.engine.handle, ctypes.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 class Engine(object):
@@ -379,6 +417,39 @@ class Engine(object):
         self._check(lib.svb_cluster_labels(self.handle, _lib.ptr(flat), _lib.ptr(npts), len(n_points), float(threshold),
                                            _lib.ptr(out)))
         return [out[i, :n].tolist() for i, n in enumerate(n_points)]
+
+    # ---- multi-GPU exchange (device resident, see csrc/exchange.cu)
+    def stream_handle(self):
+        return int(lib.svb_stream(self.handle) or 0)
+
+    def set_global_index(self, rec, global_idx):
+        idx = np.ascontiguousarray(global_idx, dtype=np.uint32)
+        assert idx.shape[0] == rec.host.n_aln
+        self._check(lib.svb_records_set_global_index(self.handle, rec.handle, _lib.ptr(idx)))
+
+    def exchange_sizes(self, table1, table2):
+        sizes = np.zeros(4, dtype=np.uint64)
+        self._check(lib.svb_exchange_sizes(table1.handle, table2.handle, _lib.ptr(sizes)))
+        return sizes
+
+    @staticmethod
+    def exchange_bytes(sizes):
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        return int(lib.svb_exchange_bytes(_lib.ptr(sizes)))
+
+    def exchange_pack(self, table1, table2, device_ptr, cap_bytes):
+        self._check(lib.svb_exchange_pack(self.handle, table1.handle, table2.handle, ctypes.c_void_p(int(device_ptr)), int(cap_bytes)))
+
+    def exchange_unpack(self, device_ptr, stride, sizes, hap, owner, rank):
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64).reshape(-1, 4)
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        out = ctypes.c_void_p()
+        self._check(lib.svb_exchange_unpack(self.handle, ctypes.c_void_p(int(device_ptr)), int(stride), _lib.ptr(sizes),
+                                            sizes.shape[0], int(hap), _lib.ptr(owner), owner.shape[0], int(rank), ctypes.byref(out)))
+        return Table(self, out)
+
+    def device_alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
 
     # ---- timing
     def timing_reset(self):

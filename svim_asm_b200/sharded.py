@@ -55,25 +55,14 @@ def remap_to_global(rows, global_idx):
     return rows
 
 
-def repack_pool(pool, off, order):
-    """Pool and offsets of rows[order] (vectorised gather of variable-length runs)."""
-    lens = (off[1:] - off[:-1]).astype(np.int64)[order]
-    new_off = np.zeros(order.shape[0] + 1, dtype=np.uint64)
-    new_off[1:] = np.cumsum(lens)
-    total = int(new_off[-1])
-    if total == 0:
-        return np.zeros(0, dtype=np.uint8), new_off
-    src = np.repeat(off[:-1].astype(np.int64)[order] - new_off[:-1].astype(np.int64), lens) + np.arange(total, dtype=np.int64)
-    return pool[src], new_off
-
-
 def pack_payload(parts):
-    """[(rows, pool, off), ...] -> one uint8 buffer (header: counts per part)."""
+    """[(rows, pool, starts), ...] -> one uint8 buffer (header: counts per part).  starts[i] = byte offset of row i's
+    sequence run inside `pool`."""
     header = np.zeros(HEADER_WORDS * len(parts), dtype=np.uint64)
     chunks = []
-    for k, (rows, pool, off) in enumerate(parts):
+    for k, (rows, pool, starts) in enumerate(parts):
         header[HEADER_WORDS * k:HEADER_WORDS * k + 2] = (rows.shape[0], pool.shape[0])
-        chunks += [rows.view(np.uint8).reshape(-1), off.view(np.uint8).reshape(-1), pool]
+        chunks += [rows.view(np.uint8).reshape(-1), np.ascontiguousarray(starts, dtype=np.uint64).view(np.uint8).reshape(-1), pool]
     return np.concatenate([header.view(np.uint8)] + chunks)
 
 
@@ -85,11 +74,11 @@ def unpack_payload(buf, n_parts, row_dtype):
         n_rows, n_pool = int(header[HEADER_WORDS * k]), int(header[HEADER_WORDS * k + 1])
         rows = buf[pos:pos + n_rows * row_dtype.itemsize].view(row_dtype)
         pos += n_rows * row_dtype.itemsize
-        off = buf[pos:pos + 8 * (n_rows + 1)].view(np.uint64)
-        pos += 8 * (n_rows + 1)
+        starts = buf[pos:pos + 8 * n_rows].view(np.uint64)
+        pos += 8 * n_rows
         pool = buf[pos:pos + n_pool]
         pos += n_pool
-        out.append((rows, pool, off))
+        out.append((rows, pool, starts))
     return out
 
 
@@ -112,24 +101,23 @@ def all_gather_bytes(buf, device):
 
 
 def merge_gathered(parts_by_rank, part):
-    """Concatenate one haplotype's (rows, pool, off) of all ranks and restore the global append order (ordinal)."""
+    """One haplotype's (rows, pool, starts) of all ranks -> the global append order (ordinal).  The pools are only
+    concatenated; the per-row start offsets move with their rows."""
     rows = np.concatenate([p[part][0] for p in parts_by_rank])
-    pools, offs, base = [], [], 0
+    pools, starts, base = [], [], 0
     for p in parts_by_rank:
         pools.append(p[part][1])
-        offs.append(p[part][2][:-1].astype(np.uint64) + np.uint64(base))
-        base += int(p[part][2][-1])
+        starts.append(p[part][2].astype(np.uint64) + np.uint64(base))
+        base += int(p[part][1].shape[0])
     pool = np.concatenate(pools) if pools else np.zeros(0, dtype=np.uint8)
-    off = np.concatenate(offs + [np.array([base], dtype=np.uint64)])
+    starts = np.concatenate(starts) if starts else np.zeros(0, dtype=np.uint64)
     order = np.argsort(rows["ordinal"], kind="stable")
-    new_pool, new_off = repack_pool(pool, off, order)
-    return rows[order], new_pool, new_off
+    return rows[order], pool, starts[order]
 
 
-def select_owned(rows, pool, off, owner, rank):
+def select_owned(rows, pool, starts, owner, rank):
     keep = np.nonzero(owner[key_contig(rows)] == rank)[0]
-    new_pool, new_off = repack_pool(pool, off, keep)
-    return rows[keep], new_pool, new_off
+    return rows[keep], pool, starts[keep]
 
 
 def order_paired(rows_by_rank, lexrank):
@@ -156,7 +144,7 @@ def sharded_step(stage, rank, owner, lexrank, device, row_dtype):
         rows, pool, off = merge_gathered(gathered, hap)
         parts.append(select_owned(rows, pool, off, owner, rank))
     paired = stage.pair(parts[0], parts[1])
-    empty = (np.zeros(0, dtype=np.uint8), np.zeros(paired.shape[0] + 1, dtype=np.uint64))
+    empty = (np.zeros(0, dtype=np.uint8), np.zeros(paired.shape[0], dtype=np.uint64))
     back = [unpack_payload(b, 1, row_dtype)[0][0] for b in all_gather_bytes(pack_payload([(paired, empty[0], empty[1])]), device)]
     return order_paired(back, lexrank)
 
@@ -188,9 +176,9 @@ class EngineStage(object):
 
     def pair(self, part1, part2):
         tables = []
-        for rows, pool, off in (part1, part2):
+        for rows, pool, starts in (part1, part2):
             t = self.eng.table_from_numpy(rows)
-            t.set_pool(pool, off)
+            t.set_pool(pool, starts)
             tables.append(t)
         paired = self.eng.pair(tables[0], tables[1], self.records[0], self.records[1], self.ref, self.params)
         out = paired.to_numpy()
@@ -200,6 +188,82 @@ class EngineStage(object):
             for r in self.records:
                 r.free()
         return out
+
+
+class DeviceStage(object):
+    """One rank's compute on its GPU with the exchange kept on the device (csrc/exchange.cu): the tables never visit
+    the host between COLLECT and the paired result."""
+
+    def __init__(self, eng, hosts, global_idx, ref, params, resident):
+        self.eng, self.hosts, self.global_idx, self.ref, self.params = eng, hosts, global_idx, ref, params
+        self.resident = resident                       # record images (sequences + global index) kept in HBM, or None
+        self.records = list(resident) if resident else [None, None]
+        self.h2d = 0
+
+    def collect(self, hap):
+        k = hap - 1
+        h = self.hosts[k]
+        if self.resident is None:                      # end-to-end leg: this step's records come from pinned host memory
+            self.records[k] = self.eng.load_records(h)
+            self.eng.set_global_index(self.records[k], self.global_idx[k])
+            self.h2d += sum(getattr(h, n).nbytes for n in ("hdr", "cigar", "seg", "sa_count")) + 4 * h.n_aln
+        table = self.eng.collect(self.records[k], self.params, hap=hap)
+        if self.resident is None:
+            table.attach_sequences_host(h)
+        else:
+            table.gather_sequences(self.records[k])
+        table.remap_records(self.records[k])
+        return table
+
+    def done(self):
+        if self.resident is None:
+            for r in self.records:
+                r.free()
+
+
+def _gather_sizes(values, world, device):
+    import torch
+    import torch.distributed as dist
+    mine = torch.from_numpy(np.asarray(values, dtype=np.int64)).to(device)
+    out = torch.empty(world * mine.shape[0], dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    return out.cpu().numpy().reshape(world, -1)
+
+
+def sharded_step_device(stage, rank, world, owner, lexrank, device, row_dtype):
+    """One step on one rank, NCCL collectives straight on the library's device buffers.  Everything is enqueued on the
+    library's own stream (torch sees it as an ExternalStream), so kernels and collectives are stream ordered."""
+    import torch
+    import torch.distributed as dist
+    from .engine import DeviceView
+    eng = stage.eng
+    with torch.cuda.stream(torch.cuda.ExternalStream(eng.stream_handle(), device=device)):
+        t1, t2 = stage.collect(1), stage.collect(2)
+        sizes = _gather_sizes(eng.exchange_sizes(t1, t2).astype(np.int64), world, device).astype(np.uint64)
+        stride = max(eng.exchange_bytes(sizes[r]) for r in range(world))
+        mine = torch.empty(stride, dtype=torch.uint8, device=device)
+        eng.exchange_pack(t1, t2, mine.data_ptr(), stride)
+        gathered = torch.empty(world * stride, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(gathered, mine)
+        t1.free()
+        t2.free()
+        u1 = eng.exchange_unpack(gathered.data_ptr(), stride, sizes, 1, owner, rank)
+        u2 = eng.exchange_unpack(gathered.data_ptr(), stride, sizes, 2, owner, rank)
+        paired = eng.pair(u1, u2, stage.records[0], stage.records[1], stage.ref, stage.params)
+        counts = _gather_sizes([len(paired)], world, device)[:, 0]
+        width = max(int(counts.max()), 1) * row_dtype.itemsize
+        rows = torch.zeros(width, dtype=torch.uint8, device=device)
+        ptr, nbytes = paired.device_rows()
+        if nbytes:
+            rows[:nbytes].copy_(torch.as_tensor(DeviceView(ptr, nbytes), device=device))
+        back = torch.empty(world * width, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(back, rows)
+        host = back.cpu().numpy().reshape(world, width)
+        for t in (u1, u2, paired):
+            t.free()
+        stage.done()
+    parts = [host[r, :int(counts[r]) * row_dtype.itemsize].view(row_dtype) for r in range(world)]
+    return order_paired(parts, lexrank)
 
 
 def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block):
@@ -227,16 +291,18 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     bases_p, _keep = pin(bases)
     ref = eng.load_reference(bases_p, off)                 # every rank keeps the whole reference (3.1 GB of 180 GB)
     resident = [eng.load_records(h, with_sequences=True) for h in hosts]
+    for rec, g in zip(resident, (g1, g2)):
+        eng.set_global_index(rec, g)
 
     def timed(stage_factory, steps, warmup):
         for _ in range(warmup):
-            table = sharded_step(stage_factory(), rank, owner, ranks, device, _lib.ROW_DTYPE)
+            table = sharded_step_device(stage_factory(), rank, world, owner, ranks, device, _lib.ROW_DTYPE)
         dist.barrier()
         torch.cuda.synchronize()
         eng.synchronize()
         t0 = time.perf_counter()
         for _ in range(steps):
-            table = sharded_step(stage_factory(), rank, owner, ranks, device, _lib.ROW_DTYPE)
+            table = sharded_step_device(stage_factory(), rank, world, owner, ranks, device, _lib.ROW_DTYPE)
         eng.synchronize()
         torch.cuda.synchronize()
         dist.barrier()
@@ -248,7 +314,7 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     eng.timing_reset()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    sec, table = timed(lambda: EngineStage(eng, hosts, [g1, g2], ref, params, resident), args.steps, warm)
+    sec, table = timed(lambda: DeviceStage(eng, hosts, [g1, g2], ref, params, resident), args.steps, warm)
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count() - launches0
     timing = eng.timing()
@@ -256,7 +322,7 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     stages = []
 
     def e2e_factory():
-        st = EngineStage(eng, hosts, [g1, g2], ref, params, None)
+        st = DeviceStage(eng, hosts, [g1, g2], ref, params, None)
         stages.append(st)
         return st
     e2e_sec, table2 = timed(e2e_factory, args.steps, warm)

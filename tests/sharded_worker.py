@@ -36,7 +36,7 @@ def _worker(rank, world, port, out_dir):
             rows = oracle.collect(hosts[hap - 1], p, hap=hap)
             # sequence pool of the INS rows, 4-bit packed like the device gather
             off = np.zeros(rows.shape[0] + 1, dtype=np.uint64)
-            chunks = []
+            chunks = [np.zeros(3, np.uint8)]          # pools need not start at offset 0
             lut = {c: i for i, c in enumerate(synth.NT16)}
             for i, r in enumerate(rows):
                 seq = hosts[hap - 1].sequence_slice(int(r["aln_idx"]), int(r["seq_pos"]), int(r["seq_len"])) if r["type"] == 2 else ""
@@ -44,13 +44,13 @@ def _worker(rank, world, port, out_dir):
                 packed = ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8) if codes.shape[0] else np.zeros(0, np.uint8)
                 chunks.append(packed)
                 off[i + 1] = off[i] + np.uint64(packed.shape[0])
-            pool = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
-            return sharded.remap_to_global(rows, shards[hap - 1][1]), pool, off
+            pool = np.concatenate(chunks)
+            return sharded.remap_to_global(rows, shards[hap - 1][1]), pool, off[:-1] + np.uint64(3)
 
         def pair(self, part1, part2):
             class PoolHost(object):
                 def __init__(self, part, host):
-                    self.rows, self.pool, self.off = part
+                    self.rows, self.pool, self.starts = part
                     self.contig_names, self.contig_lengths = host.contig_names, host.contig_lengths
                     self.index = {int(r["ordinal"]): i for i, r in enumerate(self.rows)}
 
@@ -63,7 +63,7 @@ def _worker(rank, world, port, out_dir):
                 def slicer(aln, pos, length, _hp=hp):
                     hits = np.nonzero((_hp.rows["aln_idx"] == aln) & (_hp.rows["seq_pos"] == pos) & (_hp.rows["type"] == 2))[0]
                     i = int(hits[0])
-                    raw = _hp.pool[int(_hp.off[i]):int(_hp.off[i + 1])]
+                    raw = _hp.pool[int(_hp.starts[i]):int(_hp.starts[i]) + (length + 1) // 2]
                     nib = np.empty(raw.shape[0] * 2, dtype=np.uint8)
                     nib[0::2], nib[1::2] = raw >> 4, raw & 15
                     return "".join(synth.NT16[c] for c in nib[:length])

@@ -1,0 +1,43 @@
+"""Per-job profile of the edit-distance kernel on the bench workload: which pairs are the long poles.
+
+  python tools/perf_pair.py --scale 0.25     (needs a GPU; uses the SVB_ED_PROFILE dump of csrc/edit_distance.cu)"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import bench
+from svim_asm_b200.engine import Engine, HostBatch, make_params
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=float, default=0.25)
+ap.add_argument("--out", default="gpurun_out/ed_profile.npy")
+args = ap.parse_args()
+
+cfg, rb1, rb2, bases, off = bench.build_workload(args.scale)
+eng = Engine(0)
+hosts = [HostBatch.from_record_batch(rb) for rb in (rb1, rb2)]
+recs = [eng.load_records(h, with_sequences=True) for h in hosts]
+ref = eng.load_reference(bases, off)
+params = make_params()
+tabs = [eng.collect(r, params, hap=k + 1) for k, r in enumerate(recs)]
+for _ in range(2):
+    eng.pair(tabs[0], tabs[1], recs[0], recs[1], ref, params)
+path = "/tmp/ed_profile.bin"
+os.environ["SVB_ED_PROFILE"] = path
+eng.timing_reset()
+eng.pair(tabs[0], tabs[1], recs[0], recs[1], ref, params)
+del os.environ["SVB_ED_PROFILE"]
+prof = np.fromfile(path, dtype=np.uint32).reshape(-1, 4)
+np.save(args.out, prof)
+print("edit_distance launch: %.3f ms (with the profile writes), %d jobs" % (eng.timing()["edit_distance"][0], prof.shape[0]))
+cyc = prof[:, 3].astype(np.float64)
+print("sum of job cycles %.3g, max %.3g (%.3f ms at 1.9 GHz)" % (cyc.sum(), cyc.max(), cyc.max() / 1.9e6))
+print("   rows   cols  steps   cycles  cyc/step")
+for i in np.argsort(-cyc)[:25]:
+    m, n, st, c = (int(x) for x in prof[i])
+    print("%7d %6d %6d %8d %8.1f" % (m, n, st, c, c / max(st, 1)))
+no_dp = prof[:, 2] == 0
+print("jobs finished by trimming alone: %d, their max cycles %d" % (no_dp.sum(), prof[no_dp, 3].max() if no_dp.any() else 0))
