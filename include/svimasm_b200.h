@@ -113,7 +113,7 @@ typedef struct {
 
 /* Kernel timings accumulated since svb_timing_reset(): CUDA events on the library's stream. */
 enum { SVB_K_CIGAR_SCAN = 0, SVB_K_SEGMENT_WALK = 1, SVB_K_MERGE = 2, SVB_K_SORT = 3, SVB_K_EDIT_DISTANCE = 4,
-       SVB_K_CLUSTER = 5, SVB_K_COUNT = 8 };
+       SVB_K_CLUSTER = 5, SVB_K_SCAN_FINALIZE = 6, SVB_K_COUNT = 8 };
 typedef struct {
     double ms[SVB_K_COUNT];
     uint64_t launches[SVB_K_COUNT];

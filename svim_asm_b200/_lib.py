@@ -22,7 +22,7 @@ c_void_p, c_char_p, c_int, c_double = ctypes.c_void_p, ctypes.c_char_p, ctypes.c
 P = ctypes.POINTER
 
 SVB_K_COUNT = 8
-KERNEL_NAMES = ("cigar_scan", "segment_walk", "merge", "sort", "edit_distance", "cluster")
+KERNEL_NAMES = ("cigar_scan", "segment_walk", "merge", "sort", "edit_distance", "cluster", "cigar_scan_finalize")
 
 PARAMS_DTYPE = np.dtype([(n, "<i4") for n in (
     "min_mapq", "min_sv_size", "max_sv_size", "query_gap_tolerance", "query_overlap_tolerance",

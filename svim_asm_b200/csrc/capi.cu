@@ -277,7 +277,11 @@ int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const
     };
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_hdr), hdr, sizeof(svb_aln_hdr) * n_aln);
-    if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_cigar), cigar, sizeof(uint32_t) * n_ops_padded);
+    if (e == cudaSuccess) {          // allocated in whole scan units; launch_build_chunk_index fills the tail with op 15
+        e = cudaMallocAsync(reinterpret_cast<void**>(&r->d_cigar), std::max<uint64_t>(cigar_padded_n4(r->n4), 1) * sizeof(uint4), ctx->stream);
+        if (e == cudaSuccess && n_ops_padded)
+            e = cudaMemcpyAsync(r->d_cigar, cigar, sizeof(uint32_t) * n_ops_padded, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_off4), off4.data(), sizeof(uint32_t) * off4.size());
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_seg), seg, sizeof(svb_segment) * n_seg);
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_sa_count), sa_count, sa_count ? sizeof(uint32_t) * n_aln : 0);

@@ -32,6 +32,7 @@
 //
 // Bound: HBM bandwidth.  Algorithmic bytes: 4 B/op + 32 B/alignment + 64 B/emitted row.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -128,28 +129,26 @@ __device__ __forceinline__ bool record_passes(const svb_aln_hdr& h, int32_t min_
     return h.tid >= 0 && !(h.flag & 0x4) && !(h.flag & 0x100) && static_cast<int32_t>(h.mapq) >= min_mapq;
 }
 
-// fast path of one uint4 (4 ops): packed advance sums and the rare flag
-__device__ __forceinline__ void fast_row(const uint4 d, const uint2* lut, bool in_head, uint32_t& totR, uint32_t& totQ,
-                                         uint32_t& headR, uint32_t& headQ, uint32_t& rare_rows, uint32_t row_bit) {
-    const uint2 e0 = lut[d.x & 15u], e1 = lut[d.y & 15u], e2 = lut[d.z & 15u], e3 = lut[d.w & 15u];
+// Decode table, one entry per op code: x = multiplier (bit 0: the op advances the read, bit 31: it advances the
+// reference), y = threshold of the rare test on the PACKED op (I/D: min_sv_size << 4, N/H: 16 i.e. len != 0, else never).
+// File scope so that every lookup is LDS.64 [offset + table] (a pointer parameter costs an extra add per op).
+__shared__ uint2 s_lut[16];
+
+// fast path of one uint4 (4 ops): packed advance sums (read advance in bits 0..30, reference advance from bit 31 up;
+// 4 x 2^28 < 2^31, so one uint4 cannot overflow a field) and the rare flag, accumulated over the whole chunk
+__device__ __forceinline__ unsigned long long fast_row(const uint4 d, bool& rare) {
+    const uint2 e0 = s_lut[d.x & 15u], e1 = s_lut[d.y & 15u], e2 = s_lut[d.z & 15u], e3 = s_lut[d.w & 15u];
     unsigned long long acc = static_cast<unsigned long long>(d.x >> 4) * e0.x;
     acc += static_cast<unsigned long long>(d.y >> 4) * e1.x;
     acc += static_cast<unsigned long long>(d.z >> 4) * e2.x;
     acc += static_cast<unsigned long long>(d.w >> 4) * e3.x;
-    if (d.x >= e0.y || d.y >= e1.y || d.z >= e2.y || d.w >= e3.y) rare_rows |= row_bit;
-    const uint32_t rr = static_cast<uint32_t>(acc >> 31), qq = static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
-    totR += rr;
-    totQ += qq;
-    if (in_head) {
-        headR += rr;
-        headQ += qq;
-    }
+    rare |= (d.x >= e0.y) | (d.y >= e1.y) | (d.z >= e2.y) | (d.w >= e3.y);
+    return acc;
 }
 
 // row `r` of the chunk that starts at uint4 index c4, re-read through L2 (rare paths only)
-__device__ __forceinline__ uint4 reload_row(const uint4* cigar, uint64_t n4, uint64_t c4, int r, uint32_t lane) {
-    const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
-    return g4 < n4 ? cigar[g4] : make_uint4(15u, 15u, 15u, 15u);
+__device__ __forceinline__ uint4 reload_row(const uint4* cigar, uint64_t c4, int r, uint32_t lane) {
+    return cigar[c4 + static_cast<uint64_t>(r) * 32u + lane];        // the buffer is padded to whole units (op 15)
 }
 
 struct ChunkResult {
@@ -159,7 +158,7 @@ struct ChunkResult {
 // Phase 1 of one chunk.  `rowsrc(r)` yields this lane's uint4 of row r in the unrolled fast loop (r is a
 // compile-time constant there); `raresrc(r)` serves the rare paths, where r is a run-time value.
 template <typename RowSrc, typename RareSrc>
-__device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uint2* lut, const ChunkGeom g, uint64_t c4, uint32_t lane,
+__device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const ChunkGeom g, uint64_t c4, uint32_t lane,
                                                     RowSrc rowsrc, RareSrc raresrc) {
     ChunkResult out;
     out.evbits = 0;
@@ -170,18 +169,24 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uin
     const int rows_before = (static_cast<int>(g.split_rel) - static_cast<int>(lane) + 31) / 32;
     const int nb = rows_before <= 0 ? 0 : (rows_before >= ROWS ? ROWS : rows_before);
     uint32_t headR = 0, headQ = 0, totR = 0, totQ = 0;
-    uint32_t rare_rows = 0;               // bit r: this lane's uint4 of row r holds a rare op
+    bool rare = false;                    // some op of this lane passes its class threshold (I/D >= min_sv_size, N, H)
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) fast_row(rowsrc(r), lut, r < nb, totR, totQ, headR, headQ, rare_rows, 1u << r);
+    for (int r = 0; r < ROWS; ++r) {
+        const unsigned long long acc = fast_row(rowsrc(r), rare);
+        totR += static_cast<uint32_t>(acc >> 31);
+        totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
+        if (r + 1 == nb) {                // rows 0 .. nb-1 belong to the alignment that owns the chunk start
+            headR = totR;
+            headQ = totQ;
+        }
+    }
     const uint32_t first_mask = nb >= 8 ? 0xFFFFFFFFu : ((1u << (4u * static_cast<uint32_t>(nb))) - 1u);   // ROWS <= 8
-    uint32_t warp_rows = __reduce_or_sync(0xffffffffu, rare_rows);      // rows that need the exact classification
-    const bool any_rare = warp_rows != 0u;
+    const bool any_rare = __any_sync(0xffffffffu, rare);
 
     uint32_t nhbits = 0, evbits = 0;
-    while (warp_rows) {                    // exact bits, only for the rows (usually one) that hold a rare op
-        const int r = __ffs(warp_rows) - 1;
-        warp_rows &= warp_rows - 1u;
-        if ((rare_rows >> r) & 1u) {
+    if (any_rare && rare) {               // exact bits of this lane's 32 ops (about one chunk in eight gets here)
+#pragma unroll 1
+        for (int r = 0; r < ROWS; ++r) {
             const uint4 d = raresrc(r);
             uint32_t r0 = 0, q0 = 0;
             decode_op(d.x, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 0));
@@ -190,6 +195,7 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uin
             decode_op(d.w, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 3));
         }
     }
+    __syncwarp();
     if (n_pieces <= 2u) {
         headR = __reduce_add_sync(0xffffffffu, headR);
         headQ = __reduce_add_sync(0xffffffffu, headQ);
@@ -276,8 +282,8 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const uin
 // start are flagged ROW_NEEDS_CARRY and finished by finalize_rows_kernel).  Rows go to staging slots
 // base, base+1, ...; `local0` is the index of the chunk's first row inside its unit.  `rows4` = the chunk in
 // shared memory (ring stage or spill buffer), 256 uint4.
-__device__ __forceinline__ void chunk_emit(const ScanArgs& a, const uint2* lut, const ChunkGeom g, uint64_t c4, uint32_t lane,
-                                           uint32_t evbits, const uint4* rows4, uint32_t here4, uint32_t carryR, uint32_t carryQ,
+__device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g, uint64_t c4, uint32_t lane,
+                                           uint32_t evbits, const uint4* rows4, uint32_t carryR, uint32_t carryQ,
                                            bool resolved, uint32_t unit, uint32_t local0, unsigned long long base) {
     const uint64_t c4end = min(c4 + CHUNK4, a.n4);
     const uint32_t a_lo = g.a_lo, a_hi = g.a_lo + g.n_heads;
@@ -311,9 +317,10 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const uint2* lut, 
             const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
             const uint32_t i4 = static_cast<uint32_t>(r) * 32u + lane;
             const bool in = ((in_mask >> (4 * r)) & 1u) != 0u;
-            const uint4 d = (in && i4 < here4) ? rows4[i4] : make_uint4(15u, 15u, 15u, 15u);
-            uint32_t rr = 0, qq = 0, h0 = 0, h1 = 0, rare0 = 0;
-            fast_row(d, lut, false, rr, qq, h0, h1, rare0, 1u);
+            const uint4 d = in ? rows4[i4] : make_uint4(15u, 15u, 15u, 15u);
+            bool rare0 = false;
+            const unsigned long long packed = fast_row(d, rare0);
+            const uint32_t rr = static_cast<uint32_t>(packed >> 31), qq = static_cast<uint32_t>(packed) & 0x7FFFFFFFu;
             const uint32_t rowbits = in ? ((evbits >> (4 * r)) & 0xFu) : 0u;
             uint32_t bal = __ballot_sync(0xffffffffu, rowbits != 0u);
             while (bal) {
@@ -386,7 +393,6 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
     // USE_TMA: [WARPS][STAGES][CHUNK4] ring.  LDG: [WARPS][CHUNK4] spill buffer, written only for chunks with events
     uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
     __shared__ __align__(8) unsigned long long s_mbar[WARPS][STAGES];
-    __shared__ uint2 s_lut[16];      // per op code: x = multiplier (bit 0 read advance, bit 31 reference advance), y = rare threshold
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid >= 32u && tid < 48u) {
@@ -408,9 +414,15 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
     const uint64_t w4 = static_cast<uint64_t>(unit) * (G * CHUNK4);      // this warp's first uint4
     uint4* my_buf = s_buf + static_cast<size_t>(warp) * (USE_TMA ? STAGES : 1) * CHUNK4;
 
+    // the CIGAR buffer is padded (op 15) to a whole number of 16-chunk units: a chunk that starts inside it is complete
     auto chunk_bytes = [&](int j) -> uint32_t {
-        const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
-        return c4 >= a.n4 ? 0u : static_cast<uint32_t>(min(static_cast<uint64_t>(CHUNK4), a.n4 - c4)) * 16u;
+        return w4 + static_cast<uint64_t>(j) * CHUNK4 >= a.n4 ? 0u : static_cast<uint32_t>(CHUNK4 * 16);
+    };
+    auto load_geom = [&](uint64_t chunk) -> ChunkGeom {                  // one 16-byte load
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.geom) + chunk);
+        ChunkGeom g;
+        g.a_lo = v.x; g.n_heads = v.y; g.split_rel = v.z; g.head_at_start = v.w;
+        return g;
     };
     if (USE_TMA && lane == 0) {
 #pragma unroll
@@ -423,34 +435,29 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
     uint32_t accR = 0, accQ = 0, accHead = 0, accCnt = 0;     // since the last head inside the unit / rows so far
     ChunkGeom g_next;
     g_next.a_lo = 0; g_next.n_heads = 0; g_next.split_rel = 0; g_next.head_at_start = 0;
-    if (w4 < a.n4) g_next = a.geom[w4 / CHUNK4];
+    if (w4 < a.n4) g_next = load_geom(w4 / CHUNK4);
 #pragma unroll 1
     for (int j = 0; j < G; ++j) {
         const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
         if (c4 >= a.n4) break;
         const ChunkGeom g = g_next;
-        if (j + 1 < G && c4 + CHUNK4 < a.n4) g_next = a.geom[c4 / CHUNK4 + 1];        // prefetch next chunk's geometry
-        const uint32_t here = chunk_bytes(j) / 16u;
+        if (j + 1 < G && c4 + CHUNK4 < a.n4) g_next = load_geom(c4 / CHUNK4 + 1);      // prefetch next chunk's geometry
         ChunkResult res;
         const uint4* rows4;
         if (USE_TMA) {
             mbar_wait(&s_mbar[warp][j % STAGES], static_cast<uint32_t>(j / STAGES) & 1u);
             const uint4* buf = my_buf + (j % STAGES) * CHUNK4;
-            auto from_ring = [&](int r) -> uint4 {
-                const uint32_t i4 = static_cast<uint32_t>(r) * 32u + lane;
-                return i4 < here ? buf[i4] : make_uint4(15u, 15u, 15u, 15u);
-            };
-            res = chunk_phase1(a, s_lut, g, c4, lane, from_ring, from_ring);
+            auto from_ring = [&](int r) -> uint4 { return buf[static_cast<uint32_t>(r) * 32u + lane]; };
+            res = chunk_phase1(a, g, c4, lane, from_ring, from_ring);
             rows4 = buf;
         } else {
             uint4 v[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
-                const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
-                v[r] = g4 < a.n4 ? ldg_stream(a.cigar + g4) : make_uint4(15u, 15u, 15u, 15u);
+                v[r] = ldg_stream(a.cigar + c4 + static_cast<uint64_t>(r) * 32u + lane);
             }
-            res = chunk_phase1(a, s_lut, g, c4, lane, [&](int r) -> uint4 { return v[r]; },
-                               [&](int r) -> uint4 { return reload_row(a.cigar, a.n4, c4, r, lane); });
+            res = chunk_phase1(a, g, c4, lane, [&](int r) -> uint4 { return v[r]; },
+                               [&](int r) -> uint4 { return reload_row(a.cigar, c4, r, lane); });
             if (res.cnt) {                                 // rare: park the chunk in shared memory for the row writer
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) my_buf[r * 32 + lane] = v[r];
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(a.total, static_cast<unsigned long long>(res.cnt));
             base = __shfl_sync(0xffffffffu, base, 0);
-            chunk_emit(a, s_lut, g, c4, lane, res.evbits, rows4, here, accR, accQ, accHead != 0u, unit, accCnt, base);
+            chunk_emit(a, g, c4, lane, res.evbits, rows4, accR, accQ, accHead != 0u, unit, accCnt, base);
         }
         if (res.head) { accR = res.tailR; accQ = res.tailQ; accHead = 1u; }
         else { accR += res.tailR; accQ += res.tailQ; }
@@ -484,63 +491,130 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
     if (lane == 0) a.unit_agg[unit] = make_uint4(accR, accQ, accHead, accCnt);
 }
 
-// ---- finalize 1: segmented exclusive scan of the unit aggregates (one CTA) ---------------------------------
+// ---- finalize 1: segmented exclusive scan of the unit aggregates (chained scan over CTAs) ------------------
 // carry[u] = advance sums since the last alignment head before unit u (x: ref, y: read); base[u] = rows before u.
+// One unit per thread: warp-level segmented scan by shuffles, the 32 warp totals scanned by warp 0, and the CTA's
+// exclusive prefix obtained by looking back over the aggregates of ALL earlier CTAs (n_units / 1024 of them: 25 for
+// a whole genome), which are published with one 16-byte store each {R, Q, rows, READY | head}.
 struct UnitPrefix {
     uint32_t R, Q;
     unsigned long long base;
 };
 
-__global__ void __launch_bounds__(1024) unit_scan_kernel(const uint4* __restrict__ agg, uint32_t n_units, UnitPrefix* __restrict__ prefix) {
-    __shared__ uint32_t s_R[1024], s_Q[1024], s_H[1024];
-    __shared__ unsigned long long s_C[1024];
-    const uint32_t t = threadIdx.x;
-    const uint32_t per = (n_units + 1023u) / 1024u;
-    const uint32_t lo = min(t * per, n_units), hi = min(lo + per, n_units);
-    uint32_t R = 0, Q = 0, H = 0;
-    unsigned long long C = 0;
-    for (uint32_t u = lo; u < hi; ++u) {               // aggregate of this thread's block of units
-        const uint4 x = agg[u];
-        if (x.z) { R = x.x; Q = x.y; H = 1u; } else { R += x.x; Q += x.y; }
-        C += x.w;
+struct SegSum {              // monoid of the segmented scan: x then y
+    uint32_t R, Q, H, C;
+};
+__device__ __forceinline__ SegSum seg_combine(const SegSum x, const SegSum y) {
+    SegSum o;
+    o.R = y.H ? y.R : x.R + y.R;
+    o.Q = y.H ? y.Q : x.Q + y.Q;
+    o.H = x.H | y.H;
+    o.C = x.C + y.C;
+    return o;
+}
+__device__ __forceinline__ SegSum seg_shfl_up(const SegSum v, uint32_t d) {
+    SegSum o;
+    o.R = __shfl_up_sync(0xffffffffu, v.R, d);
+    o.Q = __shfl_up_sync(0xffffffffu, v.Q, d);
+    o.H = __shfl_up_sync(0xffffffffu, v.H, d);
+    o.C = __shfl_up_sync(0xffffffffu, v.C, d);
+    return o;
+}
+__device__ __forceinline__ SegSum seg_warp_inclusive(SegSum v, uint32_t lane) {
+#pragma unroll
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+        const SegSum up = seg_shfl_up(v, d);
+        if (lane >= d) v = seg_combine(up, v);
     }
-    s_R[t] = R; s_Q[t] = Q; s_H[t] = H; s_C[t] = C;
+    return v;
+}
+
+constexpr uint32_t US_THREADS = 1024;
+
+// cta_agg[b] = {R, Q, rows (32 bit: a CTA covers at most 1024 units), head seen}; cta_ready[b] is raised after a
+// __threadfence() (the PTX memory model gives no single-copy atomicity to 16-byte vectors, so the flag is a word of its
+// own).  ticket: dynamic CTA index, so that a CTA only ever waits for CTAs that already run.  The block size is a
+// launch parameter (tests run the look-back with 32-thread CTAs on small inputs).
+__global__ void __launch_bounds__(US_THREADS) unit_scan_kernel(const uint4* __restrict__ agg, uint32_t n_units,
+                                                               UnitPrefix* __restrict__ prefix, uint4* cta_agg,
+                                                               unsigned int* cta_ready, unsigned int* ticket) {
+    __shared__ SegSum s_warp[32];
+    __shared__ uint32_t s_cta;
+    __shared__ uint32_t s_preR, s_preQ, s_preH;
+    __shared__ unsigned long long s_preC;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5, n_warps = blockDim.x >> 5;
+    if (t == 0) s_cta = atomicAdd(ticket, 1u);
     __syncthreads();
-    if (t < 32u) {                                      // exclusive segmented scan over the 1024 block aggregates
-        uint32_t bR = 0, bQ = 0, bH = 0;
-        unsigned long long bC = 0;
-        for (uint32_t k = t * 32u; k < t * 32u + 32u; ++k) {       // lane aggregate over its 32 entries
-            if (s_H[k]) { bR = s_R[k]; bQ = s_Q[k]; bH = 1u; } else { bR += s_R[k]; bQ += s_Q[k]; }
-            bC += s_C[k];
+    const uint32_t cta = s_cta;
+    const uint32_t u = cta * blockDim.x + t;
+    SegSum mine;
+    mine.R = mine.Q = mine.H = mine.C = 0u;
+    if (u < n_units) {
+        const uint4 x = __ldcg(agg + u);
+        mine.R = x.x; mine.Q = x.y; mine.H = x.z ? 1u : 0u; mine.C = x.w;
+    }
+    const SegSum incl = seg_warp_inclusive(mine, lane);
+    if (lane == 31u) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        SegSum wt;
+        wt.R = wt.Q = wt.H = wt.C = 0u;
+        if (lane < n_warps) wt = s_warp[lane];
+        const SegSum winc = seg_warp_inclusive(wt, lane);
+        if (lane == 31u) {                                  // publish the CTA aggregate before looking back
+            uint4 st;
+            st.x = winc.R; st.y = winc.Q; st.z = winc.C; st.w = winc.H;
+            __stcg(cta_agg + cta, st);
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int*>(cta_ready + cta) = 1u;
         }
-        // exclusive scan across the 32 lanes (serial in lane order through shuffles: 32 steps, trivial)
-        uint32_t eR = 0, eQ = 0;
-        unsigned long long eC = 0;
-        for (uint32_t l = 0; l < 32u; ++l) {
-            const uint32_t lR = __shfl_sync(0xffffffffu, bR, l), lQ = __shfl_sync(0xffffffffu, bQ, l), lH = __shfl_sync(0xffffffffu, bH, l);
-            const unsigned long long lC = __shfl_sync(0xffffffffu, bC, l);
-            if (l < t) {
-                if (lH) { eR = lR; eQ = lQ; } else { eR += lR; eQ += lQ; }
-                eC += lC;
+        SegSum wex = seg_shfl_up(winc, 1);                  // exclusive prefix of each warp inside the CTA
+        if (lane == 0u) wex.R = wex.Q = wex.H = wex.C = 0u;
+        s_warp[lane] = wex;
+        // look back: lanes take the predecessors cta-1-lane, cta-33-lane, ...; nearest first
+        uint32_t R = 0, Q = 0, H = 0;                       // fold of the CTAs seen so far (they FOLLOW the ones still to come)
+        unsigned long long C = 0;
+        for (int first = static_cast<int>(cta) - 1; first >= 0; first -= 32) {
+            const int p = first - static_cast<int>(lane);
+            SegSum v;
+            v.R = v.Q = v.H = v.C = 0u;
+            if (p >= 0) {
+                while (*reinterpret_cast<volatile unsigned int*>(cta_ready + p) == 0u) {
+                }
+                __threadfence();
+                const uint4 st = __ldcg(cta_agg + p);
+                v.R = st.x; v.Q = st.y; v.C = st.z; v.H = st.w;
             }
+            // lane 0 holds the NEAREST predecessor: combine in order far -> near, i.e. reversed lanes
+            SegSum rv;
+            rv.R = __shfl_sync(0xffffffffu, v.R, 31u - lane);
+            rv.Q = __shfl_sync(0xffffffffu, v.Q, 31u - lane);
+            rv.H = __shfl_sync(0xffffffffu, v.H, 31u - lane);
+            rv.C = __shfl_sync(0xffffffffu, v.C, 31u - lane);
+            const SegSum winsum = seg_warp_inclusive(rv, lane);     // lane 31: fold of this window in CTA order
+            const uint32_t wR = __shfl_sync(0xffffffffu, winsum.R, 31), wQ = __shfl_sync(0xffffffffu, winsum.Q, 31);
+            const uint32_t wH = __shfl_sync(0xffffffffu, winsum.H, 31);
+            const unsigned long long wC = __reduce_add_sync(0xffffffffu, v.C);
+            if (!H) { R += wR; Q += wQ; }                   // window precedes what was folded so far
+            H |= wH;
+            C += wC;
+            // (rows need every predecessor; the carries stop mattering once a head was seen)
         }
-        for (uint32_t k = t * 32u; k < t * 32u + 32u; ++k) {       // turn the entries into exclusive prefixes
-            const uint32_t r = s_R[k], q = s_Q[k], h = s_H[k];
-            const unsigned long long c = s_C[k];
-            s_R[k] = eR; s_Q[k] = eQ; s_C[k] = eC;
-            if (h) { eR = r; eQ = q; } else { eR += r; eQ += q; }
-            eC += c;
-        }
+        if (lane == 0u) { s_preR = R; s_preQ = Q; s_preH = H; s_preC = C; }
     }
     __syncthreads();
-    R = s_R[t]; Q = s_Q[t]; C = s_C[t];
-    for (uint32_t u = lo; u < hi; ++u) {
-        UnitPrefix p;
-        p.R = R; p.Q = Q; p.base = C;
-        prefix[u] = p;
-        const uint4 x = agg[u];
-        if (x.z) { R = x.x; Q = x.y; } else { R += x.x; Q += x.y; }
-        C += x.w;
+    SegSum ex = seg_shfl_up(incl, 1);                       // the lanes before this one
+    if (lane == 0u) ex.R = ex.Q = ex.H = ex.C = 0u;
+    if (u < n_units) {
+        // exclusive prefix of this unit: CTA prefix, then warp prefix, then the lanes before it
+        SegSum pre;
+        pre.R = s_preR; pre.Q = s_preQ; pre.H = s_preH; pre.C = 0u;
+        const SegSum wex = s_warp[warp];
+        const SegSum tot = seg_combine(seg_combine(pre, wex), ex);
+        UnitPrefix o;
+        o.R = tot.R; o.Q = tot.Q;
+        o.base = s_preC + wex.C + ex.C;
+        prefix[u] = o;
     }
 }
 
@@ -600,9 +674,25 @@ __global__ void chunk_index_kernel(const uint32_t* __restrict__ off4, uint32_t n
     geom[c] = g;
 }
 
+__global__ void pad_fill_kernel(uint4* cigar, uint64_t from4, uint64_t to4) {
+    const uint64_t i = from4 + static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < to4) cigar[i] = make_uint4(15u, 15u, 15u, 15u);
+}
+
 }  // namespace
 
+uint64_t cigar_padded_n4(uint64_t n4) {
+    const uint64_t unit4 = 16ull * CHUNK4;          // the longest unit a launch may pick (G = 16 chunks of 4 KB)
+    return (n4 + unit4 - 1) / unit4 * unit4;
+}
+
 int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec) {
+    // pad the tail of the buffer (allocated with cigar_padded_n4) so that no load of the scan needs a bounds check
+    const uint64_t pad_to = cigar_padded_n4(rec->n4);
+    if (pad_to > rec->n4) {
+        pad_fill_kernel<<<static_cast<unsigned>((pad_to - rec->n4 + 255) / 256), 256, 0, ctx->stream>>>(rec->d_cigar, rec->n4, pad_to);
+        ctx->launches += 1;
+    }
     const uint64_t n_chunks = (rec->n4 + CHUNK4 - 1) / CHUNK4;
     if (n_chunks == 0) return SVB_OK;
     SVB_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&rec->d_chunk_first), n_chunks * sizeof(ChunkGeom), ctx->stream));
@@ -620,34 +710,50 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_r
     const uint64_t n_units64 = (rec->n4 + unit4 - 1) / unit4;
     if (n_units64 > 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "too many CIGAR ops for one launch");
     const uint32_t n_units = static_cast<uint32_t>(n_units64);
-    // scratch: unit aggregates, unit prefixes, staging rows
+    // scratch: unit aggregates, unit prefixes, CTA status words of the unit scan (+ its ticket), staging rows
     const size_t agg_bytes = (sizeof(uint4) * n_units + 255) & ~static_cast<size_t>(255);
     const size_t pre_bytes = (sizeof(UnitPrefix) * n_units + 255) & ~static_cast<size_t>(255);
-    unsigned char* scratch = static_cast<unsigned char*>(svb_scratch(ctx, agg_bytes + pre_bytes + sizeof(svb_row) * a.cap));
+    uint32_t us_threads = US_THREADS;
+    if (const char* env = getenv("SVB_UNIT_SCAN_THREADS")) {            // test hook: small CTAs exercise the look-back
+        const int v = atoi(env);
+        if (v >= 32 && v <= static_cast<int>(US_THREADS) && v % 32 == 0) us_threads = static_cast<uint32_t>(v);
+    }
+    const uint32_t us_ctas = (n_units + us_threads - 1) / us_threads;
+    const size_t st_bytes = ((sizeof(uint4) + sizeof(unsigned int)) * (us_ctas + 1) + 255) & ~static_cast<size_t>(255);
+    unsigned char* scratch = static_cast<unsigned char*>(svb_scratch(ctx, agg_bytes + pre_bytes + st_bytes + sizeof(svb_row) * a.cap));
     if (!scratch) return svb_fail(ctx, SVB_ERR_NOMEM, "cigar_scan scratch");
     a.n_units = n_units;
     a.unit_agg = reinterpret_cast<uint4*>(scratch);
     UnitPrefix* prefix = reinterpret_cast<UnitPrefix*>(scratch + agg_bytes);
-    a.rows = reinterpret_cast<svb_row*>(scratch + agg_bytes + pre_bytes);
+    uint4* cta_status = reinterpret_cast<uint4*>(scratch + agg_bytes + pre_bytes);
+    unsigned int* cta_ready = reinterpret_cast<unsigned int*>(cta_status + us_ctas);
+    unsigned int* ticket = cta_ready + us_ctas;
+    a.rows = reinterpret_cast<svb_row*>(scratch + agg_bytes + pre_bytes + st_bytes);
+    SVB_CUDA(ctx, cudaMemsetAsync(cta_status, 0, st_bytes, ctx->stream));
     const unsigned blocks = (n_units + WARPS - 1) / WARPS;
-    KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);
-    if (ctx->scan_variant == 0) {
-        const size_t smem = static_cast<size_t>(WARPS) * STAGES * CHUNK4 * sizeof(uint4);
-        static bool attr_set = false;
-        if (!attr_set) {
-            SVB_CUDA(ctx, cudaFuncSetAttribute(cigar_scan_kernel<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(smem)));
-            attr_set = true;
+    {
+        KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);           // the streaming kernel alone (the roofline's launch duration)
+        if (ctx->scan_variant == 0) {
+            const size_t smem = static_cast<size_t>(WARPS) * STAGES * CHUNK4 * sizeof(uint4);
+            static bool attr_set = false;
+            if (!attr_set) {
+                SVB_CUDA(ctx, cudaFuncSetAttribute(cigar_scan_kernel<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(smem)));
+                attr_set = true;
+            }
+            cigar_scan_kernel<true, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
+        } else {
+            const size_t smem = static_cast<size_t>(WARPS) * CHUNK4 * sizeof(uint4);
+            cigar_scan_kernel<false, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
         }
-        cigar_scan_kernel<true, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
-    } else {
-        const size_t smem = static_cast<size_t>(WARPS) * CHUNK4 * sizeof(uint4);
-        cigar_scan_kernel<false, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
     }
-    unit_scan_kernel<<<1, 1024, 0, ctx->stream>>>(a.unit_agg, n_units, prefix);
-    const unsigned long long fin_blocks = (a.cap + 255) / 256;
-    finalize_rows_kernel<<<static_cast<unsigned>(std::min<unsigned long long>(fin_blocks, 0x7fffffffull)), 256, 0, ctx->stream>>>(
-        a.rows, a.total, a.cap, prefix, rec->d_hdr, rec->d_contig_len, rec->n_contig, final_rows);
+    {
+        KernelTimer timer(ctx, SVB_K_SCAN_FINALIZE);        // unit scan + per-row finalize
+        unit_scan_kernel<<<us_ctas, us_threads, 0, ctx->stream>>>(a.unit_agg, n_units, prefix, cta_status, cta_ready, ticket);
+        const unsigned long long fin_blocks = (a.cap + 255) / 256;
+        finalize_rows_kernel<<<static_cast<unsigned>(std::min<unsigned long long>(fin_blocks, 0x7fffffffull)), 256, 0, ctx->stream>>>(
+            a.rows, a.total, a.cap, prefix, rec->d_hdr, rec->d_contig_len, rec->n_contig, final_rows);
+    }
     ctx->launches += 3;
     SVB_CUDA(ctx, cudaGetLastError());
     return SVB_OK;

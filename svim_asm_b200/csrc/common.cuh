@@ -19,7 +19,7 @@ struct svb_records {
     uint64_t n4 = 0;                  // number of uint4 in cigar
     uint64_t n_ops = 0;               // sum of n_cigar (real ops)
     svb_aln_hdr* d_hdr = nullptr;     // [n_aln]
-    uint4* d_cigar = nullptr;         // [n4]
+    uint4* d_cigar = nullptr;         // [cigar_padded_n4(n4)]: the tail is filled with op 15 at load
     uint32_t* d_off4 = nullptr;       // [n_aln + 1]
     uint32_t* d_chunk_first = nullptr;// [ceil(n4 / 256)] alignment that owns the first uint4 of each 1024-op chunk
     svb_segment* d_seg = nullptr;     // [n_seg]
@@ -112,6 +112,7 @@ struct ScanOutput {
     uint64_t cap;
     unsigned long long* d_count;   // total number of emitted rows (may exceed cap)
 };
+uint64_t cigar_padded_n4(uint64_t n4);   // uint4 capacity d_cigar must be allocated with (whole 64 KB units)
 int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec);
 int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out);
 int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_row** d_rows_out,

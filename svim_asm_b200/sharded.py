@@ -300,13 +300,16 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         dist.barrier()
         torch.cuda.synchronize()
         eng.synchronize()
-        t0 = time.perf_counter()
+        # timed on the device: every kernel, copy and collective of the step is enqueued on the library's stream, so two
+        # events on that stream bracket the whole loop (host gaps between the enqueues included); max over ranks
+        eng.mark(2)
         for _ in range(steps):
             table = sharded_step_device(stage_factory(), rank, world, owner, ranks, device, _lib.ROW_DTYPE)
+        eng.mark(3)
         eng.synchronize()
         torch.cuda.synchronize()
         dist.barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        dt = torch.tensor([eng.elapsed_ms(2, 3) * 1e-3], dtype=torch.float64, device=device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         return float(dt.item()) / steps, table
 

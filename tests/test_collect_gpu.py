@@ -103,3 +103,17 @@ def test_chr20_scale_with_giant_alignment(engine):
     rb = synth.make_haploid(cfg)
     want = _compare(engine, rb)
     assert int(rb.n_cigar.max()) > 150_000 and want.shape[0] > 100
+
+
+@pytest.mark.parametrize("threads", [32, 64])
+def test_unit_scan_lookback_with_small_ctas(engine, threads, monkeypatch):
+    # the carry / row-base scan over the unit aggregates is a chained scan over CTAs (1024 units each at full size); with
+    # 32-thread CTAs a 3M-op batch already runs 45 CTAs, i.e. two look-back windows, with alignments that span many units
+    monkeypatch.setenv("SVB_UNIT_SCAN_THREADS", str(threads))
+    cfg = synth.config_c2()
+    cfg.target_ops = 3.0e6
+    cfg.n_aln = 300
+    cfg.giant_ops = 400_000
+    rb = synth.make_haploid(cfg)
+    want = _compare(engine, rb)
+    assert want.shape[0] > 100

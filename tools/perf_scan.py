@@ -42,4 +42,5 @@ for variant in (0, 1):
     alg = 4.0 * host.cigar.shape[0] + 32.0 * host.n_aln + 64.0 * n_rows
     print(json.dumps({"variant": "tma" if variant == 0 else "ldg", "rows": n_rows, "scan_ms": per,
                       "scan_GBps": alg / per / 1e6, "ops_per_s": host.n_ops / per * 1e3, "collect_wall_ms": wall,
+                      "finalize_ms": tm["cigar_scan_finalize"][0] / max(tm["cigar_scan_finalize"][1], 1),
                       "walk_ms": tm["segment_walk"][0] / args.iters, "merge_ms": tm["merge"][0] / args.iters}), flush=True)
