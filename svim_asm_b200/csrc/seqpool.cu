@@ -55,10 +55,8 @@ int table_drop_pool(svb_table* t) {
 
 extern "C" {
 
-int svb_table_gather_sequences(svb_ctx* ctx, svb_table* t, const svb_records* rec) {
-    if (!ctx || !t || !rec) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_gather_sequences") : SVB_ERR_ARG;
-    if (!rec->d_seq_off) return svb_fail(ctx, SVB_ERR_ARG, "svb_table_gather_sequences: call svb_records_set_sequences first");
-    cudaSetDevice(ctx->device);
+// sizes -> exclusive scan -> one warp per row copies its nibbles; seq4 / seq_off may live in HBM or in pinned host memory
+static int gather_pool(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off) {
     table_drop_pool(t);
     const uint32_t n = static_cast<uint32_t>(t->n);
     uint32_t* off32 = nullptr;
@@ -75,7 +73,7 @@ int svb_table_gather_sequences(svb_ctx* ctx, svb_table* t, const svb_records* re
     t->pool_bytes = ctx->h_pinned[10];
     SVB_CUDA(ctx, cudaMallocAsync(&t->d_pool, std::max<uint64_t>(t->pool_bytes, 1), ctx->stream));
     const uint64_t threads = (static_cast<uint64_t>(n) + 1) * 32;
-    pool_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(t->d_rows, n, off32, rec->d_seq4, rec->d_seq_off,
+    pool_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(t->d_rows, n, off32, seq4, seq_off,
                                                                                               t->d_pool, t->d_pool_off);
     ctx->launches += 1;
     SVB_CUDA(ctx, cudaGetLastError());
@@ -83,9 +81,34 @@ int svb_table_gather_sequences(svb_ctx* ctx, svb_table* t, const svb_records* re
     return SVB_OK;
 }
 
+// device address of a host pointer the GPU can read in place (pinned / registered memory), else nullptr
+static const void* device_view_of_host(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if ((attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged) && attr.devicePointer) return attr.devicePointer;
+    return nullptr;
+}
+
+int svb_table_gather_sequences(svb_ctx* ctx, svb_table* t, const svb_records* rec) {
+    if (!ctx || !t || !rec) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_gather_sequences") : SVB_ERR_ARG;
+    if (!rec->d_seq_off) return svb_fail(ctx, SVB_ERR_ARG, "svb_table_gather_sequences: call svb_records_set_sequences first");
+    cudaSetDevice(ctx->device);
+    return gather_pool(ctx, t, rec->d_seq4, rec->d_seq_off);
+}
+
 int svb_table_attach_sequences_host(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off) {
     if (!ctx || !t || !seq_off) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_table_attach_sequences_host") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
+    // pinned host buffers: the gather kernel reads the inserted bases in place over PCIe (a few MB of the 0.65 GB), no
+    // host pass and no staging copy.  Pageable buffers take the host gather below.
+    if (seq4) {
+        const uint8_t* dv_seq = static_cast<const uint8_t*>(device_view_of_host(seq4));
+        const uint64_t* dv_off = static_cast<const uint64_t*>(device_view_of_host(seq_off));
+        if (dv_seq && dv_off) return gather_pool(ctx, t, dv_seq, dv_off);
+    }
     table_drop_pool(t);
     const uint64_t n = t->n;
     std::vector<svb_row> rows(n);

@@ -105,3 +105,26 @@ def test_diploid_pairing_tight_partitions(engine, oracle_clib):
     cfg = synth.SynthConfig(["chrA"], [120000], 12, 1.5e4, 77, sv_per_event=6e-2, split_fraction=0.3, sv_max=300)
     got, want = _pair_both(engine, cfg, partition_max_distance=3000, max_edit_distance=150)
     assert util.rows_equal(got, want) is None, util.rows_equal(got, want)
+
+
+def test_sequence_pool_sources_agree(engine):
+    """The inserted bases of the INS rows reach the table three ways: gathered on the device from resident query sequences,
+    gathered on the host from pageable buffers, and read in place from pinned host buffers by the gather kernel.  Same
+    bytes each time (they are candidate.sequence of SVIM_intra.py:42 / SVIM_COMBINE.py:70-75)."""
+    from svim_asm_b200.bench_util import pinned_host
+    cfg = synth.SynthConfig(["chr1", "chr2"], [400000, 300000], 80, 5e4, 77, sv_per_event=8e-3, split_fraction=0.3, sv_max=3000)
+    rb = synth.make_haploid(cfg)
+    host = HostBatch.from_record_batch(rb)
+    rec = engine.load_records(host, with_sequences=True)
+    params = make_params()
+    t = engine.collect(rec, params, hap=1)
+    t.gather_sequences(rec)
+    pool_dev, off_dev = t.pool_to_numpy()
+    t.attach_sequences_host(host)                        # numpy arrays: pageable
+    pool_host, off_host = t.pool_to_numpy()
+    pinned = pinned_host(HostBatch.from_record_batch(rb))
+    t.attach_sequences_host(pinned)                      # pinned: zero-copy gather
+    pool_pin, off_pin = t.pool_to_numpy()
+    assert pool_dev.shape[0] > 1000
+    assert np.array_equal(off_dev, off_host) and np.array_equal(off_dev, off_pin)
+    assert pool_dev.tobytes() == pool_host.tobytes() == pool_pin.tobytes()
