@@ -39,6 +39,52 @@ SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_
     return static_cast<int>(out & 1u) - static_cast<int>(out >> 1);
 }
 
+// ---- sliding window over the Ukkonen band -----------------------------------------------------------
+// A global alignment of cost d never leaves the diagonals [-d, (n - m) + d] (n >= m), so with half-width K
+// only the 64-row blocks b = 0 .. (m-1)/64 on the text columns [win_jlo(b), win_jhi(b)) matter, and the
+// result is exact whenever it is <= K.  One warp holds 32 consecutive blocks of that band at a time: lane
+// b % 32 works on block b, and once block b has run out of columns the lane moves on to block b + 32.
+// That needs block b + 32 to start after block b ends, start(b) = win_jlo(b) + b (lanes are skewed by one
+// column per block): 64 * 32 + 32 - K >= 64 + (n - m) + K.  A block that enters the band starts from
+// "everything above and to the left is one more per row" (vertical deltas +1, horizontal input +1), which
+// can only overestimate cells whose optimal path leaves the band.  With S_b = sum of the block's bottom-row
+// horizontal deltas over the columns [win_jlo(b), win_jlo(b + 1)) (last block: up to n),
+//     D[m][n] = m + sum_b S_b.
+struct WinGeom {
+    uint32_t m, n, K, last_block;
+};
+constexpr uint32_t WIN_SLACK = 8;     // idle steps guaranteed between two blocks of one lane (prefetch priming)
+
+SVB_HD uint32_t win_kmax(uint32_t m, uint32_t n) {          // widest half-width one warp can slide over (0: none)
+    const uint32_t dlt = n - m, room = 64u * 32u + 32u - 64u - WIN_SLACK;
+    return dlt >= room ? 0u : (room - dlt) / 2u;
+}
+SVB_HD uint32_t win_jlo(const WinGeom& g, uint32_t b) {
+    const uint64_t x = 64ull * b;
+    return x > g.K ? static_cast<uint32_t>(x - g.K) : 0u;
+}
+SVB_HD uint32_t win_jhi(const WinGeom& g, uint32_t b) {
+    const uint64_t x = 64ull * b + 64ull + (g.n - g.m) + g.K;
+    return x < g.n ? static_cast<uint32_t>(x) : g.n;
+}
+// per-block step limits, all relative to the block's first column (rel = column - win_jlo(b)):
+//   rel < width: the block is inside the band;  rel < hin_lim: the block above is too (else +1 enters);
+//   rel < cnt_lim: the bottom-row delta counts towards D[m][n]
+struct WinBlock {
+    uint32_t start;        // global step of its first column: win_jlo(b) + b
+    uint32_t width, hin_lim, cnt_lim, hshift;
+};
+SVB_HD WinBlock win_block(const WinGeom& g, uint32_t b) {
+    WinBlock w;
+    const uint32_t lo = win_jlo(g, b), hi = win_jhi(g, b);
+    w.start = lo + b;
+    w.width = hi - lo;
+    w.hin_lim = b == 0u ? 0u : win_jhi(g, b - 1u) - lo;
+    w.cnt_lim = b == g.last_block ? w.width : win_jlo(g, b + 1u) - lo;
+    w.hshift = b == g.last_block ? ((g.m - 1u) & 63u) : 63u;
+    return w;
+}
+
 // ---- virtual haplotype strings --------------------------------------------------------------------
 // compute_distance builds  ref[lo:s] + MIDDLE + ref[e:hi]  for both candidates; MIDDLE depends on the
 // type.  Nothing is materialised: a descriptor addresses the bases in HBM.

@@ -23,14 +23,17 @@
 
 namespace {
 
-constexpr int ED_WARPS = 4;
+constexpr int ED_WARPS = 2;
 constexpr uint32_t ED_NOCLASS = ED_NCLASS;      // extra all-zero row of the match-mask table: "matches nothing"
 constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t PEQ_ROWS = ED_NCLASS + 1;
 
 struct EdShared {
-    unsigned long long peq[ED_WARPS][ED_NCLASS + 1][32];   // [class][lane]: match mask of the lane's 64 rows
+    // [buffer][class][lane]: match mask of the lane's 64 rows.  The striped path uses buffer 0; the sliding window
+    // alternates (a lane's next block is built while it still works on the current one).
+    unsigned long long peq[ED_WARPS][2][PEQ_ROWS][32];
     uint8_t cls2[512];                                     // byte -> class, complemented byte -> class
-    uint8_t tcls[ED_WARPS][64];                            // ring: symbol class of the band's columns
+    uint8_t tcls[ED_WARPS][128];                           // ring: symbol class of the band's columns
     uint8_t th[ED_WARPS][64];                              // ring: delta code entering the stripe's top row
 };
 
@@ -79,6 +82,150 @@ __device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& 
     return min(run, lim);
 }
 
+// ---- sliding window (edit_core.cuh): ONE pass of n + (m-1)/64 steps over a band of half-width K ------------------
+// Lane l works on the blocks l, l + 32, l + 64, ... one after the other; at global step t the lane that holds block b
+// is on text column t - b.  Returns the window's value, which is D[m][n] whenever it is <= K.
+// Every 32 steps ("grid point") the warp (a) moves up to 32 further text columns from registers into the 128-slot
+// class ring and requests the next 32, (b) builds the match masks of the next block that will enter the band into
+// the idle mask buffer of its lane; the pattern bytes for that were requested one grid point earlier.
+__device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc& T, uint32_t pre, uint32_t m, uint32_t n,
+                                                 uint32_t K, const uint8_t* ref, const uint8_t* sa, const uint8_t* sb,
+                                                 const uint8_t* cls2tab, unsigned long long* peqw, uint8_t* tcls, uint32_t lane) {
+    WinGeom g;
+    g.m = m; g.n = n; g.K = K; g.last_block = (m - 1u) / 64u;
+    uint32_t* peq32 = reinterpret_cast<uint32_t*>(peqw);             // [buffer][class][lane][half]
+
+    // ---- masks of the blocks 0 .. 31 (buffer 0), 32 rows per round like the striped path
+    __syncwarp();
+    for (uint32_t i = lane; i < 2u * PEQ_ROWS * 64u; i += 32u) peq32[i] = 0u;
+    for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
+    __syncwarp();
+    const uint32_t rows0 = min(m, 2048u), ngroups = (rows0 + 31u) / 32u;
+    for (uint32_t g0 = 0; g0 < ngroups; g0 += 4u) {
+        uint32_t byte[4], mode[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = (g0 + k) * 32u + lane;
+            mode[k] = TOK_NONE;
+            byte[k] = 0u;
+            if (idx < rows0) byte[k] = hap_fetch(P, pre + idx, ref, sa, sb, mode[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t cls = mode[k] == TOK_NONE ? ED_NOCLASS + 1u : tok_class(cls2tab, byte[k], mode[k]);
+            const uint32_t peers = __match_any_sync(FULL, cls);
+            if (cls < ED_NOCLASS && static_cast<uint32_t>(__ffs(peers) - 1) == lane) peq32[cls * 64u + (g0 + k)] = peers;
+        }
+    }
+    // ---- later blocks: bytes requested ahead (pat_*), masks built at a grid point
+    uint32_t next_build = 32u;                                       // next block whose masks are to be built
+    uint32_t pat_byte[2] = {0u, 0u}, pat_mode[2] = {TOK_NONE, TOK_NONE};
+    auto pattern_fetch = [&]() {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t idx = 64ull * next_build + 32u * k + lane;
+            pat_mode[k] = TOK_NONE;
+            pat_byte[k] = 0u;
+            if (next_build <= g.last_block && idx < m) pat_byte[k] = hap_fetch(P, pre + static_cast<uint32_t>(idx), ref, sa, sb, pat_mode[k]);
+        }
+    };
+    auto pattern_build = [&]() {                                     // block next_build -> buffer (b / 32) & 1, column b % 32
+        const uint32_t buf = (next_build >> 5) & 1u, col = next_build & 31u;
+        for (uint32_t i = lane; i < PEQ_ROWS * 2u; i += 32u) peq32[((buf * PEQ_ROWS + (i >> 1)) * 32u + col) * 2u + (i & 1u)] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t cls = pat_mode[k] == TOK_NONE ? ED_NOCLASS + 1u : tok_class(cls2tab, pat_byte[k], pat_mode[k]);
+            const uint32_t peers = __match_any_sync(FULL, cls);
+            if (cls < ED_NOCLASS && static_cast<uint32_t>(__ffs(peers) - 1) == lane)
+                peq32[((buf * PEQ_ROWS + cls) * 32u + col) * 2u + static_cast<uint32_t>(k)] = peers;
+        }
+        __syncwarp();
+    };
+    pattern_fetch();
+
+    // ---- column ring: columns [0, c_ins) are in; the batch [c_ins, c_ins + 32) waits in registers
+    uint32_t c_ins = 0, nxt_byte = 0, nxt_mode = TOK_NONE;
+    auto ring_fetch = [&]() {
+        const uint32_t col = c_ins + lane;
+        nxt_mode = TOK_NONE;
+        nxt_byte = 0u;
+        if (col < n) nxt_byte = hap_fetch(T, pre + col, ref, sa, sb, nxt_mode);
+    };
+    auto ring_insert = [&]() {
+        tcls[(c_ins + lane) & 127u] = static_cast<uint8_t>(nxt_mode == TOK_NONE ? ED_NOCLASS : tok_class(cls2tab, nxt_byte, nxt_mode));
+        c_ins += 32u;
+    };
+    for (int k = 0; k < 3; ++k) {
+        ring_fetch();
+        ring_insert();
+    }
+    ring_fetch();
+    __syncwarp();
+
+    // ---- per-lane block state
+    uint32_t blk = lane, buf = 0;
+    WinBlock w;
+    w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
+    if (blk <= g.last_block) w = win_block(g, blk);
+    int colbase = -static_cast<int>(blk);                            // text column of step t: t + colbase
+    uint64_t pv = ~0ull, mv = 0ull;
+    int partial = 0;
+    uint32_t hout = 0;
+    auto ring_class = [&](int col) -> uint32_t { return (col >= 0 && static_cast<uint32_t>(col) < n) ? tcls[static_cast<uint32_t>(col) & 127u] : ED_NOCLASS; };
+    uint64_t eq0 = peqw[(0u * PEQ_ROWS + ring_class(colbase)) * 32u + lane];
+    uint32_t cls1 = ring_class(colbase + 1);
+    uint32_t b_lo = 0;                                               // smallest block that still has columns to do
+    const uint32_t t_end = n + g.last_block;
+    const uint32_t src_lane = (lane + 31u) & 31u;
+
+    for (uint32_t t0 = 0; t0 < t_end; t0 += 32u) {
+        if (t0) {                                                    // grid point
+            while (b_lo <= g.last_block && win_jhi(g, b_lo) + b_lo <= t0) ++b_lo;
+            const int oldest = static_cast<int>(t0) - static_cast<int>(b_lo) - 31;     // oldest column any lane still reads
+            if (static_cast<int>(c_ins) <= oldest + 94) {
+                ring_insert();
+                ring_fetch();
+            }
+            if (next_build <= g.last_block && t0 > win_jlo(g, next_build - 32u) + (next_build - 32u)) {
+                pattern_build();                                     // its lane has moved on to block next_build - 32
+                ++next_build;
+                pattern_fetch();
+            }
+            __syncwarp();
+        }
+        const uint32_t t1 = min(t_end, t0 + 32u);
+#pragma unroll 2
+        for (uint32_t t = t0; t < t1; ++t) {
+            uint32_t hin = __shfl_sync(FULL, hout, src_lane);
+            const uint32_t rel = t - w.start;                        // wraps to a huge value before the block starts
+            hin = rel < w.hin_lim ? hin : 1u;
+            const uint64_t eq1 = peqw[(buf * PEQ_ROWS + cls1) * 32u + lane];
+            const uint32_t cls2 = tcls[static_cast<uint32_t>(static_cast<int>(t) + 2 + colbase) & 127u];
+            uint64_t npv = pv, nmv = mv;
+            const uint32_t ho = myers_step(npv, nmv, eq0, hin, w.hshift);
+            const bool active = rel < w.width;
+            pv = active ? npv : pv;
+            mv = active ? nmv : mv;
+            if (rel < w.cnt_lim) partial += static_cast<int>(ho & 1u) - static_cast<int>(ho >> 1);
+            hout = ho;
+            eq0 = eq1;
+            cls1 = cls2;
+            if (rel + 1u == w.width) {                               // out of columns: on to block blk + 32 (WIN_SLACK idle steps follow)
+                blk += 32u;
+                buf ^= 1u;
+                colbase -= 32;
+                pv = ~0ull;
+                mv = 0ull;
+                w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
+                if (blk <= g.last_block) w = win_block(g, blk);
+            }
+        }
+    }
+    __syncwarp();
+    return static_cast<long long>(m) + __reduce_add_sync(FULL, partial);
+}
+
 __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const EditJob* __restrict__ jobs, uint32_t n_jobs,
                                                                        unsigned int* next_job,
                                                                        const uint8_t* __restrict__ ref,
@@ -94,11 +241,11 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
         sh.cls2[256u + i] = class_map[hap_complement(static_cast<uint8_t>(i))];
     }
     // the maskless steady state lets lanes without a block read ring slots no refill has written yet: any class <= 32 is fine
-    for (uint32_t i = threadIdx.x; i < ED_WARPS * 64u; i += blockDim.x) (&sh.tcls[0][0])[i] = static_cast<uint8_t>(ED_NOCLASS);
+    for (uint32_t i = threadIdx.x; i < ED_WARPS * 128u; i += blockDim.x) (&sh.tcls[0][0])[i] = static_cast<uint8_t>(ED_NOCLASS);
     __syncthreads();
     uint8_t* hbuf = hbuf_pool ? hbuf_pool + (static_cast<uint64_t>(blockIdx.x) * ED_WARPS + warp) * hbuf_stride : nullptr;
-    unsigned long long (*peq)[32] = sh.peq[warp];
-    uint32_t* peq32 = reinterpret_cast<uint32_t*>(&sh.peq[warp][0][0]);       // [class][lane][half]
+    unsigned long long (*peq)[32] = sh.peq[warp][0];                          // the striped path works in buffer 0
+    uint32_t* peq32 = reinterpret_cast<uint32_t*>(&sh.peq[warp][0][0][0]);    // [class][lane][half]
     uint8_t* tcls = sh.tcls[warp];
     uint8_t* th = sh.th[warp];
 
@@ -126,11 +273,32 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             const HapDesc P = a_is_pattern ? job.a : job.b;
             const HapDesc T = a_is_pattern ? job.b : job.a;
             long long dist = n;
-            if (m != 0u) {
+            bool done = m == 0u;
+            int first_attempt = 0;
+            if (m > 2048u) {
+                // Long patterns: one sliding-window pass with the widest band a warp covers (about 1000 diagonals either
+                // side); it settles every pair whose distance is within that band in n + m/64 steps.
+                const uint32_t kw = win_kmax(m, n);
+                if (kw >= 128u) {
+                    const long long d = window_pass(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
+                    steps_total += n + (m - 1u) / 64u;
+                    if (d <= static_cast<long long>(kw)) {
+                        dist = d;
+                        done = true;
+                    } else {
+                        while ((256ull << (2 * first_attempt)) <= kw) ++first_attempt;    // the stripes start wider than that
+                    }
+                    // the maskless steady state of the striped path reads ring slots no refill has written yet
+                    __syncwarp();
+                    for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
+                    __syncwarp();
+                }
+            }
+            if (!done) {
                 // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of
                 // half-width K gives the exact distance whenever the result is <= K; otherwise widen (x4) and repeat.
                 // Single-stripe patterns are computed in full at once.
-                for (int attempt = 0;; ++attempt) {
+                for (int attempt = first_attempt;; ++attempt) {
                     unsigned long long K = 256ull << (2 * attempt);
                     const bool full_table = m <= 2048u || K >= m;
                     if (full_table) K = ~0ull >> 1;
@@ -319,7 +487,7 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
                          double* d_out) {
     if (!n_jobs) return SVB_OK;
     const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n_jobs + ED_WARPS - 1) / ED_WARPS,
-                                                                     static_cast<uint64_t>(ctx->sm_count) * 8));
+                                                                     static_cast<uint64_t>(ctx->sm_count) * 16));
     uint8_t* hbuf = nullptr;
     const uint64_t stride = (max_text_multi_stripe + 127) & ~127ull;
     if (stride) SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));

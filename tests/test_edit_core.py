@@ -1,0 +1,83 @@
+"""Host checks of the edit-distance cores shared with the CUDA kernel (csrc/edit_core.cuh, compiled by g++ in
+tests/hostcheck): the 64-row block step in stripes, and the sliding window over the Ukkonen band, both against the
+plain DP of the oracle (what edlib.align(a, b)["editDistance"] returns, reference SVIM_COMBINE.py:50-100)."""
+import numpy as np
+import pytest
+
+from tests import hostcheck
+
+
+def _mutate(rng, s, n_edits):
+    b = bytearray(s)
+    for _ in range(n_edits):
+        kind = int(rng.integers(0, 3))
+        pos = int(rng.integers(0, max(1, len(b))))
+        if kind == 0 and b:
+            b[pos % len(b)] = int(rng.choice(list(b"ACGT")))
+        elif kind == 1:
+            b.insert(pos, int(rng.choice(list(b"ACGT"))))
+        elif b:
+            del b[pos % len(b)]
+    return bytes(b)
+
+
+def test_block_step_in_stripes(oracle_clib):
+    lib = hostcheck.load()
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        m = int(rng.integers(1, 400))
+        a = bytes(rng.choice(list(b"ACGT"), m).tolist())
+        b = _mutate(rng, a, int(rng.integers(0, 60))) if rng.random() < 0.7 else bytes(rng.choice(list(b"ACGT"), int(rng.integers(1, 400))).tolist())
+        want = oracle_clib.orc_edit_distance(a, len(a), b, len(b))
+        for blocks in (1, 2, 32):
+            assert lib.hc_myers(a, len(a), b, len(b), blocks) == want
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_sliding_window_exact_within_band(oracle_clib, seed):
+    """window value == distance whenever it is <= K; never below the distance; the widest K one warp covers is accepted."""
+    lib = hostcheck.load()
+    rng = np.random.default_rng(seed)
+    cases = 0
+    for trial in range(14):
+        m = int(rng.integers(2049, 5200)) if trial % 2 else int(rng.integers(65, 2500))
+        a = bytes(rng.choice(list(b"ACGT"), m).tolist())
+        b = _mutate(rng, a, int(rng.integers(0, 700)))
+        if rng.random() < 0.3:                                   # a long private insertion in the middle
+            cut = int(rng.integers(0, len(b)))
+            b = b[:cut] + bytes(rng.choice(list(b"ACGT"), int(rng.integers(100, 900))).tolist()) + b[cut:]
+        p, t = (a, b) if len(a) <= len(b) else (b, a)
+        if not p:
+            continue
+        want = oracle_clib.orc_edit_distance(p, len(p), t, len(t))
+        kmax = lib.hc_win_kmax(len(p), len(t))
+        for K in sorted({1, 64, 300, kmax} - {0}):
+            if K > kmax:
+                continue
+            got = lib.hc_myers_window(p, len(p), t, len(t), K)
+            assert got >= want, (len(p), len(t), K, got, want)
+            if want <= K:
+                assert got == want, (len(p), len(t), K, got, want)
+                cases += 1
+            if got <= K:
+                assert got == want
+    assert cases > 8
+
+
+def test_sliding_window_edge_shapes(oracle_clib):
+    lib = hostcheck.load()
+    rng = np.random.default_rng(11)
+    for m, n in [(1, 1), (1, 300), (64, 64), (65, 64 + 65), (128, 128), (2048, 2048), (2049, 2049), (4096, 4100), (63, 1500)]:
+        p = bytes(rng.choice(list(b"AC"), m).tolist())
+        t = (p + bytes(rng.choice(list(b"AC"), n - m).tolist())) if n > m else p
+        t = _mutate(rng, t, 5)
+        if len(t) < len(p):
+            p, t = t, p
+        kmax = lib.hc_win_kmax(len(p), len(t))
+        if kmax == 0:
+            continue
+        want = oracle_clib.orc_edit_distance(p, len(p), t, len(t))
+        got = lib.hc_myers_window(p, len(p), t, len(t), kmax)
+        assert got >= want
+        if want <= kmax:
+            assert got == want, (m, n, got, want)

@@ -48,6 +48,28 @@ def test_edit_distance_matches_plain_dp(engine, oracle_clib):
     assert got.tolist() == want
 
 
+def test_edit_distance_long_patterns_window_and_stripes(engine, oracle_clib):
+    """Patterns longer than one 2048-row stripe: the sliding window settles distances inside its band (about 1000
+    either side), everything else falls through to the striped band attempts.  Distances below, at and beyond the
+    band edge; length differences that narrow the band or rule the window out; alphabets with N."""
+    rng = np.random.default_rng(23)
+    alphabet = list(b"ACGT")
+    pairs = []
+    for m, edits in ((2049, 0), (2100, 3), (3000, 120), (4500, 450), (5200, 900), (5200, 1400), (7000, 2500), (9900, 520)):
+        a = bytes(rng.choice(alphabet + list(b"N"), m).tolist())
+        pairs.append((a, _mutate(rng, a, edits, alphabet)))
+    a = bytes(rng.choice(alphabet, 6000).tolist())
+    for extra in (700, 1500, 1990, 2100, 5000):              # n - m narrows the band, then excludes the window
+        cut = int(rng.integers(0, len(a)))
+        pairs.append((a, a[:cut] + bytes(rng.choice(alphabet, extra).tolist()) + a[cut:]))
+    pairs.append((bytes(rng.choice(alphabet, 4000).tolist()), bytes(rng.choice(alphabet, 4100).tolist())))   # unrelated
+    pairs.append((b"A" * 5000, b"A" * 4990 + b"C" * 10))
+    pairs.append((b"AC" * 3000, b"CA" * 3000))
+    got = engine.edit_distance(pairs)
+    want = [port.edit_distance(x, y) for x, y in pairs]
+    assert got.tolist() == want
+
+
 def test_cluster_labels_match_scipy(engine):
     rng = np.random.default_rng(22)
     problems = []
