@@ -112,6 +112,20 @@ __device__ __forceinline__ void tma_chunk(void* dst, const void* src, uint32_t b
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// the same with shared-window addresses computed once per warp (the generic-pointer forms redo the conversion at every use)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+    uint32_t ready = 0;
+    while (!ready) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ready) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_chunk_addr(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // exact classification of one op (rare paths): advance sums, emit bit, N/H bit
 __device__ __forceinline__ void decode_op(uint32_t x, uint32_t min16, uint32_t& r, uint32_t& q, uint32_t& ev, uint32_t& nh,
                                           uint32_t bit) {
@@ -134,11 +148,12 @@ __device__ __forceinline__ bool record_passes(const svb_aln_hdr& h, int32_t min_
 // File scope so that every lookup is LDS.64 [offset + table] (a pointer parameter costs an extra add per op).
 __shared__ uint2 s_lut[16];
 
-// fast path of one uint4 (4 ops): packed advance sums (read advance in bits 0..30, reference advance from bit 31 up;
-// 4 x 2^28 < 2^31, so one uint4 cannot overflow a field) and the rare flag, accumulated over the whole chunk
-__device__ __forceinline__ unsigned long long fast_row(const uint4 d, bool& rare) {
+// fast path of one uint4 (4 ops): packed advance sums (read advance in bits 0..30, reference advance from bit 31 up)
+// added to `acc`, and the rare flag, accumulated over the whole chunk.  Lengths have 28 bits, so EIGHT ops (two uint4)
+// cannot overflow the 31-bit field: 8 x (2^28 - 1) < 2^31.
+__device__ __forceinline__ unsigned long long fast_row(const uint4 d, unsigned long long acc, bool& rare) {
     const uint2 e0 = s_lut[d.x & 15u], e1 = s_lut[d.y & 15u], e2 = s_lut[d.z & 15u], e3 = s_lut[d.w & 15u];
-    unsigned long long acc = static_cast<unsigned long long>(d.x >> 4) * e0.x;
+    acc += static_cast<unsigned long long>(d.x >> 4) * e0.x;
     acc += static_cast<unsigned long long>(d.y >> 4) * e1.x;
     acc += static_cast<unsigned long long>(d.z >> 4) * e2.x;
     acc += static_cast<unsigned long long>(d.w >> 4) * e3.x;
@@ -151,43 +166,47 @@ __device__ __forceinline__ uint4 reload_row(const uint4* cigar, uint64_t c4, int
     return cigar[c4 + static_cast<uint64_t>(r) * 32u + lane];        // the buffer is padded to whole units (op 15)
 }
 
-struct ChunkResult {
-    uint32_t tailR, tailQ, head, cnt, evbits;
+// What a warp carries from chunk to chunk inside its unit.  The advance sums of the alignment piece that is running
+// stay LANE-LOCAL (each lane adds up its own rows); they are reduced over the warp only when something needs the
+// total: an alignment head, an emitting op, the end of the unit.
+struct WarpState {
+    uint32_t laneR, laneQ;     // this lane's share of the advance sums since the last head inside the unit / the last flush
+    uint32_t cur_aln;          // alignment those sums belong to
+    uint32_t head;             // 1 once an alignment head was seen inside the unit
+    uint32_t cnt;              // rows emitted by the unit so far
 };
 
-// Phase 1 of one chunk.  `rowsrc(r)` yields this lane's uint4 of row r in the unrolled fast loop (r is a
-// compile-time constant there); `raresrc(r)` serves the rare paths, where r is a run-time value.
-template <typename RowSrc, typename RareSrc>
-__device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const ChunkGeom g, uint64_t c4, uint32_t lane,
-                                                    RowSrc rowsrc, RareSrc raresrc) {
-    ChunkResult out;
-    out.evbits = 0;
-    out.cnt = 0;
+// add warp totals to the alignment the running piece belongs to
+__device__ __forceinline__ void add_to_alignment(const ScanArgs& a, uint32_t aln, uint32_t R, uint32_t Q, uint32_t lane) {
+    if (lane == 0 && (R | Q)) {
+        atomicAdd(&a.aln_sum[aln].x, R);
+        atomicAdd(&a.aln_sum[aln].y, Q);
+    }
+}
+
+__device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g, uint64_t c4, uint32_t lane,
+                                           uint32_t evbits, const uint4* rows4, uint32_t carryR, uint32_t carryQ,
+                                           bool resolved, uint32_t unit, uint32_t local0, unsigned long long base);
+
+// Everything a chunk may need beyond the plain sums: alignment heads inside the chunk, ops that pass their class
+// threshold (emitting I/D, N, H).  About one chunk in five comes here.  totR/totQ: this lane's sums over the whole
+// chunk (from the fast loop); `rare`: this lane saw an op over its threshold; `rowsrc(r)`: the lane's uint4 of row r
+// (r is a run-time value here); `stage_rows()` makes the chunk available in shared memory and returns it.
+template <typename RowSrc, typename StageRows>
+__device__ __forceinline__ void chunk_slow(const ScanArgs& a, WarpState& st, const ChunkGeom g, uint64_t c4, uint32_t lane, uint32_t unit,
+                                           uint32_t totR, uint32_t totQ, bool rare, bool any_rare, RowSrc rowsrc, StageRows stage_rows) {
     const uint64_t c4end = min(c4 + CHUNK4, a.n4);
     const uint32_t a_lo = g.a_lo, a_hi = g.a_lo + g.n_heads, n_pieces = g.n_heads + 1u;
     // rows of this lane before the first head inside the chunk: 32 r + lane < split_rel
     const int rows_before = (static_cast<int>(g.split_rel) - static_cast<int>(lane) + 31) / 32;
     const int nb = rows_before <= 0 ? 0 : (rows_before >= ROWS ? ROWS : rows_before);
-    uint32_t headR = 0, headQ = 0, totR = 0, totQ = 0;
-    bool rare = false;                    // some op of this lane passes its class threshold (I/D >= min_sv_size, N, H)
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const unsigned long long acc = fast_row(rowsrc(r), rare);
-        totR += static_cast<uint32_t>(acc >> 31);
-        totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
-        if (r + 1 == nb) {                // rows 0 .. nb-1 belong to the alignment that owns the chunk start
-            headR = totR;
-            headQ = totQ;
-        }
-    }
     const uint32_t first_mask = nb >= 8 ? 0xFFFFFFFFu : ((1u << (4u * static_cast<uint32_t>(nb))) - 1u);   // ROWS <= 8
-    const bool any_rare = __any_sync(0xffffffffu, rare);
 
     uint32_t nhbits = 0, evbits = 0;
-    if (any_rare && rare) {               // exact bits of this lane's 32 ops (about one chunk in eight gets here)
+    if (any_rare && rare) {               // exact bits of this lane's 32 ops
 #pragma unroll 1
         for (int r = 0; r < ROWS; ++r) {
-            const uint4 d = raresrc(r);
+            const uint4 d = rowsrc(r);
             uint32_t r0 = 0, q0 = 0;
             decode_op(d.x, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 0));
             decode_op(d.y, a.min16, r0, q0, evbits, nhbits, 1u << (4 * r + 1));
@@ -196,35 +215,30 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const Chu
         }
     }
     __syncwarp();
-    if (n_pieces <= 2u) {
-        headR = __reduce_add_sync(0xffffffffu, headR);
-        headQ = __reduce_add_sync(0xffffffffu, headQ);
-        if (lane == 0 && (headR | headQ)) {
-            atomicAdd(&a.aln_sum[a_lo].x, headR);
-            atomicAdd(&a.aln_sum[a_lo].y, headQ);
-        }
-        out.tailR = headR;
-        out.tailQ = headQ;
-        if (n_pieces == 2u) {
-            const uint32_t restR = __reduce_add_sync(0xffffffffu, totR) - headR;
-            const uint32_t restQ = __reduce_add_sync(0xffffffffu, totQ) - headQ;
-            if (lane == 0 && (restR | restQ)) {
-                atomicAdd(&a.aln_sum[a_hi].x, restR);
-                atomicAdd(&a.aln_sum[a_hi].y, restQ);
-            }
-            out.tailR = restR;
-            out.tailQ = restQ;
+    // advance sums since the last head, up to the start of this chunk (what an emitted row of the running piece adds)
+    const uint32_t carryR = __reduce_add_sync(0xffffffffu, st.laneR), carryQ = __reduce_add_sync(0xffffffffu, st.laneQ);
+    const bool resolved = st.head != 0u;
+
+    // per-piece bookkeeping; afterwards st.lane* hold the LAST piece's sums inside this chunk
+    uint32_t headR = 0, headQ = 0;        // n_pieces == 2: this lane's sums over the rows of the first piece
+    uint32_t lastR = 0, lastQ = 0;        // n_pieces > 2: warp totals of the last piece
+    if (n_pieces == 1u) {
+        if (any_rare && !record_passes(a.hdr[a_lo], a.min_mapq)) evbits = 0u;          // SVIM_COLLECT.py:71
+    } else if (n_pieces == 2u) {
+#pragma unroll 1
+        for (int r = 0; r < nb; ++r) {
+            bool ignore = false;
+            const unsigned long long acc = fast_row(rowsrc(r), 0ull, ignore);
+            headR += static_cast<uint32_t>(acc >> 31);
+            headQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
         }
         if (any_rare) {
-            const bool pass0 = record_passes(a.hdr[a_lo], a.min_mapq);
-            const bool pass1 = n_pieces == 2u ? record_passes(a.hdr[a_hi], a.min_mapq) : false;
-            evbits &= (pass0 ? first_mask : 0u) | (pass1 ? ~first_mask : 0u);      // SVIM_COLLECT.py:71
+            const bool pass0 = record_passes(a.hdr[a_lo], a.min_mapq), pass1 = record_passes(a.hdr[a_hi], a.min_mapq);
+            evbits &= (pass0 ? first_mask : 0u) | (pass1 ? ~first_mask : 0u);
         }
     } else {
         // generic: several alignment heads inside one 1024-op chunk (short alignments)
         uint32_t keep = 0;
-        out.tailR = 0;
-        out.tailQ = 0;
         for (uint32_t al = a_lo; al <= a_hi; ++al) {
             const uint64_t lo = max(static_cast<uint64_t>(a.off4[al]), c4);
             const uint64_t hi = min(static_cast<uint64_t>(a.off4[al + 1]), c4end);
@@ -233,7 +247,7 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const Chu
             for (int r = 0; r < ROWS; ++r) {
                 const uint64_t g4 = c4 + static_cast<uint64_t>(r) * 32u + lane;
                 if (g4 >= lo && g4 < hi) {
-                    const uint4 d = raresrc(r);
+                    const uint4 d = rowsrc(r);
                     uint32_t e0 = 0, n0 = 0;
                     decode_op(d.x, a.min16, sR, sQ, e0, n0, 1u);
                     decode_op(d.y, a.min16, sR, sQ, e0, n0, 1u);
@@ -245,17 +259,22 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const Chu
             sR = __reduce_add_sync(0xffffffffu, sR);
             sQ = __reduce_add_sync(0xffffffffu, sQ);
             if (record_passes(a.hdr[al], a.min_mapq)) keep |= in_mask;
-            if (lane == 0 && (sR | sQ)) {
+            if (al == a_lo) {              // the running piece ends here: its carry goes with it
+                sR += carryR;
+                sQ += carryQ;
+            }
+            if (al == a_hi) {              // the last piece keeps running
+                lastR = sR;
+                lastQ = sQ;
+            } else if (lane == 0 && (sR | sQ)) {
                 atomicAdd(&a.aln_sum[al].x, sR);
                 atomicAdd(&a.aln_sum[al].y, sQ);
             }
-            out.tailR = sR;
-            out.tailQ = sQ;
         }
         evbits &= keep;
     }
     if (any_rare) {
-        out.cnt = __reduce_add_sync(0xffffffffu, __popc(evbits));
+        const uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(evbits));
         // rare: N / H ops feed reference_end / infer_read_length of the split-alignment walk
         if (__ballot_sync(0xffffffffu, nhbits != 0u)) {
             uint32_t bits = nhbits;
@@ -265,16 +284,37 @@ __device__ __forceinline__ ChunkResult chunk_phase1(const ScanArgs& a, const Chu
                 const uint64_t g4 = c4 + static_cast<uint64_t>(b >> 2) * 32u + lane;
                 uint32_t al = a_lo;
                 while (al < a_hi && static_cast<uint64_t>(a.off4[al + 1]) <= g4) ++al;
-                const uint4 d = raresrc(b >> 2);
+                const uint4 d = rowsrc(b >> 2);
                 const uint32_t x = (b & 3) == 0 ? d.x : (b & 3) == 1 ? d.y : (b & 3) == 2 ? d.z : d.w;
                 if ((x & 15u) == 3u) atomicAdd(&a.aln_sum[al].z, x >> 4);
                 else atomicAdd(&a.aln_sum[al].w, x >> 4);
             }
         }
+        if (cnt) {
+            const uint4* rows4 = stage_rows();
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.total, static_cast<unsigned long long>(cnt));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            chunk_emit(a, g, c4, lane, evbits, rows4, carryR, carryQ, resolved, unit, st.cnt, base);
+            st.cnt += cnt;
+        }
     }
-    out.evbits = evbits;
-    out.head = (g.n_heads > 0u || g.head_at_start) ? 1u : 0u;
-    return out;
+    // hand the sums on
+    if (n_pieces == 1u) {
+        st.laneR += totR;
+        st.laneQ += totQ;
+    } else if (n_pieces == 2u) {
+        add_to_alignment(a, a_lo, carryR + __reduce_add_sync(0xffffffffu, headR), carryQ + __reduce_add_sync(0xffffffffu, headQ), lane);
+        st.laneR = totR - headR;
+        st.laneQ = totQ - headQ;
+        st.cur_aln = a_hi;
+        st.head = 1u;
+    } else {
+        st.laneR = lane == 0 ? lastR : 0u;      // (the first piece, carry included, was added to its alignment above)
+        st.laneQ = lane == 0 ? lastQ : 0u;
+        st.cur_aln = a_hi;
+        st.head = 1u;
+    }
 }
 
 // Rows of one chunk that holds emitting ops.  carryR/carryQ: advance sums since the last alignment head inside
@@ -319,7 +359,7 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
             const bool in = ((in_mask >> (4 * r)) & 1u) != 0u;
             const uint4 d = in ? rows4[i4] : make_uint4(15u, 15u, 15u, 15u);
             bool rare0 = false;
-            const unsigned long long packed = fast_row(d, rare0);
+            const unsigned long long packed = fast_row(d, 0ull, rare0);
             const uint32_t rr = static_cast<uint32_t>(packed >> 31), qq = static_cast<uint32_t>(packed) & 0x7FFFFFFFu;
             const uint32_t rowbits = in ? ((evbits >> (4 * r)) & 0xFu) : 0u;
             uint32_t bal = __ballot_sync(0xffffffffu, rowbits != 0u);
@@ -424,6 +464,7 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
         g.a_lo = v.x; g.n_heads = v.y; g.split_rel = v.z; g.head_at_start = v.w;
         return g;
     };
+    const uint32_t bar_addr = smem_u32(&s_mbar[warp][0]), buf_addr = smem_u32(my_buf);
     if (USE_TMA && lane == 0) {
 #pragma unroll
         for (int j = 0; j < STAGES && j < G; ++j) {
@@ -432,7 +473,8 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
         }
     }
 
-    uint32_t accR = 0, accQ = 0, accHead = 0, accCnt = 0;     // since the last head inside the unit / rows so far
+    WarpState st;
+    st.laneR = 0; st.laneQ = 0; st.cur_aln = 0; st.head = 0; st.cnt = 0;
     ChunkGeom g_next;
     g_next.a_lo = 0; g_next.n_heads = 0; g_next.split_rel = 0; g_next.head_at_start = 0;
     if (w4 < a.n4) g_next = load_geom(w4 / CHUNK4);
@@ -442,53 +484,73 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
         if (c4 >= a.n4) break;
         const ChunkGeom g = g_next;
         if (j + 1 < G && c4 + CHUNK4 < a.n4) g_next = load_geom(c4 / CHUNK4 + 1);      // prefetch next chunk's geometry
-        ChunkResult res;
-        const uint4* rows4;
+        if (g.head_at_start) {            // an alignment starts exactly here: the running piece is complete
+            add_to_alignment(a, st.cur_aln, __reduce_add_sync(0xffffffffu, st.laneR), __reduce_add_sync(0xffffffffu, st.laneQ), lane);
+            st.laneR = 0;
+            st.laneQ = 0;
+            st.head = 1u;
+        }
+        st.cur_aln = g.a_lo;
+        uint32_t totR = 0, totQ = 0;
+        bool rare = false;                // some op of this lane passes its class threshold (I/D >= min_sv_size, N, H)
         if (USE_TMA) {
-            mbar_wait(&s_mbar[warp][j % STAGES], static_cast<uint32_t>(j / STAGES) & 1u);
+            mbar_wait_addr(bar_addr + static_cast<uint32_t>(j % STAGES) * 8u, static_cast<uint32_t>(j / STAGES) & 1u);
             const uint4* buf = my_buf + (j % STAGES) * CHUNK4;
-            auto from_ring = [&](int r) -> uint4 { return buf[static_cast<uint32_t>(r) * 32u + lane]; };
-            res = chunk_phase1(a, g, c4, lane, from_ring, from_ring);
-            rows4 = buf;
+#pragma unroll
+            for (int r = 0; r < ROWS; r += 2) {
+                unsigned long long acc = fast_row(buf[static_cast<uint32_t>(r) * 32u + lane], 0ull, rare);
+                if (r + 1 < ROWS) acc = fast_row(buf[static_cast<uint32_t>(r + 1) * 32u + lane], acc, rare);
+                totR += static_cast<uint32_t>(acc >> 31);
+                totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
+            }
+            const bool any_rare = __any_sync(0xffffffffu, rare);
+            if (g.n_heads == 0u && !any_rare) {
+                st.laneR += totR;
+                st.laneQ += totQ;
+            } else {
+                chunk_slow(a, st, g, c4, lane, unit, totR, totQ, rare, any_rare,
+                           [&](int r) -> uint4 { return buf[static_cast<uint32_t>(r) * 32u + lane]; },
+                           [&]() -> const uint4* { return buf; });
+            }
+            __syncwarp();                                  // every lane is done with this stage
+            if (lane == 0 && j + STAGES < G && c4 + static_cast<uint64_t>(STAGES) * CHUNK4 < a.n4) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_chunk_addr(buf_addr + static_cast<uint32_t>(j % STAGES) * (CHUNK4 * 16u), a.cigar + c4 + static_cast<uint64_t>(STAGES) * CHUNK4,
+                               CHUNK4 * 16u, bar_addr + static_cast<uint32_t>(j % STAGES) * 8u);
+            }
         } else {
             uint4 v[ROWS];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                v[r] = ldg_stream(a.cigar + c4 + static_cast<uint64_t>(r) * 32u + lane);
-            }
-            res = chunk_phase1(a, g, c4, lane, [&](int r) -> uint4 { return v[r]; },
-                               [&](int r) -> uint4 { return reload_row(a.cigar, c4, r, lane); });
-            if (res.cnt) {                                 // rare: park the chunk in shared memory for the row writer
+            for (int r = 0; r < ROWS; ++r) v[r] = ldg_stream(a.cigar + c4 + static_cast<uint64_t>(r) * 32u + lane);
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) my_buf[r * 32 + lane] = v[r];
-                __syncwarp();
+            for (int r = 0; r < ROWS; r += 2) {
+                unsigned long long acc = fast_row(v[r], 0ull, rare);
+                if (r + 1 < ROWS) acc = fast_row(v[r + 1 < ROWS ? r + 1 : r], acc, rare);
+                totR += static_cast<uint32_t>(acc >> 31);
+                totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
             }
-            rows4 = my_buf;
-        }
-        if (res.cnt) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.total, static_cast<unsigned long long>(res.cnt));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            chunk_emit(a, g, c4, lane, res.evbits, rows4, accR, accQ, accHead != 0u, unit, accCnt, base);
-        }
-        if (res.head) { accR = res.tailR; accQ = res.tailQ; accHead = 1u; }
-        else { accR += res.tailR; accQ += res.tailQ; }
-        accCnt += res.cnt;
-        if (USE_TMA) {
-            __syncwarp();                                  // every lane is done with this stage
-            if (lane == 0 && j + STAGES < G) {
-                const uint32_t bytes = chunk_bytes(j + STAGES);
-                if (bytes) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    tma_chunk(my_buf + (j % STAGES) * CHUNK4, a.cigar + c4 + static_cast<uint64_t>(STAGES) * CHUNK4, bytes,
-                              &s_mbar[warp][j % STAGES]);
-                }
+            const bool any_rare = __any_sync(0xffffffffu, rare);
+            if (g.n_heads == 0u && !any_rare) {
+                st.laneR += totR;
+                st.laneQ += totQ;
+            } else {
+                chunk_slow(a, st, g, c4, lane, unit, totR, totQ, rare, any_rare,
+                           [&](int r) -> uint4 { return reload_row(a.cigar, c4, r, lane); },
+                           [&]() -> const uint4* {              // park the chunk in shared memory for the row writer
+#pragma unroll
+                               for (int r = 0; r < ROWS; ++r) my_buf[r * 32 + lane] = v[r];
+                               __syncwarp();
+                               return my_buf;
+                           });
+                __syncwarp();                              // the spill buffer is reused by the next chunk with events
             }
-        } else {
-            __syncwarp();                                  // the spill buffer is reused by the next chunk with events
         }
     }
-    if (lane == 0) a.unit_agg[unit] = make_uint4(accR, accQ, accHead, accCnt);
+    {
+        const uint32_t R = __reduce_add_sync(0xffffffffu, st.laneR), Q = __reduce_add_sync(0xffffffffu, st.laneQ);
+        add_to_alignment(a, st.cur_aln, R, Q, lane);
+        if (lane == 0) a.unit_agg[unit] = make_uint4(R, Q, st.head, st.cnt);
+    }
 }
 
 // ---- finalize 1: segmented exclusive scan of the unit aggregates (chained scan over CTAs) ------------------

@@ -163,21 +163,58 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
     ring_fetch();
     __syncwarp();
 
-    // ---- per-lane block state
+    // ---- per-lane block state.  What a step does with its block depends on where it is inside the block's columns
+    // (rel = t - start): rel < width: inside the band (commit the new vertical deltas); rel < hin_lim: the block above
+    // is inside too (take its delta, else +1); rel < cnt_lim: the bottom-row delta counts.  These change four times
+    // per block, so they live in lane flags that are recomputed at EVENT steps (warp-wide minimum of every lane's
+    // next boundary); between two events the step loop is branch-free.
     uint32_t blk = lane, buf = 0;
     WinBlock w;
     w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
     if (blk <= g.last_block) w = win_block(g, blk);
     int colbase = -static_cast<int>(blk);                            // text column of step t: t + colbase
     uint64_t pv = ~0ull, mv = 0ull;
-    int partial = 0;
+    uint32_t acc_codes = 0, acc_minus = 0;                           // sum of counted delta codes (0, 1, 2) / number of -1 among them
     uint32_t hout = 0;
     auto ring_class = [&](int col) -> uint32_t { return (col >= 0 && static_cast<uint32_t>(col) < n) ? tcls[static_cast<uint32_t>(col) & 127u] : ED_NOCLASS; };
-    uint64_t eq0 = peqw[(0u * PEQ_ROWS + ring_class(colbase)) * 32u + lane];
+    const unsigned long long* peq_lane = peqw + lane;                // + (buffer * PEQ_ROWS + class) * 32
+    uint64_t eq0 = peq_lane[ring_class(colbase) * 32u];
     uint32_t cls1 = ring_class(colbase + 1);
     uint32_t b_lo = 0;                                               // smallest block that still has columns to do
     const uint32_t t_end = n + g.last_block;
     const uint32_t src_lane = (lane + 31u) & 31u;
+    bool active = false;
+    uint32_t hin_and = 0u, hin_or = 1u, cnt_mask = 0u, my_event = 0u;
+    constexpr uint32_t NEVER = 0xFFFFFFFFu;
+    auto lane_event = [&](uint32_t t) {                              // flags for the steps t, t+1, ... up to the lane's next boundary
+        if (w.width != 0u && t == w.start + w.width) {               // out of columns: on to block blk + 32 (WIN_SLACK idle steps follow)
+            blk += 32u;
+            buf ^= 1u;
+            colbase -= 32;
+            pv = ~0ull;
+            mv = 0ull;
+            peq_lane = peqw + buf * (PEQ_ROWS * 32u) + lane;
+            w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
+            if (blk <= g.last_block) w = win_block(g, blk);
+        }
+        const uint32_t rel = t - w.start;                            // wraps to a huge value before the block starts
+        active = rel < w.width;
+        const bool take = rel < w.hin_lim;
+        hin_and = take ? 3u : 0u;
+        hin_or = take ? 0u : 1u;
+        cnt_mask = rel < w.cnt_lim ? 3u : 0u;
+        uint32_t nxt = NEVER;                                        // the smallest boundary after t
+        if (w.width != 0u) {
+            const uint32_t b0 = w.start, b1 = w.start + w.cnt_lim, b2 = w.start + w.hin_lim, b3 = w.start + w.width;
+            if (b0 > t) nxt = min(nxt, b0);
+            if (b1 > t) nxt = min(nxt, b1);
+            if (b2 > t) nxt = min(nxt, b2);
+            if (b3 > t) nxt = min(nxt, b3);
+        }
+        my_event = nxt;
+    };
+    lane_event(0u);
+    uint32_t next_event = __reduce_min_sync(FULL, my_event);
 
     for (uint32_t t0 = 0; t0 < t_end; t0 += 32u) {
         if (t0) {                                                    // grid point
@@ -195,33 +232,36 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
             __syncwarp();
         }
         const uint32_t t1 = min(t_end, t0 + 32u);
-#pragma unroll 2
-        for (uint32_t t = t0; t < t1; ++t) {
-            uint32_t hin = __shfl_sync(FULL, hout, src_lane);
-            const uint32_t rel = t - w.start;                        // wraps to a huge value before the block starts
-            hin = rel < w.hin_lim ? hin : 1u;
-            const uint64_t eq1 = peqw[(buf * PEQ_ROWS + cls1) * 32u + lane];
-            const uint32_t cls2 = tcls[static_cast<uint32_t>(static_cast<int>(t) + 2 + colbase) & 127u];
-            uint64_t npv = pv, nmv = mv;
-            const uint32_t ho = myers_step(npv, nmv, eq0, hin, w.hshift);
-            const bool active = rel < w.width;
-            pv = active ? npv : pv;
-            mv = active ? nmv : mv;
-            if (rel < w.cnt_lim) partial += static_cast<int>(ho & 1u) - static_cast<int>(ho >> 1);
-            hout = ho;
-            eq0 = eq1;
-            cls1 = cls2;
-            if (rel + 1u == w.width) {                               // out of columns: on to block blk + 32 (WIN_SLACK idle steps follow)
-                blk += 32u;
-                buf ^= 1u;
-                colbase -= 32;
-                pv = ~0ull;
-                mv = 0ull;
-                w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
-                if (blk <= g.last_block) w = win_block(g, blk);
+        uint32_t t = t0;
+        while (t < t1) {
+            if (t == next_event) {
+                lane_event(t);
+                next_event = __reduce_min_sync(FULL, my_event);
+            }
+            const uint32_t t_stop = min(t1, next_event);             // next_event > t here
+            uint32_t ridx = static_cast<uint32_t>(static_cast<int>(t) + 2 + colbase);
+#pragma unroll 4
+            for (; t < t_stop; ++t) {
+                const uint32_t shin = __shfl_sync(FULL, hout, src_lane);
+                const uint32_t hin = (shin & hin_and) | hin_or;
+                const uint64_t eq1 = peq_lane[cls1 * 32u];
+                const uint32_t cls2 = tcls[ridx & 127u];
+                ++ridx;
+                uint64_t npv = pv, nmv = mv;
+                const uint32_t ho = myers_step(npv, nmv, eq0, hin, w.hshift);
+                pv = active ? npv : pv;
+                mv = active ? nmv : mv;
+                const uint32_t counted = ho & cnt_mask;
+                acc_codes += counted;
+                acc_minus += counted >> 1;
+                hout = ho;
+                eq0 = eq1;
+                cls1 = cls2;
             }
         }
     }
+    // code 1 is +1, code 2 is -1: sum of deltas = (#1) - (#2) = acc_codes - 3 * acc_minus
+    const int partial = static_cast<int>(acc_codes) - 3 * static_cast<int>(acc_minus);
     __syncwarp();
     return static_cast<long long>(m) + __reduce_add_sync(FULL, partial);
 }
@@ -233,7 +273,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                                                        const uint8_t* __restrict__ seq4_b,
                                                                        const uint8_t* __restrict__ class_map,
                                                                        uint8_t* hbuf_pool, uint64_t hbuf_stride,
-                                                                       double* __restrict__ out, uint4* __restrict__ profile) {
+                                                                       double* __restrict__ out, uint4* __restrict__ profile,
+                                                                       unsigned int* sm_tokens) {
     __shared__ EdShared sh;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
@@ -251,7 +292,19 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
 
     // Two sweeps over the job list: patterns longer than one 2048-row stripe first (they are the long poles),
     // then the single-stripe jobs.
-    for (int sweep = 0; sweep < 2; ++sweep) {
+    // Sweep 0 is the critical path of the launch (a 10,000-row pair is one warp's dependency chain for most of a
+    // millisecond), so at most ONE warp per SM sub-partition works on it: the first warp that claims the token of its
+    // (SM, scheduler) pair.  The others start with the short jobs right away.
+    bool long_worker = true;
+    if (sm_tokens) {
+        uint32_t smid, warpid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+        uint32_t won = 0;
+        if (lane == 0) won = atomicExch(sm_tokens + ((smid & 1023u) * 4u + (warpid & 3u)), 1u) == 0u ? 1u : 0u;
+        long_worker = __shfl_sync(FULL, won, 0) != 0u;
+    }
+    for (int sweep = long_worker ? 0 : 1; sweep < 2; ++sweep) {
         while (true) {
             uint32_t job_id = 0;
             if (lane == 0) job_id = atomicAdd(next_job + sweep, 1u);
@@ -286,7 +339,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         dist = d;
                         done = true;
                     } else {
-                        while ((256ull << (2 * first_attempt)) <= kw) ++first_attempt;    // the stripes start wider than that
+                        // beyond the window: these are mostly unrelated alleles, so the stripes start four times wider
+                        while ((256ull << (2 * first_attempt)) < 4ull * kw) ++first_attempt;
                     }
                     // the maskless steady state of the striped path reads ring slots no refill has written yet
                     __syncwarp();
@@ -499,12 +553,17 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
         SVB_CUDA(ctx, cudaMallocAsync(&d_profile, sizeof(uint4) * n_jobs, ctx->stream));
         SVB_CUDA(ctx, cudaMemsetAsync(d_profile, 0, sizeof(uint4) * n_jobs, ctx->stream));
     }
+    unsigned int* sm_tokens = nullptr;                 // one word per (SM, scheduler): who runs the long jobs
+    SVB_CUDA(ctx, cudaMallocAsync(&sm_tokens, sizeof(unsigned int) * 4096, ctx->stream));
+    SVB_CUDA(ctx, cudaMemsetAsync(sm_tokens, 0, sizeof(unsigned int) * 4096, ctx->stream));
     {
         KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
         edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, reinterpret_cast<unsigned int*>(ctx->d_counters + 8),
-                                                                       d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out, d_profile);
+                                                                       d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out, d_profile,
+                                                                       sm_tokens);
         ctx->launches += 1;
     }
+    SVB_CUDA(ctx, cudaFreeAsync(sm_tokens, ctx->stream));
     SVB_CUDA(ctx, cudaGetLastError());
     if (d_profile) {
         std::vector<uint4> h(n_jobs);
