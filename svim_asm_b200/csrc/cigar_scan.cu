@@ -80,12 +80,14 @@ struct ScanArgs {
     uint32_t n_units;
     int32_t min_mapq;
     uint32_t min16;           // min_sv_size << 4 : (x >= min16) <=> (len >= min_sv_size)
+    uint32_t mul28;           // 1 << 28 (see op_len)
     uint32_t hap;
     uint4* aln_sum;
     uint4* unit_agg;          // [n_units] x: ref sum since last head, y: read sum, z: head seen, w: rows emitted
     svb_row* rows;            // staging rows (slots reserved with atomics)
     unsigned long long cap;
     unsigned long long* total;     // number of staged rows (may exceed cap)
+    unsigned int* unit_counter;    // next unit to hand out (persistent warps claim units)
     uint32_t* dev_status;
 };
 
@@ -99,20 +101,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t ready = 0;
-    while (!ready) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ready) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
-__device__ __forceinline__ void tma_chunk(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// the same with shared-window addresses computed once per warp (the generic-pointer forms redo the conversion at every use)
+// mbarrier wait / TMA bulk copy on shared-window addresses computed once per warp
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
     uint32_t ready = 0;
     while (!ready) {
@@ -151,12 +140,25 @@ __shared__ uint2 s_lut[16];
 // fast path of one uint4 (4 ops): packed advance sums (read advance in bits 0..30, reference advance from bit 31 up)
 // added to `acc`, and the rare flag, accumulated over the whole chunk.  Lengths have 28 bits, so EIGHT ops (two uint4)
 // cannot overflow the 31-bit field: 8 x (2^28 - 1) < 2^31.
-__device__ __forceinline__ unsigned long long fast_row(const uint4 d, unsigned long long acc, bool& rare) {
+#ifndef K2_LEN_BY_MULHI
+#define K2_LEN_BY_MULHI 1
+#endif
+// op length = x >> 4.  The integer ALU pipe (LOP3 / SHF / ISETP) is the busiest unit of this kernel, the FMA pipe is
+// half idle, so the shift is done there: mulhi(x, 2^28) == x >> 4, with 2^28 a kernel argument the compiler cannot fold.
+__device__ __forceinline__ uint32_t op_len(uint32_t x, uint32_t mul28) {
+#if K2_LEN_BY_MULHI
+    return __umulhi(x, mul28);
+#else
+    return x >> 4;
+#endif
+}
+
+__device__ __forceinline__ unsigned long long fast_row(const uint4 d, unsigned long long acc, bool& rare, uint32_t mul28) {
     const uint2 e0 = s_lut[d.x & 15u], e1 = s_lut[d.y & 15u], e2 = s_lut[d.z & 15u], e3 = s_lut[d.w & 15u];
-    acc += static_cast<unsigned long long>(d.x >> 4) * e0.x;
-    acc += static_cast<unsigned long long>(d.y >> 4) * e1.x;
-    acc += static_cast<unsigned long long>(d.z >> 4) * e2.x;
-    acc += static_cast<unsigned long long>(d.w >> 4) * e3.x;
+    acc += static_cast<unsigned long long>(op_len(d.x, mul28)) * e0.x;
+    acc += static_cast<unsigned long long>(op_len(d.y, mul28)) * e1.x;
+    acc += static_cast<unsigned long long>(op_len(d.z, mul28)) * e2.x;
+    acc += static_cast<unsigned long long>(op_len(d.w, mul28)) * e3.x;
     rare |= (d.x >= e0.y) | (d.y >= e1.y) | (d.z >= e2.y) | (d.w >= e3.y);
     return acc;
 }
@@ -228,7 +230,7 @@ __device__ __forceinline__ void chunk_slow(const ScanArgs& a, WarpState& st, con
 #pragma unroll 1
         for (int r = 0; r < nb; ++r) {
             bool ignore = false;
-            const unsigned long long acc = fast_row(rowsrc(r), 0ull, ignore);
+            const unsigned long long acc = fast_row(rowsrc(r), 0ull, ignore, a.mul28);
             headR += static_cast<uint32_t>(acc >> 31);
             headQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
         }
@@ -359,7 +361,7 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
             const bool in = ((in_mask >> (4 * r)) & 1u) != 0u;
             const uint4 d = in ? rows4[i4] : make_uint4(15u, 15u, 15u, 15u);
             bool rare0 = false;
-            const unsigned long long packed = fast_row(d, 0ull, rare0);
+            const unsigned long long packed = fast_row(d, 0ull, rare0, a.mul28);
             const uint32_t rr = static_cast<uint32_t>(packed >> 31), qq = static_cast<uint32_t>(packed) & 0x7FFFFFFFu;
             const uint32_t rowbits = in ? ((evbits >> (4 * r)) & 0xFu) : 0u;
             uint32_t bal = __ballot_sync(0xffffffffu, rowbits != 0u);
@@ -449,107 +451,130 @@ __global__ void __launch_bounds__(THREADS, USE_TMA ? K2_TMA_CTAS : K2_LDG_CTAS) 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();                 // the only block-wide barrier: the decode table
-    const uint32_t unit = blockIdx.x * WARPS + warp;
-    if (unit >= a.n_units) return;
-    const uint64_t w4 = static_cast<uint64_t>(unit) * (G * CHUNK4);      // this warp's first uint4
     uint4* my_buf = s_buf + static_cast<size_t>(warp) * (USE_TMA ? STAGES : 1) * CHUNK4;
-
-    // the CIGAR buffer is padded (op 15) to a whole number of 16-chunk units: a chunk that starts inside it is complete
-    auto chunk_bytes = [&](int j) -> uint32_t {
-        return w4 + static_cast<uint64_t>(j) * CHUNK4 >= a.n4 ? 0u : static_cast<uint32_t>(CHUNK4 * 16);
-    };
+    constexpr uint64_t UNIT4 = static_cast<uint64_t>(G) * CHUNK4;
     auto load_geom = [&](uint64_t chunk) -> ChunkGeom {                  // one 16-byte load
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.geom) + chunk);
         ChunkGeom g;
         g.a_lo = v.x; g.n_heads = v.y; g.split_rel = v.z; g.head_at_start = v.w;
         return g;
     };
+    // Persistent warps: units are claimed from a counter, so every warp keeps streaming until the input is used up
+    // (no tail of half-empty SMs, one table/barrier set-up per CTA).  The next unit is claimed while the current one
+    // is being scanned, which lets the TMA ring run across the unit boundary without a bubble.
+    auto claim = [&]() -> uint32_t {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(a.unit_counter, 1u);
+        return __shfl_sync(0xffffffffu, u, 0);
+    };
+    // the CIGAR buffer is padded (op 15) to whole units of 16 chunks: a chunk that starts inside the data is complete
+    auto chunk_exists = [&](uint32_t u, uint32_t j) -> bool {
+        return u < a.n_units && static_cast<uint64_t>(u) * UNIT4 + static_cast<uint64_t>(j) * CHUNK4 < a.n4;
+    };
     const uint32_t bar_addr = smem_u32(&s_mbar[warp][0]), buf_addr = smem_u32(my_buf);
+    auto issue = [&](uint32_t u, uint32_t j, uint32_t stage) {           // lane 0 only
+        tma_chunk_addr(buf_addr + stage * (CHUNK4 * 16u), a.cigar + static_cast<uint64_t>(u) * UNIT4 + static_cast<uint64_t>(j) * CHUNK4,
+                       CHUNK4 * 16u, bar_addr + stage * 8u);
+    };
+
+    uint32_t unit = claim();
+    if (unit >= a.n_units) return;
     if (USE_TMA && lane == 0) {
 #pragma unroll
-        for (int j = 0; j < STAGES && j < G; ++j) {
-            const uint32_t bytes = chunk_bytes(j);
-            if (bytes) tma_chunk(my_buf + j * CHUNK4, a.cigar + w4 + static_cast<uint64_t>(j) * CHUNK4, bytes, &s_mbar[warp][j]);
-        }
+        for (uint32_t j = 0; j < static_cast<uint32_t>(STAGES); ++j)
+            if (j < static_cast<uint32_t>(G) && chunk_exists(unit, j)) issue(unit, j, j);
     }
+    uint32_t next_unit = claim();
+    uint32_t k = 0;                       // chunks this warp has consumed: ring stage k % STAGES, parity (k / STAGES) & 1
+    static_assert(G >= STAGES, "the ring is primed with the first STAGES chunks of a unit");
 
-    WarpState st;
-    st.laneR = 0; st.laneQ = 0; st.cur_aln = 0; st.head = 0; st.cnt = 0;
-    ChunkGeom g_next;
-    g_next.a_lo = 0; g_next.n_heads = 0; g_next.split_rel = 0; g_next.head_at_start = 0;
-    if (w4 < a.n4) g_next = load_geom(w4 / CHUNK4);
+    while (true) {
+        const uint64_t w4 = static_cast<uint64_t>(unit) * UNIT4;         // this unit's first uint4
+        WarpState st;
+        st.laneR = 0; st.laneQ = 0; st.cur_aln = 0; st.head = 0; st.cnt = 0;
+        ChunkGeom g_next = load_geom(w4 / CHUNK4);
 #pragma unroll 1
-    for (int j = 0; j < G; ++j) {
-        const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
-        if (c4 >= a.n4) break;
-        const ChunkGeom g = g_next;
-        if (j + 1 < G && c4 + CHUNK4 < a.n4) g_next = load_geom(c4 / CHUNK4 + 1);      // prefetch next chunk's geometry
-        if (g.head_at_start) {            // an alignment starts exactly here: the running piece is complete
-            add_to_alignment(a, st.cur_aln, __reduce_add_sync(0xffffffffu, st.laneR), __reduce_add_sync(0xffffffffu, st.laneQ), lane);
-            st.laneR = 0;
-            st.laneQ = 0;
-            st.head = 1u;
-        }
-        st.cur_aln = g.a_lo;
-        uint32_t totR = 0, totQ = 0;
-        bool rare = false;                // some op of this lane passes its class threshold (I/D >= min_sv_size, N, H)
-        if (USE_TMA) {
-            mbar_wait_addr(bar_addr + static_cast<uint32_t>(j % STAGES) * 8u, static_cast<uint32_t>(j / STAGES) & 1u);
-            const uint4* buf = my_buf + (j % STAGES) * CHUNK4;
-#pragma unroll
-            for (int r = 0; r < ROWS; r += 2) {
-                unsigned long long acc = fast_row(buf[static_cast<uint32_t>(r) * 32u + lane], 0ull, rare);
-                if (r + 1 < ROWS) acc = fast_row(buf[static_cast<uint32_t>(r + 1) * 32u + lane], acc, rare);
-                totR += static_cast<uint32_t>(acc >> 31);
-                totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
+        for (int j = 0; j < G; ++j) {
+            const uint64_t c4 = w4 + static_cast<uint64_t>(j) * CHUNK4;
+            if (c4 >= a.n4) break;
+            const ChunkGeom g = g_next;
+            if (j + 1 < G && c4 + CHUNK4 < a.n4) g_next = load_geom(c4 / CHUNK4 + 1);  // prefetch next chunk's geometry
+            if (g.head_at_start) {        // an alignment starts exactly here: the running piece is complete
+                add_to_alignment(a, st.cur_aln, __reduce_add_sync(0xffffffffu, st.laneR), __reduce_add_sync(0xffffffffu, st.laneQ), lane);
+                st.laneR = 0;
+                st.laneQ = 0;
+                st.head = 1u;
             }
-            const bool any_rare = __any_sync(0xffffffffu, rare);
-            if (g.n_heads == 0u && !any_rare) {
-                st.laneR += totR;
-                st.laneQ += totQ;
+            st.cur_aln = g.a_lo;
+            uint32_t totR = 0, totQ = 0;
+            bool rare = false;            // some op of this lane passes its class threshold (I/D >= min_sv_size, N, H)
+            if (USE_TMA) {
+                const uint32_t stage = k % STAGES;
+                mbar_wait_addr(bar_addr + stage * 8u, (k / STAGES) & 1u);
+                const uint4* buf = my_buf + stage * CHUNK4;
+#pragma unroll
+                for (int r = 0; r < ROWS; r += 2) {
+                    unsigned long long acc = fast_row(buf[static_cast<uint32_t>(r) * 32u + lane], 0ull, rare, a.mul28);
+                    if (r + 1 < ROWS) acc = fast_row(buf[static_cast<uint32_t>(r + 1) * 32u + lane], acc, rare, a.mul28);
+                    totR += static_cast<uint32_t>(acc >> 31);
+                    totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
+                }
+                const bool any_rare = __any_sync(0xffffffffu, rare);
+                if (g.n_heads == 0u && !any_rare) {
+                    st.laneR += totR;
+                    st.laneQ += totQ;
+                } else {
+                    chunk_slow(a, st, g, c4, lane, unit, totR, totQ, rare, any_rare,
+                               [&](int r) -> uint4 { return buf[static_cast<uint32_t>(r) * 32u + lane]; },
+                               [&]() -> const uint4* { return buf; });
+                }
+                __syncwarp();                              // every lane is done with this stage
+                if (lane == 0) {                           // refill it with the chunk STAGES ahead (maybe of the next unit)
+                    const uint32_t ja = static_cast<uint32_t>(j) + STAGES;
+                    const uint32_t au = ja < static_cast<uint32_t>(G) ? unit : next_unit;
+                    const uint32_t aj = ja < static_cast<uint32_t>(G) ? ja : ja - static_cast<uint32_t>(G);
+                    if (chunk_exists(au, aj)) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(au, aj, stage);
+                    }
+                }
+                ++k;
             } else {
-                chunk_slow(a, st, g, c4, lane, unit, totR, totQ, rare, any_rare,
-                           [&](int r) -> uint4 { return buf[static_cast<uint32_t>(r) * 32u + lane]; },
-                           [&]() -> const uint4* { return buf; });
-            }
-            __syncwarp();                                  // every lane is done with this stage
-            if (lane == 0 && j + STAGES < G && c4 + static_cast<uint64_t>(STAGES) * CHUNK4 < a.n4) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                tma_chunk_addr(buf_addr + static_cast<uint32_t>(j % STAGES) * (CHUNK4 * 16u), a.cigar + c4 + static_cast<uint64_t>(STAGES) * CHUNK4,
-                               CHUNK4 * 16u, bar_addr + static_cast<uint32_t>(j % STAGES) * 8u);
-            }
-        } else {
-            uint4 v[ROWS];
+                uint4 v[ROWS];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) v[r] = ldg_stream(a.cigar + c4 + static_cast<uint64_t>(r) * 32u + lane);
+                for (int r = 0; r < ROWS; ++r) v[r] = ldg_stream(a.cigar + c4 + static_cast<uint64_t>(r) * 32u + lane);
 #pragma unroll
-            for (int r = 0; r < ROWS; r += 2) {
-                unsigned long long acc = fast_row(v[r], 0ull, rare);
-                if (r + 1 < ROWS) acc = fast_row(v[r + 1 < ROWS ? r + 1 : r], acc, rare);
-                totR += static_cast<uint32_t>(acc >> 31);
-                totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
-            }
-            const bool any_rare = __any_sync(0xffffffffu, rare);
-            if (g.n_heads == 0u && !any_rare) {
-                st.laneR += totR;
-                st.laneQ += totQ;
-            } else {
-                chunk_slow(a, st, g, c4, lane, unit, totR, totQ, rare, any_rare,
-                           [&](int r) -> uint4 { return reload_row(a.cigar, c4, r, lane); },
-                           [&]() -> const uint4* {              // park the chunk in shared memory for the row writer
+                for (int r = 0; r < ROWS; r += 2) {
+                    unsigned long long acc = fast_row(v[r], 0ull, rare, a.mul28);
+                    if (r + 1 < ROWS) acc = fast_row(v[r + 1 < ROWS ? r + 1 : r], acc, rare, a.mul28);
+                    totR += static_cast<uint32_t>(acc >> 31);
+                    totQ += static_cast<uint32_t>(acc) & 0x7FFFFFFFu;
+                }
+                const bool any_rare = __any_sync(0xffffffffu, rare);
+                if (g.n_heads == 0u && !any_rare) {
+                    st.laneR += totR;
+                    st.laneQ += totQ;
+                } else {
+                    chunk_slow(a, st, g, c4, lane, unit, totR, totQ, rare, any_rare,
+                               [&](int r) -> uint4 { return reload_row(a.cigar, c4, r, lane); },
+                               [&]() -> const uint4* {          // park the chunk in shared memory for the row writer
 #pragma unroll
-                               for (int r = 0; r < ROWS; ++r) my_buf[r * 32 + lane] = v[r];
-                               __syncwarp();
-                               return my_buf;
-                           });
-                __syncwarp();                              // the spill buffer is reused by the next chunk with events
+                                   for (int r = 0; r < ROWS; ++r) my_buf[r * 32 + lane] = v[r];
+                                   __syncwarp();
+                                   return my_buf;
+                               });
+                    __syncwarp();                          // the spill buffer is reused by the next chunk with events
+                }
             }
         }
-    }
-    {
-        const uint32_t R = __reduce_add_sync(0xffffffffu, st.laneR), Q = __reduce_add_sync(0xffffffffu, st.laneQ);
-        add_to_alignment(a, st.cur_aln, R, Q, lane);
-        if (lane == 0) a.unit_agg[unit] = make_uint4(R, Q, st.head, st.cnt);
+        {
+            const uint32_t R = __reduce_add_sync(0xffffffffu, st.laneR), Q = __reduce_add_sync(0xffffffffu, st.laneQ);
+            add_to_alignment(a, st.cur_aln, R, Q, lane);
+            if (lane == 0) a.unit_agg[unit] = make_uint4(R, Q, st.head, st.cnt);
+        }
+        unit = next_unit;
+        if (unit >= a.n_units) break;
+        next_unit = claim();
     }
 }
 
@@ -781,7 +806,7 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_r
         if (v >= 32 && v <= static_cast<int>(US_THREADS) && v % 32 == 0) us_threads = static_cast<uint32_t>(v);
     }
     const uint32_t us_ctas = (n_units + us_threads - 1) / us_threads;
-    const size_t st_bytes = ((sizeof(uint4) + sizeof(unsigned int)) * (us_ctas + 1) + 255) & ~static_cast<size_t>(255);
+    const size_t st_bytes = ((sizeof(uint4) + sizeof(unsigned int)) * (us_ctas + 2) + 255) & ~static_cast<size_t>(255);
     unsigned char* scratch = static_cast<unsigned char*>(svb_scratch(ctx, agg_bytes + pre_bytes + st_bytes + sizeof(svb_row) * a.cap));
     if (!scratch) return svb_fail(ctx, SVB_ERR_NOMEM, "cigar_scan scratch");
     a.n_units = n_units;
@@ -790,9 +815,12 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_r
     uint4* cta_status = reinterpret_cast<uint4*>(scratch + agg_bytes + pre_bytes);
     unsigned int* cta_ready = reinterpret_cast<unsigned int*>(cta_status + us_ctas);
     unsigned int* ticket = cta_ready + us_ctas;
+    a.unit_counter = ticket + 1;
     a.rows = reinterpret_cast<svb_row*>(scratch + agg_bytes + pre_bytes + st_bytes);
     SVB_CUDA(ctx, cudaMemsetAsync(cta_status, 0, st_bytes, ctx->stream));
-    const unsigned blocks = (n_units + WARPS - 1) / WARPS;
+    // persistent: as many CTAs as stay resident, each warp claims units until none is left
+    const unsigned resident = static_cast<unsigned>(ctx->sm_count) * (ctx->scan_variant == 0 ? K2_TMA_CTAS : K2_LDG_CTAS);
+    const unsigned blocks = std::min<unsigned>((n_units + WARPS - 1) / WARPS, resident);
     {
         KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);           // the streaming kernel alone (the roofline's launch duration)
         if (ctx->scan_variant == 0) {
@@ -839,9 +867,11 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     const long long m = p->min_sv_size < 0 ? 0 : p->min_sv_size;
     a.min16 = m >= (1ll << 28) ? 0xFFFFFFFFu : static_cast<uint32_t>(m << 4);
     a.hap = static_cast<uint32_t>(hap);
+    a.mul28 = 1u << 28;
     a.aln_sum = rec->d_aln_sum;
     a.unit_agg = nullptr;
     a.rows = nullptr;
+    a.unit_counter = nullptr;
     a.cap = out.cap;
     a.total = out.d_count;
     a.dev_status = ctx->d_status;
