@@ -141,7 +141,7 @@ __shared__ uint2 s_lut[16];
 // added to `acc`, and the rare flag, accumulated over the whole chunk.  Lengths have 28 bits, so EIGHT ops (two uint4)
 // cannot overflow the 31-bit field: 8 x (2^28 - 1) < 2^31.
 #ifndef K2_LEN_BY_MULHI
-#define K2_LEN_BY_MULHI 1
+#define K2_LEN_BY_MULHI 0      // measured on B200: IMAD.HI costs more than it saves (0.164 ms vs 0.155 ms per whole-genome launch)
 #endif
 // op length = x >> 4.  The integer ALU pipe (LOP3 / SHF / ISETP) is the busiest unit of this kernel, the FMA pipe is
 // half idle, so the shift is done there: mulhi(x, 2^28) == x >> 4, with 2^28 a kernel argument the compiler cannot fold.
