@@ -117,3 +117,50 @@ def test_unit_scan_lookback_with_small_ctas(engine, threads, monkeypatch):
     rb = synth.make_haploid(cfg)
     want = _compare(engine, rb)
     assert want.shape[0] > 100
+
+
+def test_empty_and_degenerate_batches(engine):
+    """No records at all; records without CIGAR ops (unmapped-style, '*'); everything filtered out."""
+    empty = util.batch_from_records(["c1"], [1000], [])
+    assert _compare(engine, empty).shape[0] == 0
+    recs = [dict(tid=0, pos=5, cigar=[]), dict(tid=0, pos=10, cigar=[(0, 50), (2, 45), (0, 5)]), dict(tid=0, pos=20, cigar=[]),
+            dict(tid=0, pos=30, cigar=[], flag=4), dict(tid=0, pos=40, cigar=[(1, 60)], l_seq=60)]
+    want = _compare(engine, util.batch_from_records(["c1"], [1000], recs))
+    assert want.shape[0] == 2
+    filtered = [dict(tid=0, pos=10, cigar=[(0, 50), (2, 45), (0, 5)], mapq=3), dict(tid=0, pos=90, cigar=[(2, 100)], flag=256)]
+    assert _compare(engine, util.batch_from_records(["c1"], [1000], filtered)).shape[0] == 0
+
+
+@pytest.mark.parametrize("n_ops", [1023, 1024, 1025, 2047, 2048, 2049, 4 * 1024 * 2, 4 * 1024 * 2 + 1, 16 * 1024 + 3])
+def test_alignment_lengths_around_chunk_and_unit_boundaries(engine, n_ops):
+    """Runs that end exactly at, one before and one after a 1024-op chunk / a unit of chunks, each followed by a second
+    alignment (so a head falls on the boundary), with emitting ops on both sides of every boundary."""
+    rng = np.random.default_rng(n_ops)
+    def cig(n):
+        ops = [(7, int(x)) for x in rng.integers(1, 30, n)]
+        for i in (0, 1, n // 2, max(n - 2, 0), n - 1):
+            ops[i] = (int(rng.choice([1, 2])), int(rng.integers(40, 90)))
+        for i in range(1000, n, 1024):                   # right before / at / after every chunk boundary
+            for k in (23, 24, 25):
+                if i + k < n:
+                    ops[i + k] = (int(rng.choice([1, 2])), 50)
+        return ops
+    recs = [dict(tid=0, pos=100, cigar=cig(n_ops)), dict(tid=0, pos=5000, cigar=cig(1500)), dict(tid=0, pos=9000, cigar=cig(7))]
+    for r in recs:
+        r["l_seq"] = sum(ln for op, ln in r["cigar"] if op in (0, 1, 4, 7, 8))
+    want = _compare(engine, util.batch_from_records(["c1"], [50_000_000], recs))
+    assert want.shape[0] > 10
+
+
+def test_very_long_ops_do_not_overflow_packed_sums(engine):
+    # 28-bit lengths: eight such ops in two rows of one lane still fit the 31-bit field of the packed accumulator
+    big = (1 << 28) - 1
+    cigar = [(7, big)] * 7 + [(2, 60), (7, 5), (1, 50), (7, big)] + [(7, 1)] * 40
+    recs = [dict(tid=0, pos=0, cigar=cigar, l_seq=10)]
+    rb = util.batch_from_records(["c1"], [2**31 - 1], recs)
+    host = HostBatch.from_record_batch(rb)
+    rec = engine.load_records(host)
+    got = engine.collect(rec, make_params()).to_numpy()
+    want = port.collect(host, port.Params())
+    assert util.rows_equal(got, want) is None, util.rows_equal(got, want)
+    assert got.shape[0] == 2
