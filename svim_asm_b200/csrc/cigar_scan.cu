@@ -405,7 +405,8 @@ __device__ __forceinline__ void chunk_emit(const ScanArgs& a, const ChunkGeom g,
                                 w1.z = del ? 0u : static_cast<uint32_t>(ce);                   // dst_end
                                 w1.w = local0 + idx;                                            // (staging) index inside the unit
                                 w2.x = al;                                                      // aln_idx
-                                w2.y = pq;                                                      // seq_pos (= pos_read)
+                                // seq_pos = pos_read; an insertion's is clamped like the python slice start (SVIM_intra.py:42)
+                                w2.y = (del || needs_carry) ? pq : min(pq, h.l_seq);
                                 w2.z = seq_len;
                                 w2.w = unit;                                                    // (staging) unit
                                 w3.x = static_cast<uint32_t>(ordinal);
@@ -726,7 +727,7 @@ __global__ void finalize_rows_kernel(const svb_row* __restrict__ staged, const u
         const int32_t ce = static_cast<int32_t>(min(static_cast<long long>(clen), end));
         if (r.type == SVB_DEL) { r.src_start = cs; r.src_end = ce; r.seq_len = 0; }
         else { r.dst_start = cs; r.dst_end = ce; r.seq_len = pq >= h.l_seq ? 0u : min(len, h.l_seq - pq); }
-        r.seq_pos = pq;
+        r.seq_pos = r.type == SVB_DEL ? pq : min(pq, h.l_seq);
     }
     r.flags = 0;
     r.copies = 0;

@@ -11,6 +11,7 @@ Everything here is host logic on numpy arrays plus torch.distributed collectives
 CPU tests); the compute stages are passed in, so the same code is exercised with world_size 2 on a CPU-only box.
 """
 import os
+import sys
 import time
 
 import numpy as np
@@ -123,11 +124,18 @@ def select_owned(rows, pool, starts, owner, rank):
 def order_paired(rows_by_rank, lexrank):
     """Final order of pair_candidates' output: type, then key contig in python string order; inside one
     (type, contig) every row comes from the owning rank, already in partition / label order."""
-    rows = np.concatenate(rows_by_rank)
+    dtype = rows_by_rank[0].dtype
+    # the 64-byte rows are handled as 8 machine words each: concatenating / fancy-indexing the structured dtype is an
+    # order of magnitude slower
+    words = np.concatenate([np.ascontiguousarray(r).view(np.uint64).reshape(r.shape[0], dtype.itemsize // 8) for r in rows_by_rank])
+    rows = words.reshape(-1).view(dtype)
     if rows.shape[0] == 0:
         return rows
-    key = rows["type"].astype(np.int64) * (1 << 32) + np.asarray(lexrank, dtype=np.int64)[key_contig(rows)]
-    out = rows[np.argsort(key, kind="stable")]
+    lexrank = np.asarray(lexrank, dtype=np.int64)
+    key = rows["type"].astype(np.int64) * lexrank.shape[0] + lexrank[key_contig(rows)]
+    if int(key.max()) < 65536:
+        key = key.astype(np.uint16)                    # numpy sorts 16-bit keys with a (stable) radix sort
+    out = np.take(words, np.argsort(key, kind="stable"), axis=0).reshape(-1).view(dtype)
     out["ordinal"] = np.arange(out.shape[0], dtype=np.uint64)
     return out
 
@@ -237,19 +245,37 @@ def sharded_step_device(stage, rank, world, owner, lexrank, device, row_dtype):
     import torch.distributed as dist
     from .engine import DeviceView
     eng = stage.eng
+    prof = _PROFILE if os.environ.get("SVB_SHARD_PROFILE") else None
+
+    def tick(name):
+        if prof is not None:              # profiling aid: synchronised phase times of rank 0 (tools/perf_sharded.py)
+            eng.synchronize()
+            now = time.perf_counter()
+            prof.setdefault(name, 0.0)
+            prof[name] += now - prof["_t"]
+            prof["_t"] = now
+    if prof is not None:
+        eng.synchronize()
+        prof["_t"] = time.perf_counter()
     with torch.cuda.stream(torch.cuda.ExternalStream(eng.stream_handle(), device=device)):
         t1, t2 = stage.collect(1), stage.collect(2)
+        tick("collect x2")
         sizes = _gather_sizes(eng.exchange_sizes(t1, t2).astype(np.int64), world, device).astype(np.uint64)
+        tick("gather sizes")
         stride = max(eng.exchange_bytes(sizes[r]) for r in range(world))
         mine = torch.empty(stride, dtype=torch.uint8, device=device)
         eng.exchange_pack(t1, t2, mine.data_ptr(), stride)
+        tick("pack")
         gathered = torch.empty(world * stride, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(gathered, mine)
+        tick("all-gather tables")
         t1.free()
         t2.free()
         u1 = eng.exchange_unpack(gathered.data_ptr(), stride, sizes, 1, owner, rank)
         u2 = eng.exchange_unpack(gathered.data_ptr(), stride, sizes, 2, owner, rank)
+        tick("unpack x2")
         paired = eng.pair(u1, u2, stage.records[0], stage.records[1], stage.ref, stage.params)
+        tick("pair")
         counts = _gather_sizes([len(paired)], world, device)[:, 0]
         width = max(int(counts.max()), 1) * row_dtype.itemsize
         rows = torch.zeros(width, dtype=torch.uint8, device=device)
@@ -259,11 +285,17 @@ def sharded_step_device(stage, rank, world, owner, lexrank, device, row_dtype):
         back = torch.empty(world * width, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(back, rows)
         host = back.cpu().numpy().reshape(world, width)
+        tick("gather paired rows")
         for t in (u1, u2, paired):
             t.free()
         stage.done()
     parts = [host[r, :int(counts[r]) * row_dtype.itemsize].view(row_dtype) for r in range(world)]
-    return order_paired(parts, lexrank)
+    out = order_paired(parts, lexrank)
+    tick("order on host")
+    return out
+
+
+_PROFILE = {}
 
 
 def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block):
@@ -302,6 +334,7 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         eng.synchronize()
         # timed on the device: every kernel, copy and collective of the step is enqueued on the library's stream, so two
         # events on that stream bracket the whole loop (host gaps between the enqueues included); max over ranks
+        _PROFILE.clear()
         eng.mark(2)
         for _ in range(steps):
             table = sharded_step_device(stage_factory(), rank, world, owner, ranks, device, _lib.ROW_DTYPE)
@@ -311,6 +344,11 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         dist.barrier()
         dt = torch.tensor([eng.elapsed_ms(2, 3) * 1e-3], dtype=torch.float64, device=device)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if os.environ.get("SVB_SHARD_PROFILE") and rank == 0:
+            for name, v in _PROFILE.items():
+                if not name.startswith("_"):
+                    print("[shard profile] %-20s %8.3f ms per step" % (name, v / steps * 1e3), file=sys.stderr)
+            print("[shard profile] ---", file=sys.stderr)
         return float(dt.item()) / steps, table
 
     warm = max(args.warmup, 3)
