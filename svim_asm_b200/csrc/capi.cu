@@ -415,45 +415,58 @@ int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int h
 
     // K2: indel rows.  Capacity is a guess (1 row per 512 ops; human assemblies have about 1 per 20,000); an
     // overflow is detected from the exact count and the scan is repeated once with the right size.
+    // K4's count pass is enqueued right behind the scan (it needs the scan's per-alignment sums, not its rows), so
+    // that both counts and the device status come back with a single synchronisation.
     uint64_t cap = std::max<uint64_t>(4096, rec->n_ops / 512);
     svb_table* indel = nullptr;
-    unsigned long long n_indel = 0;
+    WalkPending* walk = nullptr;
+    unsigned long long n_indel = 0, n_walk = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         indel = table_alloc(ctx, cap);
-        if (!indel) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: indel table");
+        if (!indel) {
+            walk_discard(ctx, walk);
+            return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: indel table");
+        }
         ScanOutput so{indel->d_rows, indel->cap, ctx->d_counters};
         int rc = launch_cigar_scan(ctx, rec, p, hap, so);
+        if (rc == SVB_OK && attempt == 0) rc = walk_count_async(ctx, rec, p, hap, &walk);
         if (rc != SVB_OK) {
             svb_table_free(indel);
+            walk_discard(ctx, walk);
             return rc;
         }
-        cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+        uint32_t* h_status = reinterpret_cast<uint32_t*>(ctx->h_pinned + 12);
+        cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             svb_table_free(indel);
+            walk_discard(ctx, walk);
             return svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: cigar_scan", e);
         }
+        if (*h_status) {                  // the kernels flagged something the reference would have raised on
+            svb_table_free(indel);
+            walk_discard(ctx, walk);
+            return check_device_status(ctx);
+        }
         n_indel = ctx->h_pinned[0];
+        if (attempt == 0) n_walk = ctx->h_pinned[1];
         if (n_indel <= indel->cap) break;
         svb_table_free(indel);
         indel = nullptr;
         cap = n_indel;
     }
-    if (!indel) return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_collect: indel table overflow");
+    if (!indel) {
+        walk_discard(ctx, walk);
+        return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_collect: indel table overflow");
+    }
     indel->n = n_indel;
 
     // K4: split-alignment walk rows (own table, emission order per primary)
     svb_row* d_walk = nullptr;
-    uint64_t n_walk = 0;
-    int rc = launch_segment_walk(ctx, rec, p, hap, &d_walk, &n_walk);
+    int rc = walk_write_async(ctx, walk, n_walk, &d_walk);
     if (rc != SVB_OK) {
         svb_table_free(indel);
-        return rc;
-    }
-    rc = check_device_status(ctx);
-    if (rc != SVB_OK) {
-        svb_table_free(indel);
-        free_async(d_walk, ctx->stream);
         return rc;
     }
     if (n_walk == 0) {
@@ -467,8 +480,7 @@ int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int h
         free_async(d_walk, ctx->stream);
         return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: merged table");
     }
-    rc = launch_merge_tables(ctx, indel->d_rows, n_indel, d_walk, n_walk, merged->d_rows);
-    if (rc == SVB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: merge");
+    rc = launch_merge_tables(ctx, indel->d_rows, n_indel, d_walk, n_walk, merged->d_rows);     // stream ordered: no wait
     svb_table_free(indel);
     free_async(d_walk, ctx->stream);
     if (rc != SVB_OK) {
@@ -568,7 +580,13 @@ int svb_pair(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_r
     cudaSetDevice(ctx->device);
     int rc = run_pairing(ctx, h1, h2, rec1, rec2, ref, p, out);
     if (rc != SVB_OK) return rc;
-    return check_device_status(ctx);
+    if (*reinterpret_cast<const uint32_t*>(ctx->h_pinned + 12) == 0u) return SVB_OK;      // status word read back by run_pairing
+    rc = check_device_status(ctx);
+    if (rc != SVB_OK && *out) {
+        svb_table_free(*out);
+        *out = nullptr;
+    }
+    return rc;
 }
 
 int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,

@@ -115,8 +115,10 @@ struct ScanOutput {
 uint64_t cigar_padded_n4(uint64_t n4);   // uint4 capacity d_cigar must be allocated with (whole 64 KB units)
 int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec);
 int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out);
-int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_row** d_rows_out,
-                        uint64_t* n_out);
+struct WalkPending;   // a walk whose count pass is in flight (segment_walk.cu)
+int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, WalkPending** out);   // total -> d_counters[1]
+int walk_write_async(svb_ctx* ctx, WalkPending* w, uint64_t n_rows, svb_row** d_rows_out);                     // consumes w
+void walk_discard(svb_ctx* ctx, WalkPending* w);
 int launch_merge_tables(svb_ctx* ctx, const svb_row* a, uint64_t na, const svb_row* b, uint64_t nb, svb_row* out);
 int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
                 const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);

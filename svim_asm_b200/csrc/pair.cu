@@ -160,9 +160,10 @@ __global__ void heads_kernel(const unsigned long long* __restrict__ keys, uint32
 }
 
 __global__ void part_start_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ excl, uint32_t n,
-                                  long long max_distance, uint32_t* __restrict__ part_start, uint32_t n_parts) {
+                                  long long max_distance, uint32_t* __restrict__ part_start,
+                                  const unsigned long long* __restrict__ n_parts_dev) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) part_start[n_parts] = n;
+    if (i == 0) part_start[static_cast<uint32_t>(*n_parts_dev)] = n;
     if (i >= n) return;
     bool h = true;
     if (i > 0) {
@@ -212,9 +213,10 @@ __device__ void make_desc(const svb_row& r, long long lo, long long hi, const Pa
 }
 
 // one thread per partition: the cross-haplotype pairs that need an edit distance
-__global__ void enumerate_jobs_kernel(const PairArgs a) {
+// (launched before the host knows the number of partitions: the bound is read from the device)
+__global__ void enumerate_jobs_kernel(const PairArgs a, const unsigned long long* __restrict__ n_parts_dev) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n_parts) return;
+    if (p >= static_cast<uint32_t>(*n_parts_dev)) return;
     const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
     if (n < 2u || n > static_cast<uint32_t>(PAIR_MAX)) return;
     const svb_row r0 = a.rows[a.order[first]];
@@ -350,6 +352,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     result->device = ctx->device;
     result->stream = ctx->stream;
     if (n == 0) {
+        *reinterpret_cast<uint32_t*>(ctx->h_pinned + 12) = 0u;       // nothing ran: no device status to report
         SVB_CUDA(ctx, cudaMallocAsync(&result->d_rows, sizeof(svb_row), ctx->stream));
         result->cap = 1;
         *out = result;
@@ -419,9 +422,6 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         if (rc != SVB_OK) return fail(rc);
     }
     PAIR_CUDA(cudaGetLastError());
-    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
-    n_parts = static_cast<uint32_t>(ctx->h_pinned[2]);
 
     PairArgs a;
     a.rows = rows;
@@ -444,13 +444,18 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     PAIR_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
         KernelTimer timer(ctx, SVB_K_SORT);
-        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start, n_parts);
-        enumerate_jobs_kernel<<<(n_parts + 127) / 128, 128, 0, ctx->stream>>>(a);
+        // the number of partitions (d_counters[2]) is still on its way: both kernels take it from the device and the
+        // grid covers the upper bound (one partition per row), so that ONE synchronisation returns all three counts
+        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start,
+                                                                    ctx->d_counters + 2);
+        enumerate_jobs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, ctx->d_counters + 2);
         ctx->launches += 2;
     }
     PAIR_CUDA(cudaGetLastError());
-    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 3, ctx->d_counters + 3, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_counters + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
+    n_parts = static_cast<uint32_t>(ctx->h_pinned[2]);
+    a.n_parts = n_parts;
     const uint32_t n_jobs = static_cast<uint32_t>(ctx->h_pinned[3]);
     const uint64_t max_multi = ctx->h_pinned[4];
     if (n_jobs) {
@@ -467,12 +472,10 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         if (rc != SVB_OK) return fail(rc);
     }
     PAIR_CUDA(cudaGetLastError());
-    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 5, ctx->d_counters + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
-    const uint64_t n_out = ctx->h_pinned[5];
-    result->cap = std::max<uint64_t>(n_out, 1);
+    // pairing never makes rows (every output row is one input row or the merge of two): the table is allocated for n
+    // rows and the write pass runs without waiting for the exact count, which comes back with the final synchronisation
+    result->cap = std::max<uint64_t>(n, 1);
     PAIR_CUDA(cudaMallocAsync(&result->d_rows, sizeof(svb_row) * result->cap, ctx->stream));
-    result->n = n_out;
     a.out = result->d_rows;
     {
         KernelTimer timer(ctx, SVB_K_CLUSTER);
@@ -480,8 +483,17 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         ctx->launches += 1;
     }
     PAIR_CUDA(cudaGetLastError());
+    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 5, ctx->d_counters + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t* h_status = reinterpret_cast<uint32_t*>(ctx->h_pinned + 12);      // the device error word rides along
+    PAIR_CUDA(cudaMemcpyAsync(h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     PAIR_CUDA(cudaFreeAsync(slab, ctx->stream));
     PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
+    result->n = ctx->h_pinned[5];
+    if (*h_status) {                       // svb_pair turns it into the reference's error (check_device_status)
+        *out = result;
+        return SVB_OK;
+    }
+    if (result->n > result->cap) return fail(svb_fail(ctx, SVB_ERR_CAPACITY, "svb_pair: more rows out than in"));
 #undef PAIR_CUDA
     *out = result;
     return SVB_OK;

@@ -10,6 +10,8 @@
 // K5: the indel table (K2) and the walk table (K4) are each sorted by `ordinal`; a merge-path
 // style kernel (one binary search per row) interleaves them into the reference's append order:
 // per record, its indels first, then its walk candidates (SVIM_COLLECT.py:79-80).
+#include <new>
+
 #include "common.cuh"
 #include "walk.cuh"
 #include "pairing.cuh"
@@ -183,18 +185,31 @@ __global__ void merge_kernel(const svb_row* __restrict__ A, uint64_t na, const s
 
 }  // namespace
 
-int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_row** d_rows_out,
-                        uint64_t* n_out) {
-    *d_rows_out = nullptr;
-    *n_out = 0;
+// The walk runs in two passes (count, then write at the scanned offsets).  The count pass is enqueued without waiting
+// for anything, so that svb_collect reads the indel count, the walk count and the device status back with ONE
+// synchronisation; the write pass follows once the host knows how many rows to allocate.
+struct WalkPending {
+    WalkArgs a;
+    unsigned char* base = nullptr;
+    unsigned blocks = 0;
+};
+
+int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, WalkPending** out) {
+    *out = nullptr;
+    SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 1, 0, sizeof(unsigned long long), ctx->stream));
     if (rec->n_prim == 0) return SVB_OK;
     const size_t scratch_entries = static_cast<size_t>(rec->n_seg) + rec->n_prim;
     const size_t counts_bytes = (static_cast<size_t>(rec->n_prim) + 2) * sizeof(uint32_t);
     const size_t counts_pad = (counts_bytes + 255) & ~static_cast<size_t>(255);
-    unsigned char* base = nullptr;
-    // own allocation (the shared scratch is in use by cigar_scan's tile states on the same stream)
-    SVB_CUDA(ctx, cudaMallocAsync(&base, counts_pad + scratch_entries * sizeof(WalkScratch), ctx->stream));
-    WalkArgs a;
+    WalkPending* w = new (std::nothrow) WalkPending();
+    if (!w) return svb_fail(ctx, SVB_ERR_NOMEM, "segment_walk");
+    // own allocation (the shared scratch is in use by cigar_scan's unit states on the same stream)
+    cudaError_t e = cudaMallocAsync(&w->base, counts_pad + scratch_entries * sizeof(WalkScratch), ctx->stream);
+    if (e != cudaSuccess) {
+        delete w;
+        return svb_fail(ctx, SVB_ERR_NOMEM, "segment_walk scratch", e);
+    }
+    WalkArgs& a = w->a;
     a.hdr = rec->d_hdr;
     a.cigar = reinterpret_cast<const uint32_t*>(rec->d_cigar);
     a.seg = rec->d_seg;
@@ -213,50 +228,61 @@ int launch_segment_walk(svb_ctx* ctx, const svb_records* rec, const svb_params* 
     a.p.rgt = p->reference_gap_tolerance;
     a.p.rot = p->reference_overlap_tolerance;
     a.hap = static_cast<uint32_t>(hap);
-    a.counts = reinterpret_cast<uint32_t*>(base);
-    a.scratch = reinterpret_cast<WalkScratch*>(base + counts_pad);
+    a.counts = reinterpret_cast<uint32_t*>(w->base);
+    a.scratch = reinterpret_cast<WalkScratch*>(w->base + counts_pad);
     a.rows = nullptr;
     a.dev_status = ctx->d_status;
-    const unsigned blocks = (rec->n_prim + 127u) / 128u;
-    unsigned long long n_rows = 0;
+    w->blocks = (rec->n_prim + 127u) / 128u;
     {
         KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
-        walk_kernel<false><<<blocks, 128, 0, ctx->stream>>>(a);
+        walk_kernel<false><<<w->blocks, 128, 0, ctx->stream>>>(a);
         scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(a.counts, rec->n_prim, ctx->d_counters + 1);
         ctx->launches += 2;
     }
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    e = cudaGetLastError();
     if (e != cudaSuccess) {
-        cudaFreeAsync(base, ctx->stream);
+        cudaFreeAsync(w->base, ctx->stream);
+        delete w;
         return svb_fail(ctx, SVB_ERR_CUDA, "segment_walk count pass", e);
     }
-    n_rows = ctx->h_pinned[1];
+    *out = w;
+    return SVB_OK;
+}
+
+void walk_discard(svb_ctx* ctx, WalkPending* w) {
+    if (!w) return;
+    cudaFreeAsync(w->base, ctx->stream);
+    delete w;
+}
+
+// n_rows: the count pass's total, read back by the caller.  Consumes `w`.
+int walk_write_async(svb_ctx* ctx, WalkPending* w, uint64_t n_rows, svb_row** d_rows_out) {
+    *d_rows_out = nullptr;
+    if (!w) return SVB_OK;
+    int rc = SVB_OK;
     if (n_rows) {
         svb_row* rows = nullptr;
-        e = cudaMallocAsync(&rows, sizeof(svb_row) * n_rows, ctx->stream);
+        cudaError_t e = cudaMallocAsync(&rows, sizeof(svb_row) * n_rows, ctx->stream);
         if (e != cudaSuccess) {
-            cudaFreeAsync(base, ctx->stream);
-            return svb_fail(ctx, SVB_ERR_NOMEM, "segment_walk rows", e);
+            rc = svb_fail(ctx, SVB_ERR_NOMEM, "segment_walk rows", e);
+        } else {
+            w->a.rows = rows;
+            {
+                KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
+                walk_kernel<true><<<w->blocks, 128, 0, ctx->stream>>>(w->a);
+                ctx->launches += 1;
+            }
+            e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                cudaFreeAsync(rows, ctx->stream);
+                rc = svb_fail(ctx, SVB_ERR_CUDA, "segment_walk write pass", e);
+            } else {
+                *d_rows_out = rows;
+            }
         }
-        a.rows = rows;
-        {
-            KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
-            walk_kernel<true><<<blocks, 128, 0, ctx->stream>>>(a);
-            ctx->launches += 1;
-        }
-        e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            cudaFreeAsync(rows, ctx->stream);
-            cudaFreeAsync(base, ctx->stream);
-            return svb_fail(ctx, SVB_ERR_CUDA, "segment_walk write pass", e);
-        }
-        *d_rows_out = rows;
-        *n_out = n_rows;
     }
-    cudaFreeAsync(base, ctx->stream);
-    return SVB_OK;
+    walk_discard(ctx, w);
+    return rc;
 }
 
 int launch_scan_u32(svb_ctx* ctx, uint32_t* v, uint32_t n, unsigned long long* d_total) {
