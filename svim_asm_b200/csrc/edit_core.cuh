@@ -45,26 +45,33 @@ SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_
 // result is exact whenever it is <= K.  One warp holds 32 consecutive blocks of that band at a time: lane
 // b % 32 works on block b, and once block b has run out of columns the lane moves on to block b + 32.
 // That needs block b + 32 to start after block b ends, start(b) = win_jlo(b) + b (lanes are skewed by one
-// column per block): 64 * 32 + 32 - K >= 64 + (n - m) + K.  A block that enters the band starts from
+// column per block): 64 * 32 + 32 - K >= 64 + (n - m) + K (with 64-row blocks; 32-row blocks halve the band and the
+// work per step).  A block that enters the band starts from
 // "everything above and to the left is one more per row" (vertical deltas +1, horizontal input +1), which
 // can only overestimate cells whose optimal path leaves the band.  With S_b = sum of the block's bottom-row
 // horizontal deltas over the columns [win_jlo(b), win_jlo(b + 1)) (last block: up to n),
 //     D[m][n] = m + sum_b S_b.
 struct WinGeom {
     uint32_t m, n, K, last_block;
+    uint32_t bw;           // rows per block: 64 (one 64-bit word per lane) or 32 (half the work per step, half the band)
 };
 constexpr uint32_t WIN_SLACK = 8;     // idle steps guaranteed between two blocks of one lane (prefetch priming)
 
-SVB_HD uint32_t win_kmax(uint32_t m, uint32_t n) {          // widest half-width one warp can slide over (0: none)
-    const uint32_t dlt = n - m, room = 64u * 32u + 32u - 64u - WIN_SLACK;
+SVB_HD WinGeom win_geom(uint32_t m, uint32_t n, uint32_t K, uint32_t bw) {
+    WinGeom g;
+    g.m = m; g.n = n; g.K = K; g.bw = bw; g.last_block = (m - 1u) / bw;
+    return g;
+}
+SVB_HD uint32_t win_kmax(uint32_t m, uint32_t n, uint32_t bw) {   // widest half-width one warp can slide over (0: none)
+    const uint32_t dlt = n - m, room = bw * 32u + 32u - bw - WIN_SLACK;
     return dlt >= room ? 0u : (room - dlt) / 2u;
 }
 SVB_HD uint32_t win_jlo(const WinGeom& g, uint32_t b) {
-    const uint64_t x = 64ull * b;
+    const uint64_t x = static_cast<uint64_t>(g.bw) * b;
     return x > g.K ? static_cast<uint32_t>(x - g.K) : 0u;
 }
 SVB_HD uint32_t win_jhi(const WinGeom& g, uint32_t b) {
-    const uint64_t x = 64ull * b + 64ull + (g.n - g.m) + g.K;
+    const uint64_t x = static_cast<uint64_t>(g.bw) * b + g.bw + (g.n - g.m) + g.K;
     return x < g.n ? static_cast<uint32_t>(x) : g.n;
 }
 // per-block step limits, all relative to the block's first column (rel = column - win_jlo(b)):
@@ -81,8 +88,24 @@ SVB_HD WinBlock win_block(const WinGeom& g, uint32_t b) {
     w.width = hi - lo;
     w.hin_lim = b == 0u ? 0u : win_jhi(g, b - 1u) - lo;
     w.cnt_lim = b == g.last_block ? w.width : win_jlo(g, b + 1u) - lo;
-    w.hshift = b == g.last_block ? ((g.m - 1u) & 63u) : 63u;
+    w.hshift = b == g.last_block ? ((g.m - 1u) % g.bw) : g.bw - 1u;
     return w;
+}
+
+// The block step on a 32-row block (same recurrence as myers_step on one 32-bit word).
+SVB_HD uint32_t myers_step32(uint32_t& pv, uint32_t& mv, uint32_t eq, uint32_t hin, uint32_t hshift) {
+    const uint32_t hin_neg = hin >> 1, hin_pos = hin & 1u;
+    const uint32_t xv = eq | mv;
+    eq |= hin_neg;
+    const uint32_t xh = (((eq & pv) + pv) ^ pv) | eq;
+    uint32_t ph = mv | ~(xh | pv);
+    uint32_t mh = pv & xh;
+    const uint32_t hout = ((ph >> hshift) & 1u) | (((mh >> hshift) & 1u) << 1);
+    ph = (ph << 1) | hin_pos;
+    mh = (mh << 1) | hin_neg;
+    pv = mh | ~(xv | ph);
+    mv = ph & xv;
+    return hout;
 }
 
 // ---- virtual haplotype strings --------------------------------------------------------------------

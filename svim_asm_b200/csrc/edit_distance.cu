@@ -15,6 +15,7 @@
 // before their first use and only decoded (class lookup) when they enter the ring.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -88,19 +89,23 @@ __device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& 
 // Every 32 steps ("grid point") the warp (a) moves up to 32 further text columns from registers into the 128-slot
 // class ring and requests the next 32, (b) builds the match masks of the next block that will enter the band into
 // the idle mask buffer of its lane; the pattern bytes for that were requested one grid point earlier.
+template <int BW>
 __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc& T, uint32_t pre, uint32_t m, uint32_t n,
-                                                 uint32_t K, const uint8_t* ref, const uint8_t* sa, const uint8_t* sb,
-                                                 const uint8_t* cls2tab, unsigned long long* peqw, uint8_t* tcls, uint32_t lane) {
-    WinGeom g;
-    g.m = m; g.n = n; g.K = K; g.last_block = (m - 1u) / 64u;
-    uint32_t* peq32 = reinterpret_cast<uint32_t*>(peqw);             // [buffer][class][lane][half]
+                                              uint32_t K, const uint8_t* ref, const uint8_t* sa, const uint8_t* sb,
+                                              const uint8_t* cls2tab, unsigned long long* peq_mem, uint8_t* tcls, uint32_t lane) {
+    static_assert(BW == 64 || BW == 32, "block = one 64-bit or one 32-bit word per lane");
+    using Word = typename std::conditional<BW == 64, uint64_t, uint32_t>::type;
+    constexpr uint32_t WPB = BW / 32;                                // 32-bit words per block
+    const WinGeom g = win_geom(m, n, K, BW);
+    Word* peqw = reinterpret_cast<Word*>(peq_mem);                   // [buffer][class][lane]
+    uint32_t* peq32 = reinterpret_cast<uint32_t*>(peq_mem);          // [buffer][class][lane][word of the block]
 
     // ---- masks of the blocks 0 .. 31 (buffer 0), 32 rows per round like the striped path
     __syncwarp();
-    for (uint32_t i = lane; i < 2u * PEQ_ROWS * 64u; i += 32u) peq32[i] = 0u;
+    for (uint32_t i = lane; i < 2u * PEQ_ROWS * 32u * WPB; i += 32u) peq32[i] = 0u;
     for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
     __syncwarp();
-    const uint32_t rows0 = min(m, 2048u), ngroups = (rows0 + 31u) / 32u;
+    const uint32_t rows0 = min(m, 32u * BW), ngroups = (rows0 + 31u) / 32u;
     for (uint32_t g0 = 0; g0 < ngroups; g0 += 4u) {
         uint32_t byte[4], mode[4];
 #pragma unroll
@@ -114,16 +119,16 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
         for (int k = 0; k < 4; ++k) {
             const uint32_t cls = mode[k] == TOK_NONE ? ED_NOCLASS + 1u : tok_class(cls2tab, byte[k], mode[k]);
             const uint32_t peers = __match_any_sync(FULL, cls);
-            if (cls < ED_NOCLASS && static_cast<uint32_t>(__ffs(peers) - 1) == lane) peq32[cls * 64u + (g0 + k)] = peers;
+            if (cls < ED_NOCLASS && static_cast<uint32_t>(__ffs(peers) - 1) == lane) peq32[cls * (32u * WPB) + (g0 + k)] = peers;
         }
     }
     // ---- later blocks: bytes requested ahead (pat_*), masks built at a grid point
     uint32_t next_build = 32u;                                       // next block whose masks are to be built
-    uint32_t pat_byte[2] = {0u, 0u}, pat_mode[2] = {TOK_NONE, TOK_NONE};
+    uint32_t pat_byte[WPB], pat_mode[WPB];
     auto pattern_fetch = [&]() {
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint64_t idx = 64ull * next_build + 32u * k + lane;
+        for (int k = 0; k < static_cast<int>(WPB); ++k) {
+            const uint64_t idx = static_cast<uint64_t>(BW) * next_build + 32u * k + lane;
             pat_mode[k] = TOK_NONE;
             pat_byte[k] = 0u;
             if (next_build <= g.last_block && idx < m) pat_byte[k] = hap_fetch(P, pre + static_cast<uint32_t>(idx), ref, sa, sb, pat_mode[k]);
@@ -131,14 +136,14 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
     };
     auto pattern_build = [&]() {                                     // block next_build -> buffer (b / 32) & 1, column b % 32
         const uint32_t buf = (next_build >> 5) & 1u, col = next_build & 31u;
-        for (uint32_t i = lane; i < PEQ_ROWS * 2u; i += 32u) peq32[((buf * PEQ_ROWS + (i >> 1)) * 32u + col) * 2u + (i & 1u)] = 0u;
+        for (uint32_t i = lane; i < PEQ_ROWS * WPB; i += 32u) peq32[((buf * PEQ_ROWS + i / WPB) * 32u + col) * WPB + (i % WPB)] = 0u;
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < static_cast<int>(WPB); ++k) {
             const uint32_t cls = pat_mode[k] == TOK_NONE ? ED_NOCLASS + 1u : tok_class(cls2tab, pat_byte[k], pat_mode[k]);
             const uint32_t peers = __match_any_sync(FULL, cls);
             if (cls < ED_NOCLASS && static_cast<uint32_t>(__ffs(peers) - 1) == lane)
-                peq32[((buf * PEQ_ROWS + cls) * 32u + col) * 2u + static_cast<uint32_t>(k)] = peers;
+                peq32[((buf * PEQ_ROWS + cls) * 32u + col) * WPB + static_cast<uint32_t>(k)] = peers;
         }
         __syncwarp();
     };
@@ -165,56 +170,40 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
 
     // ---- per-lane block state.  What a step does with its block depends on where it is inside the block's columns
     // (rel = t - start): rel < width: inside the band (commit the new vertical deltas); rel < hin_lim: the block above
-    // is inside too (take its delta, else +1); rel < cnt_lim: the bottom-row delta counts.  These change four times
-    // per block, so they live in lane flags that are recomputed at EVENT steps (warp-wide minimum of every lane's
-    // next boundary); between two events the step loop is branch-free.
+    // is inside too (take its delta, else +1); rel < cnt_lim: the bottom-row delta counts.
     uint32_t blk = lane, buf = 0;
     WinBlock w;
-    w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
+    w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = BW - 1u;
     if (blk <= g.last_block) w = win_block(g, blk);
     int colbase = -static_cast<int>(blk);                            // text column of step t: t + colbase
-    uint64_t pv = ~0ull, mv = 0ull;
+    Word pv = static_cast<Word>(~0ull), mv = 0;
     uint32_t acc_codes = 0, acc_minus = 0;                           // sum of counted delta codes (0, 1, 2) / number of -1 among them
     uint32_t hout = 0;
     auto ring_class = [&](int col) -> uint32_t { return (col >= 0 && static_cast<uint32_t>(col) < n) ? tcls[static_cast<uint32_t>(col) & 127u] : ED_NOCLASS; };
-    const unsigned long long* peq_lane = peqw + lane;                // + (buffer * PEQ_ROWS + class) * 32
-    uint64_t eq0 = peq_lane[ring_class(colbase) * 32u];
+    const Word* peq_lane = peqw + lane;                              // + (buffer * PEQ_ROWS + class) * 32
+    Word eq0 = peq_lane[ring_class(colbase) * 32u];
     uint32_t cls1 = ring_class(colbase + 1);
     uint32_t b_lo = 0;                                               // smallest block that still has columns to do
     const uint32_t t_end = n + g.last_block;
     const uint32_t src_lane = (lane + 31u) & 31u;
-    bool active = false;
-    uint32_t hin_and = 0u, hin_or = 1u, cnt_mask = 0u, my_event = 0u;
+    // A lane changes block when its block has run out of columns: that is the only EVENT of the step loop (warp-wide
+    // minimum of the lanes' next switch step, one per bw + 1 steps); the three per-step conditions above are plain
+    // compares on rel, off the dependency chain of the recurrence (the loop is latency bound, they cost nothing).
     constexpr uint32_t NEVER = 0xFFFFFFFFu;
-    auto lane_event = [&](uint32_t t) {                              // flags for the steps t, t+1, ... up to the lane's next boundary
-        if (w.width != 0u && t == w.start + w.width) {               // out of columns: on to block blk + 32 (WIN_SLACK idle steps follow)
+    auto switch_step = [&]() -> uint32_t { return w.width != 0u ? w.start + w.width : NEVER; };
+    auto lane_switch = [&](uint32_t t) {
+        if (t == switch_step()) {                                    // on to block blk + 32 (WIN_SLACK idle steps follow)
             blk += 32u;
             buf ^= 1u;
             colbase -= 32;
-            pv = ~0ull;
-            mv = 0ull;
+            pv = static_cast<Word>(~0ull);
+            mv = 0;
             peq_lane = peqw + buf * (PEQ_ROWS * 32u) + lane;
-            w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = 63u;
+            w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = BW - 1u;
             if (blk <= g.last_block) w = win_block(g, blk);
         }
-        const uint32_t rel = t - w.start;                            // wraps to a huge value before the block starts
-        active = rel < w.width;
-        const bool take = rel < w.hin_lim;
-        hin_and = take ? 3u : 0u;
-        hin_or = take ? 0u : 1u;
-        cnt_mask = rel < w.cnt_lim ? 3u : 0u;
-        uint32_t nxt = NEVER;                                        // the smallest boundary after t
-        if (w.width != 0u) {
-            const uint32_t b0 = w.start, b1 = w.start + w.cnt_lim, b2 = w.start + w.hin_lim, b3 = w.start + w.width;
-            if (b0 > t) nxt = min(nxt, b0);
-            if (b1 > t) nxt = min(nxt, b1);
-            if (b2 > t) nxt = min(nxt, b2);
-            if (b3 > t) nxt = min(nxt, b3);
-        }
-        my_event = nxt;
     };
-    lane_event(0u);
-    uint32_t next_event = __reduce_min_sync(FULL, my_event);
+    uint32_t next_event = __reduce_min_sync(FULL, switch_step());
 
     for (uint32_t t0 = 0; t0 < t_end; t0 += 32u) {
         if (t0) {                                                    // grid point
@@ -235,28 +224,34 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
         uint32_t t = t0;
         while (t < t1) {
             if (t == next_event) {
-                lane_event(t);
-                next_event = __reduce_min_sync(FULL, my_event);
+                lane_switch(t);
+                next_event = __reduce_min_sync(FULL, switch_step());
             }
             const uint32_t t_stop = min(t1, next_event);             // next_event > t here
             uint32_t ridx = static_cast<uint32_t>(static_cast<int>(t) + 2 + colbase);
+            uint32_t rel = t - w.start;                              // wraps to a huge value before the block starts
+            const uint32_t width = w.width, hin_lim = w.hin_lim, cnt_lim = w.cnt_lim, hshift = w.hshift;
 #pragma unroll 4
             for (; t < t_stop; ++t) {
                 const uint32_t shin = __shfl_sync(FULL, hout, src_lane);
-                const uint32_t hin = (shin & hin_and) | hin_or;
-                const uint64_t eq1 = peq_lane[cls1 * 32u];
+                const uint32_t hin = rel < hin_lim ? shin : 1u;
+                const Word eq1 = peq_lane[cls1 * 32u];
                 const uint32_t cls2 = tcls[ridx & 127u];
                 ++ridx;
-                uint64_t npv = pv, nmv = mv;
-                const uint32_t ho = myers_step(npv, nmv, eq0, hin, w.hshift);
+                Word npv = pv, nmv = mv;
+                uint32_t ho;
+                if constexpr (BW == 64) ho = myers_step(npv, nmv, eq0, hin, hshift);
+                else ho = myers_step32(npv, nmv, eq0, hin, hshift);
+                const bool active = rel < width;
                 pv = active ? npv : pv;
                 mv = active ? nmv : mv;
-                const uint32_t counted = ho & cnt_mask;
+                const uint32_t counted = rel < cnt_lim ? ho : 0u;
                 acc_codes += counted;
                 acc_minus += counted >> 1;
                 hout = ho;
                 eq0 = eq1;
                 cls1 = cls2;
+                ++rel;
             }
         }
     }
@@ -328,25 +323,43 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             long long dist = n;
             bool done = m == 0u;
             int first_attempt = 0;
-            if (m > 2048u) {
-                // Long patterns: one sliding-window pass with the widest band a warp covers (about 1000 diagonals either
-                // side); it settles every pair whose distance is within that band in n + m/64 steps.
-                const uint32_t kw = win_kmax(m, n);
+            // Long patterns: one sliding-window pass over the Ukkonen band settles every pair whose distance is within
+            // the band in about n steps: first with 32-row blocks (band of about 500 either side, half the work per
+            // step), then with 64-row blocks (about 1000).  What is left goes to the striped band attempts.
+            unsigned long long known_above = 0;           // the distance is known to exceed this
+            if (!done && m > 1024u) {
+                const uint32_t kw = win_kmax(m, n, 32u);
                 if (kw >= 128u) {
-                    const long long d = window_pass(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
+                    const long long d = window_pass<32>(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
+                    steps_total += n + (m - 1u) / 32u;
+                    if (d <= static_cast<long long>(kw)) {
+                        dist = d;
+                        done = true;
+                    } else {
+                        known_above = kw;
+                    }
+                }
+            }
+            if (!done && m > 2048u) {
+                const uint32_t kw = win_kmax(m, n, 64u);
+                if (kw >= 128u && kw > known_above) {
+                    const long long d = window_pass<64>(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
                     steps_total += n + (m - 1u) / 64u;
                     if (d <= static_cast<long long>(kw)) {
                         dist = d;
                         done = true;
                     } else {
-                        // beyond the window: these are mostly unrelated alleles, so the stripes start four times wider
-                        while ((256ull << (2 * first_attempt)) < 4ull * kw) ++first_attempt;
+                        known_above = kw;
                     }
-                    // the maskless steady state of the striped path reads ring slots no refill has written yet
-                    __syncwarp();
-                    for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
-                    __syncwarp();
                 }
+            }
+            if (!done && m > 1024u) {
+                // beyond the windows: these are mostly unrelated alleles, so the stripes start four times wider
+                while ((256ull << (2 * first_attempt)) < 4ull * known_above) ++first_attempt;
+                // the maskless steady state of the striped path reads ring slots no refill has written yet
+                __syncwarp();
+                for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
+                __syncwarp();
             }
             if (!done) {
                 // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of

@@ -23,7 +23,7 @@ def load():
     lib.hc_myers.restype = ctypes.c_longlong
     lib.hc_myers.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_int]
     lib.hc_myers_window.restype = ctypes.c_longlong
-    lib.hc_myers_window.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_uint]
+    lib.hc_myers_window.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_uint, ctypes.c_uint]
     lib.hc_win_kmax.restype = ctypes.c_uint
-    lib.hc_win_kmax.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    lib.hc_win_kmax.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
     return lib

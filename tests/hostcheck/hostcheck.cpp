@@ -67,19 +67,20 @@ extern "C" long long hc_myers(const uint8_t* a, long long m, const uint8_t* b, l
 
 // The sliding-window pass of edit_distance.cu, emulated with the SAME step order: global step t, lane l = b % 32
 // works on column t - b of block b, horizontal deltas reach the lane below one step later, lanes move on to
-// block b + 32 when theirs has run out of columns.  Returns the window's value (exact iff <= K).
-extern "C" long long hc_myers_window(const uint8_t* a, long long m64, const uint8_t* b, long long n64, unsigned K) {
-    WinGeom g;
-    g.m = static_cast<uint32_t>(m64); g.n = static_cast<uint32_t>(n64); g.K = K; g.last_block = (g.m - 1u) / 64u;
+// block b + 32 when theirs has run out of columns.  bw = rows per block (64 or 32).  Returns the window's value
+// (exact iff <= K), -1 if K is too wide for one warp.
+extern "C" long long hc_myers_window(const uint8_t* a, long long m64, const uint8_t* b, long long n64, unsigned K, unsigned bw) {
+    const WinGeom g = win_geom(static_cast<uint32_t>(m64), static_cast<uint32_t>(n64), K, bw);
     struct Lane { uint32_t blk; bool has; WinBlock w; uint64_t pv, mv; uint32_t hout; long long partial; };
     Lane L[32];
     auto masks = [&](uint32_t blk, uint8_t c) {
         uint64_t eq = 0;
-        for (uint32_t r = 0; r < 64u && 64ull * blk + r < g.m; ++r) if (a[64ull * blk + r] == c) eq |= 1ull << r;
+        for (uint32_t r = 0; r < bw && static_cast<uint64_t>(bw) * blk + r < g.m; ++r) if (a[static_cast<uint64_t>(bw) * blk + r] == c) eq |= 1ull << r;
         return eq;
     };
+    const uint64_t fresh = bw == 64u ? ~0ull : 0xFFFFFFFFull;
     for (uint32_t l = 0; l < 32u; ++l) {
-        L[l].blk = l; L[l].has = l <= g.last_block; L[l].pv = ~0ull; L[l].mv = 0; L[l].hout = 0; L[l].partial = 0;
+        L[l].blk = l; L[l].has = l <= g.last_block; L[l].pv = fresh; L[l].mv = 0; L[l].hout = 0; L[l].partial = 0;
         if (L[l].has) L[l].w = win_block(g, l);
     }
     const uint32_t t_end = g.n + g.last_block;
@@ -93,14 +94,21 @@ extern "C" long long hc_myers_window(const uint8_t* a, long long m64, const uint
             if (rel >= 0 && static_cast<uint32_t>(rel) < x.w.width) {
                 const uint32_t j = win_jlo(g, x.blk) + static_cast<uint32_t>(rel);
                 const uint32_t hin = static_cast<uint32_t>(rel) < x.w.hin_lim ? prev_hout[(l + 31u) & 31u] : 1u;
-                const uint32_t ho = myers_step(x.pv, x.mv, masks(x.blk, b[j]), hin, x.w.hshift);
+                uint32_t ho;
+                if (bw == 64u) {
+                    ho = myers_step(x.pv, x.mv, masks(x.blk, b[j]), hin, x.w.hshift);
+                } else {
+                    uint32_t pv = static_cast<uint32_t>(x.pv), mv = static_cast<uint32_t>(x.mv);
+                    ho = myers_step32(pv, mv, static_cast<uint32_t>(masks(x.blk, b[j])), hin, x.w.hshift);
+                    x.pv = pv; x.mv = mv;
+                }
                 if (static_cast<uint32_t>(rel) < x.w.cnt_lim) x.partial += static_cast<int>(ho & 1u) - static_cast<int>(ho >> 1);
                 x.hout = ho;
             }
             if (rel + 1 == static_cast<int>(x.w.width)) {          // out of columns: move on to block blk + 32
                 x.blk += 32u;
                 x.has = x.blk <= g.last_block;
-                x.pv = ~0ull; x.mv = 0;
+                x.pv = fresh; x.mv = 0;
                 if (x.has) {
                     const WinBlock nw = win_block(g, x.blk);
                     if (nw.start < t + 1u + WIN_SLACK) return -1;  // the lane is not free in time: K too wide for one warp
@@ -113,4 +121,4 @@ extern "C" long long hc_myers_window(const uint8_t* a, long long m64, const uint
     for (uint32_t l = 0; l < 32u; ++l) total += L[l].partial;
     return total;
 }
-extern "C" unsigned hc_win_kmax(unsigned m, unsigned n) { return win_kmax(m, n); }
+extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return win_kmax(m, n, bw); }

@@ -33,8 +33,9 @@ def test_block_step_in_stripes(oracle_clib):
             assert lib.hc_myers(a, len(a), b, len(b), blocks) == want
 
 
+@pytest.mark.parametrize("bw", [64, 32])
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_sliding_window_exact_within_band(oracle_clib, seed):
+def test_sliding_window_exact_within_band(oracle_clib, seed, bw):
     """window value == distance whenever it is <= K; never below the distance; the widest K one warp covers is accepted."""
     lib = hostcheck.load()
     rng = np.random.default_rng(seed)
@@ -50,11 +51,11 @@ def test_sliding_window_exact_within_band(oracle_clib, seed):
         if not p:
             continue
         want = oracle_clib.orc_edit_distance(p, len(p), t, len(t))
-        kmax = lib.hc_win_kmax(len(p), len(t))
+        kmax = lib.hc_win_kmax(len(p), len(t), bw)
         for K in sorted({1, 64, 300, kmax} - {0}):
             if K > kmax:
                 continue
-            got = lib.hc_myers_window(p, len(p), t, len(t), K)
+            got = lib.hc_myers_window(p, len(p), t, len(t), K, bw)
             assert got >= want, (len(p), len(t), K, got, want)
             if want <= K:
                 assert got == want, (len(p), len(t), K, got, want)
@@ -64,7 +65,8 @@ def test_sliding_window_exact_within_band(oracle_clib, seed):
     assert cases > 8
 
 
-def test_sliding_window_edge_shapes(oracle_clib):
+@pytest.mark.parametrize("bw", [64, 32])
+def test_sliding_window_edge_shapes(oracle_clib, bw):
     lib = hostcheck.load()
     rng = np.random.default_rng(11)
     for m, n in [(1, 1), (1, 300), (64, 64), (65, 64 + 65), (128, 128), (2048, 2048), (2049, 2049), (4096, 4100), (63, 1500)]:
@@ -73,11 +75,11 @@ def test_sliding_window_edge_shapes(oracle_clib):
         t = _mutate(rng, t, 5)
         if len(t) < len(p):
             p, t = t, p
-        kmax = lib.hc_win_kmax(len(p), len(t))
+        kmax = lib.hc_win_kmax(len(p), len(t), bw)
         if kmax == 0:
             continue
         want = oracle_clib.orc_edit_distance(p, len(p), t, len(t))
-        got = lib.hc_myers_window(p, len(p), t, len(t), kmax)
+        got = lib.hc_myers_window(p, len(p), t, len(t), kmax, bw)
         assert got >= want
         if want <= kmax:
             assert got == want, (m, n, got, want)

@@ -55,7 +55,8 @@ def test_edit_distance_long_patterns_window_and_stripes(engine, oracle_clib):
     rng = np.random.default_rng(23)
     alphabet = list(b"ACGT")
     pairs = []
-    for m, edits in ((2049, 0), (2100, 3), (3000, 120), (4500, 450), (5200, 900), (5200, 1400), (7000, 2500), (9900, 520)):
+    for m, edits in ((1025, 0), (1100, 30), (1500, 200), (1900, 600), (2048, 480), (2049, 0), (2100, 3), (3000, 120), (4500, 450),
+                     (4500, 520), (5200, 900), (5200, 1400), (7000, 2500), (9900, 520), (9900, 400)):
         a = bytes(rng.choice(alphabet + list(b"N"), m).tolist())
         pairs.append((a, _mutate(rng, a, edits, alphabet)))
     a = bytes(rng.choice(alphabet, 6000).tolist())
