@@ -27,7 +27,9 @@ namespace {
 constexpr int ED_WARPS = 2;
 constexpr uint32_t ED_NOCLASS = ED_NCLASS;      // extra all-zero row of the match-mask table: "matches nothing"
 constexpr uint32_t FULL = 0xffffffffu;
-constexpr uint32_t PEQ_ROWS = ED_NCLASS + 1;
+constexpr uint32_t ED_SENTINEL = ED_NCLASS + 1;   // padding symbol of window_pass32: matches only itself
+constexpr uint32_t ED_SKIP = ED_NCLASS + 2;       // "no row here" while match masks are built
+constexpr uint32_t PEQ_ROWS = ED_NCLASS + 2;
 
 struct EdShared {
     // [buffer][class][lane]: match mask of the lane's 64 rows.  The striped path uses buffer 0; the sliding window
@@ -261,6 +263,198 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
     return static_cast<long long>(m) + __reduce_add_sync(FULL, partial);
 }
 
+// ---- the same window with 32-row blocks, written for the shortest dependency chain per step -------------------------
+// (the step loop is bound by ONE chain: shuffle -> block recurrence -> shuffle)
+//  * both strings are padded with a sentinel symbol to a multiple of 32 rows: D(P + S^k, T + S^k) = D(P, T), and the
+//    bottom row of EVERY block is bit 31 (a constant shift instead of a variable one);
+//  * the horizontal delta travels as two registers (is -1 / is +1) in two shuffles, so the -1 flag ORs straight into
+//    the match mask and nothing has to be unpacked on the chain:
+//    select, or-and, add, xor-or, and-or-not, shift = 6 dependent instructions between the shuffles.
+// m0, n0: the real lengths.  Returns the window's value, which is D[m0][n0] whenever it is <= K.
+__device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDesc& T, uint32_t pre, uint32_t m0, uint32_t n0,
+                                                   uint32_t K, const uint8_t* ref, const uint8_t* sa, const uint8_t* sb,
+                                                   const uint8_t* cls2tab, unsigned long long* peq_mem, uint8_t* tcls, uint32_t lane) {
+    constexpr int BW = 32;
+    using Word = uint32_t;
+    constexpr uint32_t WPB = 1;
+    const uint32_t padk = (32u - (m0 & 31u)) & 31u, m = m0 + padk, n = n0 + padk;       // padded lengths
+    const WinGeom g = win_geom(m, n, K, BW);
+    Word* peqw = reinterpret_cast<Word*>(peq_mem);                   // [buffer][class][lane]
+    uint32_t* peq32 = reinterpret_cast<uint32_t*>(peq_mem);          // [buffer][class][lane][word of the block]
+
+    // ---- masks of the blocks 0 .. 31 (buffer 0), 32 rows per round like the striped path
+    __syncwarp();
+    for (uint32_t i = lane; i < 2u * PEQ_ROWS * 32u * WPB; i += 32u) peq32[i] = 0u;
+    for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
+    __syncwarp();
+    const uint32_t rows0 = min(m, 32u * BW), ngroups = (rows0 + 31u) / 32u;
+    for (uint32_t g0 = 0; g0 < ngroups; g0 += 4u) {
+        uint32_t byte[4], mode[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = (g0 + k) * 32u + lane;
+            mode[k] = TOK_NONE;
+            byte[k] = 0u;
+            if (idx < rows0 && idx < m0) byte[k] = hap_fetch(P, pre + idx, ref, sa, sb, mode[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t idx = (g0 + k) * 32u + lane;
+            uint32_t cls = mode[k] == TOK_NONE ? ED_SKIP : tok_class(cls2tab, byte[k], mode[k]);
+            if (idx >= m0 && idx < rows0) cls = ED_SENTINEL;
+            const uint32_t peers = __match_any_sync(FULL, cls);
+            if (cls != ED_NOCLASS && cls < ED_SKIP && static_cast<uint32_t>(__ffs(peers) - 1) == lane) peq32[cls * (32u * WPB) + (g0 + k)] = peers;
+        }
+    }
+    // ---- later blocks: bytes requested ahead (pat_*), masks built at a grid point
+    uint32_t next_build = 32u;                                       // next block whose masks are to be built
+    uint32_t pat_byte[WPB], pat_mode[WPB];
+    auto pattern_fetch = [&]() {
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(WPB); ++k) {
+            const uint64_t idx = static_cast<uint64_t>(BW) * next_build + 32u * k + lane;
+            pat_mode[k] = TOK_NONE;
+            pat_byte[k] = 0u;
+            if (next_build <= g.last_block && idx < m0) pat_byte[k] = hap_fetch(P, pre + static_cast<uint32_t>(idx), ref, sa, sb, pat_mode[k]);
+        }
+    };
+    auto pattern_build = [&]() {                                     // block next_build -> buffer (b / 32) & 1, column b % 32
+        const uint32_t buf = (next_build >> 5) & 1u, col = next_build & 31u;
+        for (uint32_t i = lane; i < PEQ_ROWS * WPB; i += 32u) peq32[((buf * PEQ_ROWS + i / WPB) * 32u + col) * WPB + (i % WPB)] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < static_cast<int>(WPB); ++k) {
+            const uint64_t idx = static_cast<uint64_t>(BW) * next_build + 32u * k + lane;
+            uint32_t cls = pat_mode[k] == TOK_NONE ? ED_SKIP : tok_class(cls2tab, pat_byte[k], pat_mode[k]);
+            if (idx >= m0 && idx < m) cls = ED_SENTINEL;
+            const uint32_t peers = __match_any_sync(FULL, cls);
+            if (cls != ED_NOCLASS && cls < ED_SKIP && static_cast<uint32_t>(__ffs(peers) - 1) == lane)
+                peq32[((buf * PEQ_ROWS + cls) * 32u + col) * WPB + static_cast<uint32_t>(k)] = peers;
+        }
+        __syncwarp();
+    };
+    pattern_fetch();
+
+    // ---- column ring: columns [0, c_ins) are in; the batch [c_ins, c_ins + 32) waits in registers
+    uint32_t c_ins = 0, nxt_byte = 0, nxt_mode = TOK_NONE;
+    auto ring_fetch = [&]() {
+        const uint32_t col = c_ins + lane;
+        nxt_mode = TOK_NONE;
+        nxt_byte = 0u;
+        if (col < n0) nxt_byte = hap_fetch(T, pre + col, ref, sa, sb, nxt_mode);
+    };
+    auto ring_insert = [&]() {
+        const uint32_t col = c_ins + lane;
+        uint32_t cls = nxt_mode == TOK_NONE ? ED_NOCLASS : tok_class(cls2tab, nxt_byte, nxt_mode);
+        if (col >= n0 && col < n) cls = ED_SENTINEL;
+        tcls[col & 127u] = static_cast<uint8_t>(cls);
+        c_ins += 32u;
+    };
+    for (int k = 0; k < 3; ++k) {
+        ring_fetch();
+        ring_insert();
+    }
+    ring_fetch();
+    __syncwarp();
+
+    // ---- per-lane block state.  What a step does with its block depends on where it is inside the block's columns
+    // (rel = t - start): rel < width: inside the band (commit the new vertical deltas); rel < hin_lim: the block above
+    // is inside too (take its delta, else +1); rel < cnt_lim: the bottom-row delta counts.
+    uint32_t blk = lane, buf = 0;
+    WinBlock w;
+    w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = BW - 1u;
+    if (blk <= g.last_block) w = win_block(g, blk);
+    int colbase = -static_cast<int>(blk);                            // text column of step t: t + colbase
+    Word pv = static_cast<Word>(~0ull), mv = 0;
+    uint32_t acc_pos = 0, acc_neg = 0;                               // counted +1 / -1 deltas of the bottom rows
+    uint32_t hneg_out = 0, hpos_out = 0;
+    auto ring_class = [&](int col) -> uint32_t { return (col >= 0 && static_cast<uint32_t>(col) < n) ? tcls[static_cast<uint32_t>(col) & 127u] : ED_NOCLASS; };
+    const Word* peq_lane = peqw + lane;                              // + (buffer * PEQ_ROWS + class) * 32
+    Word eq0 = peq_lane[ring_class(colbase) * 32u];
+    uint32_t cls1 = ring_class(colbase + 1);
+    uint32_t b_lo = 0;                                               // smallest block that still has columns to do
+    const uint32_t t_end = n + g.last_block;
+    const uint32_t src_lane = (lane + 31u) & 31u;
+    // A lane changes block when its block has run out of columns: that is the only EVENT of the step loop (warp-wide
+    // minimum of the lanes' next switch step, one per bw + 1 steps); the three per-step conditions above are plain
+    // compares on rel, off the dependency chain of the recurrence (the loop is latency bound, they cost nothing).
+    constexpr uint32_t NEVER = 0xFFFFFFFFu;
+    auto switch_step = [&]() -> uint32_t { return w.width != 0u ? w.start + w.width : NEVER; };
+    auto lane_switch = [&](uint32_t t) {
+        if (t == switch_step()) {                                    // on to block blk + 32 (WIN_SLACK idle steps follow)
+            blk += 32u;
+            buf ^= 1u;
+            colbase -= 32;
+            pv = static_cast<Word>(~0ull);
+            mv = 0;
+            peq_lane = peqw + buf * (PEQ_ROWS * 32u) + lane;
+            w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = BW - 1u;
+            if (blk <= g.last_block) w = win_block(g, blk);
+        }
+    };
+    uint32_t next_event = __reduce_min_sync(FULL, switch_step());
+
+    for (uint32_t t0 = 0; t0 < t_end; t0 += 32u) {
+        if (t0) {                                                    // grid point
+            while (b_lo <= g.last_block && win_jhi(g, b_lo) + b_lo <= t0) ++b_lo;
+            const int oldest = static_cast<int>(t0) - static_cast<int>(b_lo) - 31;     // oldest column any lane still reads
+            if (static_cast<int>(c_ins) <= oldest + 94) {
+                ring_insert();
+                ring_fetch();
+            }
+            if (next_build <= g.last_block && t0 > win_jlo(g, next_build - 32u) + (next_build - 32u)) {
+                pattern_build();                                     // its lane has moved on to block next_build - 32
+                ++next_build;
+                pattern_fetch();
+            }
+            __syncwarp();
+        }
+        const uint32_t t1 = min(t_end, t0 + 32u);
+        uint32_t t = t0;
+        while (t < t1) {
+            if (t == next_event) {
+                lane_switch(t);
+                next_event = __reduce_min_sync(FULL, switch_step());
+            }
+            const uint32_t t_stop = min(t1, next_event);             // next_event > t here
+            uint32_t ridx = static_cast<uint32_t>(static_cast<int>(t) + 2 + colbase);
+            uint32_t rel = t - w.start;                              // wraps to a huge value before the block starts
+            const uint32_t width = w.width, hin_lim = w.hin_lim, cnt_lim = w.cnt_lim;
+#pragma unroll 4
+            for (; t < t_stop; ++t) {
+                const uint32_t sneg = __shfl_sync(FULL, hneg_out, src_lane), spos = __shfl_sync(FULL, hpos_out, src_lane);
+                const bool take = rel < hin_lim;
+                const uint32_t hneg = take ? sneg : 0u, hpos = take ? spos : 1u;
+                const Word eq1 = peq_lane[cls1 * 32u];
+                const uint32_t cls2 = tcls[ridx & 127u];
+                ++ridx;
+                const uint32_t xv = eq0 | mv;
+                const uint32_t eqn = eq0 | hneg;
+                const uint32_t xh = (((eqn & pv) + pv) ^ pv) | eqn;
+                uint32_t ph = mv | ~(xh | pv);
+                uint32_t mh = pv & xh;
+                const uint32_t pos_o = ph >> 31, neg_o = mh >> 31;
+                ph = (ph << 1) | hpos;
+                mh = (mh << 1) | hneg;
+                const bool active = rel < width;
+                pv = active ? (mh | ~(xv | ph)) : pv;
+                mv = active ? (ph & xv) : mv;
+                const bool cnt = rel < cnt_lim;
+                acc_pos += cnt ? pos_o : 0u;
+                acc_neg += cnt ? neg_o : 0u;
+                hpos_out = pos_o;
+                hneg_out = neg_o;
+                eq0 = eq1;
+                cls1 = cls2;
+                ++rel;
+            }
+        }
+    }
+    const int partial = static_cast<int>(acc_pos) - static_cast<int>(acc_neg);
+    __syncwarp();
+    return static_cast<long long>(m) + __reduce_add_sync(FULL, partial);
+}
+
 __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const EditJob* __restrict__ jobs, uint32_t n_jobs,
                                                                        unsigned int* next_job,
                                                                        const uint8_t* __restrict__ ref,
@@ -330,7 +524,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             if (!done && m > 1024u) {
                 const uint32_t kw = win_kmax(m, n, 32u);
                 if (kw >= 128u) {
-                    const long long d = window_pass<32>(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
+                    const long long d = window_pass32(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
                     steps_total += n + (m - 1u) / 32u;
                     if (d <= static_cast<long long>(kw)) {
                         dist = d;

@@ -83,3 +83,22 @@ def test_sliding_window_edge_shapes(oracle_clib, bw):
         assert got >= want
         if want <= kmax:
             assert got == want, (m, n, got, want)
+
+
+def test_sentinel_padding_keeps_the_distance(oracle_clib):
+    """window_pass32 pads both strings with a symbol that matches only itself up to a multiple of 32 rows:
+    D(P + S^k, T + S^k) = D(P, T), and the padded window is exact within the same band."""
+    lib = hostcheck.load()
+    rng = np.random.default_rng(17)
+    for _ in range(12):
+        m = int(rng.integers(1025, 4000))
+        a = bytes(rng.choice(list(b"ACGT"), m).tolist())
+        b = _mutate(rng, a, int(rng.integers(0, 400)))
+        p, t = (a, b) if len(a) <= len(b) else (b, a)
+        want = oracle_clib.orc_edit_distance(p, len(p), t, len(t))
+        k = (32 - len(p) % 32) % 32
+        pp, tt = p + b"#" * k, t + b"#" * k
+        assert oracle_clib.orc_edit_distance(pp, len(pp), tt, len(tt)) == want
+        kmax = lib.hc_win_kmax(len(p), len(t), 32)
+        if kmax and want <= kmax:
+            assert lib.hc_myers_window(pp, len(pp), tt, len(tt), kmax, 32) == want
