@@ -122,3 +122,9 @@ extern "C" long long hc_myers_window(const uint8_t* a, long long m64, const uint
     return total;
 }
 extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return win_kmax(m, n, bw); }
+
+#include "../../svim_asm_b200/csrc/inflate_core.cuh"
+// The per-member DEFLATE decoder of bgzf_inflate.cu, on the host: checked against zlib's output.
+extern "C" int hc_inflate(const uint8_t* src, unsigned src_len, uint8_t* dst, unsigned out_len) {
+    return inflate_member(src, src_len, dst, out_len);
+}

@@ -1,0 +1,67 @@
+"""Host check of the per-member DEFLATE decoder (csrc/inflate_core.cuh, one GPU thread per BGZF member in
+bgzf_inflate.cu) against zlib: stored, fixed-Huffman and dynamic-Huffman blocks, every compression level, data from
+incompressible to highly repetitive, and truncated / corrupt streams (which must fail, not hang or overrun)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from tests import hostcheck
+
+
+def _raw_deflate(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+def _inflate(lib, comp, n):
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    rc = lib.hc_inflate(comp, len(comp), out.ctypes.data, n)
+    return rc, out[:n].tobytes()
+
+
+def _samples():
+    rng = np.random.default_rng(3)
+    yield b""
+    yield b"A"
+    yield bytes(rng.integers(0, 256, 65280, dtype=np.uint8))                       # incompressible: stored blocks
+    yield bytes(rng.choice(list(b"ACGT"), 65280).astype(np.uint8))                 # 2 bits of entropy per byte
+    yield b"ACGT" * 16000                                                          # long matches, distance 4
+    yield bytes(rng.integers(0, 4, 30000, dtype=np.uint8)) + b"\xff" * 30000       # mixed
+    ops = ((rng.geometric(1 / 12.0, 16000).astype(np.uint32) << 4) | rng.choice([7, 8, 1, 2], 16000).astype(np.uint32))
+    yield ops.tobytes()                                                            # BAM-packed CIGAR ops
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_matches_zlib(level):
+    lib = hostcheck.load()
+    for data in _samples():
+        comp = _raw_deflate(data, level)
+        rc, got = _inflate(lib, comp, len(data))
+        assert rc == 0 and got == data, (level, len(data), rc)
+
+
+def test_fixed_huffman_blocks():
+    lib = hostcheck.load()
+    for data in _samples():
+        comp = _raw_deflate(data, 6, zlib.Z_FIXED)
+        rc, got = _inflate(lib, comp, len(data))
+        assert rc == 0 and got == data
+
+
+def test_corrupt_streams_fail_cleanly():
+    lib = hostcheck.load()
+    rng = np.random.default_rng(4)
+    data = bytes(rng.choice(list(b"ACGTN"), 20000).astype(np.uint8))
+    comp = _raw_deflate(data, 6)
+    assert _inflate(lib, comp[:len(comp) // 2], len(data))[0] != 0                 # truncated input
+    assert _inflate(lib, comp, len(data) - 7)[0] != 0                              # ISIZE too small
+    assert _inflate(lib, comp, len(data) + 7)[0] != 0                              # ISIZE too large
+    bad = 0
+    for _ in range(200):                                                           # random bit flips: error or different bytes, never a crash
+        c = bytearray(comp)
+        c[int(rng.integers(0, len(c)))] ^= 1 << int(rng.integers(0, 8))
+        rc, got = _inflate(lib, bytes(c), len(data))
+        bad += rc != 0 or got != data
+    assert bad > 150
+    assert _inflate(lib, bytes(rng.integers(0, 256, 500, dtype=np.uint8)), 4000)[0] != 0   # garbage
