@@ -164,6 +164,20 @@ const char* svb_bam_sa_text(const svb_bam* bam, int64_t record);   /* raw SA:Z v
 int svb_parse_sa(const char* sa_text, const char* const* contig_names, int32_t n_contig,
                  svb_segment* out, int32_t cap);
 
+/* Device ingest: the same BAM file, inflated and split into records ON the GPU.
+ * Replaces pysam.AlignmentFile(path) + bam.fetch + AlignedSegment.cigartuples (svim-asm:63,85-86;
+ * SVIM_COLLECT.py:65; SVIM_intra.py:37) for the hot path: `rec_out` is the record image svb_load_records would
+ * have built from svb_bam_open's arrays (bit-identical), `bam_out` holds the host-side small data (header,
+ * svb_aln_hdr array, names, SA texts and segments); its CIGAR / sequence arrays stay empty until
+ * svb_bam_materialize_host downloads them (only the per-alignment seams read them).
+ * contig_lexrank: rank of every contig name under python string order, or NULL (code-point order of the names). */
+int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, const int32_t* contig_lexrank,
+                        svb_bam** bam_out, svb_records** rec_out, char* err, int err_len);
+int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec);
+/* ms of the last svb_bam_open_device call: [0] file read, [1] H2D, [2] inflate kernel, [3] record chase,
+ * [4] field + copy kernels, [5] host SA parse + record image, [6] total wall, [7] inflated bytes */
+const double* svb_bam_device_timings(void);
+
 /* ---- device: replaces analyze_alignment_file_coordsorted (SVIM_COLLECT.py:61-83) and below ---- */
 int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar,
                      uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,

@@ -55,7 +55,7 @@ def analyze_alignment_file_coordsorted(bam, options):
         logging.info("Processing chromosome {0}...".format(contig))
     eng = get_engine()
     host = bam.host
-    records = eng.load_records(host)
+    records = getattr(bam, "records", None) or eng.load_records(host)     # a device ingest left the records in HBM
     table = eng.collect(records, make_params(options), hap=getattr(options, "_haplotype", 0))
     out = CandidateList(candidates_from_rows(table.to_numpy(), {getattr(options, "_haplotype", 0): host},
                                              list(bam.references), list(bam.lengths)))

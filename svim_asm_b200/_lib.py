@@ -71,6 +71,9 @@ SIGNATURES = {
     "svb_bam_query_name": (c_char_p, [c_void_p, c_i64]),
     "svb_bam_sa_text": (c_char_p, [c_void_p, c_i64]),
     "svb_parse_sa": (c_int, [c_char_p, P(c_char_p), c_i32, c_void_p, c_i32]),
+    "svb_bam_open_device": (c_int, [c_void_p, c_char_p, c_int, c_void_p, P(c_void_p), P(c_void_p), c_char_p, c_int]),
+    "svb_bam_materialize_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_bam_device_timings": (c_void_p, []),
     "svb_load_records": (c_int, [c_void_p, c_void_p, c_u32, c_void_p, c_u64, c_void_p, c_void_p, c_u32, c_void_p,
                                  c_void_p, c_i32, P(c_void_p)]),
     "svb_records_free": (None, [c_void_p]),

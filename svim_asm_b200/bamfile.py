@@ -123,11 +123,17 @@ class AlignedSegment(object):
 
 
 class AlignmentFile(object):
-    """BAM file opened through the multi-threaded C++ ingest (svb_bam_open)."""
+    """BAM file opened through the device ingest (svb_bam_open_device: BGZF inflate and record split on the GPU; the
+    record image is then already resident for analyze_alignment_file_coordsorted) or, with SVIM_ASM_B200_INGEST=host
+    or when no engine is passed, through the multi-threaded C++ host ingest (svb_bam_open)."""
 
-    def __init__(self, path, mode="rb", threads=0):
+    def __init__(self, path, mode="rb", threads=0, engine=None):
         self.filename = path
-        self.host = HostBatch.from_bam(path, threads)
+        self.records = None                      # device record image of a device ingest
+        if engine is not None and os.environ.get("SVIM_ASM_B200_INGEST", "device") != "host":
+            self.host, self.records = HostBatch.from_bam_device(engine, path)
+        else:
+            self.host = HostBatch.from_bam(path, threads)
         self.references = tuple(self.host.contig_names)
         self.lengths = tuple(int(x) for x in self.host.contig_lengths)
         self.nreferences = len(self.references)

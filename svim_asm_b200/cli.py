@@ -11,7 +11,8 @@ __version__ = "1.0.3"
 def _open_sorted_bam(path, which):
     """svim-asm:63-80 / 85-120: header must say SO:coordinate and an index must sit next to the file."""
     from .bamfile import AlignmentFile
-    bam = AlignmentFile(path)
+    from .runtime import get_engine
+    bam = AlignmentFile(path, engine=get_engine())      # device ingest: the records stay in HBM for COLLECT
     label = "" if which is None else ("first " if which == 1 else "second ")
     try:
         sorted_ok = bam.header["HD"]["SO"] == "coordinate"

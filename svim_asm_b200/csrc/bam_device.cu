@@ -1,0 +1,517 @@
+// Device ingest: BGZF/BAM file -> the record image of svb_load_records, built ON the GPU.
+//
+// Stands in for what the reference obtains from pysam/htslib on the host (svim-asm:63,85-86 AlignmentFile;
+// SVIM_COLLECT.py:65 bam.fetch; SVIM_intra.py:37 cigartuples incl. the CG:B,I long-CIGAR convention).  The host only
+// reads the file, walks the BGZF member headers (18 bytes each) and parses the few hundred KB of names and SA tags;
+// the compressed bytes cross PCIe once and everything else happens in HBM:
+//   bgzf_inflate_kernel   one thread per BGZF member (independent raw-deflate streams, inflate_core.cuh)
+//   bam_chase_kernel      record boundaries (each record starts where the previous one ends: one dependent load per record)
+//   bam_fields_kernel     one thread per record: fixed fields, tag walk (SA:Z, CG:B,I), source offsets
+//   bam_copy_kernel       one CTA per record: CIGAR ops into 16-byte aligned runs padded with op 15, 4-bit query
+//                         bases, read names and SA texts into flat buffers
+// The result is bit-identical to the host ingest (bam_ingest.cpp): same svb_aln_hdr array, same CIGAR / sequence
+// layout, same SA segments (the SA text itself is parsed by the same host routine, svb_parse_sa).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bam_host.h"
+#include "common.cuh"
+#include "inflate_core.cuh"
+
+extern "C" int load_records_impl(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar, uint4* d_cigar_prebuilt,
+                                 uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,
+                                 const int32_t* contig_len, const int32_t* contig_lexrank, int32_t n_contig, svb_records** out);
+
+namespace {
+
+enum : uint32_t {
+    ING_ERR_INFLATE = 1u,       // a member did not inflate to its ISIZE
+    ING_ERR_RECORD = 2u,        // truncated / malformed BAM record
+    ING_ERR_TAG = 4u            // malformed auxiliary field
+};
+
+struct DevMember {
+    uint64_t in_off, out_off;
+    uint32_t in_len, out_len;
+};
+
+__global__ void __launch_bounds__(64) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const DevMember* __restrict__ members, uint32_t n,
+                                                          uint8_t* __restrict__ out, uint32_t* status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevMember m = members[i];
+    if (inflate_member(comp + m.in_off, m.in_len, out + m.out_off, m.out_len) != INF_OK) atomicOr(status, ING_ERR_INFLATE);
+}
+
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t* p) {        // unaligned little-endian loads
+    return p[0] | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) | (static_cast<uint32_t>(p[3]) << 24);
+}
+__device__ __forceinline__ uint32_t ld_u16(const uint8_t* p) { return p[0] | (static_cast<uint32_t>(p[1]) << 8); }
+
+// body offset of every record; every hop is one dependent load (block_size), at least 36 bytes forward
+__global__ void bam_chase_kernel(const uint8_t* __restrict__ data, uint64_t start, uint64_t end, uint64_t* __restrict__ rec_off,
+                                 uint32_t cap, uint32_t* n_rec, uint32_t* status) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint64_t p = start;
+    uint32_t n = 0;
+    while (p + 4 <= end) {
+        const int32_t block = static_cast<int32_t>(ld_u32(data + p));
+        if (block < 32 || p + 4 + static_cast<uint64_t>(block) > end) {
+            atomicOr(status, ING_ERR_RECORD);
+            break;
+        }
+        if (n < cap) rec_off[n] = p + 4;
+        ++n;
+        p += 4 + static_cast<uint64_t>(block);
+    }
+    *n_rec = n;
+}
+
+struct RecInfo {                 // where the variable-length parts of one record sit in the inflated stream
+    uint64_t cigar_src;          // first real op (inside the record, or the CG:B,I payload)
+    uint64_t seq_src;
+    uint64_t sa_src;             // SA:Z value (without the NUL), sa_len == 0xFFFFFFFF if absent
+    uint64_t name_src;
+    uint32_t n_cigar, l_seq, sa_len, name_len;
+};
+
+__global__ void bam_fields_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, uint32_t n,
+                                  svb_aln_hdr* __restrict__ hdr, RecInfo* __restrict__ info, uint32_t* status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t off = rec_off[i];
+    const uint8_t* body = data + off;
+    const uint32_t block = ld_u32(body - 4);
+    const uint32_t l_name = body[8];
+    const uint32_t n_cig = ld_u16(body + 12);
+    const int32_t l_seq = static_cast<int32_t>(ld_u32(body + 16));
+    RecInfo r;
+    r.name_src = off + 32;
+    r.name_len = l_name;
+    const uint64_t cig = off + 32 + l_name;
+    r.seq_src = cig + 4ull * n_cig;
+    const uint64_t tags = r.seq_src + (static_cast<uint64_t>(l_seq < 0 ? 0 : l_seq) + 1) / 2 + static_cast<uint64_t>(l_seq < 0 ? 0 : l_seq);
+    const uint64_t rec_end = off + block;
+    r.sa_src = 0;
+    r.sa_len = 0xFFFFFFFFu;
+    uint64_t cg_src = 0;
+    uint32_t cg_n = 0;
+    bool have_cg = false;
+    if (l_seq < 0 || tags > rec_end) {
+        atomicOr(status, ING_ERR_RECORD);
+    } else {
+        uint64_t t = tags;
+        while (t + 3 <= rec_end) {               // every round advances by at least 4 bytes
+            const uint8_t a0 = data[t], a1 = data[t + 1], ty = data[t + 2];
+            t += 3;
+            uint64_t adv = 0;
+            bool bad = false;
+            switch (ty) {
+                case 'A': case 'c': case 'C': adv = 1; break;
+                case 's': case 'S': adv = 2; break;
+                case 'i': case 'I': case 'f': adv = 4; break;
+                case 'Z': case 'H': {
+                    uint64_t z = t;
+                    while (z < rec_end && data[z] != 0) ++z;
+                    if (z >= rec_end) { bad = true; break; }
+                    if (a0 == 'S' && a1 == 'A' && ty == 'Z') {
+                        r.sa_src = t;
+                        r.sa_len = static_cast<uint32_t>(z - t);
+                    }
+                    adv = z - t + 1;
+                    break;
+                }
+                case 'B': {
+                    if (t + 5 > rec_end) { bad = true; break; }
+                    const uint8_t sub = data[t];
+                    const uint32_t cnt = ld_u32(data + t + 1);
+                    const uint64_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                    if (a0 == 'C' && a1 == 'G' && sub == 'I') {
+                        cg_src = t + 5;
+                        cg_n = cnt;
+                        have_cg = true;
+                    }
+                    adv = 5 + es * cnt;
+                    break;
+                }
+                default: bad = true; break;
+            }
+            if (bad || t + adv > rec_end) {
+                atomicOr(status, ING_ERR_TAG);
+                break;
+            }
+            t += adv;
+        }
+    }
+    // long CIGAR convention: "<l_seq>S<ref_len>N" placeholder + CG:B,I (htslib restores the real CIGAR transparently)
+    r.cigar_src = cig;
+    r.n_cigar = n_cig;
+    if (have_cg && n_cig == 2u && ld_u32(data + cig) == ((static_cast<uint32_t>(l_seq) << 4) | 4u) && (ld_u32(data + cig + 4) & 15u) == 3u) {
+        r.cigar_src = cg_src;
+        r.n_cigar = cg_n;
+    }
+    r.l_seq = static_cast<uint32_t>(l_seq);
+    info[i] = r;
+    svb_aln_hdr h;
+    h.tid = static_cast<int32_t>(ld_u32(body));
+    h.pos = static_cast<int32_t>(ld_u32(body + 4));
+    h.flag = static_cast<uint16_t>(ld_u16(body + 14));
+    h.mapq = body[9];
+    h.reserved0 = 0;
+    h.n_cigar = r.n_cigar;
+    h.cigar_off = 0;             // filled in on the host (prefix sums)
+    h.l_seq = r.l_seq;
+    h.sa_first = 0;
+    hdr[i] = h;
+}
+
+struct CopyDst {                 // destination offsets of one record (host prefix sums)
+    uint64_t cigar_op;           // index of its first op in cigar[] (multiple of 4)
+    uint64_t seq_byte, name_byte, sa_byte;
+};
+
+// one CTA per record: the three variable-length parts move to their flat arrays
+__global__ void __launch_bounds__(256) bam_copy_kernel(const uint8_t* __restrict__ data, const RecInfo* __restrict__ info,
+                                                       const CopyDst* __restrict__ dst, uint32_t n, uint32_t* __restrict__ cigar,
+                                                       uint8_t* __restrict__ seq4, char* __restrict__ names, char* __restrict__ sa_text) {
+    const uint32_t i = blockIdx.x;
+    if (i >= n) return;
+    const RecInfo r = info[i];
+    const CopyDst d = dst[i];
+    const uint32_t padded = (r.n_cigar + 3u) / 4u * 4u;
+    for (uint32_t k = threadIdx.x; k < padded; k += blockDim.x)
+        cigar[d.cigar_op + k] = k < r.n_cigar ? ld_u32(data + r.cigar_src + 4ull * k) : 15u;
+    const uint32_t seq_bytes = (r.l_seq + 1u) / 2u;
+    if (seq4)
+        for (uint32_t k = threadIdx.x; k < seq_bytes; k += blockDim.x) seq4[d.seq_byte + k] = data[r.seq_src + k];
+    for (uint32_t k = threadIdx.x; k < r.name_len; k += blockDim.x) names[d.name_byte + k] = static_cast<char>(data[r.name_src + k]);
+    if (r.sa_len != 0xFFFFFFFFu)
+        for (uint32_t k = threadIdx.x; k <= r.sa_len; k += blockDim.x)
+            sa_text[d.sa_byte + k] = k < r.sa_len ? static_cast<char>(data[r.sa_src + k]) : '\0';
+}
+
+void set_err(char* err, int err_len, const std::string& msg) {
+    if (err && err_len > 0) snprintf(err, static_cast<size_t>(err_len), "%s", msg.c_str());
+}
+
+struct Cleanup {                 // frees whatever was allocated when the function leaves early
+    cudaStream_t stream;
+    std::vector<void*> dev;
+    ~Cleanup() {
+        for (void* p : dev)
+            if (p) cudaFreeAsync(p, stream);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// timings of the last svb_bam_open_device call (ms): read file, H2D, inflate, chase, fields + copy, host parse, total
+static double g_ingest_ms[8] = {0};
+const double* svb_bam_device_timings(void) { return g_ingest_ms; }
+
+int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, const int32_t* contig_lexrank_or_null, svb_bam** bam_out,
+                        svb_records** rec_out, char* err, int err_len) {
+    if (!ctx || !path || !bam_out || !rec_out) return SVB_ERR_ARG;
+    *bam_out = nullptr;
+    *rec_out = nullptr;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    Cleanup gc;
+    gc.stream = st;
+    cudaEvent_t ev[6];
+    for (auto& e : ev) cudaEventCreate(&e);
+    auto fail = [&](int code, const std::string& msg) {
+        cudaStreamSynchronize(st);
+        for (auto& e : ev) cudaEventDestroy(e);
+        set_err(err, err_len, msg);
+        return svb_fail(ctx, code, msg.c_str());
+    };
+    const auto wall0 = std::chrono::steady_clock::now();
+
+    // ---- the file (pageable: the driver stages the one copy to the device; pinning gigabytes costs more than it saves)
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(SVB_ERR_IO, std::string("cannot open ") + path);
+    fseek(fp, 0, SEEK_END);
+    const long fsize = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::vector<uint8_t> raw_v(static_cast<size_t>(std::max<long>(fsize, 1)));
+    uint8_t* raw = raw_v.data();
+    if (fsize && fread(raw, 1, static_cast<size_t>(fsize), fp) != static_cast<size_t>(fsize)) {
+        fclose(fp);
+        return fail(SVB_ERR_IO, "short read");
+    }
+    fclose(fp);
+    const auto wall_read = std::chrono::steady_clock::now();
+
+    std::vector<BgzfMember> members;
+    uint64_t total_out = 0;
+    {
+        std::string why;
+        if (!bgzf_member_table(raw, static_cast<uint64_t>(fsize), &members, &total_out, &why)) return fail(SVB_ERR_IO, why);
+    }
+    if (members.empty() || members.size() > 0x7fffffffull) return fail(SVB_ERR_IO, "not a BAM file");
+    std::vector<DevMember> dm(members.size());
+    for (size_t i = 0; i < members.size(); ++i) {
+        dm[i].in_off = members[i].in_off;
+        dm[i].out_off = members[i].out_off;
+        dm[i].in_len = static_cast<uint32_t>(members[i].in_len);
+        dm[i].out_len = static_cast<uint32_t>(members[i].out_len);
+    }
+
+    // ---- H2D + inflate
+    uint8_t *d_comp = nullptr, *d_data = nullptr;
+    DevMember* d_members = nullptr;
+    uint32_t* d_status = nullptr;      // [0] error bits, [1] record count
+#define ING_CUDA(call)                                                             \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return fail(SVB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+    ING_CUDA(cudaMallocAsync(&d_comp, static_cast<size_t>(fsize), st));
+    gc.dev.push_back(d_comp);
+    ING_CUDA(cudaMallocAsync(&d_data, std::max<uint64_t>(total_out, 1), st));
+    gc.dev.push_back(d_data);
+    ING_CUDA(cudaMallocAsync(&d_members, sizeof(DevMember) * dm.size(), st));
+    gc.dev.push_back(d_members);
+    ING_CUDA(cudaMallocAsync(&d_status, 2 * sizeof(uint32_t), st));
+    gc.dev.push_back(d_status);
+    ING_CUDA(cudaMemsetAsync(d_status, 0, 2 * sizeof(uint32_t), st));
+    cudaEventRecord(ev[0], st);
+    ING_CUDA(cudaMemcpyAsync(d_comp, raw, static_cast<size_t>(fsize), cudaMemcpyHostToDevice, st));
+    ING_CUDA(cudaMemcpyAsync(d_members, dm.data(), sizeof(DevMember) * dm.size(), cudaMemcpyHostToDevice, st));
+    cudaEventRecord(ev[1], st);
+    const uint32_t n_members = static_cast<uint32_t>(dm.size());
+    bgzf_inflate_kernel<<<(n_members + 63) / 64, 64, 0, st>>>(d_comp, d_members, n_members, d_data, d_status);
+    ctx->launches += 1;
+    cudaEventRecord(ev[2], st);
+
+    // ---- BAM header: host parse of the first bytes of the inflated stream
+    std::unique_ptr<svb_bam> bam_owner(new (std::nothrow) svb_bam());
+    svb_bam* bam = bam_owner.get();
+    if (!bam) return fail(SVB_ERR_NOMEM, "svb_bam");
+    uint64_t first_record = 0;
+    {
+        std::vector<uint8_t> head;
+        uint64_t want = std::min<uint64_t>(total_out, 1u << 20);
+        while (true) {
+            head.resize(want);
+            ING_CUDA(cudaMemcpyAsync(head.data(), d_data, want, cudaMemcpyDeviceToHost, st));
+            uint32_t h_status = 0;
+            ING_CUDA(cudaMemcpyAsync(&h_status, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            ING_CUDA(cudaStreamSynchronize(st));
+            if (h_status & ING_ERR_INFLATE) return fail(SVB_ERR_IO, "inflate failed (corrupt BGZF block)");
+            std::string why;
+            const int64_t used = bam_parse_header(head.data(), want, bam, &why);
+            if (used >= 0) {
+                first_record = static_cast<uint64_t>(used);
+                break;
+            }
+            if (used == -1 || want == total_out) return fail(SVB_ERR_IO, why);
+            want = std::min<uint64_t>(total_out, want * 8);
+        }
+    }
+    const int32_t n_ref = static_cast<int32_t>(bam->contig_names.size());
+
+    // ---- record boundaries
+    uint32_t cap = static_cast<uint32_t>(std::min<uint64_t>(0x7fffffffull, std::max<uint64_t>(1u << 16, (total_out - first_record) / 2048)));
+    uint64_t* d_rec_off = nullptr;
+    uint32_t n_rec = 0;
+    cudaEventRecord(ev[3], st);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ING_CUDA(cudaMallocAsync(&d_rec_off, sizeof(uint64_t) * cap, st));
+        bam_chase_kernel<<<1, 32, 0, st>>>(d_data, first_record, total_out, d_rec_off, cap, d_status + 1, d_status);
+        ctx->launches += 1;
+        uint32_t h2[2] = {0, 0};
+        ING_CUDA(cudaMemcpyAsync(h2, d_status, sizeof h2, cudaMemcpyDeviceToHost, st));
+        ING_CUDA(cudaStreamSynchronize(st));
+        if (h2[0] & ING_ERR_RECORD) {
+            cudaFreeAsync(d_rec_off, st);
+            return fail(SVB_ERR_IO, "truncated BAM record");
+        }
+        n_rec = h2[1];
+        if (n_rec <= cap) break;
+        cudaFreeAsync(d_rec_off, st);
+        d_rec_off = nullptr;
+        cap = n_rec;
+    }
+    gc.dev.push_back(d_rec_off);
+    cudaEventRecord(ev[4], st);
+
+    // ---- fixed fields + where the variable parts are
+    svb_aln_hdr* d_hdr = nullptr;
+    RecInfo* d_info = nullptr;
+    ING_CUDA(cudaMallocAsync(&d_hdr, sizeof(svb_aln_hdr) * std::max<uint32_t>(n_rec, 1), st));
+    gc.dev.push_back(d_hdr);
+    ING_CUDA(cudaMallocAsync(&d_info, sizeof(RecInfo) * std::max<uint32_t>(n_rec, 1), st));
+    gc.dev.push_back(d_info);
+    bam->hdr.resize(n_rec);
+    std::vector<RecInfo> info(n_rec);
+    if (n_rec) {
+        bam_fields_kernel<<<(n_rec + 127) / 128, 128, 0, st>>>(d_data, d_rec_off, n_rec, d_hdr, d_info, d_status);
+        ctx->launches += 1;
+        ING_CUDA(cudaMemcpyAsync(bam->hdr.data(), d_hdr, sizeof(svb_aln_hdr) * n_rec, cudaMemcpyDeviceToHost, st));
+        ING_CUDA(cudaMemcpyAsync(info.data(), d_info, sizeof(RecInfo) * n_rec, cudaMemcpyDeviceToHost, st));
+    }
+    {
+        uint32_t h_status = 0;
+        ING_CUDA(cudaMemcpyAsync(&h_status, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        ING_CUDA(cudaStreamSynchronize(st));
+        if (h_status & ING_ERR_RECORD) return fail(SVB_ERR_IO, "malformed BAM record");
+        if (h_status & ING_ERR_TAG) return fail(SVB_ERR_IO, "malformed auxiliary field");
+    }
+
+    // ---- host prefix sums: where everything goes
+    std::vector<CopyDst> dst(n_rec);
+    bam->seq_off.resize(static_cast<size_t>(n_rec) + 1);
+    bam->name_off.resize(static_cast<size_t>(n_rec) + 1);
+    bam->sa_text_off.assign(n_rec, -1);
+    uint64_t co = 0, so = 0, no = 0, sao = 0;
+    for (uint32_t i = 0; i < n_rec; ++i) {
+        const RecInfo& r = info[i];
+        dst[i].cigar_op = co;
+        dst[i].seq_byte = so;
+        dst[i].name_byte = no;
+        dst[i].sa_byte = sao;
+        bam->hdr[i].cigar_off = co;
+        bam->seq_off[i] = so;
+        bam->name_off[i] = no;
+        co += (static_cast<uint64_t>(r.n_cigar) + 3) / 4 * 4;
+        so += (static_cast<uint64_t>(r.l_seq) + 1) / 2;
+        no += r.name_len;
+        if (r.sa_len != 0xFFFFFFFFu) {
+            bam->sa_text_off[i] = static_cast<int64_t>(sao);
+            sao += static_cast<uint64_t>(r.sa_len) + 1;
+        }
+    }
+    bam->seq_off[n_rec] = so;
+    bam->name_off[n_rec] = no;
+    if (co / 4 >= 0xFFFFFFFFull) return fail(SVB_ERR_ARG, "more than 2^34 CIGAR ops");
+
+    // ---- copies
+    CopyDst* d_dst = nullptr;
+    uint4* d_cigar = nullptr;
+    uint8_t* d_seq4 = nullptr;
+    char *d_names = nullptr, *d_sa = nullptr;
+    ING_CUDA(cudaMallocAsync(&d_dst, sizeof(CopyDst) * std::max<uint32_t>(n_rec, 1), st));
+    gc.dev.push_back(d_dst);
+    ING_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_cigar), std::max<uint64_t>(cigar_padded_n4(co / 4), 1) * sizeof(uint4), st));
+    const size_t gc_cigar = gc.dev.size();
+    gc.dev.push_back(d_cigar);
+    if (keep_sequences) ING_CUDA(cudaMallocAsync(&d_seq4, std::max<uint64_t>(so, 1), st));
+    const size_t gc_seq = gc.dev.size();
+    gc.dev.push_back(d_seq4);
+    ING_CUDA(cudaMallocAsync(&d_names, std::max<uint64_t>(no, 1), st));
+    gc.dev.push_back(d_names);
+    ING_CUDA(cudaMallocAsync(&d_sa, std::max<uint64_t>(sao, 1), st));
+    gc.dev.push_back(d_sa);
+    bam->names.resize(no);
+    bam->sa_text.resize(sao);
+    if (n_rec) {
+        ING_CUDA(cudaMemcpyAsync(d_dst, dst.data(), sizeof(CopyDst) * n_rec, cudaMemcpyHostToDevice, st));
+        bam_copy_kernel<<<n_rec, 256, 0, st>>>(d_data, d_info, d_dst, n_rec, reinterpret_cast<uint32_t*>(d_cigar), d_seq4, d_names, d_sa);
+        ctx->launches += 1;
+        if (no) ING_CUDA(cudaMemcpyAsync(bam->names.data(), d_names, no, cudaMemcpyDeviceToHost, st));
+        if (sao) ING_CUDA(cudaMemcpyAsync(bam->sa_text.data(), d_sa, sao, cudaMemcpyDeviceToHost, st));
+    }
+    cudaEventRecord(ev[5], st);
+    {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(SVB_ERR_CUDA, std::string("device ingest: ") + cudaGetErrorString(e));
+    }
+    const auto wall_dev = std::chrono::steady_clock::now();
+
+    // ---- SA tags: the same host parser as the host ingest (retrieve_other_alignments, SVIM_COLLECT.py:8-58)
+    std::vector<const char*> name_ptrs;
+    for (auto& s : bam->contig_names) name_ptrs.push_back(s.c_str());
+    bam->sa_count.assign(n_rec, 0);
+    for (uint32_t i = 0; i < n_rec; ++i) {
+        svb_aln_hdr& h = bam->hdr[i];
+        h.sa_first = static_cast<uint32_t>(bam->seg.size());
+        if (bam->sa_text_off[i] < 0) continue;
+        const char* sa = bam->sa_text.data() + bam->sa_text_off[i];
+        const int cnt = svb_parse_sa(sa, name_ptrs.data(), n_ref, nullptr, 0);
+        if (cnt < 0) return fail(cnt, std::string("malformed SA tag (int() would raise): ") + sa);
+        bam->seg.resize(bam->seg.size() + static_cast<size_t>(cnt));
+        svb_parse_sa(sa, name_ptrs.data(), n_ref, bam->seg.data() + h.sa_first, cnt);
+        bam->sa_count[i] = static_cast<uint32_t>(cnt);
+    }
+
+    // ---- the record image (python string order of the contig names is the caller's: SVCandidate.py:352)
+    std::vector<int32_t> lexrank(static_cast<size_t>(std::max(n_ref, 0)));
+    if (contig_lexrank_or_null) {
+        std::copy(contig_lexrank_or_null, contig_lexrank_or_null + n_ref, lexrank.begin());
+    } else {                          // code-point order of the (ASCII) names == python's str order for them
+        std::vector<int32_t> order(lexrank.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int32_t>(i);
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return bam->contig_names[a] < bam->contig_names[b]; });
+        for (size_t i = 0; i < order.size(); ++i) lexrank[static_cast<size_t>(order[i])] = static_cast<int32_t>(i);
+    }
+    svb_records* rec = nullptr;
+    gc.dev[gc_cigar] = nullptr;       // the records own d_cigar from the call on, also when it fails
+    int rc = load_records_impl(ctx, bam->hdr.data(), n_rec, nullptr, d_cigar, co, bam->seg.data(), bam->sa_count.data(),
+                               static_cast<uint32_t>(bam->seg.size()), bam->contig_len.data(), lexrank.data(), n_ref, &rec);
+    if (rc != SVB_OK) {
+        cudaStreamSynchronize(st);
+        for (auto& e : ev) cudaEventDestroy(e);
+        set_err(err, err_len, svb_last_error(ctx));
+        return rc;
+    }
+    if (keep_sequences) {
+        gc.dev[gc_seq] = nullptr;
+        rec->d_seq4 = d_seq4;
+        rec->seq_bytes = so;
+        cudaError_t e = cudaMallocAsync(&rec->d_seq_off, sizeof(uint64_t) * (static_cast<size_t>(n_rec) + 1), st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(rec->d_seq_off, bam->seq_off.data(), sizeof(uint64_t) * (static_cast<size_t>(n_rec) + 1), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            svb_records_free(rec);
+            return fail(SVB_ERR_CUDA, std::string("device ingest sequences: ") + cudaGetErrorString(e));
+        }
+    }
+    const auto wall_end = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    float f = 0.f;
+    g_ingest_ms[0] = ms(wall0, wall_read);
+    cudaEventElapsedTime(&f, ev[0], ev[1]); g_ingest_ms[1] = f;
+    cudaEventElapsedTime(&f, ev[1], ev[2]); g_ingest_ms[2] = f;
+    cudaEventElapsedTime(&f, ev[3], ev[4]); g_ingest_ms[3] = f;
+    cudaEventElapsedTime(&f, ev[4], ev[5]); g_ingest_ms[4] = f;
+    g_ingest_ms[5] = ms(wall_dev, wall_end);
+    g_ingest_ms[6] = ms(wall0, wall_end);
+    g_ingest_ms[7] = static_cast<double>(total_out);
+    for (auto& e : ev) cudaEventDestroy(e);
+#undef ING_CUDA
+    *bam_out = bam_owner.release();
+    *rec_out = rec;
+    return SVB_OK;
+}
+
+// the host copies the per-alignment seams read (cigartuples, query_sequence) are NOT made by the device ingest;
+// this downloads them on demand
+int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec) {
+    if (!ctx || !bam || !rec) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_bam_materialize_host") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const uint64_t n_ops = rec->n4 * 4;
+    if (bam->cigar.size() != n_ops) {
+        bam->cigar.resize(n_ops);
+        if (n_ops) SVB_CUDA(ctx, cudaMemcpyAsync(bam->cigar.data(), rec->d_cigar, sizeof(uint32_t) * n_ops, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (rec->d_seq4 && bam->seq4.size() != rec->seq_bytes) {
+        bam->seq4.resize(rec->seq_bytes);
+        if (rec->seq_bytes) SVB_CUDA(ctx, cudaMemcpyAsync(bam->seq4.data(), rec->d_seq4, rec->seq_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
+}  // extern "C"

@@ -19,27 +19,9 @@
 
 #include "../../include/svimasm_b200.h"
 
-struct svb_bam {
-    std::vector<std::string> contig_names;
-    std::vector<int32_t> contig_len;
-    std::string sort_order;
-    std::vector<svb_aln_hdr> hdr;
-    std::vector<uint32_t> cigar;
-    std::vector<svb_segment> seg;
-    std::vector<uint32_t> sa_count;
-    std::vector<uint8_t> seq4;
-    std::vector<uint64_t> seq_off;
-    std::vector<char> names;
-    std::vector<uint64_t> name_off;
-    std::vector<char> sa_text;            // raw SA:Z values, NUL separated (get_tag("SA") of the seam-level API)
-    std::vector<int64_t> sa_text_off;     // per record: offset into sa_text or -1
-};
+#include "bam_host.h"
 
 namespace {
-
-struct Block {
-    uint64_t in_off, in_len, out_off, out_len;
-};
 
 void set_err(char* err, int err_len, const std::string& msg) {
     if (err && err_len > 0) snprintf(err, static_cast<size_t>(err_len), "%s", msg.c_str());
@@ -147,6 +129,75 @@ int parse_sa_element(const char* b, const char* e, const char* const* names, int
 
 }  // namespace
 
+bool bgzf_member_table(const uint8_t* raw, uint64_t size, std::vector<BgzfMember>* blocks, uint64_t* total_out_p, std::string* why) {
+    uint64_t in = 0, total_out = 0;
+    while (in + 18 <= size) {
+        const uint8_t* h = raw + in;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { *why = "not a BGZF file"; return false; }
+        const uint16_t xlen = rd16(h + 10);
+        uint64_t bsize = 0;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t* sub = h + 12 + x;
+            const uint16_t slen = rd16(sub + 2);
+            if (sub[0] == 'B' && sub[1] == 'C' && slen == 2) bsize = static_cast<uint64_t>(rd16(sub + 4)) + 1;
+            x += 4u + slen;
+        }
+        if (!bsize || in + bsize > size) { *why = "truncated BGZF block"; return false; }
+        const uint64_t hdr_len = 12ull + xlen;
+        BgzfMember b;
+        b.in_off = in + hdr_len;
+        b.in_len = bsize - hdr_len - 8;
+        b.out_len = rd32(raw + in + bsize - 4);
+        b.out_off = total_out;
+        total_out += b.out_len;
+        if (b.out_len) blocks->push_back(b);
+        in += bsize;
+    }
+    *total_out_p = total_out;
+    return true;
+}
+
+int64_t bam_parse_header(const uint8_t* p0, uint64_t avail, svb_bam* bam, std::string* why) {
+    const uint8_t* p = p0;
+    const uint8_t* const end = p0 + avail;
+    if (avail < 12 || memcmp(p, "BAM\1", 4) != 0) { *why = "not a BAM file"; return -1; }
+    const int32_t l_text = rdi32(p + 4);
+    if (l_text < 0) { *why = "bad BAM header"; return -1; }
+    if (p + 12 + l_text > end) { *why = "bad BAM header"; return -2; }       // -2: the caller may retry with more bytes
+    {
+        const std::string text(reinterpret_cast<const char*>(p + 8), strnlen(reinterpret_cast<const char*>(p + 8), static_cast<size_t>(l_text)));
+        size_t ls = 0;
+        while (ls < text.size()) {
+            size_t le = text.find('\n', ls);
+            if (le == std::string::npos) le = text.size();
+            if (text.compare(ls, 3, "@HD") == 0) {
+                size_t so = text.find("\tSO:", ls);
+                if (so != std::string::npos && so < le) {
+                    size_t ve = text.find_first_of("\t\n\r", so + 4);
+                    if (ve == std::string::npos || ve > le) ve = le;
+                    bam->sort_order = text.substr(so + 4, ve - so - 4);
+                }
+            }
+            ls = le + 1;
+        }
+    }
+    p += 8 + l_text;
+    const int32_t n_ref = rdi32(p);
+    p += 4;
+    bam->contig_names.clear();
+    bam->contig_len.clear();
+    for (int32_t i = 0; i < n_ref; ++i) {
+        if (p + 4 > end) { *why = "bad BAM reference list"; return -2; }
+        const int32_t l_name = rdi32(p);
+        if (l_name < 1) { *why = "bad BAM reference list"; return -1; }
+        if (p + 8 + l_name > end) { *why = "bad BAM reference list"; return -2; }
+        bam->contig_names.emplace_back(reinterpret_cast<const char*>(p + 4), static_cast<size_t>(l_name - 1));
+        bam->contig_len.push_back(rdi32(p + 4 + l_name));
+        p += 8 + l_name;
+    }
+    return p - p0;
+}
+
 extern "C" {
 
 int svb_parse_sa(const char* sa_text, const char* const* contig_names, int32_t n_contig, svb_segment* out, int32_t cap) {
@@ -182,30 +233,11 @@ int svb_bam_open(const char* path, int n_threads, svb_bam** out, char* err, int 
     if (fsize && fread(raw.data(), 1, raw.size(), fp) != raw.size()) { fclose(fp); set_err(err, err_len, "short read"); return SVB_ERR_IO; }
     fclose(fp);
 
-    // ---- BGZF member table
-    std::vector<Block> blocks;
-    uint64_t in = 0, total_out = 0;
-    while (in + 18 <= raw.size()) {
-        const uint8_t* h = raw.data() + in;
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { set_err(err, err_len, "not a BGZF file"); return SVB_ERR_IO; }
-        const uint16_t xlen = rd16(h + 10);
-        uint64_t bsize = 0;
-        for (uint32_t x = 0; x + 4 <= xlen;) {
-            const uint8_t* sub = h + 12 + x;
-            const uint16_t slen = rd16(sub + 2);
-            if (sub[0] == 'B' && sub[1] == 'C' && slen == 2) bsize = static_cast<uint64_t>(rd16(sub + 4)) + 1;
-            x += 4u + slen;
-        }
-        if (!bsize || in + bsize > raw.size()) { set_err(err, err_len, "truncated BGZF block"); return SVB_ERR_IO; }
-        const uint64_t hdr_len = 12ull + xlen;
-        Block b;
-        b.in_off = in + hdr_len;
-        b.in_len = bsize - hdr_len - 8;
-        b.out_len = rd32(raw.data() + in + bsize - 4);
-        b.out_off = total_out;
-        total_out += b.out_len;
-        if (b.out_len) blocks.push_back(b);
-        in += bsize;
+    std::vector<BgzfMember> blocks;
+    uint64_t total_out = 0;
+    {
+        std::string why;
+        if (!bgzf_member_table(raw.data(), raw.size(), &blocks, &total_out, &why)) { set_err(err, err_len, why); return SVB_ERR_IO; }
     }
     std::vector<uint8_t> data(total_out);
     {
@@ -214,7 +246,7 @@ int svb_bam_open(const char* path, int n_threads, svb_bam** out, char* err, int 
         const int nt = n_threads > 0 ? n_threads : static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
         auto work = [&]() {
             for (size_t i = next.fetch_add(1); i < blocks.size(); i = next.fetch_add(1)) {
-                const Block& b = blocks[i];
+                const BgzfMember& b = blocks[i];
                 if (!inflate_block(raw.data() + b.in_off, b.in_len, data.data() + b.out_off, b.out_len)) bad = true;
             }
         };
@@ -227,41 +259,17 @@ int svb_bam_open(const char* path, int n_threads, svb_bam** out, char* err, int 
     std::vector<uint8_t>().swap(raw);
 
     // ---- BAM header
-    if (data.size() < 12 || memcmp(data.data(), "BAM\1", 4) != 0) { set_err(err, err_len, "not a BAM file"); return SVB_ERR_IO; }
     svb_bam* bam = new (std::nothrow) svb_bam();
     if (!bam) return SVB_ERR_NOMEM;
     const uint8_t* p = data.data();
     const uint8_t* const end = p + data.size();
-    const int32_t l_text = rdi32(p + 4);
-    if (l_text < 0 || p + 12 + l_text > end) { delete bam; set_err(err, err_len, "bad BAM header"); return SVB_ERR_IO; }
     {
-        const std::string text(reinterpret_cast<const char*>(p + 8), strnlen(reinterpret_cast<const char*>(p + 8), static_cast<size_t>(l_text)));
-        size_t ls = 0;
-        while (ls < text.size()) {
-            size_t le = text.find('\n', ls);
-            if (le == std::string::npos) le = text.size();
-            if (text.compare(ls, 3, "@HD") == 0) {
-                size_t so = text.find("\tSO:", ls);
-                if (so != std::string::npos && so < le) {
-                    size_t ve = text.find_first_of("\t\n\r", so + 4);
-                    if (ve == std::string::npos || ve > le) ve = le;
-                    bam->sort_order = text.substr(so + 4, ve - so - 4);
-                }
-            }
-            ls = le + 1;
-        }
+        std::string why;
+        const int64_t used = bam_parse_header(p, data.size(), bam, &why);
+        if (used < 0) { delete bam; set_err(err, err_len, why); return SVB_ERR_IO; }
+        p += used;
     }
-    p += 8 + l_text;
-    const int32_t n_ref = rdi32(p);
-    p += 4;
-    for (int32_t i = 0; i < n_ref; ++i) {
-        if (p + 4 > end) { delete bam; set_err(err, err_len, "bad BAM reference list"); return SVB_ERR_IO; }
-        const int32_t l_name = rdi32(p);
-        if (l_name < 1 || p + 8 + l_name > end) { delete bam; set_err(err, err_len, "bad BAM reference list"); return SVB_ERR_IO; }
-        bam->contig_names.emplace_back(reinterpret_cast<const char*>(p + 4), static_cast<size_t>(l_name - 1));
-        bam->contig_len.push_back(rdi32(p + 4 + l_name));
-        p += 8 + l_name;
-    }
+    const int32_t n_ref = static_cast<int32_t>(bam->contig_names.size());
     std::vector<const char*> name_ptrs;
     for (auto& s : bam->contig_names) name_ptrs.push_back(s.c_str());
 

@@ -219,11 +219,13 @@ void svb_records_free(svb_records* r) {
     delete r;
 }
 
-int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar,
-                     uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,
-                     const int32_t* contig_len, const int32_t* contig_lexrank, int32_t n_contig,
-                     svb_records** out) {
-    if (!ctx || !out || (n_aln && !hdr) || (n_ops_padded && !cigar) || n_contig < 0 || (n_contig && (!contig_len || !contig_lexrank)))
+// `d_cigar_prebuilt`: the CIGAR array already on the device (allocated with cigar_padded_n4 uint4; the device ingest
+// builds it there); ownership passes to the records.  Otherwise `cigar` is a host array that is uploaded.
+int load_records_impl(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar, uint4* d_cigar_prebuilt,
+                      uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,
+                      const int32_t* contig_len, const int32_t* contig_lexrank, int32_t n_contig,
+                      svb_records** out) {
+    if (!ctx || !out || (n_aln && !hdr) || (n_ops_padded && !cigar && !d_cigar_prebuilt) || n_contig < 0 || (n_contig && (!contig_len || !contig_lexrank)))
         return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: null argument") : SVB_ERR_ARG;
     if (n_ops_padded % 4) return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: n_ops_padded must be a multiple of 4");
     if (n_ops_padded / 4 >= 0xFFFFFFFFull) return svb_fail(ctx, SVB_ERR_ARG, "svb_load_records: more than 2^34 ops");
@@ -277,7 +279,9 @@ int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const
     };
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = up(reinterpret_cast<void**>(&r->d_hdr), hdr, sizeof(svb_aln_hdr) * n_aln);
-    if (e == cudaSuccess) {          // allocated in whole scan units; launch_build_chunk_index fills the tail with op 15
+    if (e == cudaSuccess && d_cigar_prebuilt) {
+        r->d_cigar = d_cigar_prebuilt;
+    } else if (e == cudaSuccess) {   // allocated in whole scan units; launch_build_chunk_index fills the tail with op 15
         e = cudaMallocAsync(reinterpret_cast<void**>(&r->d_cigar), std::max<uint64_t>(cigar_padded_n4(r->n4), 1) * sizeof(uint4), ctx->stream);
         if (e == cudaSuccess && n_ops_padded)
             e = cudaMemcpyAsync(r->d_cigar, cigar, sizeof(uint32_t) * n_ops_padded, cudaMemcpyHostToDevice, ctx->stream);
@@ -302,6 +306,13 @@ int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const
     }
     *out = r;
     return SVB_OK;
+}
+
+int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar,
+                     uint64_t n_ops_padded, const svb_segment* seg, const uint32_t* sa_count, uint32_t n_seg,
+                     const int32_t* contig_len, const int32_t* contig_lexrank, int32_t n_contig,
+                     svb_records** out) {
+    return load_records_impl(ctx, hdr, n_aln, cigar, nullptr, n_ops_padded, seg, sa_count, n_seg, contig_len, contig_lexrank, n_contig, out);
 }
 
 int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq4, const uint64_t* seq_off) {

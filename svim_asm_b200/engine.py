@@ -65,6 +65,10 @@ class HostBatch(object):
             if rc == -4:
                 raise IOError(err.value.decode() or "cannot read %s" % path)
             raise RuntimeError(err.value.decode() or "svb_bam_open failed (%d)" % rc)
+        return cls._from_handle(handle, path)
+
+    @classmethod
+    def _from_handle(cls, handle, path):
         self = cls()
         self._bam = handle
         self.path = str(path)
@@ -87,6 +91,26 @@ class HostBatch(object):
         self.seq_off = view(lib.svb_bam_seq_offsets(handle), np.uint64, n + 1)
         self.seq4 = view(lib.svb_bam_seq4(handle), np.uint8, int(self.seq_off[-1]) if n else 0)
         return self
+
+    @classmethod
+    def from_bam_device(cls, engine, path, keep_sequences=True):
+        """Device ingest (svb_bam_open_device): BGZF inflate + record split on the GPU.  Returns (host, records): the
+        record image is already resident; `host` carries the small per-record data, its CIGAR / sequence arrays are
+        downloaded on first use (only the per-alignment seams and the VCF writer's INS alleles read them)."""
+        handle, rec = ctypes.c_void_p(), ctypes.c_void_p()
+        err = ctypes.create_string_buffer(512)
+        rc = lib.svb_bam_open_device(engine.handle, str(path).encode(), int(bool(keep_sequences)), None, ctypes.byref(handle),
+                                     ctypes.byref(rec), err, len(err))
+        if rc != 0:
+            if rc == -4:
+                raise IOError(err.value.decode() or "cannot read %s" % path)
+            raise RuntimeError(err.value.decode() or "svb_bam_open_device failed (%d)" % rc)
+        records = Records(engine, rec, None)
+        records.has_sequences = bool(keep_sequences)
+        self = DeviceBackedHostBatch._from_handle(handle, path)
+        records.host = self
+        self._engine, self._records = engine, records
+        return self, records
 
     @classmethod
     def from_record_batch(cls, rb):
@@ -244,6 +268,32 @@ class Table(object):
             pass
 
 
+class DeviceBackedHostBatch(HostBatch):
+    """HostBatch of a device ingest: `cigar` and `seq4` live in HBM and come to the host only when somebody reads them."""
+    _engine = None
+    _records = None
+    _materialized = False
+
+    def _materialize(self):
+        if not self._materialized and self._bam is not None and self._records is not None and self._records.handle:
+            self._engine._check(lib.svb_bam_materialize_host(self._engine.handle, self._bam, self._records.handle))
+            n = lib.svb_bam_n_records(self._bam)
+
+            def view(address, dtype, count):
+                if count == 0 or not address:
+                    return np.zeros(0, dtype=dtype)
+                buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(address)
+                return np.frombuffer(buf, dtype=dtype, count=count)
+            self.__dict__["cigar"] = view(lib.svb_bam_cigar(self._bam), np.uint32, lib.svb_bam_n_ops_padded(self._bam))
+            self.__dict__["seq4"] = view(lib.svb_bam_seq4(self._bam), np.uint8, int(self.seq_off[-1]) if n else 0)
+            self._materialized = True
+
+    def __getattribute__(self, name):
+        if name in ("cigar", "seq4") and not object.__getattribute__(self, "_materialized"):
+            object.__getattribute__(self, "_materialize")()
+        return object.__getattribute__(self, name)
+
+
 class Records(object):
     """Device-resident BAM image (svb_records*)."""
 
@@ -353,6 +403,13 @@ class Engine(object):
         host = rec.host
         self._check(lib.svb_records_set_sequences(self.handle, rec.handle, _lib.ptr(host.seq4), _lib.ptr(host.seq_off)))
         rec.has_sequences = True
+
+    def ingest_timings(self):
+        """ms of the last device ingest: file read, H2D, inflate, record chase, fields + copy, host parse, total; inflated bytes."""
+        addr = lib.svb_bam_device_timings()
+        v = np.frombuffer((ctypes.c_char * 64).from_address(addr), dtype=np.float64, count=8).copy()
+        keys = ("read_file", "h2d", "inflate", "chase", "fields_copy", "host_parse", "total", "inflated_bytes")
+        return dict(zip(keys, (float(x) for x in v)))
 
     def load_reference(self, bases, contig_off):
         """bases: uint8 upper-cased ASCII, contigs concatenated in BAM header order; contig_off: uint64[n+1]."""
