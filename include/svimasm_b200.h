@@ -173,7 +173,7 @@ int svb_parse_sa(const char* sa_text, const char* const* contig_names, int32_t n
  * contig_lexrank: rank of every contig name under python string order, or NULL (code-point order of the names). */
 int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, const int32_t* contig_lexrank,
                         svb_bam** bam_out, svb_records** rec_out, char* err, int err_len);
-int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec);
+int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec, int what);   /* what: 1 CIGAR ops, 2 query bases, 3 both */
 /* ms of the last svb_bam_open_device call: [0] file read, [1] H2D, [2] inflate kernel, [3] record chase,
  * [4] field + copy kernels, [5] host SA parse + record image, [6] total wall, [7] inflated bytes */
 const double* svb_bam_device_timings(void);
@@ -198,6 +198,12 @@ int svb_cigar_indel(svb_ctx* ctx, const uint32_t* packed_ops, uint32_t n_ops, in
 
 /* Reference genome: upper-cased bases, 1 byte each, contigs concatenated; contig_off has n_contig + 1 entries. */
 int svb_ref_load(svb_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off, int32_t n_contig, svb_ref** out);
+/* The same from the FASTA file itself (pysam.FastaFile(path), svim-asm:124): the file is copied to the device as it is and
+ * one kernel drops the line terminators and upper-cases.  fai: n_contig rows {length, offset, linebases, linewidth} of
+ * the .fai index in BAM header order; length 0 marks a contig that the FASTA does not hold. */
+int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int32_t n_contig, svb_ref** out);
+/* the resident reference back on the host (tests): bases (may be NULL), their count, the 256-entry symbol-class map */
+int svb_ref_to_host(svb_ctx* ctx, const svb_ref* ref, uint8_t* bases_dst, uint64_t cap, uint64_t* n_bases, uint8_t* class_map256_dst);
 void svb_ref_free(svb_ref* ref);
 
 /* pair_candidates (SVIM_COMBINE.py:164-366): form_partitions + compute_distance + pair_haplotypes(_breakends).

@@ -73,6 +73,9 @@ class CandidateDeletion(Candidate):
         return _vcf_record(contig, max(1, start), ref_allele, alt_allele, [], info, "GT", self.genotype)
 
 
+_REVCOMP = str.maketrans("ACGT", "TGCA")
+
+
 class CandidateInversion(Candidate):
     type = "INV"
     complement = {"A": "T", "C": "G", "G": "C", "T": "A"}
@@ -85,7 +88,7 @@ class CandidateInversion(Candidate):
         contig, start, end = self.get_source()
         if sequence_alleles:
             ref_allele = reference.fetch(contig, start, end).upper()
-            alt_allele = "".join(self.complement.get(b, b) for b in reversed(ref_allele))
+            alt_allele = ref_allele[::-1].translate(_REVCOMP)      # complement.get(b, b) per base (SVCandidate.py:106)
         else:
             ref_allele, alt_allele = "N", "<INV>"
         info = _with_reads("SVTYPE=INV;END=%d" % end, self.reads, read_names)

@@ -26,8 +26,11 @@ def _device_reference(reference, contig_names):
     cache = getattr(reference, "_svb_ref", None)
     key = tuple(contig_names)
     if cache is None or cache[0] != key:
-        bases, offsets = reference.load_upper(contig_names)
-        cache = (key, get_engine().load_reference(bases, offsets))
+        if hasattr(reference, "fai_rows"):         # our FastaFile: the bases go from the file to HBM without a host pass
+            cache = (key, get_engine().load_reference_fasta(reference.filename, reference.fai_rows(contig_names)))
+        else:
+            bases, offsets = reference.load_upper(contig_names)
+            cache = (key, get_engine().load_reference(bases, offsets))
         reference._svb_ref = cache
     return cache[1]
 

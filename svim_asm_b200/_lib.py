@@ -72,7 +72,7 @@ SIGNATURES = {
     "svb_bam_sa_text": (c_char_p, [c_void_p, c_i64]),
     "svb_parse_sa": (c_int, [c_char_p, P(c_char_p), c_i32, c_void_p, c_i32]),
     "svb_bam_open_device": (c_int, [c_void_p, c_char_p, c_int, c_void_p, P(c_void_p), P(c_void_p), c_char_p, c_int]),
-    "svb_bam_materialize_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_bam_materialize_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "svb_bam_device_timings": (c_void_p, []),
     "svb_load_records": (c_int, [c_void_p, c_void_p, c_u32, c_void_p, c_u64, c_void_p, c_void_p, c_u32, c_void_p,
                                  c_void_p, c_i32, P(c_void_p)]),
@@ -81,6 +81,8 @@ SIGNATURES = {
     "svb_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, P(c_void_p)]),
     "svb_cigar_indel": (c_int, [c_void_p, c_void_p, c_u32, c_i32, c_void_p, c_u32, P(c_u32)]),
     "svb_ref_load": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, P(c_void_p)]),
+    "svb_ref_load_fasta": (c_int, [c_void_p, c_char_p, c_void_p, c_i32, P(c_void_p)]),
+    "svb_ref_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, P(c_u64), c_void_p]),
     "svb_ref_free": (None, [c_void_p]),
     "svb_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)]),
     "svb_edit_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_void_p]),

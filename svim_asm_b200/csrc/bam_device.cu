@@ -728,15 +728,15 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
 
 // the host copies the per-alignment seams read (cigartuples, query_sequence) are NOT made by the device ingest;
 // this downloads them on demand
-int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec) {
+int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec, int what) {
     if (!ctx || !bam || !rec) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_bam_materialize_host") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
     const uint64_t n_ops = rec->n4 * 4;
-    if (bam->cigar.size() != n_ops) {
+    if ((what & 1) && bam->cigar.size() != n_ops) {
         bam->cigar.resize(n_ops);
         if (n_ops) SVB_CUDA(ctx, cudaMemcpyAsync(bam->cigar.data(), rec->d_cigar, sizeof(uint32_t) * n_ops, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (rec->d_seq4 && bam->seq4.size() != rec->seq_bytes) {
+    if ((what & 2) && rec->d_seq4 && bam->seq4.size() != rec->seq_bytes) {
         bam->seq4.resize(rec->seq_bytes);
         if (rec->seq_bytes) SVB_CUDA(ctx, cudaMemcpyAsync(bam->seq4.data(), rec->d_seq4, rec->seq_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }

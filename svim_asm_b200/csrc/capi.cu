@@ -576,6 +576,20 @@ int svb_ref_load(svb_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
     return SVB_OK;
 }
 
+// test / debugging aid: the resident reference back on the host
+int svb_ref_to_host(svb_ctx* ctx, const svb_ref* r, uint8_t* bases_dst, uint64_t cap, uint64_t* n_bases, uint8_t* class_map256_dst) {
+    if (!ctx || !r || !n_bases) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_ref_to_host") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    *n_bases = r->n_bases;
+    if (bases_dst) {
+        if (cap < r->n_bases) return svb_fail(ctx, SVB_ERR_ARG, "svb_ref_to_host: destination too small");
+        if (r->n_bases) SVB_CUDA(ctx, cudaMemcpyAsync(bases_dst, r->d_bases, r->n_bases, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (class_map256_dst) SVB_CUDA(ctx, cudaMemcpyAsync(class_map256_dst, r->d_class_map, 256, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
 void svb_ref_free(svb_ref* r) {
     if (!r) return;
     cudaSetDevice(r->device);

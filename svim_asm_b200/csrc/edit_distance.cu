@@ -723,15 +723,13 @@ __global__ void make_string_jobs(const uint64_t* __restrict__ a_off, const uint6
 
 }  // namespace
 
-int build_class_map(const uint8_t* bases, uint64_t n, uint8_t* map256, std::string* why) {
+int build_class_map_from_seen(const bool* seen, uint8_t* map256, std::string* why) {
     // classes 0..15: the nt16 letters a 4-bit query base can decode to; further classes: any other byte of
     // the (upper-cased) reference.  Equality of bytes == equality of classes, so distances stay exact.
     memset(map256, 255, 256);
     const char* nt16 = "=ACMGRSVTWYHKDBN";
     int next = 0;
     for (int i = 0; i < 16; ++i) map256[static_cast<uint8_t>(nt16[i])] = static_cast<uint8_t>(next++);
-    bool seen[256] = {false};
-    for (uint64_t i = 0; i < n; ++i) seen[bases[i]] = true;
     for (int c = 0; c < 256; ++c) {
         if (!seen[c] || map256[c] != 255) continue;
         if (next >= ED_NCLASS) {
@@ -741,6 +739,12 @@ int build_class_map(const uint8_t* bases, uint64_t n, uint8_t* map256, std::stri
         map256[c] = static_cast<uint8_t>(next++);
     }
     return SVB_OK;
+}
+
+int build_class_map(const uint8_t* bases, uint64_t n, uint8_t* map256, std::string* why) {
+    bool seen[256] = {false};
+    for (uint64_t i = 0; i < n; ++i) seen[bases[i]] = true;
+    return build_class_map_from_seen(seen, map256, why);
 }
 
 int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, uint64_t max_text_multi_stripe,

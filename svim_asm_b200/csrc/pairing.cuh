@@ -16,6 +16,7 @@ struct EditJob {
 };
 
 int build_class_map(const uint8_t* bases, uint64_t n, uint8_t* map256, std::string* why);
+int build_class_map_from_seen(const bool* seen, uint8_t* map256, std::string* why);
 int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, uint64_t max_text_multi_stripe,
                          const uint8_t* d_ref, const uint8_t* d_seq4_a, const uint8_t* d_seq4_b, const uint8_t* d_class_map,
                          double* d_out);

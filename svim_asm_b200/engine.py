@@ -269,14 +269,16 @@ class Table(object):
 
 
 class DeviceBackedHostBatch(HostBatch):
-    """HostBatch of a device ingest: `cigar` and `seq4` live in HBM and come to the host only when somebody reads them."""
+    """HostBatch of a device ingest: `cigar` and `seq4` live in HBM and come to the host only when somebody reads them
+    (each on its own: the VCF writer's INS alleles need the bases, the per-alignment seams the CIGAR ops)."""
     _engine = None
     _records = None
-    _materialized = False
+    _have = 0
 
-    def _materialize(self):
-        if not self._materialized and self._bam is not None and self._records is not None and self._records.handle:
-            self._engine._check(lib.svb_bam_materialize_host(self._engine.handle, self._bam, self._records.handle))
+    def _materialize(self, name):
+        bit = 1 if name == "cigar" else 2
+        if not (self._have & bit) and self._bam is not None and self._records is not None and self._records.handle:
+            self._engine._check(lib.svb_bam_materialize_host(self._engine.handle, self._bam, self._records.handle, bit))
             n = lib.svb_bam_n_records(self._bam)
 
             def view(address, dtype, count):
@@ -284,13 +286,15 @@ class DeviceBackedHostBatch(HostBatch):
                     return np.zeros(0, dtype=dtype)
                 buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(address)
                 return np.frombuffer(buf, dtype=dtype, count=count)
-            self.__dict__["cigar"] = view(lib.svb_bam_cigar(self._bam), np.uint32, lib.svb_bam_n_ops_padded(self._bam))
-            self.__dict__["seq4"] = view(lib.svb_bam_seq4(self._bam), np.uint8, int(self.seq_off[-1]) if n else 0)
-            self._materialized = True
+            if bit == 1:
+                self.__dict__["cigar"] = view(lib.svb_bam_cigar(self._bam), np.uint32, lib.svb_bam_n_ops_padded(self._bam))
+            else:
+                self.__dict__["seq4"] = view(lib.svb_bam_seq4(self._bam), np.uint8, int(self.seq_off[-1]) if n else 0)
+            self._have |= bit
 
     def __getattribute__(self, name):
-        if name in ("cigar", "seq4") and not object.__getattribute__(self, "_materialized"):
-            object.__getattribute__(self, "_materialize")()
+        if name == "cigar" or name == "seq4":
+            object.__getattribute__(self, "_materialize")(name)
         return object.__getattribute__(self, name)
 
 
@@ -319,6 +323,15 @@ class Reference(object):
     def __init__(self, engine, handle):
         self.engine = engine
         self.handle = handle
+
+    def to_numpy(self):
+        """(bases, class map) of the resident copy (tests)."""
+        n = ctypes.c_uint64()
+        self.engine._check(lib.svb_ref_to_host(self.engine.handle, self.handle, None, 0, ctypes.byref(n), None))
+        bases, cmap = np.zeros(int(n.value), dtype=np.uint8), np.zeros(256, dtype=np.uint8)
+        self.engine._check(lib.svb_ref_to_host(self.engine.handle, self.handle, _lib.ptr(bases), bases.shape[0], ctypes.byref(n),
+                                               cmap.ctypes.data))
+        return bases, cmap
 
     def free(self):
         if self.handle:
@@ -403,6 +416,15 @@ class Engine(object):
         host = rec.host
         self._check(lib.svb_records_set_sequences(self.handle, rec.handle, _lib.ptr(host.seq4), _lib.ptr(host.seq_off)))
         rec.has_sequences = True
+
+    def load_reference_fasta(self, path, fai_rows):
+        """Reference genome from the FASTA file itself (svb_ref_load_fasta).  fai_rows: one (length, offset, linebases,
+        linewidth) per contig in BAM header order, (0, 0, 0, 0) for a contig the FASTA lacks."""
+        out = ctypes.c_void_p()
+        fai = np.ascontiguousarray(fai_rows, dtype=np.uint64).reshape(-1, 4)
+        self._check(lib.svb_ref_load_fasta(self.handle, str(path).encode(), _lib.ptr(fai) if fai.size else None, fai.shape[0],
+                                           ctypes.byref(out)))
+        return Reference(self, out)
 
     def ingest_timings(self):
         """ms of the last device ingest: file read, H2D, inflate, record chase, fields + copy, host parse, total; inflated bytes."""

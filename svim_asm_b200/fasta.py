@@ -61,5 +61,10 @@ class FastaFile(object):
             offsets[i + 1] = offsets[i] + np.uint64(parts[-1].shape[0])
         return (np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)), offsets
 
+    def fai_rows(self, contig_names):
+        """(length, offset, linebases, linewidth) per contig of `contig_names`, zeros for contigs the FASTA lacks
+        (svb_ref_load_fasta builds the device copy from these)."""
+        return [self._index.get(name, (0, 0, 0, 0)) for name in contig_names]
+
     def close(self):
         self._fh.close()

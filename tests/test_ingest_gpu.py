@@ -76,3 +76,29 @@ def test_device_ingest_rejects_corrupt_files(engine, tmp_path):
     # the context stays usable
     got, records = HostBatch.from_bam_device(engine, path)
     assert got.n_aln == rb.n_aln
+
+
+def test_reference_from_fasta_file_matches_host_loader(engine, tmp_path):
+    """svb_ref_load_fasta (the file goes to HBM as it is; line terminators dropped and bases upper-cased by a kernel) against
+    FastaFile.load_upper + svb_ref_load: same bases, same symbol classes; contig order of the BAM header, a contig the
+    FASTA lacks, lower-case and IUPAC letters, a last line shorter than the others."""
+    from svim_asm_b200.fasta import FastaFile
+    rng = np.random.default_rng(8)
+    names = ["chrB", "chrA", "chrC"]
+    seqs = {n: bytes(rng.choice(list(b"ACGTacgtNnRY"), size).astype(np.uint8)) for n, size in zip(names, (100003, 61, 7000))}
+    path = str(tmp_path / "ref.fa")
+    with open(path, "w") as fh, open(path + ".fai", "w") as fai:
+        for n in names:
+            fh.write(">%s some description\n" % n)
+            off = fh.tell()
+            s = seqs[n].decode()
+            for i in range(0, len(s), 60):
+                fh.write(s[i:i + 60] + "\n")
+            fai.write("%s\t%d\t%d\t60\t61\n" % (n, len(s), off))
+    fa = FastaFile(path)
+    order = ["chrA", "missing", "chrC", "chrB"]
+    bases, offsets = fa.load_upper(order)
+    want = engine.load_reference(bases, offsets).to_numpy()
+    got = engine.load_reference_fasta(path, fa.fai_rows(order)).to_numpy()
+    assert got[0].tobytes() == want[0].tobytes() == b"".join(seqs[n].upper() for n in order if n in seqs)
+    assert np.array_equal(got[1], want[1])
