@@ -38,7 +38,9 @@ def test_haploid_vcf_with_options(tmp_path, built_library):
     assert got == open(os.path.join(GOLDEN, "haploid_opts", "variants.vcf")).read()
 
 
-def test_diploid_vcf_is_byte_identical(tmp_path, built_library):
+@pytest.mark.parametrize("ingest", ["device", "host"])
+def test_diploid_vcf_is_byte_identical(tmp_path, built_library, monkeypatch, ingest):
+    monkeypatch.setenv("SVIM_ASM_B200_INGEST", ingest)     # BGZF inflate + record split on the GPU / zlib on the host
     d = os.path.join(GOLDEN, "diploid")
     got = _run(tmp_path, ["diploid", os.path.join(d, "h1.bam"), os.path.join(d, "h2.bam"), os.path.join(d, "ref.fa"),
                           "--query_names"])
