@@ -6,6 +6,7 @@ In this package the objects are only a VIEW: candidates are computed on the GPU 
 for callers that want python objects.  The constructors repeat the reference's clamps and assertions so
 that hand-built objects behave identically.
 """
+import numpy as np
 
 _PLACEHOLDER = "PLACEHOLDERFORID"
 
@@ -246,12 +247,31 @@ class _Lengths(object):
         return self._len[name]
 
 
-def candidates_from_rows(rows, hosts, contig_names, contig_lengths):
+def decode_pool(rows, pool, starts):
+    """Inserted sequences of the INS rows of a table whose sequence pool was gathered on the device (4-bit packed, one
+    byte-aligned run per row): dict (aln_idx, seq_pos, seq_len) -> str."""
+    lut = np.frombuffer(b"=ACMGRSVTWYHKDBN", dtype=np.uint8)
+    out = {}
+    for i in np.nonzero((rows["type"] == 2) & (rows["seq_len"] > 0))[0]:
+        n = int(rows["seq_len"][i])
+        lo = int(starts[i])
+        raw = pool[lo:lo + (n + 1) // 2]
+        nib = np.empty(raw.shape[0] * 2, dtype=np.uint8)
+        nib[0::2] = raw >> 4
+        nib[1::2] = raw & 15
+        out[(int(rows["aln_idx"][i]), int(rows["seq_pos"][i]), n)] = lut[nib[:n]].tobytes().decode("ascii")
+    return out
+
+
+def candidates_from_rows(rows, hosts, contig_names, contig_lengths, sequences=None):
     """Materialise table rows (numpy structured array, svb_row layout) as Candidate objects.
 
     hosts: dict haplotype -> HostBatch (key 0 for a haploid run); they supply query names and the
-    inserted sequences (query_sequence slices, SVIM_intra.py:42, SVIM_inter.py:117,120)."""
+    inserted sequences (query_sequence slices, SVIM_intra.py:42, SVIM_inter.py:117,120).
+    sequences: optional dict haplotype -> decode_pool() result; rows found there do not touch the host's query bases
+    (after a device ingest those would have to be downloaded first)."""
     bam = _Lengths(contig_names, contig_lengths)
+    sequences = sequences or {}
     out = []
     for r in rows:
         hap = int(r["hap"])
@@ -268,7 +288,10 @@ def candidates_from_rows(rows, hosts, contig_names, contig_lengths):
             c = CandidateInversion(contig_names[r["src_tid"]], int(r["src_start"]), int(r["src_end"]), reads,
                                    bool(flags & F_COMPLETE), bam, gt)
         elif kind == 2:
-            seq = host.sequence_slice(int(r["aln_idx"]), int(r["seq_pos"]), int(r["seq_len"]))
+            key = (int(r["aln_idx"]), int(r["seq_pos"]), int(r["seq_len"]))
+            seq = sequences.get(hap, {}).get(key) if key[2] > 0 else ""
+            if seq is None:
+                seq = host.sequence_slice(*key)
             c = CandidateInsertion(contig_names[r["dst_tid"]], int(r["dst_start"]), int(r["dst_end"]), reads, seq, bam, gt)
         elif kind == 3:
             c = CandidateDuplicationTandem(contig_names[r["src_tid"]], int(r["src_start"]), int(r["src_end"]), int(r["copies"]),

@@ -8,7 +8,7 @@ import logging
 from .bamfile import AlignedSegment
 from .engine import make_params
 from .runtime import get_engine
-from .SVCandidate import candidates_from_rows
+from .SVCandidate import candidates_from_rows, decode_pool
 
 
 class CandidateList(list):
@@ -17,6 +17,7 @@ class CandidateList(list):
     table = None
     records = None
     host = None
+    sequences = None       # decode_pool() of the table's INS rows (device ingest: the query bases stay in HBM)
 
 
 def retrieve_other_alignments(main_alignment, bam):
@@ -56,8 +57,15 @@ def analyze_alignment_file_coordsorted(bam, options):
     eng = get_engine()
     host = bam.host
     records = getattr(bam, "records", None) or eng.load_records(host)     # a device ingest left the records in HBM
-    table = eng.collect(records, make_params(options), hap=getattr(options, "_haplotype", 0))
-    out = CandidateList(candidates_from_rows(table.to_numpy(), {getattr(options, "_haplotype", 0): host},
-                                             list(bam.references), list(bam.lengths)))
-    out.table, out.records, out.host = table, records, host
+    hap = getattr(options, "_haplotype", 0)
+    table = eng.collect(records, make_params(options), hap=hap)
+    rows = table.to_numpy()
+    sequences = None
+    if getattr(records, "has_sequences", False):       # device ingest: only the inserted bases come to the host
+        table.gather_sequences(records)
+        pool, starts = table.pool_to_numpy()
+        sequences = decode_pool(rows, pool, starts)
+    out = CandidateList(candidates_from_rows(rows, {hap: host}, list(bam.references), list(bam.lengths),
+                                             sequences={hap: sequences} if sequences is not None else None))
+    out.table, out.records, out.host, out.sequences = table, records, host, sequences
     return out

@@ -106,7 +106,9 @@ def pair_candidates(sv_candidates1, sv_candidates2, reference, bam, options):
         sides.append((table, records, host))
     ref = _device_reference(reference, names)
     paired = eng.pair(sides[0][0], sides[1][0], sides[0][1], sides[1][1], ref, make_params(options))
-    out = CandidateList(candidates_from_rows(paired.to_numpy(), {1: sides[0][2], 2: sides[1][2]}, names, lengths))
+    known = {hap: getattr(c, "sequences", None) for hap, c in ((1, sv_candidates1), (2, sv_candidates2))}
+    out = CandidateList(candidates_from_rows(paired.to_numpy(), {1: sides[0][2], 2: sides[1][2]}, names, lengths,
+                                             sequences={h: d for h, d in known.items() if d is not None}))
     out.table = paired
     return out
 

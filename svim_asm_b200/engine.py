@@ -258,7 +258,8 @@ class Table(object):
 
     def free(self):
         if self.handle:
-            lib.svb_table_free(self.handle)
+            if getattr(self.engine, "handle", None):
+                lib.svb_table_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -309,7 +310,8 @@ class Records(object):
 
     def free(self):
         if self.handle:
-            lib.svb_records_free(self.handle)
+            if getattr(self.engine, "handle", None):      # a closed context has already released its stream and pools
+                lib.svb_records_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -335,7 +337,8 @@ class Reference(object):
 
     def free(self):
         if self.handle:
-            lib.svb_ref_free(self.handle)
+            if getattr(self.engine, "handle", None):
+                lib.svb_ref_free(self.handle)
             self.handle = None
 
     def __del__(self):
