@@ -34,7 +34,19 @@ def log(msg):
         print("[bench] " + msg, file=sys.stderr, flush=True)
 
 
-def build_workload(scale, seed=1004):
+def build_reference(cfg):
+    """(bases, offsets) of the synthetic reference genome: contigs concatenated in BAM header order."""
+    from svim_asm_b200 import synth
+    t0 = time.time()
+    ref = synth.random_reference(cfg)
+    off = np.zeros(len(cfg.contig_names) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([ref[n].shape[0] for n in cfg.contig_names])
+    bases = np.concatenate([ref[n] for n in cfg.contig_names])
+    log("reference %.2f Gb in %.1fs" % (bases.shape[0] / 1e9, time.time() - t0))
+    return bases, off
+
+
+def build_workload(scale, seed=1004, with_reference=True):
     from svim_asm_b200 import synth
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:        # every rank generates the (deterministic) workload: share the host cores
@@ -43,12 +55,9 @@ def build_workload(scale, seed=1004):
     t0 = time.time()
     rb1, rb2 = synth.make_diploid(cfg)
     log("generated 2 x %d alignments, %d + %d CIGAR ops in %.1fs" % (rb1.n_aln, rb1.n_ops, rb2.n_ops, time.time() - t0))
-    t0 = time.time()
-    ref = synth.random_reference(cfg)
-    off = np.zeros(len(cfg.contig_names) + 1, dtype=np.uint64)
-    off[1:] = np.cumsum([ref[n].shape[0] for n in cfg.contig_names])
-    bases = np.concatenate([ref[n] for n in cfg.contig_names])
-    log("reference %.2f Gb in %.1fs" % (bases.shape[0] / 1e9, time.time() - t0))
+    if not with_reference:
+        return cfg, rb1, rb2, None, None
+    bases, off = build_reference(cfg)
     return cfg, rb1, rb2, bases, off
 
 
@@ -216,7 +225,7 @@ def b200_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from svim_asm_b200 import sharded
-        return sharded.bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block)
+        return sharded.bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block, build_reference)
     torch.cuda.set_device(local)
     cfg, rb1, rb2, bases, off = build_workload(args.scale)
     h1, h2 = pinned_host(HostBatch.from_record_batch(rb1)), pinned_host(HostBatch.from_record_batch(rb2))

@@ -298,7 +298,7 @@ def sharded_step_device(stage, rank, world, owner, lexrank, device, row_dtype):
 _PROFILE = {}
 
 
-def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block):
+def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block, build_reference):
     """bench.py for WORLD_SIZE > 1 (launched by torchrun): strong scaling, max over ranks."""
     import json
     import torch
@@ -310,18 +310,26 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
-    cfg, rb1, rb2, bases, off = build_workload(args.scale)
+    # host memory: every rank generates the whole (deterministic) workload but keeps only its shard; the reference
+    # genome is generated afterwards, uploaded from pageable memory and dropped (8 ranks x 3 GB pinned would not fit)
+    cfg, rb1, rb2, _b, _o = build_workload(args.scale, with_reference=False)
     n_contigs = len(cfg.contig_names)
     owner = lpt_assign(contig_weights(rb1, n_contigs) + contig_weights(rb2, n_contigs), world)
     s1, g1 = shard_records(rb1, owner, rank)
     s2, g2 = shard_records(rb2, owner, rank)
     n_aln_total, n_ops_total = rb1.n_aln + rb2.n_aln, rb1.n_ops + rb2.n_ops
+    del rb1, rb2
     hosts = [pinned_host(HostBatch.from_record_batch(s1)), pinned_host(HostBatch.from_record_batch(s2))]
+    del s1, s2
     ranks = lexrank(cfg.contig_names)
     eng = Engine(local)
     params = make_params()
-    bases_p, _keep = pin(bases)
-    ref = eng.load_reference(bases_p, off)                 # every rank keeps the whole reference (3.1 GB of 180 GB)
+    for turn in range(world):                              # one rank at a time holds the 3.1 GB host copy
+        if turn == rank:
+            bases, off = build_reference(cfg)
+            ref = eng.load_reference(bases, off)           # every rank keeps the whole reference in HBM (3.1 GB of 180 GB)
+            del bases
+        dist.barrier()
     resident = [eng.load_records(h, with_sequences=True) for h in hosts]
     for rec, g in zip(resident, (g1, g2)):
         eng.set_global_index(rec, g)
