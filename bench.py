@@ -327,6 +327,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the whole-genome workload (testing only)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: python's sys.stdout keeps the original descriptor, descriptor 1 itself is
+    # pointed at stderr so that anything a native library prints there (NCCL's version banner ...) cannot get in front
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w", buffering=1)
     if args.impl == "reference":
         reference_arm(args)
     else:
