@@ -102,3 +102,60 @@ def test_reference_from_fasta_file_matches_host_loader(engine, tmp_path):
     got = engine.load_reference_fasta(path, fa.fai_rows(order)).to_numpy()
     assert got[0].tobytes() == want[0].tobytes() == b"".join(seqs[n].upper() for n in order if n in seqs)
     assert np.array_equal(got[1], want[1])
+
+
+def _raw_bam(path, names, lengths, records, level=6, block=0xFF00):
+    """BAM file from explicit record dicts (refID, pos, flag, mapq, name, cigar [(op, len)], seq4 bytes, l_seq, tags bytes):
+    lets the tests put every auxiliary field type in front of the tag walker."""
+    import struct
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % nl for nl in zip(names, lengths))
+    stream = bytearray(b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(names)))
+    for n, ln in zip(names, lengths):
+        stream += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", ln)
+    for r in records:
+        name = r["name"].encode() + b"\0"
+        cig = b"".join(struct.pack("<I", (ln << 4) | op) for op, ln in r["cigar"])
+        l_seq = r["l_seq"]
+        core = struct.pack("<iiBBHHHiiii", r["tid"], r["pos"], len(name), r.get("mapq", 60), 4680, len(r["cigar"]), r.get("flag", 0),
+                           l_seq, -1, -1, 0)
+        body = core + name + cig + r["seq4"] + b"\xff" * l_seq + r.get("tags", b"")
+        stream += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as out:
+        for lo in range(0, len(stream), block):
+            out.write(bamio._bgzf_block(bytes(stream[lo:lo + block]), level))
+        out.write(bamio._EOF_BLOCK)
+
+
+def test_device_ingest_tag_types_unmapped_and_empty_files(engine, tmp_path):
+    import struct
+    rng = np.random.default_rng(12)
+    tags_all = (b"NMC\x05" + b"ASc\xfb" + b"XSs" + struct.pack("<h", -300) + b"YSS" + struct.pack("<H", 60000) + b"XIi" + struct.pack("<i", -5)
+                + b"YII" + struct.pack("<I", 4000000000) + b"XFf" + struct.pack("<f", 1.5) + b"XAAq" + b"MDZ10A5^AC6\0" + b"XHH1AE301\0"
+                + b"XBBc" + struct.pack("<i", 3) + b"\x01\x02\x03" + b"YBBS" + struct.pack("<i", 2) + struct.pack("<HH", 7, 8)
+                + b"ZBBf" + struct.pack("<i", 1) + struct.pack("<f", 2.0))
+    sa = b"SAZchrB,500,-,100S300M,60,3;chrA,9000,+,300M100S,13,0;\0"
+
+    def rec(tid, pos, cigar, tags=b"", flag=0, l_seq=None, name="r"):
+        n = sum(ln for op, ln in cigar if op in (0, 1, 4, 7, 8)) if l_seq is None else l_seq
+        return dict(tid=tid, pos=pos, flag=flag, name=name, cigar=cigar, l_seq=n,
+                    seq4=bytes(rng.integers(0, 256, (n + 1) // 2, dtype=np.uint8)), tags=tags)
+    records = [rec(0, 100, [(0, 300), (2, 50), (0, 100)], tags_all + sa, name="with_every_tag_type"),
+               rec(0, 700, [(4, 100), (0, 300)], sa + tags_all, name="sa_first"),
+               rec(0, 900, [(0, 50), (1, 45), (0, 50)], b"", name="no_tags"),
+               rec(1, 10, [], b"", l_seq=0, name="no_cigar_no_seq"),                     # '*' CIGAR and sequence
+               rec(1, 20, [(0, 10)], tags_all, flag=256, name="secondary"),
+               rec(-1, -1, [], b"XAAz", flag=4, l_seq=7, name="unmapped_at_the_end")]
+    path = str(tmp_path / "tags.bam")
+    _raw_bam(path, ["chrA", "chrB"], [100000, 50000], records, block=137)                  # many tiny members: records span them
+    _compare(engine, path)
+    # a header-only file, and one whose only member is the header
+    _raw_bam(str(tmp_path / "empty.bam"), ["chrA"], [1000], [])
+    got, recs = HostBatch.from_bam_device(engine, str(tmp_path / "empty.bam"))
+    assert got.n_aln == 0 and got.contig_names == ["chrA"] and len(engine.collect(recs, make_params())) == 0
+    # a truncated record and an unknown tag type are refused like on the host
+    bad = str(tmp_path / "badtag.bam")
+    _raw_bam(bad, ["chrA"], [1000], [rec(0, 1, [(0, 10)], b"XQq\x01", name="bad_type")])
+    with pytest.raises((RuntimeError, IOError)):
+        HostBatch.from_bam_device(engine, bad)
+    with pytest.raises((RuntimeError, IOError)):
+        HostBatch.from_bam(bad)
