@@ -54,12 +54,14 @@ SVB_HD int myers_block(uint64_t& pv, uint64_t& mv, uint64_t eq, int hin, uint64_
 struct WinGeom {
     uint32_t m, n, K, last_block;
     uint32_t bw;           // rows per block: 64 (one 64-bit word per lane) or 32 (half the work per step, half the band)
+    uint32_t dlt;          // upper band offset: n - m for a whole alignment; a HALF of a split alignment (first m rows of a
+                           // longer pattern, first n columns of its text) keeps the whole problem's value
 };
 constexpr uint32_t WIN_SLACK = 8;     // idle steps guaranteed between two blocks of one lane (prefetch priming)
 
 SVB_HD WinGeom win_geom(uint32_t m, uint32_t n, uint32_t K, uint32_t bw) {
     WinGeom g;
-    g.m = m; g.n = n; g.K = K; g.bw = bw; g.last_block = (m - 1u) / bw;
+    g.m = m; g.n = n; g.K = K; g.bw = bw; g.last_block = (m - 1u) / bw; g.dlt = n - m;
     return g;
 }
 SVB_HD uint32_t win_kmax(uint32_t m, uint32_t n, uint32_t bw) {   // widest half-width one warp can slide over (0: none)
@@ -71,9 +73,35 @@ SVB_HD uint32_t win_jlo(const WinGeom& g, uint32_t b) {
     return x > g.K ? static_cast<uint32_t>(x - g.K) : 0u;
 }
 SVB_HD uint32_t win_jhi(const WinGeom& g, uint32_t b) {
-    const uint64_t x = static_cast<uint64_t>(g.bw) * b + g.bw + (g.n - g.m) + g.K;
+    const uint64_t x = static_cast<uint64_t>(g.bw) * b + g.bw + g.dlt + g.K;
     return x < g.n ? static_cast<uint32_t>(x) : g.n;
 }
+// ---- split alignment (two warps per pair) ------------------------------------------------------------------------------
+// D[m][n] = min over j of F(j) + B(n - j), F(j) = D[mh][j] from the first mh pattern rows, B(j') the same quantity of the
+// REVERSED strings from their first m - mh rows.  Inside the band the optimal path crosses row mh at a column where both
+// halves are exact, everywhere else both are upper bounds, so the minimum is D[m][n] whenever it is <= K.  Each half only
+// needs the text columns its band reaches: about n / 2 + K steps instead of n, and the two halves run concurrently.
+// m and n are multiples of the block height (the caller pads with the sentinel symbol).
+struct WinSplit {
+    uint32_t rows_f, rows_b;   // pattern rows of the forward / backward half
+    uint32_t cols_f, cols_b;   // text columns each half processes
+};
+SVB_HD WinSplit win_split(uint32_t m, uint32_t n, uint32_t K, uint32_t bw) {
+    WinSplit s;
+    const uint32_t blocks = m / bw, dlt = n - m;
+    s.rows_f = (blocks / 2u) * bw;
+    s.rows_b = m - s.rows_f;
+    const uint64_t cf = static_cast<uint64_t>(s.rows_f) + dlt + K, cb = static_cast<uint64_t>(s.rows_b) + dlt + K;
+    s.cols_f = cf < n ? static_cast<uint32_t>(cf) : n;
+    s.cols_b = cb < n ? static_cast<uint32_t>(cb) : n;
+    return s;
+}
+SVB_HD WinGeom win_geom_half(uint32_t rows, uint32_t cols, uint32_t dlt, uint32_t K, uint32_t bw) {
+    WinGeom g;
+    g.m = rows; g.n = cols; g.K = K; g.bw = bw; g.last_block = (rows - 1u) / bw; g.dlt = dlt;
+    return g;
+}
+
 // per-block step limits, all relative to the block's first column (rel = column - win_jlo(b)):
 //   rel < width: the block is inside the band;  rel < hin_lim: the block above is too (else +1 enters);
 //   rel < cnt_lim: the bottom-row delta counts towards D[m][n]

@@ -38,6 +38,12 @@ struct EdShared {
     uint8_t cls2[512];                                     // byte -> class, complemented byte -> class
     uint8_t tcls[ED_WARPS][128];                           // ring: symbol class of the band's columns
     uint8_t th[ED_WARPS][64];                              // ring: delta code entering the stripe's top row
+    // split alignment of a long pair (both warps of the CTA on one job): bottom-row delta codes of each half's last block,
+    // the value they start from, the job and the verdict
+    uint8_t rec[2][1280];
+    long long half_base[2];
+    long long split_result;
+    uint32_t cta_job, cta_worker;
 };
 
 __device__ __forceinline__ uint32_t tok_class(const uint8_t* cls2, uint32_t byte, uint32_t mode) {
@@ -271,14 +277,24 @@ __device__ __forceinline__ long long window_pass(const HapDesc& P, const HapDesc
 //    the match mask and nothing has to be unpacked on the chain:
 //    select, or-and, add, xor-or, and-or-not, shift = 6 dependent instructions between the shuffles.
 // m0, n0: the real lengths.  Returns the window's value, which is D[m0][n0] whenever it is <= K.
-__device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDesc& T, uint32_t pre, uint32_t m0, uint32_t n0,
+// HALF = false: the whole alignment.  HALF = true: one half of a split alignment (edit_core.cuh, win_split): the first
+// `rows` rows of the padded pattern against the first `cols` columns of the padded text, both read from the far end when
+// `rev` is set; the last block's bottom-row deltas are not summed but recorded per column in `rec` (2-bit codes), and the
+// return value is D[rows][first column of that block], the base the caller's prefix sums start from.
+template <bool HALF>
+__device__ __forceinline__ long long window_core32(const HapDesc& P, const HapDesc& T, uint32_t pre, uint32_t m0, uint32_t n0,
                                                    uint32_t K, const uint8_t* ref, const uint8_t* sa, const uint8_t* sb,
-                                                   const uint8_t* cls2tab, unsigned long long* peq_mem, uint8_t* tcls, uint32_t lane) {
+                                                   const uint8_t* cls2tab, unsigned long long* peq_mem, uint8_t* tcls, uint32_t lane,
+                                                   uint32_t rows, uint32_t cols, bool rev, uint8_t* rec) {
     constexpr int BW = 32;
     using Word = uint32_t;
     constexpr uint32_t WPB = 1;
-    const uint32_t padk = (32u - (m0 & 31u)) & 31u, m = m0 + padk, n = n0 + padk;       // padded lengths
-    const WinGeom g = win_geom(m, n, K, BW);
+    const uint32_t padk = (32u - (m0 & 31u)) & 31u, mp = m0 + padk, np_ = n0 + padk;    // padded lengths of the whole strings
+    const uint32_t m = HALF ? rows : mp, n = HALF ? cols : np_;                          // what this pass covers
+    const WinGeom g = HALF ? win_geom_half(m, n, np_ - mp, K, BW) : win_geom(m, n, K, BW);
+    // row i / column j of this pass -> index in the padded strings (sentinel symbols sit at the far end of both)
+    auto prow = [&](uint32_t i) -> uint32_t { return (HALF && rev) ? mp - 1u - i : i; };
+    auto tcol = [&](uint32_t j) -> uint32_t { return (HALF && rev) ? np_ - 1u - j : j; };
     Word* peqw = reinterpret_cast<Word*>(peq_mem);                   // [buffer][class][lane]
     uint32_t* peq32 = reinterpret_cast<uint32_t*>(peq_mem);          // [buffer][class][lane][word of the block]
 
@@ -295,13 +311,13 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
             const uint32_t idx = (g0 + k) * 32u + lane;
             mode[k] = TOK_NONE;
             byte[k] = 0u;
-            if (idx < rows0 && idx < m0) byte[k] = hap_fetch(P, pre + idx, ref, sa, sb, mode[k]);
+            if (idx < rows0 && prow(idx) < m0) byte[k] = hap_fetch(P, pre + prow(idx), ref, sa, sb, mode[k]);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t idx = (g0 + k) * 32u + lane;
             uint32_t cls = mode[k] == TOK_NONE ? ED_SKIP : tok_class(cls2tab, byte[k], mode[k]);
-            if (idx >= m0 && idx < rows0) cls = ED_SENTINEL;
+            if (idx < rows0 && prow(idx) >= m0) cls = ED_SENTINEL;
             const uint32_t peers = __match_any_sync(FULL, cls);
             if (cls != ED_NOCLASS && cls < ED_SKIP && static_cast<uint32_t>(__ffs(peers) - 1) == lane) peq32[cls * (32u * WPB) + (g0 + k)] = peers;
         }
@@ -315,7 +331,8 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
             const uint64_t idx = static_cast<uint64_t>(BW) * next_build + 32u * k + lane;
             pat_mode[k] = TOK_NONE;
             pat_byte[k] = 0u;
-            if (next_build <= g.last_block && idx < m0) pat_byte[k] = hap_fetch(P, pre + static_cast<uint32_t>(idx), ref, sa, sb, pat_mode[k]);
+            if (next_build <= g.last_block && idx < m && prow(static_cast<uint32_t>(idx)) < m0)
+                pat_byte[k] = hap_fetch(P, pre + prow(static_cast<uint32_t>(idx)), ref, sa, sb, pat_mode[k]);
         }
     };
     auto pattern_build = [&]() {                                     // block next_build -> buffer (b / 32) & 1, column b % 32
@@ -326,7 +343,7 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
         for (int k = 0; k < static_cast<int>(WPB); ++k) {
             const uint64_t idx = static_cast<uint64_t>(BW) * next_build + 32u * k + lane;
             uint32_t cls = pat_mode[k] == TOK_NONE ? ED_SKIP : tok_class(cls2tab, pat_byte[k], pat_mode[k]);
-            if (idx >= m0 && idx < m) cls = ED_SENTINEL;
+            if (idx < m && prow(static_cast<uint32_t>(idx)) >= m0) cls = ED_SENTINEL;
             const uint32_t peers = __match_any_sync(FULL, cls);
             if (cls != ED_NOCLASS && cls < ED_SKIP && static_cast<uint32_t>(__ffs(peers) - 1) == lane)
                 peq32[((buf * PEQ_ROWS + cls) * 32u + col) * WPB + static_cast<uint32_t>(k)] = peers;
@@ -341,12 +358,12 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
         const uint32_t col = c_ins + lane;
         nxt_mode = TOK_NONE;
         nxt_byte = 0u;
-        if (col < n0) nxt_byte = hap_fetch(T, pre + col, ref, sa, sb, nxt_mode);
+        if (col < n && tcol(col) < n0) nxt_byte = hap_fetch(T, pre + tcol(col), ref, sa, sb, nxt_mode);
     };
     auto ring_insert = [&]() {
         const uint32_t col = c_ins + lane;
         uint32_t cls = nxt_mode == TOK_NONE ? ED_NOCLASS : tok_class(cls2tab, nxt_byte, nxt_mode);
-        if (col >= n0 && col < n) cls = ED_SENTINEL;
+        if (col < n && tcol(col) >= n0) cls = ED_SENTINEL;
         tcls[col & 127u] = static_cast<uint8_t>(cls);
         c_ins += 32u;
     };
@@ -364,6 +381,8 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
     WinBlock w;
     w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = BW - 1u;
     if (blk <= g.last_block) w = win_block(g, blk);
+    bool is_last = HALF && blk == g.last_block;
+    if (is_last) w.cnt_lim = 0u;
     int colbase = -static_cast<int>(blk);                            // text column of step t: t + colbase
     Word pv = static_cast<Word>(~0ull), mv = 0;
     uint32_t acc_pos = 0, acc_neg = 0;                               // counted +1 / -1 deltas of the bottom rows
@@ -390,6 +409,8 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
             peq_lane = peqw + buf * (PEQ_ROWS * 32u) + lane;
             w.start = 0; w.width = 0; w.hin_lim = 0; w.cnt_lim = 0; w.hshift = BW - 1u;
             if (blk <= g.last_block) w = win_block(g, blk);
+            is_last = HALF && blk == g.last_block;
+            if (is_last) w.cnt_lim = 0u;
         }
     };
     uint32_t next_event = __reduce_min_sync(FULL, switch_step());
@@ -442,6 +463,7 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
                 const bool cnt = rel < cnt_lim;
                 acc_pos += cnt ? pos_o : 0u;
                 acc_neg += cnt ? neg_o : 0u;
+                if (HALF && is_last && active) rec[rel] = static_cast<uint8_t>(pos_o | (neg_o << 1));
                 hpos_out = pos_o;
                 hneg_out = neg_o;
                 eq0 = eq1;
@@ -453,6 +475,12 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
     const int partial = static_cast<int>(acc_pos) - static_cast<int>(acc_neg);
     __syncwarp();
     return static_cast<long long>(m) + __reduce_add_sync(FULL, partial);
+}
+
+__device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDesc& T, uint32_t pre, uint32_t m0, uint32_t n0,
+                                                   uint32_t K, const uint8_t* ref, const uint8_t* sa, const uint8_t* sb,
+                                                   const uint8_t* cls2tab, unsigned long long* peq_mem, uint8_t* tcls, uint32_t lane) {
+    return window_core32<false>(P, T, pre, m0, n0, K, ref, sa, sb, cls2tab, peq_mem, tcls, lane, 0u, 0u, false, nullptr);
 }
 
 __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const EditJob* __restrict__ jobs, uint32_t n_jobs,
@@ -484,20 +512,31 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
     // Sweep 0 is the critical path of the launch (a 10,000-row pair is one warp's dependency chain for most of a
     // millisecond), so at most ONE warp per SM sub-partition works on it: the first warp that claims the token of its
     // (SM, scheduler) pair.  The others start with the short jobs right away.
-    bool long_worker = true;
-    if (sm_tokens) {
-        uint32_t smid, warpid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
-        uint32_t won = 0;
-        if (lane == 0) won = atomicExch(sm_tokens + ((smid & 1023u) * 4u + (warpid & 3u)), 1u) == 0u ? 1u : 0u;
-        long_worker = __shfl_sync(FULL, won, 0) != 0u;
+    // (CTA level: both warps of a worker CTA take the SAME long job, one half each, see below)
+    if (threadIdx.x == 0) {
+        uint32_t won = 1u;
+        if (sm_tokens) {
+            uint32_t smid, warpid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+            won = atomicExch(sm_tokens + ((smid & 1023u) * 4u + ((warpid >> 1) & 1u)), 1u) == 0u ? 1u : 0u;
+        }
+        sh.cta_worker = won;
     }
+    __syncthreads();
+    const bool long_worker = sh.cta_worker != 0u;
     for (int sweep = long_worker ? 0 : 1; sweep < 2; ++sweep) {
         while (true) {
             uint32_t job_id = 0;
-            if (lane == 0) job_id = atomicAdd(next_job + sweep, 1u);
-            job_id = __shfl_sync(FULL, job_id, 0);
+            if (sweep == 0) {              // the whole CTA takes one long job (two barriers per round, both warps always)
+                if (threadIdx.x == 0) sh.cta_job = atomicAdd(next_job, 1u);
+                __syncthreads();
+                job_id = sh.cta_job;
+                __syncthreads();
+            } else {
+                if (lane == 0) job_id = atomicAdd(next_job + 1, 1u);
+                job_id = __shfl_sync(FULL, job_id, 0);
+            }
             if (job_id >= n_jobs) break;
             const EditJob job = jobs[job_id];
             const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
@@ -521,7 +560,66 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             // the band in about n steps: first with 32-row blocks (band of about 500 either side, half the work per
             // step), then with 64-row blocks (about 1000).  What is left goes to the striped band attempts.
             unsigned long long known_above = 0;           // the distance is known to exceed this
-            if (!done && m > 1024u) {
+            if (sweep == 0) {
+                // Both warps of the CTA on this pair: D[m][n] = min_j F(j) + B(n - j) with F from the top half of the rows
+                // (warp 0) and B from the bottom half of the REVERSED strings (warp 1); each half needs about n / 2 + K
+                // steps and they run at the same time.  Exact whenever the minimum is inside the band.
+                const uint32_t padk = (32u - (m & 31u)) & 31u, mp = m + padk, np_ = n + padk;
+                const uint32_t kw = win_kmax(mp, np_, 32u);
+                const bool split = !done && kw >= 128u && mp >= 2048u;
+                if (split) {
+                    const WinSplit sp = win_split(mp, np_, kw, 32u);
+                    const uint32_t rows = warp == 0 ? sp.rows_f : sp.rows_b, cols = warp == 0 ? sp.cols_f : sp.cols_b;
+                    const long long base = window_core32<true>(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0],
+                                                               tcls, lane, rows, cols, warp != 0, sh.rec[warp]);
+                    steps_total += cols + (rows - 1u) / 32u;
+                    // values along the meeting row, F(j) for j = jlo .. jhi of this half's last block: inclusive scan of the
+                    // recorded deltas, kept in this warp's (now idle) mask buffer
+                    const WinGeom gh = win_geom_half(rows, cols, np_ - mp, kw, 32u);
+                    const uint32_t jlo = win_jlo(gh, gh.last_block), len = win_jhi(gh, gh.last_block) - jlo;
+                    int* val = reinterpret_cast<int*>(&sh.peq[warp][0][0][0]);
+                    __syncwarp();
+                    int running = static_cast<int>(base);
+                    if (lane == 0) val[0] = running;
+                    for (uint32_t c0 = 0; c0 < len; c0 += 32u) {
+                        const uint32_t c = c0 + lane;
+                        const uint32_t code = c < len ? sh.rec[warp][c] : 0u;
+                        int d = static_cast<int>(code & 1u) - static_cast<int>(code >> 1);
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int up = __shfl_up_sync(FULL, d, o);
+                            if (static_cast<int>(lane) >= o) d += up;
+                        }
+                        if (c < len) val[c + 1u] = running + d;
+                        running += __shfl_sync(FULL, d, 31);
+                    }
+                    if (lane == 0) sh.half_base[warp] = (static_cast<long long>(jlo) << 32) | len;     // geometry for the other warp
+                    __syncthreads();
+                    if (warp == 0) {
+                        const int* vf = val;
+                        const int* vb = reinterpret_cast<const int*>(&sh.peq[1][0][0][0]);
+                        const uint32_t jlo_b = static_cast<uint32_t>(sh.half_base[1] >> 32), len_b = static_cast<uint32_t>(sh.half_base[1]);
+                        int best = 0x7fffffff;
+                        for (uint32_t i = lane; i <= len; i += 32u) {
+                            const long long j = static_cast<long long>(jlo) + i;
+                            const long long ib = static_cast<long long>(np_) - j - static_cast<long long>(jlo_b);
+                            if (ib >= 0 && ib <= static_cast<long long>(len_b)) best = min(best, vf[i] + vb[ib]);
+                        }
+                        best = __reduce_min_sync(FULL, best);
+                        if (lane == 0) sh.split_result = best == 0x7fffffff ? -1ll : static_cast<long long>(best);
+                    }
+                    __syncthreads();
+                    const long long d = sh.split_result;
+                    if (d >= 0 && d <= static_cast<long long>(kw)) {
+                        dist = d;
+                        done = true;
+                    } else {
+                        known_above = kw;
+                    }
+                }
+                if (warp != 0) continue;       // what is left of this pair (fallbacks, the result) is warp 0's
+            }
+            if (!done && m > 1024u && known_above == 0) {
                 const uint32_t kw = win_kmax(m, n, 32u);
                 if (kw >= 128u) {
                     const long long d = window_pass32(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
@@ -536,7 +634,9 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             }
             if (!done && m > 2048u) {
                 const uint32_t kw = win_kmax(m, n, 64u);
-                if (kw >= 128u && kw > known_above) {
+                // (after a failed 32-row pass the wider window rarely succeeds: only worth it against an expensive full table)
+                const unsigned long long full_cost = static_cast<unsigned long long>((m + 2047u) / 2048u) * (n + 31u);
+                if (kw >= 128u && kw > known_above && (known_above == 0 || full_cost > 3ull * n)) {
                     const long long d = window_pass<64>(P, T, pre, m, n, kw, ref, seq4_a, seq4_b, sh.cls2, &sh.peq[warp][0][0][0], tcls, lane);
                     steps_total += n + (m - 1u) / 64u;
                     if (d <= static_cast<long long>(kw)) {
@@ -555,23 +655,43 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                 for (uint32_t i = lane; i < 128u; i += 32u) tcls[i] = static_cast<uint8_t>(ED_NOCLASS);
                 __syncwarp();
             }
+            // The stripes may take either string as the pattern: a full table costs ceil(rows / 2048) x (columns + 31) steps,
+            // and for a short pattern against a long text (two unrelated insertions next to each other) the transposed table
+            // is several times cheaper.  The band attempts need n >= m, so the swap implies the full table.
+            uint32_t m_s = m, n_s = n;
+            HapDesc P_s = P, T_s = T;
+            bool force_full = false;
+            if (!done) {
+                // the distance is at least n - m: attempts with a narrower band cannot succeed
+                while ((256ull << (2 * first_attempt)) < static_cast<unsigned long long>(n - m)) ++first_attempt;
+                const unsigned long long K0 = 256ull << (2 * first_attempt);
+                if (m <= 2048u || K0 >= m) {
+                    const unsigned long long as_is = static_cast<unsigned long long>((m + 2047u) / 2048u) * (n + 31u);
+                    const unsigned long long swapped = static_cast<unsigned long long>((n + 2047u) / 2048u) * (m + 31u);
+                    if (swapped < as_is) {
+                        m_s = n; n_s = m;
+                        P_s = T; T_s = P;
+                        force_full = true;
+                    }
+                }
+            }
             if (!done) {
                 // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of
                 // half-width K gives the exact distance whenever the result is <= K; otherwise widen (x4) and repeat.
                 // Single-stripe patterns are computed in full at once.
                 for (int attempt = first_attempt;; ++attempt) {
                     unsigned long long K = 256ull << (2 * attempt);
-                    const bool full_table = m <= 2048u || K >= m;
+                    const bool full_table = force_full || m_s <= 2048u || K >= m_s;
                     if (full_table) K = ~0ull >> 1;
                     long long anchor = 0;                      // D'[last row of the previous stripe, jlo - 1]
                     uint32_t prev_jhi = 0;
-                    for (uint32_t row0 = 0; row0 < m; row0 += 2048u) {
-                        const uint32_t rows = min(2048u, m - row0);
-                        const bool final_stripe = row0 + rows == m;
+                    for (uint32_t row0 = 0; row0 < m_s; row0 += 2048u) {
+                        const uint32_t rows = min(2048u, m_s - row0);
+                        const bool final_stripe = row0 + rows == m_s;
                         const uint32_t nblk = (rows + 63u) / 64u, last_lane = nblk - 1u;
                         const uint32_t jlo = static_cast<unsigned long long>(row0) > K ? static_cast<uint32_t>(row0 - K) : 0u;
-                        const uint32_t jhi = static_cast<uint32_t>(min(static_cast<unsigned long long>(n),
-                                                                       static_cast<unsigned long long>(row0) + rows + (n - m) + K));
+                        const uint32_t jhi = static_cast<uint32_t>(min(static_cast<unsigned long long>(n_s),
+                                                                       static_cast<unsigned long long>(row0) + rows + (n_s - m_s) + K));
                         // first column of the NEXT stripe's band: the running anchor stops there
                         const uint32_t next_row0 = row0 + rows;
                         const uint32_t next_jlo = static_cast<unsigned long long>(next_row0) > K ? static_cast<uint32_t>(next_row0 - K) : 0u;
@@ -591,7 +711,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                 const uint32_t idx = (g0 + k) * 32u + lane;
                                 mode[k] = TOK_NONE;
                                 byte[k] = 0u;
-                                if (idx < rows) byte[k] = hap_fetch(P, pre + row0 + idx, ref, seq4_a, seq4_b, mode[k]);
+                                if (idx < rows) byte[k] = hap_fetch(P_s, pre + row0 + idx, ref, seq4_a, seq4_b, mode[k]);
                             }
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -610,7 +730,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                             nxt_h = 1u;                                             // outside the previous band: +1
                             if (rel < width) {
                                 const uint32_t j = jlo + static_cast<uint32_t>(rel);
-                                nxt_byte = hap_fetch(T, pre + j, ref, seq4_a, seq4_b, nxt_mode);
+                                nxt_byte = hap_fetch(T_s, pre + j, ref, seq4_a, seq4_b, nxt_mode);
                                 if (row0 != 0u && j < prev_jhi) nxt_h = __ldcg(hbuf + j);
                             }
                         };
@@ -754,8 +874,11 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
     const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n_jobs + ED_WARPS - 1) / ED_WARPS,
                                                                      static_cast<uint64_t>(ctx->sm_count) * 16));
     uint8_t* hbuf = nullptr;
-    const uint64_t stride = (max_text_multi_stripe + 127) & ~127ull;
-    if (stride) SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));
+    // parked bottom-row deltas of multi-stripe tables, one byte per text column: the longest text of a pair whose shorter
+    // string exceeds a stripe, and at least one stripe's worth (a short pattern against a long text is transposed, its text
+    // then is the short string)
+    const uint64_t stride = (std::max<uint64_t>(max_text_multi_stripe, 2048) + 127) & ~127ull;
+    SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));
     SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, sizeof(unsigned long long), ctx->stream));   // two 32-bit job counters
     // profiling aid: SVB_ED_PROFILE=<file> dumps one uint4 per job {rows, columns, column steps, SM cycles} of the launch
     const char* profile_path = getenv("SVB_ED_PROFILE");

@@ -26,6 +26,8 @@ def load():
     lib.hc_myers_window.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_uint, ctypes.c_uint]
     lib.hc_win_kmax.restype = ctypes.c_uint
     lib.hc_win_kmax.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
+    lib.hc_myers_window_split.restype = ctypes.c_longlong
+    lib.hc_myers_window_split.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_uint]
     lib.hc_inflate.restype = ctypes.c_int
     lib.hc_inflate.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint]
     return lib

@@ -128,3 +128,87 @@ extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return wi
 extern "C" int hc_inflate(const uint8_t* src, unsigned src_len, uint8_t* dst, unsigned out_len) {
     return inflate_member(src, src_len, dst, out_len);
 }
+
+// ---- split window (two halves meeting at row mh), the algorithm of window_pass_split in edit_distance.cu ---------------
+namespace {
+struct HalfResult { long long base; uint32_t jlo; std::vector<int> delta; bool ok; };
+
+// window over the first g.m rows of P and the first g.n columns of T (32-row blocks); the LAST block does not count
+// towards the sum: its bottom-row deltas are recorded per column instead
+template <typename PF, typename TF>
+HalfResult emulate_half(const WinGeom& g, PF P, TF T) {
+    struct Lane { uint32_t blk; bool has; WinBlock w; uint32_t pv, mv, hout; long long partial; };
+    Lane L[32];
+    HalfResult out;
+    out.ok = true;
+    out.jlo = win_jlo(g, g.last_block);
+    out.delta.assign(win_jhi(g, g.last_block) - out.jlo, 0);
+    for (uint32_t l = 0; l < 32u; ++l) {
+        L[l].blk = l; L[l].has = l <= g.last_block; L[l].pv = 0xFFFFFFFFu; L[l].mv = 0; L[l].hout = 0; L[l].partial = 0;
+        if (L[l].has) L[l].w = win_block(g, l);
+    }
+    const uint32_t t_end = g.n + g.last_block;
+    for (uint32_t t = 0; t < t_end; ++t) {
+        uint32_t prev_hout[32];
+        for (uint32_t l = 0; l < 32u; ++l) prev_hout[l] = L[l].hout;
+        for (uint32_t l = 0; l < 32u; ++l) {
+            Lane& x = L[l];
+            if (!x.has) continue;
+            const int rel = static_cast<int>(t) - static_cast<int>(x.w.start);
+            if (rel >= 0 && static_cast<uint32_t>(rel) < x.w.width) {
+                const uint32_t j = win_jlo(g, x.blk) + static_cast<uint32_t>(rel);
+                uint32_t eq = 0;
+                for (uint32_t r = 0; r < 32u; ++r) if (P(32u * x.blk + r) == T(j)) eq |= 1u << r;
+                const uint32_t hin = static_cast<uint32_t>(rel) < x.w.hin_lim ? prev_hout[(l + 31u) & 31u] : 1u;
+                const uint32_t ho = myers_step32(x.pv, x.mv, eq, hin, 31u);
+                const int d = static_cast<int>(ho & 1u) - static_cast<int>(ho >> 1);
+                if (x.blk == g.last_block) out.delta[j - out.jlo] = d;
+                else if (static_cast<uint32_t>(rel) < x.w.cnt_lim) x.partial += d;
+                x.hout = ho;
+            }
+            if (rel + 1 == static_cast<int>(x.w.width)) {
+                x.blk += 32u;
+                x.has = x.blk <= g.last_block;
+                x.pv = 0xFFFFFFFFu; x.mv = 0;
+                if (x.has) {
+                    const WinBlock nw = win_block(g, x.blk);
+                    if (nw.start < t + 1u + WIN_SLACK) out.ok = false;
+                    x.w = nw;
+                }
+            }
+        }
+    }
+    out.base = g.m;
+    for (uint32_t l = 0; l < 32u; ++l) out.base += L[l].partial;
+    return out;
+}
+}  // namespace
+
+extern "C" long long hc_myers_window_split(const uint8_t* a, long long m0, const uint8_t* b, long long n0, unsigned K) {
+    const uint32_t pad = (32u - (static_cast<uint32_t>(m0) & 31u)) & 31u;
+    const uint32_t m = static_cast<uint32_t>(m0) + pad, n = static_cast<uint32_t>(n0) + pad, dlt = n - m;
+    auto P = [&](uint32_t i) -> int { return i < static_cast<uint32_t>(m0) ? a[i] : (i < m ? 256 : -1); };      // 256: the sentinel
+    auto T = [&](uint32_t j) -> int { return j < static_cast<uint32_t>(n0) ? b[j] : (j < n ? 256 : -2); };
+    auto PR = [&](uint32_t i) -> int { return i < m ? P(m - 1u - i) : -1; };
+    auto TR = [&](uint32_t j) -> int { return j < n ? T(n - 1u - j) : -2; };
+    const WinSplit sp = win_split(m, n, K, 32u);
+    if (sp.rows_f == 0 || sp.rows_b == 0) return -1;
+    const HalfResult f = emulate_half(win_geom_half(sp.rows_f, sp.cols_f, dlt, K, 32u), P, T);
+    const HalfResult r = emulate_half(win_geom_half(sp.rows_b, sp.cols_b, dlt, K, 32u), PR, TR);
+    if (!f.ok || !r.ok) return -1;
+    // F(j), j in [f.jlo, f.jlo + len]; B(j'), j' in [r.jlo, r.jlo + len]; D = min F(j) + B(n - j)
+    std::vector<long long> F(f.delta.size() + 1), B(r.delta.size() + 1);
+    F[0] = f.base;
+    for (size_t i = 0; i < f.delta.size(); ++i) F[i + 1] = F[i] + f.delta[i];
+    B[0] = r.base;
+    for (size_t i = 0; i < r.delta.size(); ++i) B[i + 1] = B[i] + r.delta[i];
+    long long best = -2;
+    for (size_t i = 0; i < F.size(); ++i) {
+        const long long j = static_cast<long long>(f.jlo) + static_cast<long long>(i);
+        const long long jb = static_cast<long long>(n) - j - static_cast<long long>(r.jlo);
+        if (jb < 0 || jb >= static_cast<long long>(B.size())) continue;
+        const long long v = F[i] + B[static_cast<size_t>(jb)];
+        if (best < 0 || v < best) best = v;
+    }
+    return best;
+}

@@ -102,3 +102,33 @@ def test_sentinel_padding_keeps_the_distance(oracle_clib):
         kmax = lib.hc_win_kmax(len(p), len(t), 32)
         if kmax and want <= kmax:
             assert lib.hc_myers_window(pp, len(pp), tt, len(tt), kmax, 32) == want
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_split_window_meets_in_the_middle(oracle_clib, seed):
+    """Two halves (forward from the top rows, backward from the bottom rows of the reversed strings) meeting at the middle
+    row: min_j F(j) + B(n - j) is the distance whenever it is inside the band, and never below it."""
+    lib = hostcheck.load()
+    rng = np.random.default_rng(seed)
+    exact = 0
+    for trial in range(10):
+        m = int(rng.integers(1100, 5000))
+        a = bytes(rng.choice(list(b"ACGT"), m).tolist())
+        b = _mutate(rng, a, int(rng.integers(0, 450)))
+        if trial % 3 == 0:
+            cut = int(rng.integers(0, len(b)))
+            b = b[:cut] + bytes(rng.choice(list(b"ACGT"), int(rng.integers(50, 400))).tolist()) + b[cut:]
+        p, t = (a, b) if len(a) <= len(b) else (b, a)
+        want = oracle_clib.orc_edit_distance(p, len(p), t, len(t))
+        kmax = lib.hc_win_kmax(len(p) + 31, len(t) + 31, 32)
+        for K in sorted({40, 200, kmax} - {0}):
+            if K > kmax:
+                continue
+            got = lib.hc_myers_window_split(p, len(p), t, len(t), K)
+            if got == -1:
+                continue
+            assert got == -2 or got >= want, (len(p), len(t), K, got, want)
+            if want <= K:
+                assert got == want, (len(p), len(t), K, got, want)
+                exact += 1
+    assert exact > 8

@@ -64,6 +64,8 @@ def test_edit_distance_long_patterns_window_and_stripes(engine, oracle_clib):
         cut = int(rng.integers(0, len(a)))
         pairs.append((a, a[:cut] + bytes(rng.choice(alphabet, extra).tolist()) + a[cut:]))
     pairs.append((bytes(rng.choice(alphabet, 4000).tolist()), bytes(rng.choice(alphabet, 4100).tolist())))   # unrelated
+    for m, n in ((300, 9000), (1300, 10900), (820, 9900), (2000, 2300), (2218, 2425), (64, 5000), (1, 4000)):   # transposed full tables
+        pairs.append((bytes(rng.choice(alphabet, m).tolist()), bytes(rng.choice(alphabet, n).tolist())))
     pairs.append((b"A" * 5000, b"A" * 4990 + b"C" * 10))
     pairs.append((b"AC" * 3000, b"CA" * 3000))
     got = engine.edit_distance(pairs)
