@@ -44,6 +44,7 @@ struct EdShared {
     long long half_base[2];
     long long split_result;
     uint32_t cta_job, cta_worker;
+    uint32_t trim[2];
 };
 
 __device__ __forceinline__ uint32_t tok_class(const uint8_t* cls2, uint32_t byte, uint32_t mode) {
@@ -53,18 +54,20 @@ __device__ __forceinline__ uint32_t tok_class(const uint8_t* cls2, uint32_t byte
     return min(c, ED_NOCLASS);
 }
 
-// Length of the common prefix (REVERSED = false) or suffix of the two strings, at most `lim`; 128 positions per round so
-// that four loads per string are in flight.
+// Length of the common prefix (REVERSED = false) or suffix of the two strings, at most `lim`, given that the first
+// `start` positions are known to agree; 128 positions per round so that four loads per string are in flight (eight per
+// string were measured slower).
 template <bool REVERSED>
 __device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& B, uint32_t la, uint32_t lb, uint32_t lim,
                                                const uint8_t* ref, const uint8_t* sa, const uint8_t* sb, const uint8_t* cls2,
-                                               uint32_t lane) {
-    uint32_t run = 0;
+                                               uint32_t lane, uint32_t start = 0u) {
+    constexpr int U = 4;
+    uint32_t run = start;
     bool done = false;
     while (run < lim && !done) {
-        uint32_t ba[4], ma[4], bb[4], mb[4];
+        uint32_t ba[U], ma[U], bb[U], mb[U];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < U; ++k) {
             const uint32_t i = run + 32u * k + lane;
             ma[k] = mb[k] = TOK_NONE;
             ba[k] = bb[k] = 0u;
@@ -74,7 +77,7 @@ __device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& 
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < U; ++k) {
             bool same = false;
             if (ma[k] != TOK_NONE) {
                 const uint32_t ca = tok_class(cls2, ba[k], ma[k]);
@@ -86,7 +89,7 @@ __device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& 
                 done = true;
             }
         }
-        if (!done) run += 128u;
+        if (!done) run += 32u * U;
     }
     return min(run, lim);
 }
@@ -507,8 +510,8 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
     uint8_t* tcls = sh.tcls[warp];
     uint8_t* th = sh.th[warp];
 
-    // Two sweeps over the job list: patterns longer than one 2048-row stripe first (they are the long poles),
-    // then the single-stripe jobs.
+    // Two sweeps over the job list: pairs with a string longer than one 2048-row stripe first (they are the long poles),
+    // then the short ones.
     // Sweep 0 is the critical path of the launch (a 10,000-row pair is one warp's dependency chain for most of a
     // millisecond), so at most ONE warp per SM sub-partition works on it: the first warp that claims the token of its
     // (SM, scheduler) pair.  The others start with the short jobs right away.
@@ -525,29 +528,51 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
     }
     __syncthreads();
     const bool long_worker = sh.cta_worker != 0u;
-    for (int sweep = long_worker ? 0 : 1; sweep < 2; ++sweep) {
+    // Long pairs are handed out longest first (three size classes of the longer string, one pass over the job list each):
+    // with 2 worker CTAs per SM the makespan is max(longest pair, total / workers) only if the big ones start early.
+    for (int pass = long_worker ? 0 : 3; pass < 4; ++pass) {
+        const int sweep = pass < 3 ? 0 : 1;
         while (true) {
             uint32_t job_id = 0;
             if (sweep == 0) {              // the whole CTA takes one long job (two barriers per round, both warps always)
-                if (threadIdx.x == 0) sh.cta_job = atomicAdd(next_job, 1u);
+                if (threadIdx.x == 0) sh.cta_job = atomicAdd(next_job + pass, 1u);
                 __syncthreads();
                 job_id = sh.cta_job;
                 __syncthreads();
             } else {
-                if (lane == 0) job_id = atomicAdd(next_job + 1, 1u);
+                if (lane == 0) job_id = atomicAdd(next_job + 3, 1u);
                 job_id = __shfl_sync(FULL, job_id, 0);
             }
             if (job_id >= n_jobs) break;
             const EditJob job = jobs[job_id];
             const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
-            if ((min(la0, lb0) > 2048u) != (sweep == 0)) continue;
+            const uint32_t longer = max(la0, lb0);      // classes: >= 8192, >= 4096, > 2048 (one stripe), the rest
+            if ((longer >= 8192u ? 0 : longer >= 4096u ? 1 : longer > 2048u ? 2 : 3) != pass) continue;
             const long long clock_begin = profile ? clock64() : 0ll;
             uint32_t steps_total = 0;
             // The edit distance does not change when the common prefix and suffix are removed; the two haplotypes of
             // a shared variant are mostly identical, so this alone finishes most pairs (warp-parallel compare).
             const uint32_t lim = min(la0, lb0);
-            const uint32_t pre = common_run<false>(job.a, job.b, la0, lb0, lim, ref, seq4_a, seq4_b, sh.cls2, lane);
-            const uint32_t suf = common_run<true>(job.a, job.b, la0, lb0, lim - pre, ref, seq4_a, seq4_b, sh.cls2, lane);
+            uint32_t pre, suf;
+            if (sweep == 0) {
+                // The CTA's two warps scan from the two ends at the same time, each at most half of the shorter string (an
+                // identical pair, the common case, is settled in half the time).  If one side ran into its half-way mark
+                // and the other did not, the first continues into the other half (both warps do, to stay in step).
+                const uint32_t half = (lim + 1u) / 2u;
+                const uint32_t r = warp == 0 ? common_run<false>(job.a, job.b, la0, lb0, half, ref, seq4_a, seq4_b, sh.cls2, lane)
+                                             : common_run<true>(job.a, job.b, la0, lb0, lim - half, ref, seq4_a, seq4_b, sh.cls2, lane);
+                if (lane == 0) sh.trim[warp] = r;
+                __syncthreads();           // (the next write to trim[] comes after the next round's claim barriers)
+                pre = sh.trim[0];
+                suf = sh.trim[1];
+                if (pre == half && suf < lim - half)
+                    pre = common_run<false>(job.a, job.b, la0, lb0, lim - suf, ref, seq4_a, seq4_b, sh.cls2, lane, half);
+                else if (suf == lim - half && pre < half)
+                    suf = common_run<true>(job.a, job.b, la0, lb0, lim - pre, ref, seq4_a, seq4_b, sh.cls2, lane, lim - half);
+            } else {
+                pre = common_run<false>(job.a, job.b, la0, lb0, lim, ref, seq4_a, seq4_b, sh.cls2, lane);
+                suf = common_run<true>(job.a, job.b, la0, lb0, lim - pre, ref, seq4_a, seq4_b, sh.cls2, lane);
+            }
             const uint32_t la = la0 - pre - suf, lb = lb0 - pre - suf;
             const bool a_is_pattern = la <= lb;                // pattern = the shorter string
             const uint32_t m = a_is_pattern ? la : lb, n = a_is_pattern ? lb : la;
@@ -560,6 +585,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             // the band in about n steps: first with 32-row blocks (band of about 500 either side, half the work per
             // step), then with 64-row blocks (about 1000).  What is left goes to the striped band attempts.
             unsigned long long known_above = 0;           // the distance is known to exceed this
+            bool col_split = false;
             if (sweep == 0) {
                 // Both warps of the CTA on this pair: D[m][n] = min_j F(j) + B(n - j) with F from the top half of the rows
                 // (warp 0) and B from the bottom half of the REVERSED strings (warp 1); each half needs about n / 2 + K
@@ -617,7 +643,14 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         known_above = kw;
                     }
                 }
-                if (warp != 0) continue;       // what is left of this pair (fallbacks, the result) is warp 0's
+                // A short pattern against a long text (two unrelated insertions side by side: n - m far beyond any band) needs
+                // the full table, n steps for one warp.  Two warps split the TEXT: every alignment path crosses the line
+                // between text columns nh - 1 | nh at some row i, so D[m][n] = min_i Df[i][nh] + Db[m - i][n - nh] with Df the
+                // table of P against T[0:nh] and Db that of the reversed strings; the column values are the vertical deltas
+                // left in the lanes' registers after the last column.  n / 2 steps each, at the same time.
+                col_split = !done && m != 0u && m <= 2048u && n >= 4096u &&
+                            static_cast<unsigned long long>(n) / 2u + 64u < static_cast<unsigned long long>((n + 2047u) / 2048u) * (m + 31u);
+                if (warp != 0 && !col_split) continue;       // what is left of this pair (fallbacks, the result) is warp 0's
             }
             if (!done && m > 1024u && known_above == 0) {
                 const uint32_t kw = win_kmax(m, n, 32u);
@@ -661,7 +694,9 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
             uint32_t m_s = m, n_s = n;
             HapDesc P_s = P, T_s = T;
             bool force_full = false;
-            if (!done) {
+            const bool rev_s = col_split && warp != 0;                   // this warp reads both strings from the far end
+            const uint32_t n_view = !col_split ? 0u : (warp == 0 ? n / 2u : n - n / 2u);     // text columns of this warp's half
+            if (!done && !col_split) {
                 // the distance is at least n - m: attempts with a narrower band cannot succeed
                 while ((256ull << (2 * first_attempt)) < static_cast<unsigned long long>(n - m)) ++first_attempt;
                 const unsigned long long K0 = 256ull << (2 * first_attempt);
@@ -690,7 +725,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         const bool final_stripe = row0 + rows == m_s;
                         const uint32_t nblk = (rows + 63u) / 64u, last_lane = nblk - 1u;
                         const uint32_t jlo = static_cast<unsigned long long>(row0) > K ? static_cast<uint32_t>(row0 - K) : 0u;
-                        const uint32_t jhi = static_cast<uint32_t>(min(static_cast<unsigned long long>(n_s),
+                        const uint32_t jhi = static_cast<uint32_t>(min(static_cast<unsigned long long>(col_split ? n_view : n_s),
                                                                        static_cast<unsigned long long>(row0) + rows + (n_s - m_s) + K));
                         // first column of the NEXT stripe's band: the running anchor stops there
                         const uint32_t next_row0 = row0 + rows;
@@ -711,7 +746,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                                 const uint32_t idx = (g0 + k) * 32u + lane;
                                 mode[k] = TOK_NONE;
                                 byte[k] = 0u;
-                                if (idx < rows) byte[k] = hap_fetch(P_s, pre + row0 + idx, ref, seq4_a, seq4_b, mode[k]);
+                                if (idx < rows) byte[k] = hap_fetch(P_s, pre + (rev_s ? m_s - 1u - (row0 + idx) : row0 + idx), ref, seq4_a, seq4_b, mode[k]);
                             }
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -730,7 +765,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                             nxt_h = 1u;                                             // outside the previous band: +1
                             if (rel < width) {
                                 const uint32_t j = jlo + static_cast<uint32_t>(rel);
-                                nxt_byte = hap_fetch(T_s, pre + j, ref, seq4_a, seq4_b, nxt_mode);
+                                nxt_byte = hap_fetch(T_s, pre + (rev_s ? n_s - 1u - j : j), ref, seq4_a, seq4_b, nxt_mode);
                                 if (row0 != 0u && j < prev_jhi) nxt_h = __ldcg(hbuf + j);
                             }
                         };
@@ -809,6 +844,23 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                             t = t_end;
                         }
                         __syncwarp();
+                        if (col_split) {       // D[i][n_view] for i = 0 .. m_s (one stripe): prefix sums of the vertical deltas
+                            int* val = reinterpret_cast<int*>(&sh.peq[warp][1][0][0]);      // the second mask buffer is idle here
+                            const uint32_t valid = lane < nblk ? min(64u, rows - 64u * lane) : 0u;
+                            const uint64_t vmask = valid == 64u ? ~0ull : ((1ull << valid) - 1ull);
+                            int incl = __popcll(pv & vmask) - __popcll(mv & vmask);
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int up = __shfl_up_sync(FULL, incl, o);
+                                if (static_cast<int>(lane) >= o) incl += up;
+                            }
+                            const int excl = incl - (__popcll(pv & vmask) - __popcll(mv & vmask));
+                            if (lane == 0) val[0] = static_cast<int>(n_view);
+                            for (uint32_t r = 0; r < valid; ++r) {
+                                const uint64_t bits = r == 63u ? ~0ull : ((2ull << r) - 1ull);
+                                val[64u * lane + r + 1u] = static_cast<int>(n_view) + excl + __popcll(pv & bits) - __popcll(mv & bits);
+                            }
+                        }
                         if (anchor_rel >= width) sum_anchor = sum_all;
                         sum_all = __shfl_sync(FULL, sum_all, last_lane);
                         sum_anchor = __shfl_sync(FULL, sum_anchor, last_lane);
@@ -818,6 +870,18 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                     }
                     if (full_table || static_cast<unsigned long long>(dist) <= K) break;      // exact
                 }
+            }
+            if (col_split) {
+                __syncthreads();
+                if (warp == 0) {
+                    const int* vf = reinterpret_cast<const int*>(&sh.peq[0][1][0][0]);
+                    const int* vb = reinterpret_cast<const int*>(&sh.peq[1][1][0][0]);
+                    int best = 0x7fffffff;
+                    for (uint32_t i = lane; i <= m_s; i += 32u) best = min(best, vf[i] + vb[m_s - i]);
+                    dist = __reduce_min_sync(FULL, best);
+                }
+                __syncthreads();
+                if (warp != 0) continue;
             }
             if (lane == 0) out[job.out_index] = static_cast<double>(dist);
             if (profile && lane == 0)      // SVB_ED_PROFILE: {trimmed pattern rows, trimmed text columns, column steps, cycles}
@@ -879,7 +943,6 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
     // then is the short string)
     const uint64_t stride = (std::max<uint64_t>(max_text_multi_stripe, 2048) + 127) & ~127ull;
     SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));
-    SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, sizeof(unsigned long long), ctx->stream));   // two 32-bit job counters
     // profiling aid: SVB_ED_PROFILE=<file> dumps one uint4 per job {rows, columns, column steps, SM cycles} of the launch
     const char* profile_path = getenv("SVB_ED_PROFILE");
     uint4* d_profile = nullptr;
@@ -888,11 +951,11 @@ int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, u
         SVB_CUDA(ctx, cudaMemsetAsync(d_profile, 0, sizeof(uint4) * n_jobs, ctx->stream));
     }
     unsigned int* sm_tokens = nullptr;                 // one word per (SM, scheduler): who runs the long jobs
-    SVB_CUDA(ctx, cudaMallocAsync(&sm_tokens, sizeof(unsigned int) * 4096, ctx->stream));
-    SVB_CUDA(ctx, cudaMemsetAsync(sm_tokens, 0, sizeof(unsigned int) * 4096, ctx->stream));
+    SVB_CUDA(ctx, cudaMallocAsync(&sm_tokens, sizeof(unsigned int) * (4096 + 8), ctx->stream));      // + the four job counters
+    SVB_CUDA(ctx, cudaMemsetAsync(sm_tokens, 0, sizeof(unsigned int) * (4096 + 8), ctx->stream));
     {
         KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
-        edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, reinterpret_cast<unsigned int*>(ctx->d_counters + 8),
+        edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, sm_tokens + 4096,
                                                                        d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out, d_profile,
                                                                        sm_tokens);
         ctx->launches += 1;

@@ -64,8 +64,12 @@ def test_edit_distance_long_patterns_window_and_stripes(engine, oracle_clib):
         cut = int(rng.integers(0, len(a)))
         pairs.append((a, a[:cut] + bytes(rng.choice(alphabet, extra).tolist()) + a[cut:]))
     pairs.append((bytes(rng.choice(alphabet, 4000).tolist()), bytes(rng.choice(alphabet, 4100).tolist())))   # unrelated
-    for m, n in ((300, 9000), (1300, 10900), (820, 9900), (2000, 2300), (2218, 2425), (64, 5000), (1, 4000)):   # transposed full tables
+    # short pattern against a long text: transposed full tables, or the text split between the two warps of a CTA
+    for m, n in ((300, 9000), (1300, 10900), (820, 9900), (2000, 2300), (2218, 2425), (64, 5000), (1, 4000), (2000, 12000),
+                 (1500, 4100), (2048, 4096), (1999, 4097)):
         pairs.append((bytes(rng.choice(alphabet, m).tolist()), bytes(rng.choice(alphabet, n).tolist())))
+    core = bytes(rng.choice(alphabet, 1800).tolist())                   # related strings with a long private insertion
+    pairs.append((core, core[:900] + bytes(rng.choice(alphabet, 5000).tolist()) + _mutate(rng, core[900:], 30, alphabet)))
     pairs.append((b"A" * 5000, b"A" * 4990 + b"C" * 10))
     pairs.append((b"AC" * 3000, b"CA" * 3000))
     got = engine.edit_distance(pairs)
