@@ -281,7 +281,7 @@ def b200_arm(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launch_ms": scan_avg, "algorithmic_bytes_per_launch": alg_bytes,
                 "finalize_ms": fin_avg, "frac_with_finalize": alg_bytes / ((scan_avg + fin_avg) * 1e-3) / 1e9 / peak,
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items()}}
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in timing.items() if v[1]}}
     rec1.free(), rec2.free()
 
     # ---- e2e: host buffers in, paired table out, every step

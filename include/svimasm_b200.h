@@ -113,7 +113,7 @@ typedef struct {
 
 /* Kernel timings accumulated since svb_timing_reset(): CUDA events on the library's stream. */
 enum { SVB_K_CIGAR_SCAN = 0, SVB_K_SEGMENT_WALK = 1, SVB_K_MERGE = 2, SVB_K_SORT = 3, SVB_K_EDIT_DISTANCE = 4,
-       SVB_K_CLUSTER = 5, SVB_K_SCAN_FINALIZE = 6, SVB_K_COUNT = 8 };
+       SVB_K_CLUSTER = 5, SVB_K_SCAN_FINALIZE = 6, SVB_K_VCF = 7, SVB_K_COUNT = 8 };
 typedef struct {
     double ms[SVB_K_COUNT];
     uint64_t launches[SVB_K_COUNT];
@@ -248,6 +248,25 @@ int svb_exchange_pack(svb_ctx* ctx, const svb_table* t1, const svb_table* t2, vo
 int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, const uint64_t* sizes, int world, int hap,
                         const int32_t* owner, int n_contig, int rank, svb_table** out);
 const void* svb_table_device_rows(const svb_table* t);            /* device pointer of the rows (all-gather of paired rows) */
+
+/* ---- VCF body: the text of write_final_vcf's record lines (SVIM_COMBINE.py:428-475) and of
+ * Candidate*.get_vcf_entry* (SVCandidate.py:53-78,99-125,151-176,203-261,296-347,389-443), assembled on the device: REF /
+ * ALT alleles are gathered from the HBM-resident reference and the 4-bit query sequences, one warp per record.
+ * The caller has put the entries into the writer's order (sorted_nicely, SVIM_COMBINE.py:369-376) and numbered the IDs. */
+enum { SVB_VCF_DEL = 0, SVB_VCF_INV = 1, SVB_VCF_INS = 2, SVB_VCF_TAN_AS_INS = 3, SVB_VCF_TAN_AS_DUP = 4,
+       SVB_VCF_INT_AS_INS = 5, SVB_VCF_INT_AS_DUP = 6, SVB_VCF_BND = 7, SVB_VCF_BND_MATE = 8 };
+enum { SVB_VCF_SYMBOLIC = 1 };                /* flags: options.symbolic_alleles */
+typedef struct {
+    uint32_t row;          /* index into the table */
+    uint32_t id;           /* number after "svim_asm.<LABEL>." (1-based, per label, in output order) */
+    uint32_t mode;         /* SVB_VCF_* : which get_vcf_entry* of the row's class */
+} svb_vcf_entry;
+/* rec[h] = record image holding the query sequences of haplotype slot h (0 haploid, 1, 2; NULL when unused).
+ * names / name_off: contig names concatenated, n_contig + 1 offsets.  *text points into a pinned host buffer owned
+ * by ctx, valid until the next svb_vcf_body call or svb_destroy. */
+int svb_vcf_body(svb_ctx* ctx, const svb_table* t, const svb_records* const rec[3], const svb_ref* ref, const char* names,
+                 const uint32_t* name_off, int32_t n_contig, const svb_vcf_entry* entries, uint64_t n_entries, uint32_t flags,
+                 const uint8_t** text, uint64_t* n_bytes);
 
 /* Sequence pools: the inserted bases of the INS rows (candidate.sequence, SVIM_intra.py:42, SVIM_inter.py:117,120)
  * copied next to the table so that it can be paired -- or sent to another rank -- without the record image. */

@@ -6,6 +6,7 @@ bit-parallel edit distances, complete-linkage clustering, genotype rules).  writ
 ##fileDate line.
 """
 import logging
+import os
 import re
 import time
 from collections import defaultdict
@@ -86,14 +87,20 @@ def pair_candidates(sv_candidates1, sv_candidates2, reference, bam, options):
     eng = get_engine()
     names, lengths = list(bam.references), list(bam.lengths)
     counts = defaultdict(int)
-    for c in list(sv_candidates1) + list(sv_candidates2):
-        counts[c.type] += 1
+    for cands in (sv_candidates1, sv_candidates2):
+        if getattr(cands, "rows", None) is not None:           # device-backed list: count without building objects
+            for kind, k in zip(TYPE_NAMES, np.bincount(cands.rows["type"], minlength=len(TYPE_NAMES))):
+                counts[kind] += int(k)
+        else:
+            for c in cands:
+                counts[c.type] += 1
     for label, kind in (("deletions", "DEL"), ("inversions", "INV"), ("insertions", "INS"),
                         ("tandem duplications", "DUP_TAN"), ("interspersed duplications", "DUP_INT"), ("breakends", "BND")):
         logging.info("Pairing {0} {1}...".format(counts[kind], label))
     sides = []
     for hap, cands in ((1, sv_candidates1), (2, sv_candidates2)):
-        if getattr(cands, "table", None) is not None:
+        if (getattr(cands, "table", None) is not None and getattr(cands, "records", None) is not None
+                and cands.rows.shape[0] == len(cands.table)):          # the untouched result of a collect: reuse its device table
             table, records, host = cands.table, cands.records, cands.host
             if not records.has_sequences:
                 eng.set_sequences(records)
@@ -106,10 +113,11 @@ def pair_candidates(sv_candidates1, sv_candidates2, reference, bam, options):
         sides.append((table, records, host))
     ref = _device_reference(reference, names)
     paired = eng.pair(sides[0][0], sides[1][0], sides[0][1], sides[1][1], ref, make_params(options))
-    known = {hap: getattr(c, "sequences", None) for hap, c in ((1, sv_candidates1), (2, sv_candidates2))}
-    out = CandidateList(candidates_from_rows(paired.to_numpy(), {1: sides[0][2], 2: sides[1][2]}, names, lengths,
-                                             sequences={h: d for h, d in known.items() if d is not None}))
-    out.table = paired
+    def known():
+        found = {hap: getattr(c, "sequences", None) for hap, c in ((1, sv_candidates1), (2, sv_candidates2))}
+        return {h: d for h, d in found.items() if d is not None}
+    out = CandidateList.from_rows(paired.to_numpy(), {1: sides[0][2], 2: sides[1][2]}, names, lengths, known, paired,
+                                  {1: sides[0][1], 2: sides[1][1]})
     return out
 
 
@@ -147,9 +155,96 @@ def compute_distance(candidate_with_haplotype1, candidate_with_haplotype2, refer
 
 def sorted_nicely(vcf_entries):
     """SVIM_COMBINE.py:369-376: natural ("human") order of contig names, then start, then end; stable."""
-    def natural(name):
-        return [int(tok) if tok.isdigit() else tok for tok in re.split("([0-9]+)", str(name))]
-    return sorted(vcf_entries, key=lambda entry: (natural(entry[0][0]), entry[0][1], entry[0][2]))
+    return sorted(vcf_entries, key=lambda entry: (_natural_key(entry[0][0]), entry[0][1], entry[0][2]))
+
+
+def _natural_key(name):
+    return [int(tok) if tok.isdigit() else tok for tok in re.split("([0-9]+)", str(name))]
+
+
+def natural_ranks(contig_names):
+    """Dense rank of every contig under sorted_nicely's natural order (names with equal keys share a rank)."""
+    keys = [_natural_key(n) for n in contig_names]
+    rank = np.zeros(len(keys), dtype=np.int64)
+    r, prev = -1, None
+    for i in sorted(range(len(keys)), key=lambda k: keys[k]):
+        if keys[i] != prev:
+            r, prev = r + 1, keys[i]
+        rank[i] = r
+    return rank
+
+
+VCF_DEL, VCF_INV, VCF_INS, VCF_TAN_AS_INS, VCF_TAN_AS_DUP, VCF_INT_AS_INS, VCF_INT_AS_DUP, VCF_BND, VCF_BND_MATE = range(9)
+_LABEL_OF_MODE = np.array([0, 1, 2, 2, 3, 2, 4, 5, 5])        # DEL, INV, INS, DUP_TANDEM, DUP_INT, BND share a counter each
+
+
+def vcf_entries(rows, row_index, contig_names, types_to_output, tan_as_ins, int_as_ins):
+    """write_final_vcf's record list (SVIM_COMBINE.py:428-475) for table rows, without objects: which rows are written,
+    through which get_vcf_entry* (mode), in sorted_nicely's order (natural contig order, start, end; stable over the
+    append order of :431-464), with the running number of every ID label.  Returns svb_vcf_entry rows."""
+    kind = rows["type"]
+    rank = natural_ranks(contig_names)
+    blocks = []                                         # (indices into rows, mode, tid, key start, key end) in append order
+
+    def add(sel, mode, tid, start, end):
+        blocks.append((sel, np.full(sel.shape[0], mode, dtype=np.uint32), tid[sel], start[sel], end[sel]))
+    s, e, ds, de = (rows[n].astype(np.int64) for n in ("src_start", "src_end", "dst_start", "dst_end"))
+    st, dt = rows["src_tid"].astype(np.int64), rows["dst_tid"].astype(np.int64)
+    if "DEL" in types_to_output:
+        add(np.nonzero(kind == 0)[0], VCF_DEL, st, np.maximum(1, s), e)
+    if "INV" in types_to_output:
+        add(np.nonzero(kind == 1)[0], VCF_INV, st, s + 1, e)
+    if "INS" in types_to_output:
+        add(np.nonzero(kind == 2)[0], VCF_INS, dt, np.maximum(1, ds), de)
+    if tan_as_ins:
+        if "INS" in types_to_output:
+            add(np.nonzero(kind == 3)[0], VCF_TAN_AS_INS, st, s + 1, e)
+    elif "DUP:TANDEM" in types_to_output:
+        add(np.nonzero(kind == 3)[0], VCF_TAN_AS_DUP, st, s + 1, e)
+    if int_as_ins:
+        if "INS" in types_to_output:
+            add(np.nonzero(kind == 4)[0], VCF_INT_AS_INS, dt, np.maximum(1, ds), de)
+    elif "DUP:INT" in types_to_output:
+        add(np.nonzero(kind == 4)[0], VCF_INT_AS_DUP, st, s + 1, e)
+    if "BND" in types_to_output:
+        sel = np.repeat(np.nonzero(kind == 5)[0], 2)                     # the record and its mate, adjacent
+        mate = np.arange(sel.shape[0]) % 2 == 1
+        blocks.append((sel, np.where(mate, VCF_BND_MATE, VCF_BND).astype(np.uint32), np.where(mate, dt[sel], st[sel]),
+                       np.where(mate, ds[sel], s[sel]) + 1, np.where(mate, ds[sel], s[sel]) + 2))
+    out = np.zeros(sum(b[0].shape[0] for b in blocks), dtype=_lib.VCF_ENTRY_DTYPE)
+    if out.shape[0] == 0:
+        return out
+    sel, mode, tid, k1, k2 = (np.concatenate([b[k] for b in blocks]) for k in range(5))
+    order = np.lexsort((k2, k1, rank[tid]))                             # stable: ties keep the append order
+    sel, mode = sel[order], mode[order]
+    out["row"], out["mode"] = row_index[sel], mode
+    label = _LABEL_OF_MODE[mode]
+    for k in range(6):
+        hit = np.nonzero(label == k)[0]
+        out["id"][hit] = np.arange(1, hit.shape[0] + 1)
+    return out
+
+
+def _device_lists(lists):
+    """The six per-class lists are untouched views of ONE device table (CandidateList.of_type): (table, rows, row_index,
+    records_by_hap), else None."""
+    table, parts = None, []
+    for kind, cands in lists:
+        if getattr(cands, "table", None) is None or getattr(cands, "rows", None) is None:
+            if len(cands) == 0:
+                continue
+            return None
+        if table is not None and cands.table is not table:
+            return None
+        if cands.rows.shape[0] and not np.all(cands.rows["type"] == TYPE_NAMES.index(kind)):
+            return None
+        table = cands.table
+        parts.append(cands)
+    if table is None:
+        return None
+    rows = np.concatenate([c.rows for c in parts])
+    index = np.concatenate([c.row_index for c in parts]).astype(np.uint32)
+    return table, rows, index, parts[0].records_by_hap
 
 
 _HEADER_ALT = (("DEL", "Deletion"), ("INV", "Inversion"))
@@ -184,6 +279,30 @@ def write_final_vcf(int_duplication_candidates, inversion_candidates, tandem_dup
     if want_tan:
         lines.append('##FORMAT=<ID=CN,Number=1,Type=Integer,Description="Copy number of tandem duplication (e.g. 2 for one additional copy)">')
     lines.append("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + options.sample)
+
+    device = None if options.query_names or os.environ.get("SVIM_ASM_B200_VCF", "device") == "host" else _device_lists(
+        (("DUP_INT", int_duplication_candidates), ("INV", inversion_candidates), ("DUP_TAN", tandem_duplication_candidates),
+         ("DEL", deletion_candidates), ("INS", insertion_candidates), ("BND", breakend_candidates)))
+    if device is not None:
+        # the candidates never left the GPU as objects: the record lines are assembled there too (svb_vcf_body), the REF / ALT
+        # bases gathered from the resident reference and query sequences
+        table, rows, row_index, records_by_hap = device
+        eng = table.engine
+        entries = vcf_entries(rows, row_index, contig_names, types_to_output, tan_as_ins, int_as_ins)
+        symbolic = bool(options.symbolic_alleles)
+        records_by_hap = dict(records_by_hap or {})
+        if not symbolic:
+            for hap in np.unique(rows["hap"][(rows["type"] == 2) & (rows["seq_len"] > 0)]):
+                records = records_by_hap.get(int(hap))
+                if records is not None and not records.has_sequences:
+                    eng.set_sequences(records)
+        body = eng.vcf_body(table, records_by_hap, _device_reference(reference, list(contig_names)), contig_names, entries, symbolic)
+        if not symbolic:
+            reference.close()
+        with open(options.working_dir + "/variants.vcf", "wb") as out:
+            out.write(("\n".join(lines) + "\n").encode())
+            out.write(body)
+        return
 
     alleles = not options.symbolic_alleles
     names = options.query_names

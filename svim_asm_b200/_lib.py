@@ -22,7 +22,9 @@ c_void_p, c_char_p, c_int, c_double = ctypes.c_void_p, ctypes.c_char_p, ctypes.c
 P = ctypes.POINTER
 
 SVB_K_COUNT = 8
-KERNEL_NAMES = ("cigar_scan", "segment_walk", "merge", "sort", "edit_distance", "cluster", "cigar_scan_finalize")
+KERNEL_NAMES = ("cigar_scan", "segment_walk", "merge", "sort", "edit_distance", "cluster", "cigar_scan_finalize", "vcf_body")
+
+VCF_ENTRY_DTYPE = np.dtype([("row", "<u4"), ("id", "<u4"), ("mode", "<u4")])      # svb_vcf_entry
 
 PARAMS_DTYPE = np.dtype([(n, "<i4") for n in (
     "min_mapq", "min_sv_size", "max_sv_size", "query_gap_tolerance", "query_overlap_tolerance",
@@ -94,6 +96,7 @@ SIGNATURES = {
     "svb_table_import": (c_int, [c_void_p, c_void_p, c_u64, P(c_void_p)]),
     "svb_table_free": (None, [c_void_p]),
     "svb_table_gather_sequences": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_vcf_body": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_char_p, c_void_p, c_i32, c_void_p, c_u64, c_u32, P(c_void_p), P(c_u64)]),
     "svb_table_attach_sequences_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "svb_table_pool_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_void_p, P(c_u64)]),
     "svb_stream": (c_void_p, [c_void_p]),

@@ -105,7 +105,8 @@ def _run(options):
         logging.info("****************** STEP 2: PAIR ******************")
         final = pair_candidates(sv_candidates1, sv_candidates2, reference, aln_file1, options)
         logging.info("****************** STEP 3: OUTPUT ******************")
-    by_type = {t: [c for c in final if c.type == t] for t in ("DEL", "INS", "INV", "DUP_TAN", "BND", "DUP_INT")}
+    split = getattr(final, "of_type", None)        # device-backed list: per-class views, no python objects built
+    by_type = {t: (split(t) if split else [c for c in final if c.type == t]) for t in ("DEL", "INS", "INV", "DUP_TAN", "BND", "DUP_INT")}
     for label, key in (("deletion", "DEL"), ("inversion", "INV"), ("insertion", "INS"), ("tandem duplication", "DUP_TAN"),
                        ("interspersed duplication", "DUP_INT"), ("breakend", "BND")):
         logging.info("Found {0} {1} candidates.".format(len(by_type[key]), label))

@@ -128,6 +128,7 @@ void svb_destroy(svb_ctx* ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_text) cudaFreeHost(ctx->h_text);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

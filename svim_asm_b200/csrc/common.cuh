@@ -78,6 +78,8 @@ struct svb_ctx {
     uint32_t* d_status = nullptr;     // device error word (atomicOr of DEV_ERR_*)
     unsigned long long* d_counters = nullptr;   // 64 device counters
     unsigned long long* h_pinned = nullptr;     // 64-word pinned readback area
+    uint8_t* h_text = nullptr;        // grow-only pinned buffer the VCF body is returned in (vcf_device.cu)
+    size_t h_text_cap = 0;
 };
 
 enum : uint32_t {

@@ -457,6 +457,20 @@ class Engine(object):
                                  reference.handle, _lib.ptr(params), ctypes.byref(out)))
         return Table(self, out)
 
+    def vcf_body(self, table, records_by_hap, reference, contig_names, entries, symbolic=False):
+        """Record lines of variants.vcf for `entries` (svb_vcf_entry rows, already in output order) as bytes; the alleles
+        are gathered on the device from the resident reference and query sequences (svb_vcf_body)."""
+        entries = np.ascontiguousarray(entries, dtype=_lib.VCF_ENTRY_DTYPE)
+        encoded = [str(n).encode() for n in contig_names]
+        name_off = np.zeros(len(encoded) + 1, dtype=np.uint32)
+        name_off[1:] = np.cumsum([len(b) for b in encoded])
+        recs = (ctypes.c_void_p * 3)(*[(records_by_hap[h].handle if records_by_hap.get(h) is not None else None) for h in range(3)])
+        text, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(lib.svb_vcf_body(self.handle, table.handle, recs, reference.handle, b"".join(encoded) + b"\0", _lib.ptr(name_off),
+                                     len(encoded), _lib.ptr(entries) if entries.shape[0] else None, entries.shape[0],
+                                     1 if symbolic else 0, ctypes.byref(text), ctypes.byref(n)))
+        return ctypes.string_at(text.value, int(n.value)) if n.value else b""
+
     def table_from_numpy(self, rows):
         out = ctypes.c_void_p()
         rows = np.ascontiguousarray(rows, dtype=_lib.ROW_DTYPE)

@@ -9,7 +9,7 @@ _SO = os.path.join(_HERE, "_build", "hostcheck.so")
 
 def load():
     src = os.path.join(_HERE, "hostcheck.cpp")
-    deps = [src] + [os.path.join(_HERE, "..", "..", "svim_asm_b200", "csrc", f) for f in ("linkage.cuh", "walk.cuh", "edit_core.cuh", "inflate_core.cuh")]
+    deps = [src] + [os.path.join(_HERE, "..", "..", "svim_asm_b200", "csrc", f) for f in ("linkage.cuh", "walk.cuh", "edit_core.cuh", "inflate_core.cuh", "vcf_core.cuh")]
     if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", _SO, src])
@@ -30,4 +30,6 @@ def load():
     lib.hc_myers_window_split.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_uint]
     lib.hc_inflate.restype = ctypes.c_int
     lib.hc_inflate.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint]
+    lib.hc_vcf_body.restype = ctypes.c_longlong
+    lib.hc_vcf_body.argtypes = [vp, vp, ctypes.c_longlong, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint, vp, ctypes.c_longlong]
     return lib

@@ -212,3 +212,32 @@ extern "C" long long hc_myers_window_split(const uint8_t* a, long long m0, const
     }
     return best;
 }
+
+#include "../../svim_asm_b200/csrc/vcf_core.cuh"
+
+// VCF body lines of `n_entries` entries on the host: the plan of vcf_core.cuh executed byte by byte.
+// Returns the number of bytes (written up to `cap`).
+extern "C" long long hc_vcf_body(const svb_row* rows, const svb_vcf_entry* entries, long long n_entries, const uint8_t* bases,
+                                 const uint64_t* contig_off, int n_contig, const uint8_t* names, const uint32_t* name_off,
+                                 const uint8_t* seq4_0, const uint64_t* seq_off_0, const uint8_t* seq4_1, const uint64_t* seq_off_1,
+                                 const uint8_t* seq4_2, const uint64_t* seq_off_2, unsigned flags, uint8_t* dst, long long cap) {
+    VcfEnv env = {};
+    env.bases = bases;
+    env.contig_off = contig_off;
+    env.n_contig = n_contig;
+    env.names = names;
+    env.name_off = name_off;
+    env.seq4[0] = seq4_0; env.seq_off[0] = seq_off_0;
+    env.seq4[1] = seq4_1; env.seq_off[1] = seq_off_1;
+    env.seq4[2] = seq4_2; env.seq_off[2] = seq_off_2;
+    env.flags = flags;
+    long long pos = 0;
+    VcfPlan plan;
+    for (long long e = 0; e < n_entries; ++e) {
+        vcf_plan(rows[entries[e].row], entries[e], env, plan);
+        for (uint32_t k = 0; k < plan.n_pieces; ++k)
+            for (uint64_t i = 0; i < plan.piece[k].len; ++i, ++pos)
+                if (pos < cap) dst[pos] = vcf_piece_byte(plan, plan.piece[k], env, i);
+    }
+    return pos;
+}
