@@ -129,6 +129,7 @@ void svb_destroy(svb_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_text) cudaFreeHost(ctx->h_text);
+    upload_release(ctx);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -80,6 +80,7 @@ struct svb_ctx {
     unsigned long long* h_pinned = nullptr;     // 64-word pinned readback area
     uint8_t* h_text = nullptr;        // grow-only pinned buffer the VCF body is returned in (vcf_device.cu)
     size_t h_text_cap = 0;
+    void* uploader = nullptr;         // pinned staging slots + streams of upload_file_range (file_upload.cu)
 };
 
 enum : uint32_t {
@@ -106,6 +107,8 @@ struct KernelTimer {
     ~KernelTimer();
 };
 
+int upload_file_range(svb_ctx* ctx, int fd, uint64_t offset, uint64_t n, void* d_dst);   // file bytes -> device, parallel pread + pinned staging
+void upload_release(svb_ctx* ctx);
 void* svb_scratch(svb_ctx* ctx, size_t bytes);   // grow-only device scratch (nullptr on failure)
 
 // ---- kernels (host launchers) -----------------------------------------------------------------

@@ -62,12 +62,6 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
         return svb_fail(ctx, SVB_ERR_IO, "svb_ref_load_fasta: cannot stat the FASTA file");
     }
     const size_t fsize = static_cast<size_t>(sb.st_size);
-    void* mp = mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
-    if (mp == MAP_FAILED) {
-        close(fd);
-        return svb_fail(ctx, SVB_ERR_IO, "svb_ref_load_fasta: cannot map the FASTA file");
-    }
-    madvise(mp, fsize, MADV_SEQUENTIAL);
     std::vector<FaiEntry> entries(static_cast<size_t>(n_contig));
     std::vector<uint64_t> contig_off(static_cast<size_t>(n_contig) + 1, 0);
     for (int32_t i = 0; i < n_contig; ++i) {
@@ -81,7 +75,6 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
     }
     svb_ref* r = new (std::nothrow) svb_ref();
     if (!r) {
-        munmap(mp, fsize);
         close(fd);
         return svb_fail(ctx, SVB_ERR_NOMEM, "svb_ref_load_fasta");
     }
@@ -93,7 +86,12 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
     uint32_t* d_seen = nullptr;      // [8] presence bits, [8] status
     uint32_t h_seen[9] = {0};
     cudaError_t e = cudaMalloc(&d_raw, fsize);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_raw, mp, fsize, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && upload_file_range(ctx, fd, 0, fsize, d_raw) != SVB_OK) {
+        close(fd);
+        cudaFree(d_raw);
+        svb_ref_free(r);
+        return SVB_ERR_IO;
+    }
     if (e == cudaSuccess) e = cudaMalloc(&d_fai, sizeof(FaiEntry) * std::max<size_t>(entries.size(), 1));
     if (e == cudaSuccess && n_contig) e = cudaMemcpyAsync(d_fai, entries.data(), sizeof(FaiEntry) * entries.size(), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&d_seen, sizeof(uint32_t) * 9);
@@ -109,7 +107,6 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_seen, d_seen, sizeof h_seen, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    munmap(mp, fsize);
     close(fd);
     cudaFree(d_raw);
     cudaFree(d_fai);
