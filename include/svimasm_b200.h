@@ -175,7 +175,8 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
                         svb_bam** bam_out, svb_records** rec_out, char* err, int err_len);
 int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec, int what);   /* what: 1 CIGAR ops, 2 query bases, 3 both */
 /* ms of the last svb_bam_open_device call: [0] file read, [1] H2D, [2] inflate kernel, [3] record chase,
- * [4] field + copy kernels, [5] host SA parse + record image, [6] total wall, [7] inflated bytes */
+ * [4] field + copy kernels, [5] host SA parse + record image, [6] total wall, [7] inflated bytes,
+ * [8] resident inflate CTAs per SM, [9] mean clock cycles per BGZF member, [10] members */
 const double* svb_bam_device_timings(void);
 
 /* ---- device: replaces analyze_alignment_file_coordsorted (SVIM_COLLECT.py:61-83) and below ---- */

@@ -202,3 +202,321 @@ SVB_HD int inflate_member(const uint8_t* src, uint32_t src_len, uint8_t* dst, ui
     } while (!last);
     return pos == out_len ? INF_OK : INF_ERR_SIZE;
 }
+
+// ---- the fast symbol loop of the device decoder (bam_device.cu; one WARP per member, this part runs in lane 0) -------------
+// The kernel is bound by instruction issue, not by latency (dozens of warps per SM, one active lane each), so what counts
+// is instructions per symbol:
+//   * the bit buffer is refilled 32 bits at a time from aligned words (bytewise only at a member's unaligned head and tail),
+//   * the direct tables hold finished entries -- literal value, or length / distance BASE with the number of extra bits --
+//     so that a symbol is one table load plus shifts,
+//   * matches of up to INF_SHORT_MATCH bytes (98 % of those in BAM data: 4-byte CIGAR words, short repeats) are copied by
+//     the decoding lane itself; only longer ones are handed to the whole warp.
+constexpr int INF_LEN_BITS = 10, INF_DIST_BITS = 8;
+constexpr uint32_t INF_SHORT_MATCH = 16;
+// table entry: bits 0-3 code length (0 = code longer than the table: slow path), 4-5 kind, 8-11 extra bits, 16-31 value
+enum : uint32_t { INF_K_LIT = 0u, INF_K_LEN = 1u << 4, INF_K_EOB = 2u << 4, INF_K_BAD = 3u << 4, INF_K_MASK = 3u << 4 };
+
+SVB_HD uint32_t inf_len_entry(uint32_t sym, uint32_t code_len) {
+    static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    if (sym < 256u) return (sym << 16) | INF_K_LIT | code_len;
+    if (sym == 256u) return INF_K_EOB | code_len;
+    if (sym >= 286u) return INF_K_BAD | code_len;
+    return (static_cast<uint32_t>(lbase[sym - 257u]) << 16) | (static_cast<uint32_t>(lext[sym - 257u]) << 8) | INF_K_LEN | code_len;
+}
+SVB_HD uint32_t inf_dist_entry(uint32_t sym, uint32_t code_len) {
+    static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    if (sym >= 30u) return INF_K_BAD | code_len;
+    return (static_cast<uint32_t>(dbase[sym]) << 16) | (static_cast<uint32_t>(dext[sym]) << 8) | INF_K_LEN | code_len;
+}
+
+SVB_HD uint32_t inf_bitrev(uint32_t v, int n) {          // the low n bits of v, reversed
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+}
+
+// Direct table of a canonical code: entry for every `bits`-bit window whose leading bits are a code of length <= bits.
+// Lanes split the symbols (lane, n_lanes); the caller has zeroed the table and synchronises afterwards.  Deflate packs codes most
+// significant bit first into a stream read least significant bit first, hence the reversal.
+SVB_HD void inf_fill_table(const uint16_t* count, const uint16_t* symbol, uint32_t* table, int bits, bool dist, uint32_t lane,
+                           uint32_t n_lanes) {
+    const uint32_t size = 1u << bits;
+    uint32_t total = 0;
+    for (int len = 1; len <= 15; ++len) total += count[len];
+    for (uint32_t j = lane; j < total; j += n_lanes) {
+        uint32_t code = 0, first_idx = 0;
+        int L = 0;
+        for (int len = 1; len <= 15; ++len) {
+            const uint32_t cnt = count[len];
+            if (j < first_idx + cnt) {
+                L = len;
+                code += j - first_idx;
+                break;
+            }
+            code = (code + cnt) << 1;
+            first_idx += cnt;
+        }
+        if (L == 0 || L > bits) continue;
+        const uint32_t entry = dist ? inf_dist_entry(symbol[j], static_cast<uint32_t>(L)) : inf_len_entry(symbol[j], static_cast<uint32_t>(L));
+        for (uint32_t k = inf_bitrev(code, L); k < size; k += 1u << L) table[k] = entry;
+    }
+}
+
+// at least 32 bits in the buffer afterwards (zeros past the end of the input, counted in virt)
+SVB_HD void inf_refill(InfBits& b) {
+    if ((reinterpret_cast<uintptr_t>(b.p) & 3u) == 0u && b.end - b.p >= 4) {
+#ifdef __CUDA_ARCH__
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(b.p));
+#else
+        const uint32_t w = static_cast<uint32_t>(b.p[0]) | (static_cast<uint32_t>(b.p[1]) << 8) | (static_cast<uint32_t>(b.p[2]) << 16) |
+                           (static_cast<uint32_t>(b.p[3]) << 24);
+#endif
+        b.buf |= static_cast<uint64_t>(w) << b.cnt;              // cnt < 32 here
+        b.p += 4;
+        b.cnt += 32;
+        return;
+    }
+    // bytewise: the unaligned head of a member (on until the pointer is aligned), its last bytes, virtual zeros beyond
+    while (b.cnt < 32 || ((reinterpret_cast<uintptr_t>(b.p) & 3u) != 0u && b.cnt <= 56 && b.p < b.end)) {
+        uint64_t byte = 0;
+        if (b.p < b.end) byte = *b.p++;
+        else b.virt += 8;
+        b.buf |= byte << b.cnt;
+        b.cnt += 8;
+    }
+}
+
+// ---- output window -------------------------------------------------------------------------------------------------------
+// The decoder writes into a ring of INF_RING bytes (shared memory on the device) that is both the staging buffer for the
+// output -- flushed to the member's place in global memory in 16-byte vectors by the whole warp -- and the window recent
+// matches are copied from.  Why: with bytes stored one by one to global memory and matches reading them back, every
+// match is a round trip to L2 (or to DRAM: the lines of all resident members do not fit L2) and every literal a partial
+// sector write; measured 850 clock cycles per symbol.  With the ring, the symbol loop only touches shared memory and the
+// compressed input.  Ring index of output byte p = (address of that byte in global memory) mod INF_RING, so ring and
+// global memory agree on 16-byte alignment.  A match whose source is no longer in the ring (distance + length >
+// INF_RING) reads global memory: that range has been flushed, because at most INF_FLUSH_AT + 258 bytes are ever unflushed.
+// (Measured on B200: the symbol loop is bound by dependent-instruction latency, about 5 cycles per instruction per warp, so
+// the sizes are chosen for 7 CTAs = 28 decoding warps per SM rather than for the largest window.)
+constexpr uint32_t INF_RING = 2048, INF_FLUSH_AT = 1024, INF_RMASK = INF_RING - 1u;
+struct InfOut {
+    uint8_t* ring;
+    uint8_t* data;          // where the member's first byte goes in global memory
+    uint32_t rbase;         // ring index of data[0]
+    uint32_t pos;           // bytes produced so far
+    uint32_t flushed;       // data[0 .. flushed) is in global memory
+    uint32_t out_len;       // the member's ISIZE
+};
+SVB_HD InfOut inf_out(uint8_t* ring, uint8_t* data, uint32_t out_len) {
+    InfOut o;
+    o.ring = ring;
+    o.data = data;
+    o.rbase = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data)) & INF_RMASK;
+    o.pos = 0;
+    o.flushed = 0;
+    o.out_len = out_len;
+    return o;
+}
+
+// data[flushed .. upto) <- ring, by n_lanes lanes; the caller synchronises around it and sets o.flushed = upto afterwards
+SVB_HD void inf_flush(const InfOut& o, uint32_t upto, uint32_t lane, uint32_t n_lanes) {
+    const uint32_t f = o.flushed;
+    const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(o.data + f)) & 15u;
+    uint32_t a = mis ? f + (16u - mis) : f;                       // first 16-byte boundary of global memory
+    if (a > upto) a = upto;
+    for (uint32_t p = f + lane; p < a; p += n_lanes) o.data[p] = o.ring[(o.rbase + p) & INF_RMASK];
+    const uint32_t n_vec = (upto - a) / 16u;
+    for (uint32_t v = lane; v < n_vec; v += n_lanes) {
+        const uint32_t p = a + 16u * v;
+#ifdef __CUDA_ARCH__
+        *reinterpret_cast<uint4*>(o.data + p) = *reinterpret_cast<const uint4*>(o.ring + ((o.rbase + p) & INF_RMASK));
+#else
+        for (uint32_t k = 0; k < 16u; ++k) o.data[p + k] = o.ring[(o.rbase + p + k) & INF_RMASK];
+#endif
+    }
+    for (uint32_t p = a + 16u * n_vec + lane; p < upto; p += n_lanes) o.data[p] = o.ring[(o.rbase + p) & INF_RMASK];
+}
+
+// len <= 4 bytes at offset `at` of a match whose source the destination does not overlap: all loads first, then the stores
+template <bool RING_SOURCE>
+SVB_HD void inf_copy_apart4(const InfOut& o, uint32_t at, uint32_t len, uint32_t dist) {
+    const uint32_t w = o.rbase + o.pos + at;
+    uint8_t t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (static_cast<uint32_t>(i) < len) t[i] = RING_SOURCE ? o.ring[(w - dist + i) & INF_RMASK] : o.data[o.pos + at - dist + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (static_cast<uint32_t>(i) < len) o.ring[(w + i) & INF_RMASK] = t[i];
+}
+template <bool RING_SOURCE>
+SVB_HD void inf_copy_apart(const InfOut& o, uint32_t len, uint32_t dist) {
+    for (uint32_t at = 0; at < len; at += 4u) inf_copy_apart4<RING_SOURCE>(o, at, len - at < 4u ? len - at : 4u, dist);
+}
+
+// a match of any length, its bytes split between n_lanes lanes (the long matches of the device decoder: the whole warp)
+SVB_HD void inf_copy_long(const InfOut& o, uint32_t len, uint32_t dist, uint32_t lane, uint32_t n_lanes) {
+    const uint32_t w = o.rbase + o.pos;
+    const bool in_ring = dist + len <= INF_RING;
+    for (uint32_t i = lane; i < len; i += n_lanes) {
+        const uint32_t k = dist >= len ? i : (dist == 1u ? 0u : i % dist);     // an overlapping run repeats its last dist bytes
+        o.ring[(w + i) & INF_RMASK] = in_ring ? o.ring[(w - dist + k) & INF_RMASK] : o.data[o.pos - dist + k];
+    }
+}
+
+enum : uint32_t { INF_EV_EOB = 0, INF_EV_MATCH = 1, INF_EV_FLUSH = 2 };
+
+// Symbols of the current block, run by the decoding lane, until one of:
+//   INF_EV_EOB    end of the block
+//   INF_EV_MATCH  a match longer than INF_SHORT_MATCH, NOT copied: the caller runs inf_copy_long, adds *ev_len to o.pos
+//   INF_EV_FLUSH  INF_FLUSH_AT or more bytes are waiting in the ring: the caller flushes and calls again
+// Returns INF_OK or an error.
+SVB_HD int inf_run(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, const uint32_t* tlen, const uint32_t* tdist,
+                   InfOut& o, uint32_t* event, uint32_t* ev_len, uint32_t* ev_dist) {
+    *ev_len = 0;
+    *ev_dist = 0;
+    while (true) {
+        if (o.pos - o.flushed >= INF_FLUSH_AT) {
+            *event = INF_EV_FLUSH;
+            return INF_OK;
+        }
+        if (b.cnt < 32) inf_refill(b);
+        uint32_t e = tlen[static_cast<uint32_t>(b.buf) & ((1u << INF_LEN_BITS) - 1u)];
+        if ((e & 15u) == 0u) {                                   // code longer than the table
+            const int sym = inf_decode(b, lencode);
+            if (sym < 0) return INF_ERR_CODE;
+            e = inf_len_entry(static_cast<uint32_t>(sym), 0u);
+        } else {
+            b.buf >>= (e & 15u);
+            b.cnt -= static_cast<int>(e & 15u);
+        }
+        const uint32_t kind = e & INF_K_MASK;
+        if (kind == INF_K_LIT) {
+            if (o.pos >= o.out_len) return INF_ERR_OUTPUT;
+            o.ring[(o.rbase + o.pos) & INF_RMASK] = static_cast<uint8_t>(e >> 16);
+            ++o.pos;
+            continue;
+        }
+        if (kind != INF_K_LEN) {
+            if (kind == INF_K_BAD) return INF_ERR_CODE;
+            *event = INF_EV_EOB;
+            return inf_overrun(b) ? INF_ERR_INPUT : INF_OK;
+        }
+        const uint32_t xl = (e >> 8) & 15u;
+        const uint32_t len = (e >> 16) + (static_cast<uint32_t>(b.buf) & ((1u << xl) - 1u));
+        b.buf >>= xl;
+        b.cnt -= static_cast<int>(xl);
+        if (b.cnt < 32) inf_refill(b);
+        uint32_t d = tdist[static_cast<uint32_t>(b.buf) & ((1u << INF_DIST_BITS) - 1u)];
+        if ((d & 15u) == 0u) {
+            const int dsym = inf_decode(b, distcode);
+            if (dsym < 0) return INF_ERR_CODE;
+            d = inf_dist_entry(static_cast<uint32_t>(dsym), 0u);
+        } else {
+            b.buf >>= (d & 15u);
+            b.cnt -= static_cast<int>(d & 15u);
+        }
+        if ((d & INF_K_MASK) == INF_K_BAD) return INF_ERR_CODE;
+        const uint32_t xd = (d >> 8) & 15u;
+        const uint32_t dist = (d >> 16) + (static_cast<uint32_t>(b.buf) & ((1u << xd) - 1u));
+        b.buf >>= xd;
+        b.cnt -= static_cast<int>(xd);
+        if (dist > o.pos) return INF_ERR_CODE;
+        if (o.pos + len > o.out_len) return INF_ERR_OUTPUT;
+        if (len > INF_SHORT_MATCH) {
+            if (inf_overrun(b)) return INF_ERR_INPUT;
+            *event = INF_EV_MATCH;
+            *ev_len = len;
+            *ev_dist = dist;
+            return INF_OK;
+        }
+        if (dist + len > INF_RING) {                             // the source has left the ring: it is in global memory
+            inf_copy_apart<false>(o, len, dist);
+        } else if (dist >= len) {
+            inf_copy_apart<true>(o, len, dist);
+        } else {                                                 // overlapping: byte by byte in order
+            const uint32_t w = o.rbase + o.pos;
+            for (uint32_t i = 0; i < len; ++i) o.ring[(w + i) & INF_RMASK] = o.ring[(w - dist + i) & INF_RMASK];
+        }
+        o.pos += len;
+    }
+}
+
+// Header of the next block, read by the decoding lane: *last, *type; a stored block (type 0) reports where its bytes are
+// (*st_off from `src`, *st_len) and the reader is moved past them; for Huffman blocks the canonical codes are constructed
+// in lencode / distcode (`lengths` is 320 bytes of scratch).  Returns INF_OK or an error.
+SVB_HD int inf_block_header(InfBits& b, const uint8_t* src, uint32_t pos, uint32_t out_len, InfHuff& lencode, InfHuff& distcode,
+                            uint8_t* lengths, int* last, uint32_t* type, uint32_t* st_off, uint32_t* st_len) {
+    static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    *last = static_cast<int>(inf_bits(b, 1));
+    *type = inf_bits(b, 2);
+    *st_off = 0;
+    *st_len = 0;
+    if (*type == 0u) {
+        if (inf_overrun(b)) return INF_ERR_INPUT;
+        b.p -= (b.cnt - b.virt) >> 3;                  // give back whole bytes of look-ahead, drop the rest of the current byte
+        b.buf = 0;
+        b.cnt = 0;
+        b.virt = 0;
+        if (b.end - b.p < 4) return INF_ERR_INPUT;
+        const uint32_t len = b.p[0] | (static_cast<uint32_t>(b.p[1]) << 8);
+        const uint32_t nlen = b.p[2] | (static_cast<uint32_t>(b.p[3]) << 8);
+        b.p += 4;
+        if (len != (~nlen & 0xFFFFu)) return INF_ERR_CODE;
+        if (static_cast<uint32_t>(b.end - b.p) < len) return INF_ERR_INPUT;
+        if (pos + len > out_len) return INF_ERR_OUTPUT;
+        *st_off = static_cast<uint32_t>(b.p - src);
+        *st_len = len;
+        b.p += len;
+        return INF_OK;
+    }
+    if (*type == 1u) {
+        int s = 0;
+        for (; s < 144; ++s) lengths[s] = 8;
+        for (; s < 256; ++s) lengths[s] = 9;
+        for (; s < 280; ++s) lengths[s] = 7;
+        for (; s < 288; ++s) lengths[s] = 8;
+        inf_construct(lencode, lengths, 288);
+        for (s = 0; s < 30; ++s) lengths[s] = 5;
+        inf_construct(distcode, lengths, 30);
+        return INF_OK;
+    }
+    if (*type != 2u) return INF_ERR_CODE;
+    const int nlen = static_cast<int>(inf_bits(b, 5)) + 257;
+    const int ndist = static_cast<int>(inf_bits(b, 5)) + 1;
+    const int ncode = static_cast<int>(inf_bits(b, 4)) + 4;
+    if (nlen > 286 || ndist > 30) return INF_ERR_CODE;
+    int idx = 0;
+    for (; idx < ncode; ++idx) lengths[order[idx]] = static_cast<uint8_t>(inf_bits(b, 3));
+    for (; idx < 19; ++idx) lengths[order[idx]] = 0;
+    if (inf_construct(lencode, lengths, 19) != 0) return INF_ERR_CODE;      // the code-length code must be complete
+    idx = 0;
+    while (idx < nlen + ndist) {
+        const int sym = inf_decode(b, lencode);
+        if (sym < 0) return INF_ERR_CODE;
+        if (sym < 16) {
+            lengths[idx++] = static_cast<uint8_t>(sym);
+        } else {
+            int len = 0, rep;
+            if (sym == 16) {
+                if (idx == 0) return INF_ERR_CODE;
+                len = lengths[idx - 1];
+                rep = 3 + static_cast<int>(inf_bits(b, 2));
+            } else if (sym == 17) {
+                rep = 3 + static_cast<int>(inf_bits(b, 3));
+            } else {
+                rep = 11 + static_cast<int>(inf_bits(b, 7));
+            }
+            if (idx + rep > nlen + ndist) return INF_ERR_CODE;
+            while (rep--) lengths[idx++] = static_cast<uint8_t>(len);
+        }
+    }
+    if (lengths[256] == 0) return INF_ERR_CODE;         // no end-of-block code
+    // the distance code first: constructing the length code afterwards does not disturb `lengths + nlen`
+    int e1 = inf_construct(distcode, lengths + nlen, ndist);
+    if (e1 < 0 || (e1 > 0 && ndist - distcode.count[0] != 1)) return INF_ERR_CODE;
+    e1 = inf_construct(lencode, lengths, nlen);
+    if (e1 < 0 || (e1 > 0 && nlen - lencode.count[0] != 1)) return INF_ERR_CODE;
+    return INF_OK;
+}

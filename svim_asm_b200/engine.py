@@ -432,8 +432,9 @@ class Engine(object):
     def ingest_timings(self):
         """ms of the last device ingest: file read, H2D, inflate, record chase, fields + copy, host parse, total; inflated bytes."""
         addr = lib.svb_bam_device_timings()
-        v = np.frombuffer((ctypes.c_char * 64).from_address(addr), dtype=np.float64, count=8).copy()
-        keys = ("read_file", "h2d", "inflate", "chase", "fields_copy", "host_parse", "total", "inflated_bytes")
+        v = np.frombuffer((ctypes.c_char * 88).from_address(addr), dtype=np.float64, count=11).copy()
+        keys = ("read_file", "h2d", "inflate", "chase", "fields_copy", "host_parse", "total", "inflated_bytes",
+                "inflate_ctas_per_sm", "inflate_cycles_per_member", "members")
         return dict(zip(keys, (float(x) for x in v)))
 
     def load_reference(self, bases, contig_off):

@@ -30,6 +30,8 @@ def load():
     lib.hc_myers_window_split.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_uint]
     lib.hc_inflate.restype = ctypes.c_int
     lib.hc_inflate.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint]
+    lib.hc_inflate_fast.restype = ctypes.c_int
+    lib.hc_inflate_fast.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint]
     lib.hc_vcf_body.restype = ctypes.c_longlong
     lib.hc_vcf_body.argtypes = [vp, vp, ctypes.c_longlong, vp, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_uint, vp, ctypes.c_longlong]
     return lib

@@ -3,6 +3,7 @@
 // product: the product path is the CUDA library only.
 #include <stdint.h>
 #include <vector>
+#include <algorithm>
 #include "../../svim_asm_b200/csrc/linkage.cuh"
 #include "../../svim_asm_b200/csrc/walk.cuh"
 
@@ -127,6 +128,62 @@ extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return wi
 // The per-member DEFLATE decoder of bgzf_inflate.cu, on the host: checked against zlib's output.
 extern "C" int hc_inflate(const uint8_t* src, unsigned src_len, uint8_t* dst, unsigned out_len) {
     return inflate_member(src, src_len, dst, out_len);
+}
+
+// The device decoder's flow (bam_device.cu: block header, direct tables, the fast symbol loop of the decoding lane, long
+// matches copied by the whole warp) with one host thread standing in for the warp.  `misalign` shifts the compressed
+// bytes inside their buffer: the word refill must cope with any alignment of a member.
+extern "C" int hc_inflate_fast(const uint8_t* src_in, unsigned src_len, uint8_t* dst, unsigned out_len, unsigned misalign) {
+    std::vector<uint32_t> backing((src_len + 16) / 4 + 4);
+    uint8_t* src = reinterpret_cast<uint8_t*>(backing.data()) + (misalign & 3u);
+    memcpy(src, src_in, src_len);
+    uint16_t lencnt[16], lensym[288], distcnt[16], distsym[32];
+    uint8_t lengths[320];
+    std::vector<uint32_t> tlen(1u << INF_LEN_BITS), tdist(1u << INF_DIST_BITS);
+    std::vector<uint8_t> ring(INF_RING, 0xEE);
+    InfHuff lencode{lencnt, lensym}, distcode{distcnt, distsym};
+    InfBits b{src, src + src_len, 0ull, 0, 0};
+    InfOut o = inf_out(ring.data(), dst, out_len);
+    auto flush = [&]() {
+        for (uint32_t lane = 0; lane < 32u; ++lane) inf_flush(o, o.pos, lane, 32u);
+        o.flushed = o.pos;
+    };
+    int last = 0;
+    do {
+        uint32_t type = 0, st_off = 0, st_len = 0;
+        int err = inf_block_header(b, src, o.pos, out_len, lencode, distcode, lengths, &last, &type, &st_off, &st_len);
+        if (err) return err;
+        if (type == 0u) {                                   // stored: through the ring in pieces, later matches may point into it
+            for (uint32_t done = 0; done < st_len;) {
+                const uint32_t chunk = std::min(st_len - done, INF_FLUSH_AT);
+                for (uint32_t i = 0; i < chunk; ++i) ring[(o.rbase + o.pos + i) & INF_RMASK] = src[st_off + done + i];
+                o.pos += chunk;
+                done += chunk;
+                flush();
+            }
+            continue;
+        }
+        std::fill(tlen.begin(), tlen.end(), 0u);
+        std::fill(tdist.begin(), tdist.end(), 0u);
+        for (uint32_t lane = 0; lane < 32u; ++lane) {
+            inf_fill_table(lencnt, lensym, tlen.data(), INF_LEN_BITS, false, lane, 32u);
+            inf_fill_table(distcnt, distsym, tdist.data(), INF_DIST_BITS, true, lane, 32u);
+        }
+        while (true) {
+            uint32_t event = 0, ev_len = 0, ev_dist = 0;
+            err = inf_run(b, lencode, distcode, tlen.data(), tdist.data(), o, &event, &ev_len, &ev_dist);
+            if (err) return err;
+            if (event == INF_EV_EOB) break;
+            if (event == INF_EV_FLUSH) {
+                flush();
+                continue;
+            }
+            for (uint32_t lane = 0; lane < 32u; ++lane) inf_copy_long(o, ev_len, ev_dist, lane, 32u);
+            o.pos += ev_len;
+        }
+    } while (!last);
+    flush();
+    return o.pos == out_len ? INF_OK : INF_ERR_SIZE;
 }
 
 // ---- split window (two halves meeting at row mh), the algorithm of window_pass_split in edit_distance.cu ---------------

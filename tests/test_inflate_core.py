@@ -15,9 +15,20 @@ def _raw_deflate(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
 
 
 def _inflate(lib, comp, n):
+    """Both decoders: the plain one (inflate_member) and the device flow (direct tables, word refill, short matches inline)
+    at every alignment of the compressed bytes; they must agree."""
     out = np.zeros(max(n, 1), dtype=np.uint8)
     rc = lib.hc_inflate(comp, len(comp), out.ctypes.data, n)
-    return rc, out[:n].tobytes()
+    got = out[:n].tobytes()
+    for misalign in range(4):
+        out2 = np.zeros(n + 8, dtype=np.uint8)
+        out2[n:] = 0xA5
+        rc2 = lib.hc_inflate_fast(comp, len(comp), out2.ctypes.data, n, misalign)
+        assert (rc2 == 0) == (rc == 0), (rc, rc2, misalign)
+        assert bytes(out2[n:]) == b"\xa5" * 8                                      # nothing written past the declared size
+        if rc == 0:
+            assert out2[:n].tobytes() == got, misalign
+    return rc, got
 
 
 def _samples():
@@ -30,6 +41,9 @@ def _samples():
     yield bytes(rng.integers(0, 4, 30000, dtype=np.uint8)) + b"\xff" * 30000       # mixed
     ops = ((rng.geometric(1 / 12.0, 16000).astype(np.uint32) << 4) | rng.choice([7, 8, 1, 2], 16000).astype(np.uint32))
     yield ops.tobytes()                                                            # BAM-packed CIGAR ops
+    yield bytes((rng.geometric(0.04, 60000) % 256).astype(np.uint8))               # skewed: Huffman codes longer than the direct tables
+    far = bytes(rng.integers(0, 256, 3000, dtype=np.uint8))
+    yield far + bytes(rng.integers(0, 8, 28000, dtype=np.uint8)) + far + b"\xff" * 3000 + far[:40]   # distances near 32 KB, long runs
 
 
 @pytest.mark.parametrize("level", [0, 1, 6, 9])
