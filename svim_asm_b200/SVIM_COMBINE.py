@@ -8,6 +8,7 @@ bit-parallel edit distances, complete-linkage clustering, genotype rules).  writ
 import logging
 import os
 import re
+import threading
 import time
 from collections import defaultdict
 
@@ -22,12 +23,58 @@ from .SVCandidate import (F_COMPLETE, F_CUTPASTE, F_DST_FWD, F_FULLY_COVERED, F_
 from .SVIM_COLLECT import CandidateList
 
 
+_PREFETCH = {}        # (absolute FASTA path, contig names) -> ReferencePrefetch
+
+
+class ReferencePrefetch(threading.Thread):
+    """FASTA -> HBM on a context (stream, staging buffers) of its own while the main thread ingests the BAM files: the two
+    only share the PCIe link, and the ingest is mostly the inflate kernel.  The CLI starts one as soon as the first BAM
+    header has named the contigs; _device_reference picks the result up.  A failure is kept quiet here: the synchronous
+    load that follows raises it where the reference would."""
+
+    def __init__(self, fasta_path, contig_names):
+        threading.Thread.__init__(self, daemon=True)
+        self.key = (os.path.abspath(fasta_path), tuple(contig_names))
+        self.path, self.names, self.result = fasta_path, list(contig_names), None
+        _PREFETCH[self.key] = self
+        self.start()
+
+    def run(self):
+        try:
+            from .engine import Engine
+            from .fasta import FastaFile
+            from .runtime import get_engine
+            fasta = FastaFile(self.path)
+            rows = fasta.fai_rows(self.names)
+            fasta.close()
+            engine = Engine(get_engine().device)
+            self.result = engine.load_reference_fasta(self.path, rows)
+            self.result.loader = engine                  # keeps the context alive as long as the reference
+        except Exception:
+            self.result = None
+
+
+def drop_prefetches():
+    """Wait for background loads nobody picked up and release what they produced."""
+    while _PREFETCH:
+        _key, pending = _PREFETCH.popitem()
+        pending.join()
+        if pending.result is not None:
+            pending.result.free()
+            pending.result = None
+
+
 def _device_reference(reference, contig_names):
     """Upload the FASTA once per (FastaFile, contig list): upper-cased bases in BAM header order."""
     cache = getattr(reference, "_svb_ref", None)
     key = tuple(contig_names)
     if cache is None or cache[0] != key:
-        if hasattr(reference, "fai_rows"):         # our FastaFile: the bases go from the file to HBM without a host pass
+        pending = _PREFETCH.pop((os.path.abspath(getattr(reference, "filename", "") or ""), key), None)
+        if pending is not None:
+            pending.join()
+        if pending is not None and pending.result is not None:
+            cache = (key, pending.result)
+        elif hasattr(reference, "fai_rows"):       # our FastaFile: the bases go from the file to HBM without a host pass
             cache = (key, get_engine().load_reference_fasta(reference.filename, reference.fai_rows(contig_names)))
         else:
             bases, offsets = reference.load_upper(contig_names)

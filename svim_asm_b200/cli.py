@@ -51,9 +51,20 @@ def main(argv=None):
     try:
         return _run(options)
     finally:
+        from .SVIM_COMBINE import drop_prefetches
+        drop_prefetches()                  # a run that stopped early (bad second BAM, ...) must not leave the loader running
         for h in handlers:
             root.removeHandler(h)
             h.close()
+
+
+def _prefetch_reference(options, bam):
+    """Start the FASTA -> HBM load in the background (needed by PAIR and by the VCF alleles) once the contigs are known."""
+    if os.environ.get("SVIM_ASM_B200_PREFETCH", "1") == "0":
+        return
+    if os.path.exists(options.genome) and os.path.exists(options.genome + ".fai") and getattr(bam, "records", None) is not None:
+        from .SVIM_COMBINE import ReferencePrefetch
+        ReferencePrefetch(options.genome, bam.references)
 
 
 def _run(options):
@@ -73,6 +84,7 @@ def _run(options):
         aln_file1 = _open_sorted_bam(options.bam_file, None)
         if aln_file1 is None:
             return
+        _prefetch_reference(options, aln_file1)
         options._haplotype = 0
         sv_candidates = analyze_alignment_file_coordsorted(aln_file1, options)
     else:
@@ -82,6 +94,7 @@ def _run(options):
         aln_file1 = _open_sorted_bam(options.bam_file1, 1)
         if aln_file1 is None:
             return
+        _prefetch_reference(options, aln_file1)
         options._haplotype = 1
         sv_candidates1 = analyze_alignment_file_coordsorted(aln_file1, options)
         aln_file2 = _open_sorted_bam(options.bam_file2, 2)
