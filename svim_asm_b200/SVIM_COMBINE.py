@@ -36,7 +36,6 @@ class ReferencePrefetch(threading.Thread):
         threading.Thread.__init__(self, daemon=True)
         self.key = (os.path.abspath(fasta_path), tuple(contig_names))
         self.path, self.names, self.result = fasta_path, list(contig_names), None
-        self.device = get_engine().device
         _PREFETCH[self.key] = self
         self.start()
 
@@ -44,10 +43,11 @@ class ReferencePrefetch(threading.Thread):
         try:
             from .engine import Engine
             from .fasta import FastaFile
+            from .runtime import get_engine
             fasta = FastaFile(self.path)
             rows = fasta.fai_rows(self.names)
             fasta.close()
-            engine = Engine(self.device)
+            engine = Engine(get_engine().device)
             self.result = engine.load_reference_fasta(self.path, rows)
             self.result.loader = engine                  # keeps the context alive as long as the reference
         except Exception:

@@ -3,49 +3,16 @@ same sub-commands, flags, log lines, checks and output files (variants.vcf, SVIM
 import logging
 import os
 import sys
-import threading
 from time import localtime, strftime
 
 __version__ = "1.0.3"
 
 
-_BACKGROUND = []      # ingests started ahead of time (joined before main() returns, whatever happened)
-
-
-class _BamPrefetch(threading.Thread):
-    """Device ingest of the SECOND haplotype's BAM on a context of its own while the first one is ingested: the two
-    inflate kernels queue behind each other on the GPU, everything else (file -> HBM, record chase, host-side parse)
-    overlaps.  Errors are kept and raised where the synchronous open would have raised them."""
-
-    def __init__(self, path):
-        from .runtime import get_engine
-        threading.Thread.__init__(self, daemon=True)
-        self.path, self.bam, self.error = path, None, None
-        self.device = get_engine().device      # (creates the process-wide engine in the calling thread, not in both)
-        _BACKGROUND.append(self)
-        self.start()
-
-    def run(self):
-        try:
-            from .bamfile import AlignmentFile
-            from .engine import Engine
-            self.bam = AlignmentFile(self.path, engine=Engine(self.device))
-        except BaseException as exc:           # noqa: B902 -- handed to the main thread
-            self.error = exc
-
-    def take(self):
-        self.join()
-        if self.error is not None:
-            raise self.error
-        return self.bam
-
-
-def _open_sorted_bam(path, which, prefetched=None):
+def _open_sorted_bam(path, which):
     """svim-asm:63-80 / 85-120: header must say SO:coordinate and an index must sit next to the file."""
     from .bamfile import AlignmentFile
     from .runtime import get_engine
-    # device ingest: the records stay in HBM for COLLECT
-    bam = prefetched.take() if prefetched is not None else AlignmentFile(path, engine=get_engine())
+    bam = AlignmentFile(path, engine=get_engine())      # device ingest: the records stay in HBM for COLLECT
     label = "" if which is None else ("first " if which == 1 else "second ")
     try:
         sorted_ok = bam.header["HD"]["SO"] == "coordinate"
@@ -86,8 +53,6 @@ def main(argv=None):
     finally:
         from .SVIM_COMBINE import drop_prefetches
         drop_prefetches()                  # a run that stopped early (bad second BAM, ...) must not leave the loader running
-        while _BACKGROUND:
-            _BACKGROUND.pop().join()
         for h in handlers:
             root.removeHandler(h)
             h.close()
@@ -126,17 +91,13 @@ def _run(options):
         logging.info("MODE: diploid")
         logging.info("INPUT1: {0}".format(os.path.abspath(options.bam_file1)))
         logging.info("INPUT2: {0}".format(os.path.abspath(options.bam_file2)))
-        ahead = None
-        if (os.environ.get("SVIM_ASM_B200_PREFETCH", "1") != "0" and os.environ.get("SVIM_ASM_B200_INGEST", "device") != "host"
-                and os.path.exists(options.bam_file1) and os.path.exists(options.bam_file2)):
-            ahead = _BamPrefetch(options.bam_file2)
         aln_file1 = _open_sorted_bam(options.bam_file1, 1)
         if aln_file1 is None:
             return
         _prefetch_reference(options, aln_file1)
         options._haplotype = 1
         sv_candidates1 = analyze_alignment_file_coordsorted(aln_file1, options)
-        aln_file2 = _open_sorted_bam(options.bam_file2, 2, ahead)
+        aln_file2 = _open_sorted_bam(options.bam_file2, 2)
         if aln_file2 is None:
             return
         options._haplotype = 2
