@@ -21,13 +21,14 @@ def _inflate(lib, comp, n):
     rc = lib.hc_inflate(comp, len(comp), out.ctypes.data, n)
     got = out[:n].tobytes()
     for misalign in range(4):
-        out2 = np.zeros(n + 8, dtype=np.uint8)
-        out2[n:] = 0xA5
-        rc2 = lib.hc_inflate_fast(comp, len(comp), out2.ctypes.data, n, misalign)
+        shift = (5 * misalign + 1) % 16                                            # the member's place in the output: any alignment
+        out2 = np.zeros(n + 8 + 16, dtype=np.uint8)
+        out2[:] = 0xA5
+        rc2 = lib.hc_inflate_fast(comp, len(comp), out2.ctypes.data + shift, n, misalign)
         assert (rc2 == 0) == (rc == 0), (rc, rc2, misalign)
-        assert bytes(out2[n:]) == b"\xa5" * 8                                      # nothing written past the declared size
+        assert bytes(out2[:shift]) == b"\xa5" * shift and bytes(out2[shift + n:]) == b"\xa5" * (24 - shift)   # nothing outside the member
         if rc == 0:
-            assert out2[:n].tobytes() == got, misalign
+            assert out2[shift:shift + n].tobytes() == got, misalign
     return rc, got
 
 
