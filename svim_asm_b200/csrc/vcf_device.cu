@@ -101,16 +101,28 @@ extern "C" int svb_vcf_body(svb_ctx* ctx, const svb_table* t, const svb_records*
         ctx->h_text_cap = cap;
     }
     const uint32_t names_bytes = name_off[n_contig];
+    struct Scratch {                     // stream-ordered device scratch, released on every way out
+        cudaStream_t stream;
+        std::vector<void*> ptrs;
+        ~Scratch() {
+            for (void* q : ptrs) cudaFreeAsync(q, stream);
+        }
+        cudaError_t get(void** out, size_t bytes) {
+            const cudaError_t e = cudaMallocAsync(out, bytes, stream);
+            if (e == cudaSuccess) ptrs.push_back(*out);
+            return e;
+        }
+    } scratch{ctx->stream, {}};
     uint8_t* d_out = nullptr;
     uint8_t* d_names = nullptr;
     uint32_t* d_name_off = nullptr;
     svb_vcf_entry* d_entries = nullptr;
     uint64_t* d_line_off = nullptr;
-    SVB_CUDA(ctx, cudaMallocAsync(&d_out, std::max<uint64_t>(total, 1), ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_names, std::max<uint32_t>(names_bytes, 1u), ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_name_off, sizeof(uint32_t) * (static_cast<size_t>(n_contig) + 1), ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_entries, sizeof(svb_vcf_entry) * n_entries, ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_line_off, sizeof(uint64_t) * (n_entries + 1), ctx->stream));
+    SVB_CUDA(ctx, scratch.get(reinterpret_cast<void**>(&d_out), std::max<uint64_t>(total, 1)));
+    SVB_CUDA(ctx, scratch.get(reinterpret_cast<void**>(&d_names), std::max<uint32_t>(names_bytes, 1u)));
+    SVB_CUDA(ctx, scratch.get(reinterpret_cast<void**>(&d_name_off), sizeof(uint32_t) * (static_cast<size_t>(n_contig) + 1)));
+    SVB_CUDA(ctx, scratch.get(reinterpret_cast<void**>(&d_entries), sizeof(svb_vcf_entry) * n_entries));
+    SVB_CUDA(ctx, scratch.get(reinterpret_cast<void**>(&d_line_off), sizeof(uint64_t) * (n_entries + 1)));
     if (names_bytes) SVB_CUDA(ctx, cudaMemcpyAsync(d_names, names, names_bytes, cudaMemcpyHostToDevice, ctx->stream));
     SVB_CUDA(ctx, cudaMemcpyAsync(d_name_off, name_off, sizeof(uint32_t) * (static_cast<size_t>(n_contig) + 1), cudaMemcpyHostToDevice, ctx->stream));
     SVB_CUDA(ctx, cudaMemcpyAsync(d_entries, entries, sizeof(svb_vcf_entry) * n_entries, cudaMemcpyHostToDevice, ctx->stream));
@@ -134,11 +146,6 @@ extern "C" int svb_vcf_body(svb_ctx* ctx, const svb_table* t, const svb_records*
     }
     SVB_CUDA(ctx, cudaGetLastError());
     if (total) SVB_CUDA(ctx, cudaMemcpyAsync(ctx->h_text, d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
-    cudaFreeAsync(d_out, ctx->stream);
-    cudaFreeAsync(d_names, ctx->stream);
-    cudaFreeAsync(d_name_off, ctx->stream);
-    cudaFreeAsync(d_entries, ctx->stream);
-    cudaFreeAsync(d_line_off, ctx->stream);
     SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *text = ctx->h_text;
     *n_bytes = total;
