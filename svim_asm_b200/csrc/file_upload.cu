@@ -36,9 +36,10 @@ Uploader* uploader_of(svb_ctx* ctx) {
         ok = cudaStreamCreateWithFlags(&u->stream[t], cudaStreamNonBlocking) == cudaSuccess;
         for (int s = 0; ok && s < 2; ++s) ok = cudaEventCreateWithFlags(&u->sent[t][s], cudaEventDisableTiming) == cudaSuccess;
     }
-    ctx->uploader = u;                               // released by upload_release, also when half built
-    if (!ok) {
+    ctx->uploader = u;
+    if (!ok) {                                       // half built: give everything back, the next call tries again
         cudaGetLastError();
+        upload_release(ctx);
         return nullptr;
     }
     return u;
