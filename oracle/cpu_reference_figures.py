@@ -1,9 +1,11 @@
-"""The three CPU figures of BASELINE.md section 3 for the UNMODIFIED reference, run in the build container
+"""TEST INFRASTRUCTURE (lives under oracle/: nothing in the product imports it).
+
+The three CPU figures of BASELINE.md section 3 for the UNMODIFIED reference, run in the build container
 (/root/reference through oracle/refrun.py; pysam / edlib are this repo's pure-python stand-ins when the real packages
 are absent, so "file ->" figures include OUR BAM decoder, not htslib; the loop-only figure is the reference's own code on
 pre-materialised tuples and does not depend on the stand-ins).  One core.
 
-    python tools/cpu_reference_figures.py [--config C1|C2]
+    python oracle/cpu_reference_figures.py [--config C1|C2]
 """
 import argparse
 import os
