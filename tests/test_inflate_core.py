@@ -56,6 +56,19 @@ def test_matches_zlib(level):
         assert rc == 0 and got == data, (level, len(data), rc)
 
 
+@pytest.mark.parametrize("strategy", [zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FILTERED])
+def test_other_encoder_strategies(strategy):
+    """Streams no BGZF writer produces by default but the format allows: runs only (distance 1), literals only, filtered;
+    with memLevel 1 the encoder also emits many short dynamic blocks (the tables are rebuilt every few hundred symbols)."""
+    lib = hostcheck.load()
+    for data in _samples():
+        for mem_level in (1, 9):
+            c = zlib.compressobj(6, zlib.DEFLATED, -15, mem_level, strategy)
+            comp = c.compress(data) + c.flush()
+            rc, got = _inflate(lib, comp, len(data))
+            assert rc == 0 and got == data, (strategy, mem_level, len(data), rc)
+
+
 def test_fixed_huffman_blocks():
     lib = hostcheck.load()
     for data in _samples():
