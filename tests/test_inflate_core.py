@@ -69,6 +69,20 @@ def test_other_encoder_strategies(strategy):
             assert rc == 0 and got == data, (strategy, mem_level, len(data), rc)
 
 
+def test_flush_markers_inside_a_stream():
+    """Z_SYNC_FLUSH / Z_FULL_FLUSH leave empty stored blocks between Huffman blocks (bgzip never does, other writers may)."""
+    lib = hostcheck.load()
+    rng = np.random.default_rng(5)
+    data = bytes(rng.choice(list(b"ACGTN"), 50000).astype(np.uint8)) + b"\xff" * 5000
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = b""
+    for k, lo in enumerate(range(0, len(data), 7000)):
+        comp += c.compress(data[lo:lo + 7000]) + c.flush(zlib.Z_SYNC_FLUSH if k % 2 else zlib.Z_FULL_FLUSH)
+    comp += c.flush()
+    rc, got = _inflate(lib, comp, len(data))
+    assert rc == 0 and got == data
+
+
 def test_fixed_huffman_blocks():
     lib = hostcheck.load()
     for data in _samples():
