@@ -212,6 +212,14 @@ void svb_ref_free(svb_ref* ref);
 int svb_pair(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
              const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);
 
+/* form_partitions (SVIM_COMBINE.py:15-32) for caller-built keys: key = (group << 32) | position with group = rank of
+ * (type, contig) under python tuple order and 0 <= position < 2^31.  Stable sort by key (sorted(), :17), then the split
+ * of :20-31: a new partition where the group changes or CONSECUTIVE positions are more than max_distance apart.
+ * order[i] = input index of the i-th sorted item; part_start[p] = first sorted index of partition p, part_start[n_parts] = n
+ * (capacity n + 1). */
+int svb_form_partitions(svb_ctx* ctx, const uint64_t* keys, uint32_t n, int64_t max_distance, uint32_t* order,
+                        uint32_t* part_start, uint32_t* n_parts);
+
 /* compute_distance for explicit strings (edlib.align(a,b)["editDistance"], SVIM_COMBINE.py:50): test hook of K8. */
 int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
                       uint32_t n_pairs, int64_t* out);

@@ -128,6 +128,50 @@ def _rows_from_objects(cands, hap, contig_names):
     return rows, rb
 
 
+def _onto_first_header(eng, side, names):
+    """The reference pairs by contig NAME and takes every length from the first BAM (SVIM_COMBINE.py:164-366 pass `bam` =
+    aln_file1 to the constructors).  The device rows carry tids of their own file: when the second BAM lists its contigs in
+    another order (or lists other contigs), its rows are renumbered onto the first header before svb_pair sees them."""
+    table, records, host = side
+    other = list(getattr(host, "contig_names", names))
+    if other == list(names):
+        return side
+    first = {n: t for t, n in enumerate(names)}
+    remap = np.array([first.get(n, -1) for n in other] + [-1], dtype=np.int32)        # last slot: tid -1 stays -1
+    rows = table.to_numpy()
+    for field in ("src_tid", "dst_tid"):
+        tid = rows[field]
+        used = tid >= 0
+        bad = used & (remap[np.where(used, tid, -1)] < 0)
+        if np.any(bad):
+            raise KeyError(other[int(tid[np.nonzero(bad)[0][0]])])       # bam.get_reference_length(name) of the first BAM would raise
+        rows[field] = np.where(used, remap[np.where(used, tid, -1)], tid)
+    renumbered = eng.table_from_numpy(rows)
+    if not records.has_sequences:
+        eng.set_sequences(records)
+    renumbered.gather_sequences(records)          # the inserted bases travel with the table: svb_pair no longer needs its image
+    return renumbered, records, host
+
+
+def _require_fasta_contigs(reference, names, tables):
+    """reference.fetch(contig, ...) raises KeyError for a contig the FASTA does not hold (SVIM_COMBINE.py:48-99); the device
+    copy would silently read it as empty.  Every contig that carries a candidate with sequence context must be there."""
+    have = getattr(reference, "references", None)
+    if have is None:
+        return
+    have = set(have)
+    missing = [t for t, n in enumerate(names) if n not in have]
+    if not missing:
+        return
+    for table in tables:
+        rows = table.to_numpy()
+        rows = rows[rows["type"] != 5]
+        for field in ("src_tid", "dst_tid"):
+            hit = np.isin(rows[field], missing)
+            if np.any(hit):
+                raise KeyError(names[int(rows[field][np.nonzero(hit)[0][0]])])
+
+
 def pair_candidates(sv_candidates1, sv_candidates2, reference, bam, options):
     """SVIM_COMBINE.py:164-366 on the GPU.  Accepts the CandidateList objects of
     analyze_alignment_file_coordsorted (device tables are reused) or plain lists of Candidate objects."""
@@ -158,6 +202,8 @@ def pair_candidates(sv_candidates1, sv_candidates2, reference, bam, options):
             records = eng.load_records(host, with_sequences=True)
             table = eng.table_from_numpy(rows)
         sides.append((table, records, host))
+    sides[1] = _onto_first_header(eng, sides[1], names)
+    _require_fasta_contigs(reference, names, [side[0] for side in sides])
     ref = _device_reference(reference, names)
     paired = eng.pair(sides[0][0], sides[1][0], sides[0][1], sides[1][1], ref, make_params(options))
     def known():
@@ -168,11 +214,8 @@ def pair_candidates(sv_candidates1, sv_candidates2, reference, bam, options):
     return out
 
 
-def compute_distance(candidate_with_haplotype1, candidate_with_haplotype2, reference):
-    """SVIM_COMBINE.py:35-102 for one pair: the edit distance comes from the GPU kernel (svb_edit_distance)."""
-    (hap1, c1), (hap2, c2) = candidate_with_haplotype1, candidate_with_haplotype2
-    if hap1 == hap2:
-        return 1000000000
+def _haplotype_strings(c1, c2, reference):
+    """The two haplotype strings compute_distance aligns (SVIM_COMBINE.py:43-100), as bytes."""
     comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
 
     def fetch(contig, s, e):
@@ -196,8 +239,98 @@ def compute_distance(candidate_with_haplotype1, candidate_with_haplotype2, refer
         length = reference.get_reference_length(c1.dest_contig)
         lo = max(0, min(c1.dest_start, c2.dest_start) - 100)
         hi = min(length, max(c1.dest_start, c2.dest_start) + 100)
-    a, b = build(c1, lo, hi).encode("latin-1"), build(c2, lo, hi).encode("latin-1")
-    return int(get_engine().edit_distance([(a, b)])[0])
+    return build(c1, lo, hi).encode("latin-1"), build(c2, lo, hi).encode("latin-1")
+
+
+def compute_distance(candidate_with_haplotype1, candidate_with_haplotype2, reference):
+    """SVIM_COMBINE.py:35-102 for one pair: the edit distance comes from the GPU kernel (svb_edit_distance)."""
+    (hap1, c1), (hap2, c2) = candidate_with_haplotype1, candidate_with_haplotype2
+    if hap1 == hap2:
+        return 1000000000
+    return int(get_engine().edit_distance([_haplotype_strings(c1, c2, reference)])[0])
+
+
+def form_partitions(sv_candidates_with_haplotype, max_distance):
+    """SVIM_COMBINE.py:15-32: stable sort of (haplotype, candidate) items by candidate.get_key(), split where type or contig
+    change or consecutive key positions are more than max_distance apart.  The sort and the split run on the device
+    (svb_form_partitions: LSD radix sort + head flags); the keys are ranked here the way python orders the tuples."""
+    items = list(sv_candidates_with_haplotype)
+    if not items:
+        return []
+    keys = [c.get_key() for _hap, c in items]
+    groups = {g: k for k, g in enumerate(sorted(set((key[0], key[1]) for key in keys)))}
+    packed = np.zeros(len(items), dtype=np.uint64)
+    for i, key in enumerate(keys):
+        pos = int(key[2])
+        if not 0 <= pos < (1 << 31):
+            raise ValueError("form_partitions: key position %d outside [0, 2^31)" % pos)
+        packed[i] = (groups[(key[0], key[1])] << 32) | pos
+    order, part_start = get_engine().form_partitions(packed, max_distance)
+    return [[items[int(k)] for k in order[part_start[p]:part_start[p + 1]]] for p in range(part_start.shape[0] - 1)]
+
+
+def span_position_distance_breakends(candidate1, candidate2):
+    """SVIM_COMBINE.py:105-117 on (haplotype, pos1, dir1, pos2, dir2) rows (the destination contig is never compared)."""
+    hap1, pos1a, dir1a, pos2a, dir2a = candidate1
+    hap2, pos1b, dir1b, pos2b, dir2b = candidate2
+    if hap1 != hap2 and dir1a == dir1b and dir2a == dir2b:
+        return (abs(pos1a - pos1b) + abs(pos2a - pos2b)) / 3000
+    return 99999
+
+
+def _clusters_by_label(partitions, condensed_of, threshold):
+    """pair_haplotypes' frame (SVIM_COMBINE.py:120-140 / :143-161): singletons pass, partitions above 10 are dropped,
+    the rest is clustered by complete linkage cut at `threshold` (svb_cluster_labels reproduces scipy's labels, hence the
+    order of the clusters)."""
+    todo = [k for k, part in enumerate(partitions) if 2 <= len(part) <= 10]
+    labels = dict(zip(todo, get_engine().cluster_labels([condensed_of(partitions[k]) for k in todo], threshold))) if todo else {}
+    out = []
+    for k, part in enumerate(partitions):
+        if len(part) < 2:
+            out.append(part)
+        elif len(part) > 10:
+            if part and hasattr(part[0][1], "get_key"):
+                logging.debug("Ignored partition of size {0} and type {1}: {2}".format(
+                    len(part), part[0][1].get_key()[0], ",".join("{0}:{1}".format(c.get_key()[1], c.get_key()[2]) for _h, c in part)))
+            continue
+        else:
+            lab = labels[k]
+            clusters = [[] for _ in range(max(lab))]
+            for item, which in zip(part, lab):
+                clusters[which - 1].append(item)
+            out.extend(clusters)
+    return out
+
+
+def pair_haplotypes(partitions, reference, edit_distance_threshold=10):
+    """SVIM_COMBINE.py:120-140.  Every cross-haplotype edit distance of every partition goes to the GPU in ONE batch
+    (svb_edit_distance), then every partition's linkage in one (svb_cluster_labels)."""
+    partitions = list(partitions)
+    jobs, slots = [], {}
+    for k, part in enumerate(partitions):
+        if 2 <= len(part) <= 10:
+            for i in range(len(part) - 1):
+                for j in range(i + 1, len(part)):
+                    if part[i][0] != part[j][0]:
+                        slots[(k, i, j)] = len(jobs)
+                        jobs.append(_haplotype_strings(part[i][1], part[j][1], reference))
+    dist = get_engine().edit_distance(jobs) if jobs else []
+    index = {id(part): k for k, part in enumerate(partitions)}
+
+    def condensed(part):
+        k = index[id(part)]
+        return [1000000000 if part[i][0] == part[j][0] else int(dist[slots[(k, i, j)]])
+                for i in range(len(part) - 1) for j in range(i + 1, len(part))]
+    return _clusters_by_label(partitions, condensed, edit_distance_threshold)
+
+
+def pair_haplotypes_breakends(partitions, span_position_distance_threshold=0.3):
+    """SVIM_COMBINE.py:143-161: clusters from the span-position distance of breakends."""
+    def condensed(part):
+        data = [(hap, c.get_source()[1], 1 if c.source_direction == "fwd" else 0, c.get_destination()[1],
+                 1 if c.dest_direction == "fwd" else 0) for hap, c in part]
+        return [float(span_position_distance_breakends(data[i], data[j])) for i in range(len(data) - 1) for j in range(i + 1, len(data))]
+    return _clusters_by_label(list(partitions), condensed, span_position_distance_threshold)
 
 
 def sorted_nicely(vcf_entries):

@@ -88,6 +88,7 @@ SIGNATURES = {
     "svb_ref_free": (None, [c_void_p]),
     "svb_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)]),
     "svb_edit_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_void_p]),
+    "svb_form_partitions": (c_int, [c_void_p, c_void_p, c_u32, c_i64, c_void_p, c_void_p, P(c_u32)]),
     "svb_cluster_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_u32, c_double, c_void_p]),
     "svb_table_size": (c_i64, [c_void_p]),
     "svb_table_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, P(c_u64)]),

@@ -17,8 +17,9 @@ def _open_sorted_bam(path, which):
     try:
         sorted_ok = bam.header["HD"]["SO"] == "coordinate"
     except KeyError:
+        # (svim-asm:79,100,119: only the first-BAM message of the diploid mode lacks the trailing " Exiting..")
         logging.error("Is the given {0}input BAM file coordinate-sorted? It does not contain a sorting order in its "
-                      "header line. Exiting..".format(label))
+                      "header line.{1}".format(label, "" if which == 1 else " Exiting.."))
         return None
     if not sorted_ok:
         logging.error("{0} BAM file needs to be coordinate-sorted. Exiting..".format(

@@ -242,6 +242,7 @@ int load_records_impl(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, cons
     r->n_seg = n_seg;
     r->n_contig = n_contig;
     r->n4 = n_ops_padded / 4;
+    if (n_contig) r->h_contig_len.assign(contig_len, contig_len + n_contig);
 
     // host-side derived index: off4[] and the list of records that carry SA segments
     std::vector<uint32_t> off4(static_cast<size_t>(n_aln) + 1), prim;
@@ -621,6 +622,13 @@ int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, con
     if (!ctx || !a_off || !b_off || (n_pairs && !out)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_edit_distance") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
     return run_edit_distance_strings(ctx, a, a_off, b, b_off, n_pairs, out);
+}
+
+int svb_form_partitions(svb_ctx* ctx, const uint64_t* keys, uint32_t n, int64_t max_distance, uint32_t* order,
+                        uint32_t* part_start, uint32_t* n_parts) {
+    if (!ctx || !n_parts || (n && (!keys || !order || !part_start))) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_form_partitions") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return run_form_partitions(ctx, keys, n, max_distance, order, part_start, n_parts);
 }
 
 int svb_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,

@@ -33,6 +33,7 @@ struct svb_records {
     uint64_t* d_seq_off = nullptr;    // [n_aln + 1]
     uint32_t* d_global_idx = nullptr; // optional [n_aln]: index of each record in the unsharded batch (exchange.cu)
     uint64_t seq_bytes = 0;
+    std::vector<int32_t> h_contig_len; // host copy of the contig table (svb_pair checks that both haplotypes share it)
 };
 
 struct svb_table {
@@ -129,5 +130,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
                 const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);
 int run_edit_distance_strings(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b,
                               const uint64_t* b_off, uint32_t n_pairs, int64_t* out);
+int run_form_partitions(svb_ctx* ctx, const uint64_t* keys_host, uint32_t n, int64_t max_distance, uint32_t* order_out,
+                        uint32_t* part_start_out, uint32_t* n_parts_out);
 int run_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,
                        double threshold, int32_t* labels_out);

@@ -175,11 +175,15 @@ __global__ void part_start_kernel(const unsigned long long* __restrict__ keys, c
     if (h) part_start[excl[i]] = i;
 }
 
+// Coordinates come from BAM records, the bases from the FASTA: a FASTA contig shorter than the BAM header says (or absent:
+// length 0) must not be read past its end.  FastaFile.fetch truncates at the contig end, so every piece is clamped to the
+// FASTA length of its contig (`lo` / `hi` already are, SVIM_COMBINE.py:45-46,68-69).
 __device__ void make_desc(const svb_row& r, long long lo, long long hi, const PairArgs& a, HapDesc& d) {
     d.m_kind = HAP_MID_NONE; d.m_len = 0; d.m_base = 0; d.m_unit = 1; d.seq_sel = 0;
     if (r.type == SVB_DEL || r.type == SVB_INV || r.type == SVB_DUP_TAN) {
         const uint64_t base = a.ref_off[r.src_tid];
-        const long long s = r.src_start, e = r.src_end;
+        const long long clen = static_cast<long long>(a.ref_off[r.src_tid + 1] - base);
+        const long long s = min(static_cast<long long>(r.src_start), clen), e = min(static_cast<long long>(r.src_end), clen);
         d.l_base = base + static_cast<uint64_t>(lo);
         d.l_len = static_cast<uint32_t>(s > lo ? s - lo : 0);
         d.r_base = base + static_cast<uint64_t>(e);
@@ -193,7 +197,8 @@ __device__ void make_desc(const svb_row& r, long long lo, long long hi, const Pa
         }
     } else {   // INS, DUP_INT: the window is anchored on dest_start (SVIM_COMBINE.py:68-69,92-93)
         const uint64_t base = a.ref_off[r.dst_tid];
-        const long long s = r.dst_start;
+        const long long clen = static_cast<long long>(a.ref_off[r.dst_tid + 1] - base);
+        const long long s = min(static_cast<long long>(r.dst_start), clen);
         d.l_base = base + static_cast<uint64_t>(lo);
         d.l_len = static_cast<uint32_t>(s > lo ? s - lo : 0);
         d.r_base = base + static_cast<uint64_t>(s);
@@ -205,8 +210,12 @@ __device__ void make_desc(const svb_row& r, long long lo, long long hi, const Pa
                 d.m_len = r.seq_len;
             }
         } else {
-            const long long ss = r.src_start, se = r.src_end;
-            d.m_kind = HAP_MID_REF; d.m_base = a.ref_off[r.src_tid] + static_cast<uint64_t>(ss);
+            const bool src_ok = r.src_tid >= 0 && r.src_tid < a.ref_n_contig;
+            const uint64_t sbase = src_ok ? a.ref_off[r.src_tid] : 0ull;
+            const long long slen = src_ok ? static_cast<long long>(a.ref_off[r.src_tid + 1] - sbase) : 0ll;
+            const long long ss = min(static_cast<long long>(r.src_start), slen), se = min(static_cast<long long>(r.src_end), slen);
+            if (!src_ok) atomicOr(a.dev_status, DEV_ERR_BAD_TID);
+            d.m_kind = HAP_MID_REF; d.m_base = sbase + static_cast<uint64_t>(ss);
             d.m_len = static_cast<uint32_t>(se > ss ? se - ss : 0);
         }
     }
@@ -359,6 +368,13 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         return SVB_OK;
     }
     if (!rec1 || !rec2) { delete result; return svb_fail(ctx, SVB_ERR_ARG, "svb_pair: records of both haplotypes are required"); }
+    // rows of both tables are keyed, clamped and named by tid: the two record images must share one contig table
+    // (pair_candidates takes every name and length from the first BAM, SVIM_COMBINE.py:164-366)
+    // (a table that brings its own sequence pool does not consult its record image: it may have been renumbered already)
+    if (!h2->d_pool_off && rec1->h_contig_len != rec2->h_contig_len) {
+        delete result;
+        return svb_fail(ctx, SVB_ERR_ARG, "svb_pair: the two record images list different contigs; renumber the second table onto the first header");
+    }
     const svb_records* rec = rec1;
     uint32_t rank_bits = 1;
     while ((1u << rank_bits) < static_cast<uint32_t>(std::max(rec->n_contig, 1))) ++rank_bits;
@@ -496,6 +512,70 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     if (result->n > result->cap) return fail(svb_fail(ctx, SVB_ERR_CAPACITY, "svb_pair: more rows out than in"));
 #undef PAIR_CUDA
     *out = result;
+    return SVB_OK;
+}
+
+// ---- form_partitions for explicit keys (svb_form_partitions): the K6 sort + K7 split on caller-supplied keys ------
+namespace {
+__global__ void iota_kernel(uint32_t* v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+}  // namespace
+
+int run_form_partitions(svb_ctx* ctx, const uint64_t* keys_host, uint32_t n, int64_t max_distance, uint32_t* order_out,
+                        uint32_t* part_start_out, uint32_t* n_parts_out) {
+    *n_parts_out = 0;
+    if (!n) return SVB_OK;
+    const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+    auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    const size_t sz_keys = align(sizeof(unsigned long long) * n), sz_vals = align(sizeof(uint32_t) * (static_cast<size_t>(n) + 1));
+    const size_t sz_hist = align(sizeof(uint32_t) * (256ull * n_blocks + 1));
+    unsigned char* slab = nullptr;
+    SVB_CUDA(ctx, cudaMallocAsync(&slab, 2 * sz_keys + 4 * sz_vals + sz_hist, ctx->stream));
+    unsigned char* cur = slab;
+    auto carve = [&](size_t bytes) { unsigned char* q = cur; cur += bytes; return q; };
+    unsigned long long* keys[2] = {reinterpret_cast<unsigned long long*>(carve(sz_keys)), reinterpret_cast<unsigned long long*>(carve(sz_keys))};
+    uint32_t* vals[2] = {reinterpret_cast<uint32_t*>(carve(sz_vals)), reinterpret_cast<uint32_t*>(carve(sz_vals))};
+    uint32_t* head = reinterpret_cast<uint32_t*>(carve(sz_vals));
+    uint32_t* part_start = reinterpret_cast<uint32_t*>(carve(sz_vals));
+    uint32_t* hist = reinterpret_cast<uint32_t*>(carve(sz_hist));
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeAsync(slab, ctx->stream);
+        return rc;
+    };
+    cudaError_t e = cudaMemcpyAsync(keys[0], keys_host, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return fail(svb_fail(ctx, SVB_ERR_CUDA, "svb_form_partitions upload", e));
+    int cur_buf = 0;
+    {
+        KernelTimer timer(ctx, SVB_K_SORT);
+        iota_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(vals[0], n);
+        ctx->launches += 1;
+        for (uint32_t shift = 0; shift < 64; shift += 8) {
+            radix_hist_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], n, shift, hist, n_blocks);
+            int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, ctx->d_counters + 9);
+            if (rc != SVB_OK) return fail(rc);
+            radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], vals[cur_buf], keys[cur_buf ^ 1], vals[cur_buf ^ 1], n,
+                                                                           shift, hist, n_blocks);
+            cur_buf ^= 1;
+            ctx->launches += 2;
+        }
+        heads_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], n, max_distance, head);
+        ctx->launches += 1;
+        int rc = launch_scan_u32(ctx, head, n, ctx->d_counters + 2);
+        if (rc != SVB_OK) return fail(rc);
+        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, max_distance, part_start, ctx->d_counters + 2);
+        ctx->launches += 1;
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(order_out, vals[cur_buf], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part_start_out, part_start, sizeof(uint32_t) * (static_cast<size_t>(n) + 1), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(svb_fail(ctx, SVB_ERR_CUDA, "svb_form_partitions", e));
+    *n_parts_out = static_cast<uint32_t>(ctx->h_pinned[2]);
+    cudaFreeAsync(slab, ctx->stream);
     return SVB_OK;
 }
 

@@ -501,6 +501,16 @@ class Engine(object):
                                           len(pairs), _lib.ptr(out)))
         return out
 
+    def form_partitions(self, keys, max_distance):
+        """svb_form_partitions: (order, part_start) of the stable key sort + the consecutive-gap split (SVIM_COMBINE.py:15-32)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = keys.shape[0]
+        order, part_start = np.zeros(n, dtype=np.uint32), np.zeros(n + 1, dtype=np.uint32)
+        n_parts = ctypes.c_uint32()
+        self._check(lib.svb_form_partitions(self.handle, _lib.ptr(keys), n, int(max_distance), _lib.ptr(order), _lib.ptr(part_start),
+                                            ctypes.byref(n_parts)))
+        return order, part_start[:n_parts.value + 1].copy()
+
     def cluster_labels(self, condensed_list, threshold):
         n_points = []
         for d in condensed_list:

@@ -61,3 +61,51 @@ def test_reference_bam_fixtures_on_gpu(engine, stem):
         rows = engine.collect(rec, make_params(min_sv_size=int(min_sv))).to_numpy()
         got = [util.canon_row(r, {0: host}, host.contig_names) for r in rows]
         assert got == _as_tuples(z.expected[min_sv])
+
+
+def _permuted_contigs(rb, perm):
+    """The same alignments in a BAM whose header lists the contigs in another order (records re-sorted by the new tid)."""
+    from svim_asm_b200 import synth
+    new_tid_of = np.zeros(len(perm), dtype=np.int32)
+    new_tid_of[np.asarray(perm)] = np.arange(len(perm), dtype=np.int32)           # old tid -> new tid
+    order = np.argsort(new_tid_of[rb.tid], kind="stable")
+    sub = rb.subset(order)
+    return synth.RecordBatch([rb.contig_names[t] for t in perm], np.asarray(rb.contig_lengths)[list(perm)].astype(np.int32),
+                             new_tid_of[sub.tid], sub.pos, sub.flag, sub.mapq, sub.n_cigar, sub.cigar_off, sub.l_seq, sub.seq_off,
+                             sub.cigar, sub.seq4, sub.names, sub.sa)
+
+
+def test_second_bam_with_another_contig_order(tmp_path, built_library):
+    """The reference pairs by contig NAME and takes the lengths from the first BAM (SVIM_COMBINE.py:164-366): a second BAM
+    whose @SQ lines come in another order must give the same VCF (rows carry tids of their own file)."""
+    from svim_asm_b200 import bamio, synth
+    cfg = synth.SynthConfig(["chr1", "chr10", "chr2"], [300000, 200000, 250000], 60, 4e4, 515, sv_per_event=8e-3,
+                            split_fraction=0.5, sv_max=900)
+    rb1, rb2 = synth.make_diploid(cfg)
+    ref = synth.random_reference(cfg)
+    d = tmp_path / "in"
+    d.mkdir()
+    bamio.write_fasta(str(d / "ref.fa"), ref, cfg.contig_names)
+    bamio.write_bam(str(d / "h1.bam"), rb1)
+    bamio.write_bam(str(d / "h2.bam"), rb2)
+    bamio.write_bam(str(d / "h2p.bam"), _permuted_contigs(rb2, [2, 0, 1]))
+    same = _run(tmp_path / "a", ["diploid", str(d / "h1.bam"), str(d / "h2.bam"), str(d / "ref.fa"), "--query_names"])
+    perm = _run(tmp_path / "b", ["diploid", str(d / "h1.bam"), str(d / "h2p.bam"), str(d / "ref.fa"), "--query_names"])
+    assert same.count("\n") > 60
+    assert perm == same
+
+
+def test_fasta_without_a_contig_that_carries_candidates(tmp_path, built_library):
+    """reference.fetch raises KeyError for a contig the FASTA lacks (SVIM_COMBINE.py:48); the device copy must not read it
+    as an empty contig."""
+    from svim_asm_b200 import bamio, cli, synth
+    cfg = synth.SynthConfig(["chr1", "chr2"], [200000, 150000], 40, 3e4, 616, sv_per_event=8e-3, split_fraction=0.3, sv_max=600)
+    rb1, rb2 = synth.make_diploid(cfg)
+    ref = synth.random_reference(cfg)
+    d = tmp_path / "in"
+    d.mkdir()
+    bamio.write_fasta(str(d / "ref.fa"), ref, ["chr1"])
+    bamio.write_bam(str(d / "h1.bam"), rb1)
+    bamio.write_bam(str(d / "h2.bam"), rb2)
+    with pytest.raises(KeyError):
+        cli.main(["diploid", str(tmp_path / "out"), str(d / "h1.bam"), str(d / "h2.bam"), str(d / "ref.fa")])
