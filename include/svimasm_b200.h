@@ -111,13 +111,6 @@ typedef struct {
     uint64_t reserved0;
 } svb_row;
 
-/* Kernel timings accumulated since svb_timing_reset(): CUDA events on the library's stream. */
-enum { SVB_K_CIGAR_SCAN = 0, SVB_K_SEGMENT_WALK = 1, SVB_K_MERGE = 2, SVB_K_SORT = 3, SVB_K_EDIT_DISTANCE = 4,
-       SVB_K_CLUSTER = 5, SVB_K_SCAN_FINALIZE = 6, SVB_K_VCF = 7, SVB_K_COUNT = 8 };
-typedef struct {
-    double ms[SVB_K_COUNT];
-    uint64_t launches[SVB_K_COUNT];
-} svb_timing;
 
 typedef struct svb_ctx svb_ctx;
 typedef struct svb_records svb_records;   /* one BAM file (one haplotype) resident in HBM */
@@ -131,14 +124,6 @@ int svb_create(int device, svb_ctx** out);
 void svb_destroy(svb_ctx* ctx);
 const char* svb_last_error(const svb_ctx* ctx);          /* valid until the next call on ctx */
 int svb_synchronize(svb_ctx* ctx);
-int svb_timing_reset(svb_ctx* ctx);
-int svb_timing_get(svb_ctx* ctx, svb_timing* out);       /* synchronises the stream first */
-int svb_set_scan_variant(svb_ctx* ctx, int variant);      /* cigar_scan loads: 0 = per-warp TMA bulk-copy ring (default), 1 = LDG.128.nc */
-/* Step timing on the library's own stream: record marker `slot` (0..15) now; elapsed ms between two markers
- * (synchronises on the later one).  bench.py brackets its timed region with these. */
-int svb_launch_count(svb_ctx* ctx, uint64_t* out);       /* kernels this context has launched so far */
-int svb_mark(svb_ctx* ctx, int slot);
-int svb_elapsed_ms(svb_ctx* ctx, int slot_begin, int slot_end, double* ms);
 
 /* ---- host ingest: replaces pysam.AlignmentFile / bam.fetch (svim-asm:63,85-86; SVIM_COLLECT.py:62-65)
  * and retrieve_other_alignments (SVIM_COLLECT.py:8-58). Pure host code (zlib inflate, thread pool). */
@@ -174,10 +159,6 @@ int svb_parse_sa(const char* sa_text, const char* const* contig_names, int32_t n
 int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, const int32_t* contig_lexrank,
                         svb_bam** bam_out, svb_records** rec_out, char* err, int err_len);
 int svb_bam_materialize_host(svb_ctx* ctx, svb_bam* bam, const svb_records* rec, int what);   /* what: 1 CIGAR ops, 2 query bases, 3 both */
-/* ms of the last svb_bam_open_device call: [0] file read, [1] H2D, [2] inflate kernel, [3] record chase,
- * [4] field + copy kernels, [5] host SA parse + record image, [6] total wall, [7] inflated bytes,
- * [8] resident inflate CTAs per SM, [9] mean clock cycles per BGZF member, [10] members */
-const double* svb_bam_device_timings(void);
 
 /* ---- device: replaces analyze_alignment_file_coordsorted (SVIM_COLLECT.py:61-83) and below ---- */
 int svb_load_records(svb_ctx* ctx, const svb_aln_hdr* hdr, uint32_t n_aln, const uint32_t* cigar,
@@ -203,8 +184,6 @@ int svb_ref_load(svb_ctx* ctx, const uint8_t* bases, const uint64_t* contig_off,
  * one kernel drops the line terminators and upper-cases.  fai: n_contig rows {length, offset, linebases, linewidth} of
  * the .fai index in BAM header order; length 0 marks a contig that the FASTA does not hold. */
 int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int32_t n_contig, svb_ref** out);
-/* the resident reference back on the host (tests): bases (may be NULL), their count, the 256-entry symbol-class map */
-int svb_ref_to_host(svb_ctx* ctx, const svb_ref* ref, uint8_t* bases_dst, uint64_t cap, uint64_t* n_bases, uint8_t* class_map256_dst);
 void svb_ref_free(svb_ref* ref);
 
 /* pair_candidates (SVIM_COMBINE.py:164-366): form_partitions + compute_distance + pair_haplotypes(_breakends).
@@ -220,11 +199,16 @@ int svb_pair(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_r
 int svb_form_partitions(svb_ctx* ctx, const uint64_t* keys, uint32_t n, int64_t max_distance, uint32_t* order,
                         uint32_t* part_start, uint32_t* n_parts);
 
-/* compute_distance for explicit strings (edlib.align(a,b)["editDistance"], SVIM_COMBINE.py:50): test hook of K8. */
+/* compute_distance for explicit strings (edlib.align(a,b)["editDistance"], SVIM_COMBINE.py:50): one pair of compute_distance (python seam). */
 int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
                       uint32_t n_pairs, int64_t* out);
+/* The same with edlib's k parameter (edlib.align(a, b, k=max_distance)): out[i] = the distance if it is <= max_distance,
+ * else -1.  This is the question pair_haplotypes asks of most pairs (fcluster(Z, max_edit_distance, 'distance'),
+ * SVIM_COMBINE.py:135): it runs the thresholded wavefront kernel svb_pair uses (O(max_distance^2 + length) per pair). */
+int svb_edit_distance_bounded(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
+                              uint32_t n_pairs, int64_t max_distance, int64_t* out);
 /* scipy linkage(method="complete") + fcluster(t, "distance") labels for n <= 32 points given condensed
- * distances (SVIM_COMBINE.py:134-135, SVIM_inter.py:47-48): test hook of K9. */
+ * distances (SVIM_COMBINE.py:134-135, SVIM_inter.py:47-48): pair_haplotypes[_breakends] (python seams). */
 int svb_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,
                        double threshold, int32_t* labels_out /* 32 per problem */);
 

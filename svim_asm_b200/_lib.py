@@ -42,7 +42,7 @@ ROW_DTYPE = np.dtype([("type", "u1"), ("flags", "u1"), ("genotype", "u1"), ("hap
                       ("mate_aln", "<u4"), ("ordinal", "<u8"), ("reserved0", "<u8")])
 assert HDR_DTYPE.itemsize == 32 and SEG_DTYPE.itemsize == 32 and ROW_DTYPE.itemsize == 64
 
-# every symbol include/svimasm_b200.h declares: name -> (restype, argtypes)
+# every symbol include/svimasm_b200.h and include/svimasm_b200_debug.h declare: name -> (restype, argtypes)
 SIGNATURES = {
     "svb_abi_version": (c_int, []),
     "svb_create": (c_int, [c_int, P(c_void_p)]),
@@ -75,7 +75,7 @@ SIGNATURES = {
     "svb_parse_sa": (c_int, [c_char_p, P(c_char_p), c_i32, c_void_p, c_i32]),
     "svb_bam_open_device": (c_int, [c_void_p, c_char_p, c_int, c_void_p, P(c_void_p), P(c_void_p), c_char_p, c_int]),
     "svb_bam_materialize_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
-    "svb_bam_device_timings": (c_void_p, []),
+    "svb_bam_device_timings": (c_int, [c_void_p, c_void_p]),
     "svb_load_records": (c_int, [c_void_p, c_void_p, c_u32, c_void_p, c_u64, c_void_p, c_void_p, c_u32, c_void_p,
                                  c_void_p, c_i32, P(c_void_p)]),
     "svb_records_free": (None, [c_void_p]),
@@ -88,7 +88,9 @@ SIGNATURES = {
     "svb_ref_free": (None, [c_void_p]),
     "svb_pair": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(c_void_p)]),
     "svb_edit_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_void_p]),
+    "svb_edit_distance_bounded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_i64, c_void_p]),
     "svb_form_partitions": (c_int, [c_void_p, c_void_p, c_u32, c_i64, c_void_p, c_void_p, P(c_u32)]),
+    "svb_pair_stats": (c_int, [c_void_p, c_void_p]),
     "svb_cluster_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_u32, c_double, c_void_p]),
     "svb_table_size": (c_i64, [c_void_p]),
     "svb_table_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, P(c_u64)]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvimasm_b200.so")
-SOURCES = ["capi.cu", "cigar_scan.cu", "segment_walk.cu", "pair.cu", "edit_distance.cu", "seqpool.cu", "exchange.cu", "bam_device.cu", "fasta_device.cu", "vcf_device.cu", "file_upload.cu", "bam_ingest.cpp"]
+SOURCES = ["capi.cu", "cigar_scan.cu", "segment_walk.cu", "pair.cu", "edit_distance.cu", "wfa.cu", "seqpool.cu", "exchange.cu", "bam_device.cu", "fasta_device.cu", "vcf_device.cu", "file_upload.cu", "bam_ingest.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--threads", "4"]
 

@@ -312,8 +312,12 @@ struct Cleanup {                 // frees whatever was allocated when the functi
 extern "C" {
 
 // timings of the last svb_bam_open_device call (ms): read file, H2D, inflate, chase, fields + copy, host parse, total
-static double g_ingest_ms[12] = {0};   // [8] resident inflate CTAs per SM, [9] mean cycles per member, [10] members
-const double* svb_bam_device_timings(void) { return g_ingest_ms; }
+// (kept per context: two contexts ingesting at the same time do not share a buffer)
+int svb_bam_device_timings(svb_ctx* ctx, double out[12]) {
+    if (!ctx || !out) return SVB_ERR_ARG;
+    for (int i = 0; i < 12; ++i) out[i] = ctx->ingest_ms[i];
+    return SVB_OK;
+}
 
 int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, const int32_t* contig_lexrank_or_null, svb_bam** bam_out,
                         svb_records** rec_out, char* err, int err_len) {
@@ -601,17 +605,17 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
     float f = 0.f;
-    g_ingest_ms[0] = ms(wall0, wall_read);
-    g_ingest_ms[1] = h2d_ms;                 // host wall clock: parallel pread + staged copies (file_upload.cu)
-    cudaEventElapsedTime(&f, ev[1], ev[2]); g_ingest_ms[2] = f;
-    cudaEventElapsedTime(&f, ev[3], ev[4]); g_ingest_ms[3] = f;
-    cudaEventElapsedTime(&f, ev[4], ev[5]); g_ingest_ms[4] = f;
-    g_ingest_ms[5] = ms(wall_dev, wall_end);
-    g_ingest_ms[6] = ms(wall0, wall_end);
-    g_ingest_ms[7] = static_cast<double>(total_out);
-    g_ingest_ms[8] = inflate_ctas_per_sm;
-    g_ingest_ms[9] = n_members ? static_cast<double>(inflate_cycles) / n_members : 0.0;
-    g_ingest_ms[10] = n_members;
+    ctx->ingest_ms[0] = ms(wall0, wall_read);
+    ctx->ingest_ms[1] = h2d_ms;                 // host wall clock: parallel pread + staged copies (file_upload.cu)
+    cudaEventElapsedTime(&f, ev[1], ev[2]); ctx->ingest_ms[2] = f;
+    cudaEventElapsedTime(&f, ev[3], ev[4]); ctx->ingest_ms[3] = f;
+    cudaEventElapsedTime(&f, ev[4], ev[5]); ctx->ingest_ms[4] = f;
+    ctx->ingest_ms[5] = ms(wall_dev, wall_end);
+    ctx->ingest_ms[6] = ms(wall0, wall_end);
+    ctx->ingest_ms[7] = static_cast<double>(total_out);
+    ctx->ingest_ms[8] = inflate_ctas_per_sm;
+    ctx->ingest_ms[9] = n_members ? static_cast<double>(inflate_cycles) / n_members : 0.0;
+    ctx->ingest_ms[10] = n_members;
     for (auto& e : ev) cudaEventDestroy(e);
 #undef ING_CUDA
     *bam_out = bam_owner.release();

@@ -1,6 +1,7 @@
 // C-ABI glue of libsvimasm_b200.so (include/svimasm_b200.h): context, uploads, collect, tables.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -89,6 +90,10 @@ int svb_create(int device, svb_ctx** out) {
     if (!ctx) return SVB_ERR_NOMEM;
     ctx->device = device;
     memset(&ctx->timing, 0, sizeof ctx->timing);
+    if (const char* env = getenv("SVB_ED_STRIDE")) {          // test hook: a small slice exercises the grow-and-repeat path
+        const long long v = atoll(env);
+        if (v > 0) ctx->ed_stride = static_cast<uint64_t>(v);
+    }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
@@ -197,6 +202,12 @@ int svb_elapsed_ms(svb_ctx* ctx, int slot_begin, int slot_end, double* ms) {
 int svb_launch_count(svb_ctx* ctx, uint64_t* out) {
     if (!ctx || !out) return SVB_ERR_ARG;
     *out = ctx->launches;
+    return SVB_OK;
+}
+
+int svb_pair_stats(svb_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return SVB_ERR_ARG;
+    for (int i = 0; i < 4; ++i) out[i] = ctx->last_pair_stats[i];
     return SVB_OK;
 }
 
@@ -621,7 +632,15 @@ int svb_edit_distance(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, con
                       uint32_t n_pairs, int64_t* out) {
     if (!ctx || !a_off || !b_off || (n_pairs && !out)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_edit_distance") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
-    return run_edit_distance_strings(ctx, a, a_off, b, b_off, n_pairs, out);
+    return run_edit_distance_strings(ctx, a, a_off, b, b_off, n_pairs, -1, out);
+}
+
+int svb_edit_distance_bounded(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
+                              uint32_t n_pairs, int64_t max_distance, int64_t* out) {
+    if (!ctx || !a_off || !b_off || (n_pairs && !out) || max_distance < 0)
+        return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_edit_distance_bounded") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return run_edit_distance_strings(ctx, a, a_off, b, b_off, n_pairs, max_distance, out);
 }
 
 int svb_form_partitions(svb_ctx* ctx, const uint64_t* keys, uint32_t n, int64_t max_distance, uint32_t* order,

@@ -826,11 +826,12 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_r
         KernelTimer timer(ctx, SVB_K_CIGAR_SCAN);           // the streaming kernel alone (the roofline's launch duration)
         if (ctx->scan_variant == 0) {
             const size_t smem = static_cast<size_t>(WARPS) * STAGES * CHUNK4 * sizeof(uint4);
-            static bool attr_set = false;
-            if (!attr_set) {
+            // function attributes are per DEVICE: remembered per context (one context per device), not per process
+            constexpr int slot = G == 2 ? 0 : G == 4 ? 1 : G == 8 ? 2 : G == 16 ? 3 : G == 32 ? 4 : G == 64 ? 5 : 6;
+            if (!ctx->scan_attr_set[slot]) {
                 SVB_CUDA(ctx, cudaFuncSetAttribute(cigar_scan_kernel<true, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    static_cast<int>(smem)));
-                attr_set = true;
+                ctx->scan_attr_set[slot] = true;
             }
             cigar_scan_kernel<true, G><<<blocks, THREADS, smem, ctx->stream>>>(a);
         } else {

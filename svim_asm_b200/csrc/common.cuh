@@ -5,7 +5,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/svimasm_b200.h"
+#include "../../include/svimasm_b200_debug.h"
 
 // ---- device image of one BAM file -----------------------------------------------------------
 // cigar: BAM-packed ops (len << 4 | op) as uint4 (4 ops = 16 B); every alignment's run starts on
@@ -81,6 +81,11 @@ struct svb_ctx {
     unsigned long long* h_pinned = nullptr;     // 64-word pinned readback area
     uint8_t* h_text = nullptr;        // grow-only pinned buffer the VCF body is returned in (vcf_device.cu)
     size_t h_text_cap = 0;
+    bool wfa_attr_set = false;        // cudaFuncSetAttribute is per device: one flag per context, not per process
+    bool scan_attr_set[8] = {};
+    uint64_t ed_stride = 512u * 1024u; // bytes per worker warp for parked bottom-row deltas of the exact edit-distance kernel (grows on demand)
+    uint64_t last_pair_stats[4] = {};  // partitions, cross-haplotype pairs, pairs that needed the exact kernel (last svb_pair)
+    double ingest_ms[12] = {};        // stage times of the last svb_bam_open_device on this context (svb_bam_device_timings)
     void* uploader = nullptr;         // pinned staging slots + streams of upload_file_range (file_upload.cu)
 };
 
@@ -129,7 +134,7 @@ int launch_merge_tables(svb_ctx* ctx, const svb_row* a, uint64_t na, const svb_r
 int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
                 const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);
 int run_edit_distance_strings(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b,
-                              const uint64_t* b_off, uint32_t n_pairs, int64_t* out);
+                              const uint64_t* b_off, uint32_t n_pairs, int64_t max_distance, int64_t* out);
 int run_form_partitions(svb_ctx* ctx, const uint64_t* keys_host, uint32_t n, int64_t max_distance, uint32_t* order_out,
                         uint32_t* part_start_out, uint32_t* n_parts_out);
 int run_cluster_labels(svb_ctx* ctx, const double* condensed, const uint32_t* n_points, uint32_t n_problems,

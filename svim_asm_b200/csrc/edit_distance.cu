@@ -21,12 +21,13 @@
 #include "common.cuh"
 #include "edit_core.cuh"
 #include "pairing.cuh"
+#include "edit_strings.cuh"
+#include "wfa_core.cuh"
 
 namespace {
+using namespace edstr;
 
 constexpr int ED_WARPS = 2;
-constexpr uint32_t ED_NOCLASS = ED_NCLASS;      // extra all-zero row of the match-mask table: "matches nothing"
-constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t ED_SENTINEL = ED_NCLASS + 1;   // padding symbol of window_pass32: matches only itself
 constexpr uint32_t ED_SKIP = ED_NCLASS + 2;       // "no row here" while match masks are built
 constexpr uint32_t PEQ_ROWS = ED_NCLASS + 2;
@@ -46,108 +47,6 @@ struct EdShared {
     uint32_t cta_job, cta_worker;
     uint32_t trim[2];
 };
-
-__device__ __forceinline__ uint32_t tok_class(const uint8_t* cls2, uint32_t byte, uint32_t mode) {
-    uint32_t c;
-    if (mode >= TOK_NIB_HI) c = (mode == TOK_NIB_HI) ? (byte >> 4) : (byte & 15u);      // class i == nt16 code i
-    else c = cls2[mode * 256u + byte];
-    return min(c, ED_NOCLASS);
-}
-
-// A run of `count` consecutive positions starting at `first` (ascending) that lies inside ONE linearly stored piece of the
-// virtual string: the left / right reference slice, a reference middle (DUP_INT) or the 4-bit inserted bases.  Returns
-// false when the run touches a piece boundary or a reverse-complemented / repeated middle (the caller then takes the
-// general per-position path).  On success position first + k is byte `base[(nib0 + k) >> shift]`, nibble parity
-// (nib0 + k) & 1 when shift == 1.
-struct LinearRun {
-    const uint8_t* base;
-    uint64_t nib0;          // shift == 1: nibble index of the first position; shift == 0: unused (0)
-    uint32_t shift;         // 0: one byte per position (reference), 1: two positions per byte (4-bit query bases)
-};
-__device__ __forceinline__ bool linear_run(const HapDesc& d, uint32_t first, uint32_t count, const uint8_t* ref, const uint8_t* sa,
-                                           const uint8_t* sb, LinearRun& out) {
-    out.nib0 = 0;
-    out.shift = 0;
-    if (first + count <= d.l_len) {
-        out.base = ref + d.l_base + first;
-        return true;
-    }
-    if (first < d.l_len) return false;
-    const uint32_t im = first - d.l_len;
-    if (im + count <= d.m_len) {
-        if (d.m_kind == HAP_MID_SEQ4) {
-            out.base = d.seq_sel ? sb : sa;
-            out.nib0 = d.m_base + im;
-            out.shift = 1;
-            return true;
-        }
-        if (d.m_kind == HAP_MID_REF) {
-            out.base = ref + d.m_base + im;
-            return true;
-        }
-        return false;
-    }
-    if (im < d.m_len) return false;
-    out.base = ref + d.r_base + (im - d.m_len);
-    return true;
-}
-
-// Length of the common prefix (REVERSED = false) or suffix of the two strings, at most `lim`, given that the first
-// `start` positions are known to agree; 128 positions per round so that four loads per string are in flight (eight per
-// string were measured slower).  Rounds that stay inside one linearly stored piece of both strings (nearly all of them)
-// address their bytes directly instead of walking the piece table per position.
-template <bool REVERSED>
-__device__ __forceinline__ uint32_t common_run(const HapDesc& A, const HapDesc& B, uint32_t la, uint32_t lb, uint32_t lim,
-                                               const uint8_t* ref, const uint8_t* sa, const uint8_t* sb, const uint8_t* cls2,
-                                               uint32_t lane, uint32_t start = 0u) {
-    constexpr int U = 4;
-    uint32_t run = start;
-    bool done = false;
-    while (run < lim && !done) {
-        uint32_t ba[U], ma[U], bb[U], mb[U];
-        LinearRun ra, rb;
-        const bool whole = run + 32u * U <= lim;         // a full round: positions run .. run + 127 of both strings
-        // ascending position of the round's LAST element when scanning backwards, of its first otherwise
-        const uint32_t fa = REVERSED ? la - run - 32u * U : run, fb = REVERSED ? lb - run - 32u * U : run;
-        if (whole && linear_run(A, fa, 32u * U, ref, sa, sb, ra) && linear_run(B, fb, 32u * U, ref, sa, sb, rb)) {
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const uint32_t off = REVERSED ? 32u * U - 1u - (32u * k + lane) : 32u * k + lane;     // offset inside the run
-                const uint64_t na = ra.nib0 + off, nb = rb.nib0 + off;
-                ba[k] = ra.shift ? ra.base[na >> 1] : ra.base[off];
-                bb[k] = rb.shift ? rb.base[nb >> 1] : rb.base[off];
-                ma[k] = ra.shift ? TOK_NIB_HI + static_cast<uint32_t>(na & 1ull) : TOK_REF;
-                mb[k] = rb.shift ? TOK_NIB_HI + static_cast<uint32_t>(nb & 1ull) : TOK_REF;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const uint32_t i = run + 32u * k + lane;
-                ma[k] = mb[k] = TOK_NONE;
-                ba[k] = bb[k] = 0u;
-                if (i < lim) {
-                    ba[k] = hap_fetch(A, REVERSED ? la - 1u - i : i, ref, sa, sb, ma[k]);
-                    bb[k] = hap_fetch(B, REVERSED ? lb - 1u - i : i, ref, sa, sb, mb[k]);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            bool same = false;
-            if (ma[k] != TOK_NONE) {
-                const uint32_t ca = tok_class(cls2, ba[k], ma[k]);
-                same = ca < ED_NOCLASS && ca == tok_class(cls2, bb[k], mb[k]);
-            }
-            const uint32_t mask = __ballot_sync(FULL, same);
-            if (!done && mask != FULL) {
-                run += 32u * k + static_cast<uint32_t>(__ffs(~mask) - 1);
-                done = true;
-            }
-        }
-        if (!done) run += 32u * U;
-    }
-    return min(run, lim);
-}
 
 // ---- sliding window (edit_core.cuh): ONE pass of n + (m-1)/64 steps over a band of half-width K ------------------
 // Lane l works on the blocks l, l + 32, l + 64, ... one after the other; at global step t the lane that holds block b
@@ -541,16 +440,21 @@ __device__ __forceinline__ long long window_pass32(const HapDesc& P, const HapDe
     return window_core32<false>(P, T, pre, m0, n0, K, ref, sa, sb, cls2tab, peq_mem, tcls, lane, 0u, 0u, false, nullptr);
 }
 
-__global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const EditJob* __restrict__ jobs, uint32_t n_jobs,
+__global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const EditJob* __restrict__ jobs,
+                                                                       const uint32_t* __restrict__ job_list,
+                                                                       const unsigned long long* __restrict__ n_list_dev,
                                                                        unsigned int* next_job,
                                                                        const uint8_t* __restrict__ ref,
                                                                        const uint8_t* __restrict__ seq4_a,
                                                                        const uint8_t* __restrict__ seq4_b,
                                                                        const uint8_t* __restrict__ class_map,
                                                                        uint8_t* hbuf_pool, uint64_t hbuf_stride,
-                                                                       double* __restrict__ out, uint4* __restrict__ profile,
-                                                                       unsigned int* sm_tokens) {
+                                                                       double* __restrict__ out, double* __restrict__ out_hi,
+                                                                       uint4* __restrict__ profile,
+                                                                       unsigned int* sm_tokens, unsigned long long* need) {
     __shared__ EdShared sh;
+    const uint32_t n_jobs = static_cast<uint32_t>(*n_list_dev);
+    if (n_jobs == 0u) return;                         // the usual case: the wavefront kernel settled every pair
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
         sh.cls2[i] = class_map[i];
@@ -559,7 +463,6 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
     // the maskless steady state lets lanes without a block read ring slots no refill has written yet: any class <= 32 is fine
     for (uint32_t i = threadIdx.x; i < ED_WARPS * 128u; i += blockDim.x) (&sh.tcls[0][0])[i] = static_cast<uint8_t>(ED_NOCLASS);
     __syncthreads();
-    uint8_t* hbuf = hbuf_pool ? hbuf_pool + (static_cast<uint64_t>(blockIdx.x) * ED_WARPS + warp) * hbuf_stride : nullptr;
     unsigned long long (*peq)[32] = sh.peq[warp][0];                          // the striped path works in buffer 0
     uint32_t* peq32 = reinterpret_cast<uint32_t*>(&sh.peq[warp][0][0][0]);    // [class][lane][half]
     uint8_t* tcls = sh.tcls[warp];
@@ -571,18 +474,18 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
     // millisecond), so at most ONE warp per SM sub-partition works on it: the first warp that claims the token of its
     // (SM, scheduler) pair.  The others start with the short jobs right away.
     // (CTA level: both warps of a worker CTA take the SAME long job, one half each, see below)
+    // Only the workers run tables of several stripes, so only they own a slice of the parked-delta pool (slot = order of
+    // winning a token; at most two per SM).
     if (threadIdx.x == 0) {
-        uint32_t won = 1u;
-        if (sm_tokens) {
-            uint32_t smid, warpid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
-            won = atomicExch(sm_tokens + ((smid & 1023u) * 4u + ((warpid >> 1) & 1u)), 1u) == 0u ? 1u : 0u;
-        }
-        sh.cta_worker = won;
+        uint32_t smid, warpid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+        const bool won = atomicExch(sm_tokens + ((smid & 1023u) * 4u + ((warpid >> 1) & 1u)), 1u) == 0u;
+        sh.cta_worker = won ? 1u + atomicAdd(next_job + 4, 1u) : 0u;
     }
     __syncthreads();
     const bool long_worker = sh.cta_worker != 0u;
+    uint8_t* hbuf = long_worker ? hbuf_pool + (static_cast<uint64_t>(sh.cta_worker - 1u) * ED_WARPS + warp) * hbuf_stride : nullptr;
     // Long pairs are handed out longest first (three size classes of the longer string, one pass over the job list each):
     // with 2 worker CTAs per SM the makespan is max(longest pair, total / workers) only if the big ones start early.
     for (int pass = long_worker ? 0 : 3; pass < 4; ++pass) {
@@ -599,7 +502,7 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                 job_id = __shfl_sync(FULL, job_id, 0);
             }
             if (job_id >= n_jobs) break;
-            const EditJob job = jobs[job_id];
+            const EditJob job = jobs[job_list[job_id]];
             const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
             const uint32_t longer = max(la0, lb0);      // classes: >= 8192, >= 4096, > 2048 (one stripe), the rest
             if ((longer >= 8192u ? 0 : longer >= 4096u ? 1 : longer > 2048u ? 2 : 3) != pass) continue;
@@ -764,6 +667,15 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                         force_full = true;
                     }
                 }
+            }
+            if (!done && m_s > 2048u && static_cast<uint64_t>(n_s) > hbuf_stride) {
+                // several stripes park one byte per text column: this pair needs a longer slice than the pool has.  It stays
+                // unknown (negative), the longest such text is reported and the host repeats the call with a larger stride.
+                if (lane == 0) {
+                    atomicMax(need, static_cast<unsigned long long>(n_s));
+                    out[job.out_index] = -2.0;
+                }
+                continue;
             }
             if (!done) {
                 // Ukkonen cut-off: an alignment of cost d stays on the diagonals [-d, (n - m) + d], so a band of
@@ -938,7 +850,10 @@ __global__ void __launch_bounds__(ED_WARPS * 32) edit_distance_kernel(const Edit
                 __syncthreads();
                 if (warp != 0) continue;
             }
-            if (lane == 0) out[job.out_index] = static_cast<double>(dist);
+            if (lane == 0) {
+                out[job.out_index] = static_cast<double>(dist);
+                out_hi[job.out_index] = static_cast<double>(dist);
+            }
             if (profile && lane == 0)      // SVB_ED_PROFILE: {trimmed pattern rows, trimmed text columns, column steps, cycles}
                 profile[job_id] = make_uint4(m, n, steps_total, static_cast<uint32_t>(clock64() - clock_begin));
         }
@@ -986,53 +901,78 @@ int build_class_map(const uint8_t* bases, uint64_t n, uint8_t* map256, std::stri
     return build_class_map_from_seen(seen, map256, why);
 }
 
-int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, uint32_t n_jobs, uint64_t max_text_multi_stripe,
-                         const uint8_t* d_ref, const uint8_t* d_seq4_a, const uint8_t* d_seq4_b, const uint8_t* d_class_map,
-                         double* d_out) {
-    if (!n_jobs) return SVB_OK;
-    const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((n_jobs + ED_WARPS - 1) / ED_WARPS,
-                                                                     static_cast<uint64_t>(ctx->sm_count) * 16));
+int launch_edit_distance(svb_ctx* ctx, const EditJob* d_jobs, const uint32_t* d_list, const unsigned long long* d_n_list,
+                         uint32_t max_jobs, const uint8_t* d_ref, const uint8_t* d_seq4_a, const uint8_t* d_seq4_b,
+                         const uint8_t* d_class_map, double* d_dist, double* d_dist_hi, unsigned long long* d_need) {
+    if (!max_jobs) return SVB_OK;
+    // persistent grid: two worker CTAs per SM for the long pairs plus two for the short ones; every CTA leaves at once when
+    // the list is empty (the count is read on the device: the host does not wait for it)
+    const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>((static_cast<uint64_t>(max_jobs) + ED_WARPS - 1) / ED_WARPS,
+                                                                     static_cast<uint64_t>(ctx->sm_count) * 4));
+    // parked bottom-row deltas of multi-stripe tables, one byte per text column, one slice per worker warp
+    const uint64_t stride = (std::max<uint64_t>(ctx->ed_stride, 2048) + 127) & ~127ull;
+    const uint64_t workers = std::min<uint64_t>(blocks, static_cast<uint64_t>(ctx->sm_count) * 2);
     uint8_t* hbuf = nullptr;
-    // parked bottom-row deltas of multi-stripe tables, one byte per text column: the longest text of a pair whose shorter
-    // string exceeds a stripe, and at least one stripe's worth (a short pattern against a long text is transposed, its text
-    // then is the short string)
-    const uint64_t stride = (std::max<uint64_t>(max_text_multi_stripe, 2048) + 127) & ~127ull;
-    SVB_CUDA(ctx, cudaMallocAsync(&hbuf, stride * blocks * ED_WARPS, ctx->stream));
-    // profiling aid: SVB_ED_PROFILE=<file> dumps one uint4 per job {rows, columns, column steps, SM cycles} of the launch
-    const char* profile_path = getenv("SVB_ED_PROFILE");
     uint4* d_profile = nullptr;
+    unsigned int* sm_tokens = nullptr;                 // one word per (SM, scheduler): who runs the long jobs; + counters
+    auto release = [&]() {
+        if (hbuf) cudaFreeAsync(hbuf, ctx->stream);
+        if (d_profile) cudaFreeAsync(d_profile, ctx->stream);
+        if (sm_tokens) cudaFreeAsync(sm_tokens, ctx->stream);
+    };
+#define ED_CUDA(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            release();                                                             \
+            return svb_fail(ctx, SVB_ERR_CUDA, #call, e__);                        \
+        }                                                                          \
+    } while (0)
+    ED_CUDA(cudaMallocAsync(&hbuf, stride * workers * ED_WARPS, ctx->stream));
+    // profiling aid: SVB_ED_PROFILE=<file> dumps one uint4 per listed job {rows, columns, column steps, SM cycles}
+    const char* profile_path = getenv("SVB_ED_PROFILE");
     if (profile_path) {
-        SVB_CUDA(ctx, cudaMallocAsync(&d_profile, sizeof(uint4) * n_jobs, ctx->stream));
-        SVB_CUDA(ctx, cudaMemsetAsync(d_profile, 0, sizeof(uint4) * n_jobs, ctx->stream));
+        ED_CUDA(cudaMallocAsync(&d_profile, sizeof(uint4) * max_jobs, ctx->stream));
+        ED_CUDA(cudaMemsetAsync(d_profile, 0, sizeof(uint4) * max_jobs, ctx->stream));
     }
-    unsigned int* sm_tokens = nullptr;                 // one word per (SM, scheduler): who runs the long jobs
-    SVB_CUDA(ctx, cudaMallocAsync(&sm_tokens, sizeof(unsigned int) * (4096 + 8), ctx->stream));      // + the four job counters
-    SVB_CUDA(ctx, cudaMemsetAsync(sm_tokens, 0, sizeof(unsigned int) * (4096 + 8), ctx->stream));
+    ED_CUDA(cudaMallocAsync(&sm_tokens, sizeof(unsigned int) * (4096 + 8), ctx->stream));      // + four pass counters, the worker counter
+    ED_CUDA(cudaMemsetAsync(sm_tokens, 0, sizeof(unsigned int) * (4096 + 8), ctx->stream));
     {
         KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
-        edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, n_jobs, sm_tokens + 4096,
-                                                                       d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_out, d_profile,
-                                                                       sm_tokens);
+        edit_distance_kernel<<<blocks, ED_WARPS * 32, 0, ctx->stream>>>(d_jobs, d_list, d_n_list, sm_tokens + 4096,
+                                                                       d_ref, d_seq4_a, d_seq4_b, d_class_map, hbuf, stride, d_dist, d_dist_hi,
+                                                                       d_profile, sm_tokens, d_need);
         ctx->launches += 1;
     }
-    SVB_CUDA(ctx, cudaFreeAsync(sm_tokens, ctx->stream));
-    SVB_CUDA(ctx, cudaGetLastError());
+    ED_CUDA(cudaGetLastError());
     if (d_profile) {
-        std::vector<uint4> h(n_jobs);
-        SVB_CUDA(ctx, cudaMemcpyAsync(h.data(), d_profile, sizeof(uint4) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
-        SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<uint4> h(max_jobs);
+        ED_CUDA(cudaMemcpyAsync(h.data(), d_profile, sizeof(uint4) * max_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+        ED_CUDA(cudaStreamSynchronize(ctx->stream));
         if (FILE* f = fopen(profile_path, "wb")) {
-            fwrite(h.data(), sizeof(uint4), n_jobs, f);
+            fwrite(h.data(), sizeof(uint4), max_jobs, f);
             fclose(f);
         }
-        cudaFreeAsync(d_profile, ctx->stream);
     }
-    if (hbuf) SVB_CUDA(ctx, cudaFreeAsync(hbuf, ctx->stream));
+#undef ED_CUDA
+    release();
     return SVB_OK;
 }
 
+// jobs whose wavefront pass did not settle them (dist < 0), or all jobs (bounded == 0) -> list for the exact kernel
+namespace {
+__global__ void list_jobs_kernel(const double* __restrict__ dist, uint32_t n, int only_unknown, uint32_t* __restrict__ list,
+                                 unsigned long long* __restrict__ count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!only_unknown || dist[i] < 0.0) list[atomicAdd(count, 1ull)] = i;
+}
+}  // namespace
+
+// max_distance < 0: exact distances (edlib.align(a, b)["editDistance"]).  max_distance >= 0: edlib's k parameter -- the
+// distance if it is <= max_distance, else -1 -- through the wavefront kernel (wfa.cu), the way svb_pair computes them.
 int run_edit_distance_strings(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_off, const uint8_t* b, const uint64_t* b_off,
-                              uint32_t n_pairs, int64_t* out) {
+                              uint32_t n_pairs, int64_t max_distance, int64_t* out) {
     if (!n_pairs) return SVB_OK;
     const uint64_t na = a_off[n_pairs], nb = b_off[n_pairs];
     std::vector<uint8_t> both(na + nb);
@@ -1051,39 +991,73 @@ int run_edit_distance_strings(svb_ctx* ctx, const uint8_t* a, const uint64_t* a_
                 map[c] = static_cast<uint8_t>(next++);
             }
     }
-    uint64_t max_multi = 0;
-    for (uint32_t i = 0; i < n_pairs; ++i) {
-        const uint64_t la = a_off[i + 1] - a_off[i], lb = b_off[i + 1] - b_off[i];
-        if (std::min(la, lb) > 2048) max_multi = std::max(max_multi, std::max(la, lb));
+    const bool bounded = max_distance >= 0 && max_distance <= static_cast<int64_t>(WFA_MAX_T);
+    unsigned char* slab = nullptr;
+    auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+    const size_t sz_bytes = align(std::max<uint64_t>(both.size(), 1)), sz_off = align(sizeof(uint64_t) * (n_pairs + 1));
+    const size_t sz_jobs = align(sizeof(EditJob) * n_pairs), sz_d = align(sizeof(double) * n_pairs), sz_list = align(sizeof(uint32_t) * n_pairs);
+    const size_t sz_big = align(sizeof(uint4) * n_pairs), sz_cnt = 256;
+    SVB_CUDA(ctx, cudaMallocAsync(&slab, sz_bytes + 256 + 2 * sz_off + sz_jobs + 2 * sz_d + sz_list + sz_big + sz_cnt, ctx->stream));
+    unsigned char* cur = slab;
+    auto carve = [&](size_t bytes) { unsigned char* q = cur; cur += bytes; return q; };
+    uint8_t* d_bytes = carve(sz_bytes);
+    uint8_t* d_map = carve(256);
+    uint64_t* d_aoff = reinterpret_cast<uint64_t*>(carve(sz_off));
+    uint64_t* d_boff = reinterpret_cast<uint64_t*>(carve(sz_off));
+    EditJob* d_jobs = reinterpret_cast<EditJob*>(carve(sz_jobs));
+    double* d_dist = reinterpret_cast<double*>(carve(sz_d));
+    double* d_hi = reinterpret_cast<double*>(carve(sz_d));
+    uint32_t* d_list = reinterpret_cast<uint32_t*>(carve(sz_list));
+    uint4* d_big = reinterpret_cast<uint4*>(carve(sz_big));
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(carve(sz_cnt));     // [0] n jobs, [1] list size, [2] need, [4..] wfa counters
+    auto fail = [&](int rc) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeAsync(slab, ctx->stream);
+        return rc;
+    };
+#define STR_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) return fail(svb_fail(ctx, SVB_ERR_CUDA, #call, e__));    \
+    } while (0)
+    std::vector<double> h(n_pairs), h_hi(n_pairs);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        unsigned long long h_cnt[32] = {0};
+        h_cnt[0] = n_pairs;
+        STR_CUDA(cudaMemcpyAsync(d_cnt, h_cnt, sz_cnt, cudaMemcpyHostToDevice, ctx->stream));
+        if (!both.empty()) STR_CUDA(cudaMemcpyAsync(d_bytes, both.data(), both.size(), cudaMemcpyHostToDevice, ctx->stream));
+        STR_CUDA(cudaMemcpyAsync(d_map, map, 256, cudaMemcpyHostToDevice, ctx->stream));
+        STR_CUDA(cudaMemcpyAsync(d_aoff, a_off, sizeof(uint64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
+        STR_CUDA(cudaMemcpyAsync(d_boff, b_off, sizeof(uint64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
+        make_string_jobs<<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(d_aoff, d_boff, na, n_pairs, d_jobs);
+        ctx->launches += 1;
+        if (bounded) {
+            WfaArgs w;
+            w.jobs = d_jobs; w.n_jobs_dev = d_cnt; w.counters = reinterpret_cast<unsigned int*>(d_cnt + 4);
+            w.big = d_big; w.big_cap = n_pairs; w.ref = d_bytes; w.seq4_a = nullptr; w.seq4_b = nullptr; w.class_map = d_map;
+            w.dist = d_dist; w.dist_hi = d_hi; w.t = static_cast<uint32_t>(max_distance); w.cap_chars = 0; w.stage = 0;
+            int rc = launch_wfa(ctx, w);
+            if (rc != SVB_OK) return fail(rc);
+        }
+        list_jobs_kernel<<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(d_dist, n_pairs, bounded ? 1 : 0, d_list, d_cnt + 1);
+        ctx->launches += 1;
+        STR_CUDA(cudaGetLastError());
+        int rc = launch_edit_distance(ctx, d_jobs, d_list, d_cnt + 1, n_pairs, d_bytes, nullptr, nullptr, d_map, d_dist, d_hi, d_cnt + 2);
+        if (rc != SVB_OK) return fail(rc);
+        STR_CUDA(cudaMemcpyAsync(h.data(), d_dist, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        STR_CUDA(cudaMemcpyAsync(h_hi.data(), d_hi, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        STR_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        STR_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_cnt[2] == 0) break;
+        if (attempt == 1) return fail(svb_fail(ctx, SVB_ERR_CAPACITY, "svb_edit_distance: parked-delta stride"));
+        ctx->ed_stride = h_cnt[2] + 4096;               // a multi-stripe table with a longer text than the slices: once more
     }
-    uint8_t *d_bytes = nullptr, *d_map = nullptr;
-    uint64_t *d_aoff = nullptr, *d_boff = nullptr;
-    EditJob* d_jobs = nullptr;
-    double* d_out = nullptr;
-    SVB_CUDA(ctx, cudaMallocAsync(&d_bytes, std::max<uint64_t>(both.size(), 1), ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_map, 256, ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_aoff, sizeof(uint64_t) * (n_pairs + 1), ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_boff, sizeof(uint64_t) * (n_pairs + 1), ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_jobs, sizeof(EditJob) * n_pairs, ctx->stream));
-    SVB_CUDA(ctx, cudaMallocAsync(&d_out, sizeof(double) * n_pairs, ctx->stream));
-    if (!both.empty()) SVB_CUDA(ctx, cudaMemcpyAsync(d_bytes, both.data(), both.size(), cudaMemcpyHostToDevice, ctx->stream));
-    SVB_CUDA(ctx, cudaMemcpyAsync(d_map, map, 256, cudaMemcpyHostToDevice, ctx->stream));
-    SVB_CUDA(ctx, cudaMemcpyAsync(d_aoff, a_off, sizeof(uint64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
-    SVB_CUDA(ctx, cudaMemcpyAsync(d_boff, b_off, sizeof(uint64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, ctx->stream));
-    make_string_jobs<<<(n_pairs + 127) / 128, 128, 0, ctx->stream>>>(d_aoff, d_boff, na, n_pairs, d_jobs);
-    ctx->launches += 1;
-    SVB_CUDA(ctx, cudaGetLastError());
-    int rc = launch_edit_distance(ctx, d_jobs, n_pairs, max_multi, d_bytes, nullptr, nullptr, d_map, d_out);
-    if (rc != SVB_OK) return rc;
-    std::vector<double> h(n_pairs);
-    SVB_CUDA(ctx, cudaMemcpyAsync(h.data(), d_out, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
-    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n_pairs; ++i) out[i] = static_cast<int64_t>(h[i]);
-    cudaFreeAsync(d_bytes, ctx->stream);
-    cudaFreeAsync(d_map, ctx->stream);
-    cudaFreeAsync(d_aoff, ctx->stream);
-    cudaFreeAsync(d_boff, ctx->stream);
-    cudaFreeAsync(d_jobs, ctx->stream);
-    cudaFreeAsync(d_out, ctx->stream);
+#undef STR_CUDA
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        const bool exact = h[i] == h_hi[i];
+        if (max_distance < 0) out[i] = static_cast<int64_t>(h[i]);
+        else out[i] = (exact && h[i] <= static_cast<double>(max_distance)) ? static_cast<int64_t>(h[i]) : -1;
+    }
+    cudaFreeAsync(slab, ctx->stream);
     return SVB_OK;
 }

@@ -14,6 +14,7 @@
 
 #include "pairing.cuh"
 #include "walk.cuh"
+#include "wfa_core.cuh"
 
 namespace {
 
@@ -25,18 +26,24 @@ struct PairArgs {
     const svb_row* rows;            // concatenated h1 ++ h2 (hap set)
     const uint32_t* order;          // sorted position -> index into rows
     const uint32_t* part_start;     // [n_parts + 1]
-    uint32_t n_parts;
+    const unsigned long long* n_parts_dev;   // number of partitions, on the device (the host does not wait for it)
+    uint32_t n_rows;                // h1 + h2: upper bound of the number of partitions
     const int32_t* contig_len;      // BAM header lengths (constructor clamps)
     const int32_t* contig_lexrank;
     int32_t n_contig;
     const uint64_t* ref_off;        // reference contig offsets (get_reference_length of the FASTA)
     int32_t ref_n_contig;
     double max_edit_distance;
-    double* dist;                   // [n_parts * PAIR_DIST_STRIDE]
+    double* dist;                   // per job: the distance, or the lower end of what is known about it (pairing.cuh)
+    double* dist_hi;                // per job: the upper end (== dist when exact)
+    uint32_t* job_slot;             // [partition * PAIR_DIST_STRIDE + condensed index] -> job
     EditJob* jobs;
     unsigned long long* job_count;
-    unsigned long long* max_multi;
-    uint32_t* counts;               // [n_parts + 1]
+    uint32_t* exact_list;           // jobs the exact kernel has to run
+    unsigned long long* exact_count;
+    unsigned long long* cell_count;  // sum of la x lb over the jobs: the full tables an exhaustive aligner would fill (bench.py)
+    int all_exact;                  // the wavefront kernel did not run (threshold too large): every job is exact
+    uint32_t* counts;               // [n_rows + 1]
     svb_row* out;
     uint32_t* dev_status;
 };
@@ -250,14 +257,68 @@ __global__ void enumerate_jobs_kernel(const PairArgs a, const unsigned long long
             EditJob job;
             make_desc(ri, lo, hi, a, job.a);
             make_desc(rj, lo, hi, a, job.b);
-            job.out_index = p * PAIR_DIST_STRIDE + static_cast<uint32_t>(link_cidx(static_cast<int>(n), static_cast<int>(i), static_cast<int>(j)));
-            job.pad = 0;
             const unsigned long long slot = atomicAdd(a.job_count, 1ull);
+            job.out_index = static_cast<uint32_t>(slot);
+            job.pad = 0;
             a.jobs[slot] = job;
-            const uint32_t la = hap_length(job.a), lb = hap_length(job.b);
-            if (min(la, lb) > 2048u) atomicMax(a.max_multi, static_cast<unsigned long long>(max(la, lb)));
+            atomicAdd(a.cell_count, static_cast<unsigned long long>(hap_length(job.a)) * hap_length(job.b));
+            a.job_slot[static_cast<size_t>(p) * PAIR_DIST_STRIDE + static_cast<uint32_t>(link_cidx(static_cast<int>(n), static_cast<int>(i), static_cast<int>(j)))] =
+                static_cast<uint32_t>(slot);
         }
     }
+}
+
+// Which pairs need their EXACT distance?  The wavefront kernel (wfa.cu) left, for every cross-haplotype pair, either the
+// distance (it is <= t), or an interval [lo, hi] above t, or "unknown".  Complete linkage + fcluster only COMPARE distances
+// (linkage.cuh), so the clustering is run once on the intervals: if no comparison's outcome depended on where inside their
+// intervals the far values lie, any representative (the cluster kernel uses `lo`) gives the labels of the true values and
+// nothing has to be computed.  A partition of two has a single pair above t: never.  A shared variant next to a private
+// one, or two shared variants close together: the far values only ever meet exact values below t or the
+// same-haplotype constant above every interval: never.  Two far pairs that are compared with each other (App. D's
+// A2, B, A, A3): their order decides scipy's labels, all far pairs of that partition go to the exact kernel.
+// One thread per partition.
+__global__ void resolve_kernel(const PairArgs a) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= static_cast<uint32_t>(*a.n_parts_dev)) return;
+    const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
+    if (n < 2u || n > static_cast<uint32_t>(PAIR_MAX)) return;
+    if (a.rows[a.order[first]].type == SVB_BND) return;
+    uint8_t hap[PAIR_MAX];
+    for (uint32_t i = 0; i < n; ++i) hap[i] = a.rows[a.order[first + i]].hap;
+    LinkInterval D[PAIR_DIST_STRIDE];
+    bool unknown = a.all_exact != 0, any_far = false;
+    int m = 0;
+    for (uint32_t i = 0; i + 1 < n; ++i)
+        for (uint32_t j = i + 1; j < n; ++j, ++m) {
+            LinkInterval v;
+            v.id = 0xFFFFFFFFu;
+            if (hap[i] == hap[j]) {
+                v.lo = v.hi = 1000000000.0;            // SVIM_COMBINE.py:40-41
+            } else {
+                v.id = a.job_slot[static_cast<size_t>(p) * PAIR_DIST_STRIDE + m];
+                if (a.all_exact) {
+                    v.lo = 0.0; v.hi = 1.0 / 0.0;
+                } else {
+                    v.lo = a.dist[v.id];
+                    v.hi = a.dist_hi[v.id];
+                }
+                if (v.lo < 0.0) unknown = true;
+                if (v.lo < v.hi) any_far = true;
+            }
+            D[m] = v;
+        }
+    if (!unknown && !any_far) return;
+    bool need = unknown;
+    if (!need && n > 2u) {
+        LinkInterval work[PAIR_DIST_STRIDE];
+        int labels[PAIR_MAX];
+        for (int x = 0; x < m; ++x) work[x] = D[x];
+        need = !link_labels_determined(static_cast<int>(n), work, a.max_edit_distance, labels);
+    }
+    if (!need) return;
+    for (int x = 0; x < m; ++x)
+        if (D[x].id != 0xFFFFFFFFu && (a.all_exact || D[x].lo < D[x].hi || D[x].lo < 0.0))
+            a.exact_list[atomicAdd(a.exact_count, 1ull)] = D[x].id;
 }
 
 // pair_candidates' per-cluster rules (SVIM_COMBINE.py:184-365) for one cluster of 1 or 2 members
@@ -288,7 +349,10 @@ __device__ void emit_cluster(const svb_row& first, const svb_row* second, const 
 template <bool WRITE>
 __global__ void __launch_bounds__(64) cluster_kernel(const PairArgs a) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.n_parts) return;
+    if (p >= static_cast<uint32_t>(*a.n_parts_dev)) {
+        if (!WRITE && p <= a.n_rows) a.counts[p] = 0u;          // the scan runs over the upper bound
+        return;
+    }
     const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
     uint32_t slot = WRITE ? a.counts[p] : 0u;
     uint32_t produced = 0;
@@ -317,7 +381,7 @@ __global__ void __launch_bounds__(64) cluster_kernel(const PairArgs a) {
                 } else if (ri.hap == rj.hap) {
                     d = 1000000000.0;                                                      // :40-41
                 } else {
-                    d = a.dist[static_cast<size_t>(p) * PAIR_DIST_STRIDE + m];
+                    d = a.dist[a.job_slot[static_cast<size_t>(p) * PAIR_DIST_STRIDE + m]];
                 }
                 D[m] = d;
             }
@@ -350,9 +414,12 @@ __global__ void __launch_bounds__(64) cluster_kernel(const PairArgs a) {
 
 }  // namespace
 
-int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1, const svb_records* rec2,
-                const svb_ref* ref, const svb_params* p, svb_table** out) {
+// One stream-ordered chain, ONE synchronisation at the end: every count the next kernel needs (partitions, jobs, pairs for
+// the exact kernel, output rows) stays on the device; grids cover the upper bound h1 + h2.
+static int run_pairing_once(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1, const svb_records* rec2,
+                            const svb_ref* ref, const svb_params* p, svb_table** out, unsigned long long* need_out) {
     *out = nullptr;
+    *need_out = 0;
     const uint64_t n64 = h1->n + h2->n;
     if (n64 >= 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "svb_pair: too many candidates");
     const uint32_t n1 = static_cast<uint32_t>(h1->n), n2 = static_cast<uint32_t>(h2->n), n = n1 + n2;
@@ -380,13 +447,15 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     while ((1u << rank_bits) < static_cast<uint32_t>(std::max(rec->n_contig, 1))) ++rank_bits;
     const uint32_t key_bits = 32u + rank_bits + 3u;
     const uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+    const uint32_t max_jobs = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(n) * 5 / 2 + 1, 0x7fffffffull));
 
     // one slab for everything that lives only during this call
     auto align = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
     const size_t sz_rows = align(sizeof(svb_row) * n), sz_keys = align(sizeof(unsigned long long) * n), sz_vals = align(sizeof(uint32_t) * n);
-    const size_t sz_hist = align(sizeof(uint32_t) * (256ull * n_blocks + 1)), sz_head = align(sizeof(uint32_t) * (static_cast<size_t>(n) + 1));
-    const size_t sz_dist = align(sizeof(double) * PAIR_DIST_STRIDE * n), sz_jobs = align(sizeof(EditJob) * (static_cast<size_t>(n) * 5 / 2 + 1));
-    const size_t total = sz_rows + 2 * sz_keys + 2 * sz_vals + sz_hist + 3 * sz_head + sz_dist + sz_jobs;
+    const size_t sz_hist = align(sizeof(uint32_t) * (256ull * n_blocks + 1)), sz_head = align(sizeof(uint32_t) * (static_cast<size_t>(n) + 2));
+    const size_t sz_slot = align(sizeof(uint32_t) * PAIR_DIST_STRIDE * n), sz_jobs = align(sizeof(EditJob) * max_jobs);
+    const size_t sz_dist = align(sizeof(double) * max_jobs), sz_list = align(sizeof(uint32_t) * max_jobs), sz_big = align(sizeof(uint4) * max_jobs);
+    const size_t total = sz_rows + 2 * sz_keys + 2 * sz_vals + sz_hist + 3 * sz_head + sz_slot + sz_jobs + 2 * sz_dist + sz_list + sz_big;
     unsigned char* slab = nullptr;
     if (cudaMallocAsync(&slab, total, ctx->stream) != cudaSuccess) { delete result; return svb_fail(ctx, SVB_ERR_NOMEM, "svb_pair: scratch"); }
     unsigned char* cur = slab;
@@ -398,8 +467,12 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     uint32_t* head = reinterpret_cast<uint32_t*>(carve(sz_head));
     uint32_t* part_start = reinterpret_cast<uint32_t*>(carve(sz_head));
     uint32_t* counts = reinterpret_cast<uint32_t*>(carve(sz_head));
-    double* dist = reinterpret_cast<double*>(carve(sz_dist));
+    uint32_t* job_slot = reinterpret_cast<uint32_t*>(carve(sz_slot));
     EditJob* jobs = reinterpret_cast<EditJob*>(carve(sz_jobs));
+    double* dist = reinterpret_cast<double*>(carve(sz_dist));
+    double* dist_hi = reinterpret_cast<double*>(carve(sz_dist));
+    uint32_t* exact_list = reinterpret_cast<uint32_t*>(carve(sz_list));
+    uint4* big = reinterpret_cast<uint4*>(carve(sz_big));
 
     auto fail = [&](int rc) {
         cudaStreamSynchronize(ctx->stream);
@@ -414,8 +487,11 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         if (e__ != cudaSuccess) return fail(svb_fail(ctx, SVB_ERR_CUDA, #call, e__));     \
     } while (0)
 
+    // device counters of this call: [2] partitions, [3] jobs, [4] pairs for the exact kernel, [5] output rows,
+    // [6] longest text the exact kernel could not park, [7..8] the wavefront kernel's three 32-bit counters
+    unsigned long long* cnt = ctx->d_counters;
+    PAIR_CUDA(cudaMemsetAsync(cnt + 2, 0, 9 * sizeof(unsigned long long), ctx->stream));      // [9] radix scan total, [10] table cells
     int cur_buf = 0;
-    uint32_t n_parts = 0;
     {
         KernelTimer timer(ctx, SVB_K_SORT);
         concat_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h1->d_rows, n1, h2->d_rows, n2, h1->d_pool_off, h2->d_pool_off,
@@ -425,7 +501,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         ctx->launches += 1;
         for (uint32_t shift = 0; shift < key_bits; shift += 8) {
             radix_hist_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], n, shift, hist, n_blocks);
-            int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, ctx->d_counters + 9);
+            int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, cnt + 9);
             if (rc != SVB_OK) return fail(rc);
             radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], vals[cur_buf], keys[cur_buf ^ 1], vals[cur_buf ^ 1], n,
                                                                            shift, hist, n_blocks);
@@ -434,7 +510,7 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
         }
         heads_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], n, p->partition_max_distance, head);
         ctx->launches += 1;
-        int rc = launch_scan_u32(ctx, head, n, ctx->d_counters + 2);
+        int rc = launch_scan_u32(ctx, head, n, cnt + 2);
         if (rc != SVB_OK) return fail(rc);
     }
     PAIR_CUDA(cudaGetLastError());
@@ -443,7 +519,8 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     a.rows = rows;
     a.order = vals[cur_buf];
     a.part_start = part_start;
-    a.n_parts = n_parts;
+    a.n_parts_dev = cnt + 2;
+    a.n_rows = n;
     a.contig_len = rec->d_contig_len;
     a.contig_lexrank = rec->d_contig_lexrank;
     a.n_contig = rec->n_contig;
@@ -451,40 +528,50 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     a.ref_n_contig = ref->n_contig;
     a.max_edit_distance = static_cast<double>(p->max_edit_distance);
     a.dist = dist;
+    a.dist_hi = dist_hi;
+    a.job_slot = job_slot;
     a.jobs = jobs;
-    a.job_count = ctx->d_counters + 3;
-    a.max_multi = ctx->d_counters + 4;
+    a.job_count = cnt + 3;
+    a.exact_list = exact_list;
+    a.exact_count = cnt + 4;
+    a.cell_count = cnt + 10;
+    a.all_exact = (p->max_edit_distance < 0 || static_cast<uint32_t>(p->max_edit_distance) > WFA_MAX_T) ? 1 : 0;
     a.counts = counts;
     a.out = nullptr;
     a.dev_status = ctx->d_status;
-    PAIR_CUDA(cudaMemsetAsync(ctx->d_counters + 3, 0, 2 * sizeof(unsigned long long), ctx->stream));
     {
         KernelTimer timer(ctx, SVB_K_SORT);
-        // the number of partitions (d_counters[2]) is still on its way: both kernels take it from the device and the
-        // grid covers the upper bound (one partition per row), so that ONE synchronisation returns all three counts
-        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start,
-                                                                    ctx->d_counters + 2);
-        enumerate_jobs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, ctx->d_counters + 2);
+        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start, cnt + 2);
+        enumerate_jobs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, cnt + 2);
         ctx->launches += 2;
     }
     PAIR_CUDA(cudaGetLastError());
-    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_counters + 2, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
-    n_parts = static_cast<uint32_t>(ctx->h_pinned[2]);
-    a.n_parts = n_parts;
-    const uint32_t n_jobs = static_cast<uint32_t>(ctx->h_pinned[3]);
-    const uint64_t max_multi = ctx->h_pinned[4];
-    if (n_jobs) {
-        // INS pairs read the 4-bit query bases of both haplotypes
-        int rc = launch_edit_distance(ctx, jobs, n_jobs, max_multi, ref->d_bases, h1->d_pool_off ? h1->d_pool : rec1->d_seq4,
-                                      h2->d_pool_off ? h2->d_pool : rec2->d_seq4, ref->d_class_map, dist);
+    // K8: thresholded wavefronts for every pair, then the exact kernel for the few pairs whose exact value can matter
+    const uint8_t* seq_a = h1->d_pool_off ? h1->d_pool : rec1->d_seq4;
+    const uint8_t* seq_b = h2->d_pool_off ? h2->d_pool : rec2->d_seq4;
+    if (!a.all_exact) {
+        WfaArgs w;
+        w.jobs = jobs; w.n_jobs_dev = cnt + 3; w.counters = reinterpret_cast<unsigned int*>(cnt + 7);
+        w.big = big; w.big_cap = max_jobs; w.ref = ref->d_bases; w.seq4_a = seq_a; w.seq4_b = seq_b; w.class_map = ref->d_class_map;
+        w.dist = dist; w.dist_hi = dist_hi; w.t = static_cast<uint32_t>(p->max_edit_distance); w.cap_chars = 0; w.stage = 0;
+        int rc = launch_wfa(ctx, w);
+        if (rc != SVB_OK) return fail(rc);
+    }
+    {
+        KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
+        resolve_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(a);
+        ctx->launches += 1;
+    }
+    PAIR_CUDA(cudaGetLastError());
+    {
+        int rc = launch_edit_distance(ctx, jobs, exact_list, cnt + 4, max_jobs, ref->d_bases, seq_a, seq_b, ref->d_class_map, dist, dist_hi, cnt + 6);
         if (rc != SVB_OK) return fail(rc);
     }
     {
         KernelTimer timer(ctx, SVB_K_CLUSTER);
-        cluster_kernel<false><<<(n_parts + 63) / 64, 64, 0, ctx->stream>>>(a);
+        cluster_kernel<false><<<(n + 64) / 64, 64, 0, ctx->stream>>>(a);
         ctx->launches += 1;
-        int rc = launch_scan_u32(ctx, counts, n_parts, ctx->d_counters + 5);
+        int rc = launch_scan_u32(ctx, counts, n, cnt + 5);
         if (rc != SVB_OK) return fail(rc);
     }
     PAIR_CUDA(cudaGetLastError());
@@ -495,16 +582,21 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
     a.out = result->d_rows;
     {
         KernelTimer timer(ctx, SVB_K_CLUSTER);
-        cluster_kernel<true><<<(n_parts + 63) / 64, 64, 0, ctx->stream>>>(a);
+        cluster_kernel<true><<<(n + 64) / 64, 64, 0, ctx->stream>>>(a);
         ctx->launches += 1;
     }
     PAIR_CUDA(cudaGetLastError());
-    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 5, ctx->d_counters + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, cnt + 2, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     uint32_t* h_status = reinterpret_cast<uint32_t*>(ctx->h_pinned + 12);      // the device error word rides along
     PAIR_CUDA(cudaMemcpyAsync(h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     PAIR_CUDA(cudaFreeAsync(slab, ctx->stream));
     PAIR_CUDA(cudaStreamSynchronize(ctx->stream));
     result->n = ctx->h_pinned[5];
+    ctx->last_pair_stats[0] = ctx->h_pinned[2];
+    ctx->last_pair_stats[1] = ctx->h_pinned[3];
+    ctx->last_pair_stats[2] = ctx->h_pinned[4];
+    ctx->last_pair_stats[3] = ctx->h_pinned[10];
+    *need_out = ctx->h_pinned[6];
     if (*h_status) {                       // svb_pair turns it into the reference's error (check_device_status)
         *out = result;
         return SVB_OK;
@@ -513,6 +605,20 @@ int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const sv
 #undef PAIR_CUDA
     *out = result;
     return SVB_OK;
+}
+
+int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1, const svb_records* rec2,
+                const svb_ref* ref, const svb_params* p, svb_table** out) {
+    for (int attempt = 0;; ++attempt) {
+        unsigned long long need = 0;
+        int rc = run_pairing_once(ctx, h1, h2, rec1, rec2, ref, p, out, &need);
+        if (rc != SVB_OK || need == 0) return rc;
+        // a multi-stripe table of the exact kernel had a text longer than a worker's slice of parked deltas (Mb-scale pair
+        // that the wavefront kernel could not settle): grow the slices and run the call again
+        if (*out) { svb_table_free(*out); *out = nullptr; }
+        if (attempt == 1) return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_pair: parked-delta stride");
+        ctx->ed_stride = need + 4096;
+    }
 }
 
 // ---- form_partitions for explicit keys (svb_form_partitions): the K6 sort + K7 split on caller-supplied keys ------

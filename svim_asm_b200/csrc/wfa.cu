@@ -1,0 +1,242 @@
+// K8a wfa -- THRESHOLDED edit distance of haplotype-string pairs: "is edlib.align(h1, h2)['editDistance'] <= t, and
+// if so what is it?", one CTA per pair.
+//
+// pair_haplotypes (reference SVIM_COMBINE.py:120-140) feeds compute_distance's values (:35-102) into complete linkage cut
+// at t = max_edit_distance.  Complete linkage is ordinal (nearest-neighbour chain, max, stable sort, `<= t`): a distance
+// above t is only ever COMPARED, so for a partition of two candidates -- 99 % of a diploid sample -- "more than t" is all
+// the clustering needs, and in larger partitions the exact value of a far pair matters only when it could tie or swap
+// with another far pair of the same partition (pair.cu: resolve_kernel sends exactly those to the exact kernel,
+// edit_distance.cu).  This kernel therefore computes furthest-reaching wavefronts (wfa_core.cuh) up to wave t:
+//   * common prefix / suffix stripped by two warps from both ends (most shared variants end here),
+//   * |la - lb| > t: far, nothing to compute,
+//   * the trimmed strings become symbol-class bytes in shared memory (sentinels behind both: no bounds checks),
+//   * wave s: one thread per diagonal (at most t + 1 after pruning), three shared-memory reads, a word-wise match
+//     extension of up to 32 symbols; a diagonal that is still matching after that (the optimal path of two similar
+//     haplotypes) is extended by the whole warp, 128 symbols per round; one barrier per wave doubles as the "done" vote.
+// Work per pair is O(t^2 + length) instead of O(length^2 / 64): the 10,000-base insertion pairs that were the critical
+// path of the exact kernel (0.5 ms for one warp) take tens of microseconds here.
+// Two launches of the same kernel: `stage 0` takes every job, trims it and runs the ones whose strings fit a small
+// shared-memory window (many CTAs per SM); the few that do not are queued, with their trim, for `stage 1` (one CTA per SM,
+// the whole 227 KB).  What fits neither is reported as unknown and goes to the exact kernel.
+#include <algorithm>
+
+#include "edit_strings.cuh"
+#include "wfa_core.cuh"
+
+namespace {
+using namespace edstr;
+
+constexpr int WFA_THREADS = 128;
+constexpr uint32_t WFA_SLACK = 160;               // readable bytes behind the second string (warp-wide extension reads ahead)
+
+struct WfaControl {
+    uint32_t job;
+    uint32_t trim[2];
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
+    extern __shared__ uint32_t smem_w[];
+    const int t = static_cast<int>(a.t), W = 2 * t + 7, mid = t + 3;
+    int* F0 = reinterpret_cast<int*>(smem_w);
+    int* F1 = F0 + W;
+    uint8_t* cls2 = reinterpret_cast<uint8_t*>(F1 + W);
+    WfaControl* ctl = reinterpret_cast<WfaControl*>(cls2 + 512);
+    uint32_t* Aw = reinterpret_cast<uint32_t*>(ctl + 1);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t i = tid; i < 256u; i += WFA_THREADS) {
+        cls2[i] = a.class_map[i];
+        cls2[256u + i] = a.class_map[hap_complement(static_cast<uint8_t>(i))];
+    }
+    const uint32_t n_jobs = a.stage == 0 ? static_cast<uint32_t>(*a.n_jobs_dev) : min(a.counters[1], a.big_cap);
+    while (true) {
+        __syncthreads();
+        if (tid == 0) ctl->job = atomicAdd(a.counters + (a.stage == 0 ? 0 : 2), 1u);
+        __syncthreads();
+        const uint32_t claim = ctl->job;
+        if (claim >= n_jobs) break;
+        uint32_t job_id = claim, pre = 0, suf = 0;
+        if (a.stage != 0) {
+            const uint4 e = a.big[claim];
+            job_id = e.x; pre = e.y; suf = e.z;
+        }
+        const EditJob job = a.jobs[job_id];
+        const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
+        if (a.stage == 0) {
+            // common prefix (warp 0) and suffix (warp 1) at the same time, each at most half of the shorter string; the side
+            // that ran into its half-way mark goes on if the other one stopped early
+            const uint32_t lim = min(la0, lb0), half = (lim + 1u) / 2u;
+            if (warp < 2u) {
+                const uint32_t r = warp == 0 ? common_run<false>(job.a, job.b, la0, lb0, half, a.ref, a.seq4_a, a.seq4_b, cls2, lane)
+                                             : common_run<true>(job.a, job.b, la0, lb0, lim - half, a.ref, a.seq4_a, a.seq4_b, cls2, lane);
+                if (lane == 0) ctl->trim[warp] = r;
+            }
+            __syncthreads();
+            pre = ctl->trim[0];
+            suf = ctl->trim[1];
+            __syncthreads();
+            if (pre == half && suf < lim - half) {
+                if (warp == 0) {
+                    const uint32_t r = common_run<false>(job.a, job.b, la0, lb0, lim - suf, a.ref, a.seq4_a, a.seq4_b, cls2, lane, half);
+                    if (lane == 0) ctl->trim[0] = r;
+                }
+                __syncthreads();
+                pre = ctl->trim[0];
+            } else if (suf == lim - half && pre < half) {
+                if (warp == 0) {
+                    const uint32_t r = common_run<true>(job.a, job.b, la0, lb0, lim - pre, a.ref, a.seq4_a, a.seq4_b, cls2, lane, lim - half);
+                    if (lane == 0) ctl->trim[1] = r;
+                }
+                __syncthreads();
+                suf = ctl->trim[1];
+            }
+        }
+        const uint32_t la = la0 - pre - suf, lb = lb0 - pre - suf;
+        const uint32_t longer = max(la, lb), gap = la > lb ? la - lb : lb - la;
+        double lo, hi;
+        bool settled = true;
+        if (min(la, lb) == 0u) {                       // one string is a prefix + suffix of the other
+            lo = hi = static_cast<double>(longer);
+        } else if (gap > a.t) {                        // the distance is at least the length difference
+            lo = static_cast<double>(gap);
+            hi = static_cast<double>(longer);
+        } else {
+            settled = false;
+            lo = hi = 0.0;
+        }
+        if (settled) {
+            if (tid == 0) { a.dist[job.out_index] = lo; a.dist_hi[job.out_index] = hi; }
+            continue;
+        }
+        const uint32_t a_bytes = (la + WFA_PAD + 3u) & ~3u, b_bytes = (lb + WFA_PAD + 3u) & ~3u;
+        if (a_bytes + b_bytes + WFA_SLACK > a.cap_chars) {
+            if (tid == 0) {
+                bool queued = false;
+                if (a.stage == 0) {
+                    const uint32_t slot = atomicAdd(a.counters + 1, 1u);
+                    if (slot < a.big_cap) { a.big[slot] = make_uint4(job_id, pre, suf, 0u); queued = true; }
+                }
+                if (!queued) { a.dist[job.out_index] = -1.0; a.dist_hi[job.out_index] = static_cast<double>(longer); }      // unknown: exact kernel
+            }
+            continue;
+        }
+        // ---- the trimmed strings as class bytes in shared memory
+        uint32_t* Bw = Aw + a_bytes / 4u;
+        uint8_t* As = reinterpret_cast<uint8_t*>(Aw);
+        uint8_t* Bs = reinterpret_cast<uint8_t*>(Bw);
+        for (uint32_t i0 = 0; i0 < longer; i0 += 4u * WFA_THREADS) {
+            uint32_t ba[4], ma[4], bb[4], mb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * WFA_THREADS + tid;
+                ma[u] = mb[u] = TOK_NONE;
+                ba[u] = bb[u] = 0u;
+                if (i < la) ba[u] = hap_fetch(job.a, pre + i, a.ref, a.seq4_a, a.seq4_b, ma[u]);
+                if (i < lb) bb[u] = hap_fetch(job.b, pre + i, a.ref, a.seq4_a, a.seq4_b, mb[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + u * WFA_THREADS + tid;
+                if (i < la) {
+                    const uint32_t c = tok_class(cls2, ba[u], ma[u]);
+                    As[i] = c < ED_NOCLASS ? static_cast<uint8_t>(c) : WFA_NOCLASS_A;
+                }
+                if (i < lb) {
+                    const uint32_t c = tok_class(cls2, bb[u], mb[u]);
+                    Bs[i] = c < ED_NOCLASS ? static_cast<uint8_t>(c) : WFA_NOCLASS_B;
+                }
+            }
+        }
+        for (uint32_t i = la + tid; i < a_bytes; i += WFA_THREADS) As[i] = WFA_END_A;
+        for (uint32_t i = lb + tid; i < b_bytes + WFA_SLACK; i += WFA_THREADS) Bs[i] = WFA_END_B;
+        for (int x = static_cast<int>(tid); x < 2 * W; x += WFA_THREADS) F0[x] = WFA_NEG;
+        __syncthreads();
+
+        // ---- waves
+        const int ila = static_cast<int>(la), ilb = static_cast<int>(lb), kd = ilb - ila;
+        int* prev = F0;
+        int* cur = F1;
+        int result = -1;
+        for (int s = 0; s <= t; ++s) {
+            int klo, khi;
+            wfa_range(s, t, kd, ila, ilb, klo, khi);
+            int found = 0;
+            for (int base = klo; base <= khi; base += WFA_THREADS) {
+                const int k = base + static_cast<int>(tid);
+                const bool active = k <= khi;
+                int v = WFA_NEG;
+                bool more = false;
+                if (active) {
+                    v = s == 0 ? 0 : wfa_next(prev[mid + k - 1], prev[mid + k], prev[mid + k + 1], k, ila, ilb);
+                    if (v > WFA_NEG / 2) v += static_cast<int>(wfa_extend(Aw, Bw, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), 32u, &more));
+                }
+                // a diagonal that is still matching: the whole warp goes on, 128 symbols per round
+                uint32_t pending = __ballot_sync(FULL, more);
+                while (pending) {
+                    const int src = __ffs(static_cast<int>(pending)) - 1;
+                    pending &= pending - 1u;
+                    const uint32_t i0 = static_cast<uint32_t>(__shfl_sync(FULL, v, src));
+                    const uint32_t j0 = i0 + static_cast<uint32_t>(__shfl_sync(FULL, k, src));
+                    uint32_t run = 0;
+                    while (true) {
+                        const uint32_t x = wfa_load4(Aw, i0 + run + 4u * lane) ^ wfa_load4(Bw, j0 + run + 4u * lane);
+                        const uint32_t bal = __ballot_sync(FULL, x != 0u);
+                        if (bal) {
+                            const int f = __ffs(static_cast<int>(bal)) - 1;
+                            const uint32_t xf = __shfl_sync(FULL, x, f);
+                            run += 4u * static_cast<uint32_t>(f) + wfa_first_diff(xf);
+                            break;
+                        }
+                        run += 128u;
+                    }
+                    if (static_cast<int>(lane) == src) v = static_cast<int>(i0 + run);
+                }
+                if (active) {
+                    cur[mid + k] = v;
+                    if (k == kd && v >= ila) found = 1;
+                }
+            }
+            if (tid == 0) {            // the next wave reads one diagonal beyond this range on either side
+                cur[mid + klo - 1] = cur[mid + klo - 2] = WFA_NEG;
+                cur[mid + khi + 1] = cur[mid + khi + 2] = WFA_NEG;
+            }
+            if (__syncthreads_or(found)) {
+                result = s;
+                break;
+            }
+            int* tmp = prev; prev = cur; cur = tmp;
+        }
+        if (tid == 0) {
+            if (result >= 0) {
+                a.dist[job.out_index] = a.dist_hi[job.out_index] = static_cast<double>(result);
+            } else {                                   // more than t edits: only bounds are known
+                a.dist[job.out_index] = static_cast<double>(a.t + 1u);
+                a.dist_hi[job.out_index] = static_cast<double>(longer);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// counters: [0] next job of stage 0, [1] size of the queue for stage 1, [2] next job of stage 1 (zeroed by the caller)
+int launch_wfa(svb_ctx* ctx, WfaArgs a) {
+    if (a.t > WFA_MAX_T) return svb_fail(ctx, SVB_ERR_ARG, "launch_wfa: threshold too large");
+    const size_t fixed = sizeof(int) * 2u * (2u * a.t + 7u) + 512u + sizeof(WfaControl);
+    const size_t small = fixed + 24u * 1024u;          // pairs of up to about 12,000 trimmed symbols each: 7-8 CTAs per SM
+    const size_t big = 227u * 1024u - 1024u;           // the rest, one CTA per SM
+    if (!ctx->wfa_attr_set) {                          // per context = per device (function attributes are per device)
+        SVB_CUDA(ctx, cudaFuncSetAttribute(wfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big)));
+        ctx->wfa_attr_set = true;
+    }
+    KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
+    a.stage = 0;
+    a.cap_chars = static_cast<uint32_t>(small - fixed);
+    wfa_kernel<<<static_cast<unsigned>(ctx->sm_count) * 7u, WFA_THREADS, small, ctx->stream>>>(a);
+    a.stage = 1;
+    a.cap_chars = static_cast<uint32_t>(big - fixed);
+    wfa_kernel<<<static_cast<unsigned>(ctx->sm_count), WFA_THREADS, big, ctx->stream>>>(a);
+    ctx->launches += 2;
+    SVB_CUDA(ctx, cudaGetLastError());
+    return SVB_OK;
+}

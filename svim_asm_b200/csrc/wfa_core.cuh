@@ -1,0 +1,106 @@
+// K8 core of the THRESHOLDED edit distance: furthest-reaching wavefronts (Myers 1986 O(ND) / Ukkonen 1985).
+//
+// pair_haplotypes clusters a partition by complete linkage cut at max_edit_distance (reference SVIM_COMBINE.py:120-140,
+// fcluster(Z, t, 'distance')).  Complete linkage only compares distances, so for most pairs the only question is
+// "d <= t, and if so which value?": wave s holds, for every diagonal k = j - i, the furthest row i reachable with s
+// edits; the distance is the first s whose wave reaches (la, lb), and after wave t the answer is "more than t" without
+// ever touching the rest of the table.  Cost O(t^2 + la) instead of O(la * lb / 64): a 10,000-base pair of haplotypes
+// that differ by 500 edits stops after 200 waves of at most 201 diagonals.
+//
+// Building blocks shared by the device kernel (wfa.cu: one CTA per pair, diagonals across the threads) and the host
+// build (tests/hostcheck: serial driver checked against a plain DP).  Strings are symbol-class bytes followed by
+// WFA_PAD sentinel bytes (different for the two strings), so the match extension needs no bounds checks.
+#pragma once
+#include <stdint.h>
+
+#include "linkage.cuh"   // SVB_HD
+
+constexpr int WFA_NEG = -(1 << 29);              // "diagonal not reached"
+constexpr uint32_t WFA_PAD = 8;                  // sentinel bytes behind each string (word-wise extension reads ahead)
+constexpr uint8_t WFA_END_A = 0xFD, WFA_END_B = 0xFC, WFA_NOCLASS_A = 0xFB, WFA_NOCLASS_B = 0xFA;
+constexpr uint32_t WFA_MAX_T = 1024;             // thresholds above this take the exact kernel (t^2 work stops paying)
+
+SVB_HD int wfa_imax(int a, int b) { return a > b ? a : b; }
+SVB_HD int wfa_imin(int a, int b) { return a < b ? a : b; }
+
+// Diagonals wave s has to compute: reachable with s edits (|k| <= s), still able to reach the end diagonal kd = lb - la with
+// the t - s edits that remain, inside the table.  A diagonal outside this range is never read by a later wave's range.
+SVB_HD void wfa_range(int s, int t, int kd, int la, int lb, int& klo, int& khi) {
+    klo = wfa_imax(wfa_imax(-s, kd - (t - s)), -la);
+    khi = wfa_imin(wfa_imin(s, kd + (t - s)), lb);
+}
+
+// Furthest row on diagonal k after one more edit, from the previous wave's rows on k - 1, k, k + 1:
+//   substitution (k): (i, j) -> (i + 1, j + 1);  insertion (from k - 1): (i, j) -> (i, j + 1);  deletion (from k + 1): (i, j) -> (i + 1, j)
+// A move that leaves the table is not made.
+SVB_HD int wfa_next(int fm1, int f0, int fp1, int k, int la, int lb) {
+    int v = WFA_NEG;
+    if (f0 > WFA_NEG / 2 && f0 + 1 <= la && f0 + 1 + k <= lb) v = f0 + 1;
+    if (fm1 > WFA_NEG / 2 && fm1 + k <= lb) v = wfa_imax(v, fm1);
+    if (fp1 > WFA_NEG / 2 && fp1 + 1 <= la) v = wfa_imax(v, fp1 + 1);
+    return v;
+}
+
+// four bytes starting at byte offset `off` of a word-aligned buffer (little endian)
+SVB_HD uint32_t wfa_load4(const uint32_t* w, uint32_t off) {
+    const uint32_t idx = off >> 2, sh = (off & 3u) * 8u;
+    const uint32_t lo = w[idx], hi = w[idx + 1u];
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+
+SVB_HD uint32_t wfa_first_diff(uint32_t x) {     // index of the lowest non-zero byte of x (x != 0)
+#ifdef __CUDA_ARCH__
+    return (static_cast<uint32_t>(__ffs(static_cast<int>(x))) - 1u) >> 3;
+#else
+    uint32_t n = 0;
+    while (!(x & 0xFFu)) { x >>= 8; ++n; }
+    return n;
+#endif
+}
+
+// Slide down the diagonal while the strings agree, at most `limit` symbols (a multiple of 4).  Returns the number of
+// matching symbols; `*more` is set when the limit was reached with every symbol matching (the caller goes on, in the
+// kernel with the whole warp).  The sentinels behind the strings end every run.
+SVB_HD uint32_t wfa_extend(const uint32_t* A, const uint32_t* B, uint32_t i, uint32_t j, uint32_t limit, bool* more) {
+    uint32_t run = 0;
+    *more = false;
+    while (run < limit) {
+        const uint32_t x = wfa_load4(A, i + run) ^ wfa_load4(B, j + run);
+        if (x) return run + wfa_first_diff(x);
+        run += 4u;
+    }
+    *more = true;
+    return run;
+}
+
+// Serial driver (host check, and the specification of what the kernel computes): the distance if it is <= t, else -1.
+// A, B: word-aligned class bytes with sentinels; F0, F1: 2 t + 7 ints each.
+SVB_HD long long wfa_distance_serial(const uint32_t* A, int la, const uint32_t* B, int lb, int t, int* F0, int* F1) {
+    const int kd = lb - la, W = 2 * t + 7, mid = t + 3;
+    if ((kd < 0 ? -kd : kd) > t) return -1;
+    for (int x = 0; x < W; ++x) F0[x] = F1[x] = WFA_NEG;
+    int* prev = F0;
+    int* cur = F1;
+    for (int s = 0; s <= t; ++s) {
+        int klo, khi;
+        wfa_range(s, t, kd, la, lb, klo, khi);
+        for (int k = klo; k <= khi; ++k) {
+            int v = s == 0 ? 0 : wfa_next(prev[mid + k - 1], prev[mid + k], prev[mid + k + 1], k, la, lb);
+            if (v > WFA_NEG / 2) {
+                bool more = true;
+                while (more) v += static_cast<int>(wfa_extend(A, B, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), 32u, &more));
+            }
+            cur[mid + k] = v;
+            if (k == kd && v >= la) return s;
+        }
+        // the next wave reads one diagonal beyond this range on either side
+        cur[mid + klo - 1] = cur[mid + klo - 2] = WFA_NEG;
+        cur[mid + khi + 1] = cur[mid + khi + 2] = WFA_NEG;
+        int* tmp = prev; prev = cur; cur = tmp;
+    }
+    return -1;
+}

@@ -431,8 +431,8 @@ class Engine(object):
 
     def ingest_timings(self):
         """ms of the last device ingest: file read, H2D, inflate, record chase, fields + copy, host parse, total; inflated bytes."""
-        addr = lib.svb_bam_device_timings()
-        v = np.frombuffer((ctypes.c_char * 88).from_address(addr), dtype=np.float64, count=11).copy()
+        v = np.zeros(12, dtype=np.float64)
+        self._check(lib.svb_bam_device_timings(self.handle, _lib.ptr(v)))
         keys = ("read_file", "h2d", "inflate", "chase", "fields_copy", "host_parse", "total", "inflated_bytes",
                 "inflate_ctas_per_sm", "inflate_cycles_per_member", "members")
         return dict(zip(keys, (float(x) for x in v)))
@@ -488,8 +488,9 @@ class Engine(object):
                                         ctypes.byref(n)))
         return [(int(r[0]), int(r[1]), int(r[2]), "DEL" if r[3] else "INS") for r in out[:n.value]]
 
-    def edit_distance(self, pairs):
-        """Unit-cost global edit distance of each (a, b) byte-string pair (edlib.align(a, b)['editDistance'])."""
+    def edit_distance(self, pairs, max_distance=None):
+        """Unit-cost global edit distance of each (a, b) byte-string pair (edlib.align(a, b)['editDistance']); with
+        max_distance = k: edlib.align(a, b, k=k), i.e. -1 where the distance exceeds k (thresholded wavefront kernel)."""
         a = b"".join(p[0] for p in pairs)
         b = b"".join(p[1] for p in pairs)
         a_off = np.cumsum([0] + [len(p[0]) for p in pairs]).astype(np.uint64)
@@ -497,8 +498,12 @@ class Engine(object):
         av = np.frombuffer(a, dtype=np.uint8) if a else np.zeros(0, dtype=np.uint8)
         bv = np.frombuffer(b, dtype=np.uint8) if b else np.zeros(0, dtype=np.uint8)
         out = np.zeros(len(pairs), dtype=np.int64)
-        self._check(lib.svb_edit_distance(self.handle, _lib.ptr(av), _lib.ptr(a_off), _lib.ptr(bv), _lib.ptr(b_off),
-                                          len(pairs), _lib.ptr(out)))
+        if max_distance is None:
+            self._check(lib.svb_edit_distance(self.handle, _lib.ptr(av), _lib.ptr(a_off), _lib.ptr(bv), _lib.ptr(b_off),
+                                              len(pairs), _lib.ptr(out)))
+        else:
+            self._check(lib.svb_edit_distance_bounded(self.handle, _lib.ptr(av), _lib.ptr(a_off), _lib.ptr(bv), _lib.ptr(b_off),
+                                                      len(pairs), int(max_distance), _lib.ptr(out)))
         return out
 
     def form_partitions(self, keys, max_distance):
@@ -568,6 +573,12 @@ class Engine(object):
         ms = buf[:_lib.SVB_K_COUNT].view(np.float64)
         launches = buf[_lib.SVB_K_COUNT:]
         return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(_lib.KERNEL_NAMES)}
+
+    def pair_stats(self):
+        """The last pair(): partitions, cross-haplotype pairs (edit-distance jobs), pairs that needed the exact kernel."""
+        v = np.zeros(4, dtype=np.uint64)
+        self._check(lib.svb_pair_stats(self.handle, _lib.ptr(v)))
+        return {"partitions": int(v[0]), "pairs": int(v[1]), "exact_pairs": int(v[2]), "table_cells": int(v[3])}
 
     def launch_count(self):
         n = ctypes.c_uint64()

@@ -13,6 +13,14 @@ extern "C" int hc_cluster_labels(const double* condensed, int n, double threshol
     return link_complete_fcluster(n, work, threshold, labels);
 }
 
+// The interval run of the linkage (pair.cu resolve_kernel): 1 when the labels are the same for every choice of values inside
+// [lo[i], hi[i]] (then written to `labels`), else 0.  Every non-degenerate interval is its own unknown (id = index).
+extern "C" int hc_labels_determined(const double* lo, const double* hi, int n, double threshold, int* labels) {
+    LinkInterval work[LINK_MAXN * (LINK_MAXN - 1) / 2];
+    for (int i = 0; i < n * (n - 1) / 2; ++i) { work[i].lo = lo[i]; work[i].hi = hi[i]; work[i].id = static_cast<uint32_t>(i); }
+    return link_labels_determined(n, work, threshold, labels) ? 1 : 0;
+}
+
 // segs: k rows of (q_start, q_end, tid, ref_start, ref_end, rev), primary first.  params: min_mapq,
 // min_sv, max_sv, qgt, qot, rgt, rot.  Returns the number of rows, or -(error bits) on a reference abort.
 extern "C" int hc_walk(const int32_t* segs, int k, int32_t read_len, uint32_t l_seq, const int32_t* params,
@@ -122,6 +130,20 @@ extern "C" long long hc_myers_window(const uint8_t* a, long long m64, const uint
     for (uint32_t l = 0; l < 32u; ++l) total += L[l].partial;
     return total;
 }
+#include "../../svim_asm_b200/csrc/wfa_core.cuh"
+// The thresholded wavefront distance of wfa.cu through its serial driver: strings as bytes (any value below 0xFA), padded
+// with the sentinels here.  Returns the distance if it is <= t, else -1 (what edlib.align(a, b, k=t) answers).
+extern "C" long long hc_wfa(const uint8_t* a, long long la, const uint8_t* b, long long lb, int t) {
+    std::vector<uint32_t> A((static_cast<size_t>(la) + WFA_PAD + 7) / 4 + 1, 0u), B((static_cast<size_t>(lb) + WFA_PAD + 7) / 4 + 1, 0u);
+    uint8_t* pa = reinterpret_cast<uint8_t*>(A.data());
+    uint8_t* pb = reinterpret_cast<uint8_t*>(B.data());
+    for (long long i = 0; i < la; ++i) pa[i] = a[i];
+    for (long long i = 0; i < lb; ++i) pb[i] = b[i];
+    for (uint32_t i = 0; i < WFA_PAD; ++i) { pa[la + i] = WFA_END_A; pb[lb + i] = WFA_END_B; }
+    std::vector<int> F0(2 * static_cast<size_t>(t) + 7), F1(2 * static_cast<size_t>(t) + 7);
+    return wfa_distance_serial(A.data(), static_cast<int>(la), B.data(), static_cast<int>(lb), t, F0.data(), F1.data());
+}
+
 extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return win_kmax(m, n, bw); }
 
 #include "../../svim_asm_b200/csrc/inflate_core.cuh"

@@ -7,8 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(built_library):
     from svim_asm_b200 import _lib
-    header = open(os.path.join(ROOT, "include", "svimasm_b200.h")).read()
-    declared = set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", header))
+    declared = set()
+    for name in ("svimasm_b200.h", "svimasm_b200_debug.h"):          # the drop-in surface + the measurement / test hooks
+        declared |= set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", name)).read()))
     assert declared, "no declarations found"
     for name in sorted(declared):
         assert hasattr(_lib.lib, name), "library does not export %s" % name

@@ -132,3 +132,33 @@ def test_split_window_meets_in_the_middle(oracle_clib, seed):
                 assert got == want, (len(p), len(t), K, got, want)
                 exact += 1
     assert exact > 8
+
+
+def test_wavefront_threshold_core_matches_plain_dp():
+    """wfa_core.cuh (the thresholded wavefront distance of wfa.cu) through its serial driver: the distance when it is <= t,
+    -1 otherwise; thresholds 0 .. 200, related / unrelated / empty / low-complexity strings."""
+    from oracle import port
+    lib = hostcheck.load()
+    rng = np.random.default_rng(5)
+    alphabet = list(b"ACGT")
+
+    def mutate(s, k):
+        b = list(s)
+        for _ in range(k):
+            kind, pos = int(rng.integers(0, 3)), int(rng.integers(0, max(1, len(b))))
+            if kind == 0 and b:
+                b[pos % len(b)] = int(rng.choice(alphabet))
+            elif kind == 1:
+                b.insert(pos, int(rng.choice(alphabet)))
+            elif b:
+                del b[pos % len(b)]
+        return bytes(b)
+    cases = [(b"A" * 500, b"A" * 490 + b"C" * 10, 20), (b"AC" * 300, b"CA" * 300, 5), (b"ACGT" * 100, b"ACGT" * 99, 4),
+             (b"A" * 100, b"A" * 100, 0), (b"", b"", 0), (b"", b"AAA", 3), (b"", b"AAA", 2), (b"AAA", b"", 3)]
+    for _ in range(1500):
+        a = bytes(rng.choice(alphabet, int(rng.integers(0, 400))).tolist())
+        b = mutate(a, int(rng.integers(0, 60))) if rng.random() < 0.7 else bytes(rng.choice(alphabet, int(rng.integers(0, 400))).tolist())
+        cases.append((a, b, int(rng.choice([0, 1, 5, 10, 30, 200]))))
+    for a, b, t in cases:
+        d = port.edit_distance(a, b)
+        assert lib.hc_wfa(a, len(a), b, len(b), t) == (d if d <= t else -1), (len(a), len(b), t, d)

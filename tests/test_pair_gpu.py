@@ -77,6 +77,74 @@ def test_edit_distance_long_patterns_window_and_stripes(engine, oracle_clib):
     assert got.tolist() == want
 
 
+def test_edit_distance_bounded_matches_plain_dp(engine, oracle_clib):
+    """svb_edit_distance_bounded = edlib.align(a, b, k=t): the thresholded wavefront kernel svb_pair runs on every pair
+    (wfa.cu).  Exact whenever the distance is <= t, -1 otherwise; every threshold the kernel accepts, distances at the
+    threshold, empty strings, low-complexity strings (many tied diagonals), length differences around t."""
+    rng = np.random.default_rng(29)
+    alphabet = list(b"ACGT")
+    pairs = [(b"", b""), (b"", b"ACGT"), (b"ACGT", b""), (b"kitten", b"sitting"), (b"A" * 64, b"A" * 64), (b"A" * 65, b"C" * 63),
+             (b"A" * 500, b"A" * 490 + b"C" * 10), (b"AC" * 300, b"CA" * 300), (b"ACGT" * 100, b"ACGT" * 99)]
+    for _ in range(400):
+        m = int(rng.integers(1, 900))
+        a = bytes(rng.choice(alphabet, m).tolist())
+        if rng.random() < 0.7:
+            b = _mutate(rng, a, int(rng.integers(0, 260)), alphabet)
+        else:
+            b = bytes(rng.choice(alphabet, int(rng.integers(1, 900))).tolist())
+        pairs.append((a, b))
+    want = [port.edit_distance(a, b) for a, b in pairs]
+    for t in (0, 1, 10, 200, 201, 1024):
+        got = engine.edit_distance(pairs, max_distance=t)
+        assert got.tolist() == [d if d <= t else -1 for d in want], t
+    d199 = [(a, b) for (a, b), d in zip(pairs, want) if 150 <= d <= 260]
+    assert len(d199) > 10                        # the cut itself is exercised (200 merges, 201 does not)
+
+
+def test_edit_distance_bounded_long_pairs(engine, oracle_clib):
+    """Long haplotype pairs: the whole-warp match extension, the one-CTA-per-SM stage for strings beyond the small
+    shared-memory window, and the hand-over to the exact kernel for strings beyond shared memory altogether."""
+    rng = np.random.default_rng(30)
+    alphabet = list(b"ACGT")
+    pairs = []
+    for m, edits in ((9900, 0), (9900, 3), (9900, 150), (9900, 199), (9900, 230), (9900, 520), (12500, 40), (30000, 120), (30000, 400),
+                     (60000, 90), (100000, 20), (130000, 15)):
+        a = bytes(rng.choice(alphabet + list(b"N"), m).tolist())
+        pairs.append((a, _mutate(rng, a, edits, alphabet)))
+    a = bytes(rng.choice(alphabet, 8000).tolist())
+    pairs.append((a, a[:4000] + bytes(rng.choice(alphabet, 150).tolist()) + a[4000:]))          # one 150-base insertion
+    pairs.append((a, a[:4000] + bytes(rng.choice(alphabet, 250).tolist()) + a[4000:]))          # length difference beyond t
+    pairs.append((bytes(rng.choice(alphabet, 5000).tolist()), bytes(rng.choice(alphabet, 5100).tolist())))      # unrelated
+    pairs.append((b"ACGT" * 3000, b"ACGT" * 2990 + b"TTTT" * 10))
+    want = []
+    for x, y in pairs:
+        want.append(port.edit_distance(x, y) if len(x) * len(y) <= 4e8 else None)
+    got = engine.edit_distance(pairs, max_distance=200)
+    exact = engine.edit_distance(pairs)
+    for g, e, w in zip(got.tolist(), exact.tolist(), want):
+        if w is not None:
+            assert e == w
+        assert g == (e if e <= 200 else -1)
+
+
+def test_edit_distance_parked_delta_stride_grows(built_library, oracle_clib, monkeypatch):
+    """A table of several stripes parks one byte per text column in a per-worker slice; a pair whose text is longer than
+    the slice makes the call grow the slices and run again (the pool no longer scales with the longest pair
+    times every CTA)."""
+    from svim_asm_b200.engine import Engine
+    monkeypatch.setenv("SVB_ED_STRIDE", "2048")
+    eng = Engine(0)
+    try:
+        rng = np.random.default_rng(31)
+        alphabet = list(b"ACGT")
+        pairs = [(bytes(rng.choice(alphabet, 5000).tolist()), bytes(rng.choice(alphabet, 4100).tolist())),
+                 (bytes(rng.choice(alphabet, 300).tolist()), bytes(rng.choice(alphabet, 280).tolist()))]
+        got = eng.edit_distance(pairs)
+        assert got.tolist() == [port.edit_distance(a, b) for a, b in pairs]
+    finally:
+        eng.close()
+
+
 def test_cluster_labels_match_scipy(engine):
     rng = np.random.default_rng(22)
     problems = []

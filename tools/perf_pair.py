@@ -25,19 +25,31 @@ params = make_params()
 tabs = [eng.collect(r, params, hap=k + 1) for k, r in enumerate(recs)]
 for _ in range(2):
     eng.pair(tabs[0], tabs[1], recs[0], recs[1], ref, params)
+eng.timing_reset()
+for _ in range(5):
+    eng.pair(tabs[0], tabs[1], recs[0], recs[1], ref, params)
+t = eng.timing()
+stats = eng.pair_stats()
+print("pair x5: K8 (wavefront x2 + resolve + exact kernel) %.3f ms per call, sort %.3f, cluster %.3f" % (
+    t["edit_distance"][0] / 5, t["sort"][0] / 5, t["cluster"][0] / 5))
+print("pair stats: %(partitions)d partitions, %(pairs)d cross-haplotype pairs, %(exact_pairs)d needed the exact kernel, "
+      "%(table_cells).3g full-table cells" % stats)
+print("K8: %.3g equivalent cell updates per second" % (stats["table_cells"] / (t["edit_distance"][0] / 5 * 1e-3)))
 path = "/tmp/ed_profile.bin"
 os.environ["SVB_ED_PROFILE"] = path
 eng.timing_reset()
 eng.pair(tabs[0], tabs[1], recs[0], recs[1], ref, params)
 del os.environ["SVB_ED_PROFILE"]
+if not os.path.exists(path) or stats["exact_pairs"] == 0:
+    print("no pair went to the exact kernel")
+    sys.exit(0)
 prof = np.fromfile(path, dtype=np.uint32).reshape(-1, 4)
+prof = prof[prof[:, 3] > 0]
 np.save(args.out, prof)
-print("edit_distance launch: %.3f ms (with the profile writes), %d jobs" % (eng.timing()["edit_distance"][0], prof.shape[0]))
+print("exact kernel: %d jobs" % prof.shape[0])
 cyc = prof[:, 3].astype(np.float64)
 print("sum of job cycles %.3g, max %.3g (%.3f ms at 1.9 GHz)" % (cyc.sum(), cyc.max(), cyc.max() / 1.9e6))
 print("   rows   cols  steps   cycles  cyc/step")
 for i in np.argsort(-cyc)[:25]:
     m, n, st, c = (int(x) for x in prof[i])
     print("%7d %6d %6d %8d %8.1f" % (m, n, st, c, c / max(st, 1)))
-no_dp = prof[:, 2] == 0
-print("jobs finished by trimming alone: %d, their max cycles %d" % (no_dp.sum(), prof[no_dp, 3].max() if no_dp.any() else 0))
