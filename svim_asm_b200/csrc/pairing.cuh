@@ -22,7 +22,7 @@ struct EditJob {
 struct WfaArgs {
     const EditJob* jobs;
     const unsigned long long* n_jobs_dev;
-    unsigned int* counters;          // [0] next job of stage 0, [1] jobs queued for stage 1, [2] next job of stage 1
+    unsigned int* counters;          // [0] next job of stage 0 (long pairs), [1] jobs queued for stage 1, [2] next job of stage 1, [3] next job of stage 0 (the rest)
     uint4* big;                      // stage-1 queue: {job, trimmed prefix, trimmed suffix, -}
     uint32_t big_cap;
     const uint8_t* ref;
@@ -34,6 +34,7 @@ struct WfaArgs {
     uint32_t t;                      // max_edit_distance
     uint32_t cap_chars;              // set by launch_wfa
     int stage;                       // set by launch_wfa
+    uint4* profile;                  // SVB_WFA_PROFILE: per job {trimmed la, trimmed lb, waves | stage << 16, cycles}; else NULL (set by launch_wfa)
 };
 int launch_wfa(svb_ctx* ctx, WfaArgs a);
 

@@ -19,6 +19,9 @@
 // shared-memory window (many CTAs per SM); the few that do not are queued, with their trim, for `stage 1` (one CTA per SM,
 // the whole 227 KB).  What fits neither is reported as unknown and goes to the exact kernel.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "edit_strings.cuh"
 #include "wfa_core.cuh"
@@ -49,19 +52,26 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
         cls2[256u + i] = a.class_map[hap_complement(static_cast<uint8_t>(i))];
     }
     const uint32_t n_jobs = a.stage == 0 ? static_cast<uint32_t>(*a.n_jobs_dev) : min(a.counters[1], a.big_cap);
+    // stage 0 goes over the job list twice: the long pairs first (a 200-wave pair claimed last would be the tail of the launch)
+    int pass = a.stage == 0 ? 0 : 1;
     while (true) {
         __syncthreads();
-        if (tid == 0) ctl->job = atomicAdd(a.counters + (a.stage == 0 ? 0 : 2), 1u);
+        if (tid == 0) ctl->job = atomicAdd(a.counters + (a.stage != 0 ? 2 : (pass == 0 ? 0 : 3)), 1u);
         __syncthreads();
         const uint32_t claim = ctl->job;
-        if (claim >= n_jobs) break;
+        if (claim >= n_jobs) {
+            if (a.stage == 0 && pass == 0) { pass = 1; continue; }
+            break;
+        }
         uint32_t job_id = claim, pre = 0, suf = 0;
         if (a.stage != 0) {
             const uint4 e = a.big[claim];
             job_id = e.x; pre = e.y; suf = e.z;
         }
         const EditJob job = a.jobs[job_id];
+        const long long clock_begin = a.profile ? clock64() : 0ll;
         const uint32_t la0 = hap_length(job.a), lb0 = hap_length(job.b);
+        if (a.stage == 0 && (min(la0, lb0) >= 2048u) != (pass == 0)) continue;
         if (a.stage == 0) {
             // common prefix (warp 0) and suffix (warp 1) at the same time, each at most half of the shorter string; the side
             // that ran into its half-way mark goes on if the other one stopped early
@@ -105,7 +115,10 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
             lo = hi = 0.0;
         }
         if (settled) {
-            if (tid == 0) { a.dist[job.out_index] = lo; a.dist_hi[job.out_index] = hi; }
+            if (tid == 0) {
+                a.dist[job.out_index] = lo; a.dist_hi[job.out_index] = hi;
+                if (a.profile) a.profile[job_id] = make_uint4(la, lb, 0xFFFFu, static_cast<uint32_t>(clock64() - clock_begin));
+            }
             continue;
         }
         const uint32_t a_bytes = (la + WFA_PAD + 3u) & ~3u, b_bytes = (lb + WFA_PAD + 3u) & ~3u;
@@ -156,8 +169,9 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
         const int ila = static_cast<int>(la), ilb = static_cast<int>(lb), kd = ilb - ila;
         int* prev = F0;
         int* cur = F1;
-        int result = -1;
+        int result = -1, waves = 0;
         for (int s = 0; s <= t; ++s) {
+            waves = s + 1;
             int klo, khi;
             wfa_range(s, t, kd, ila, ilb, klo, khi);
             int found = 0;
@@ -168,7 +182,7 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
                 bool more = false;
                 if (active) {
                     v = s == 0 ? 0 : wfa_next(prev[mid + k - 1], prev[mid + k], prev[mid + k + 1], k, ila, ilb);
-                    if (v > WFA_NEG / 2) v += static_cast<int>(wfa_extend(Aw, Bw, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), 32u, &more));
+                    if (v > WFA_NEG / 2) v += static_cast<int>(wfa_extend8(Aw, Bw, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), &more));
                 }
                 // a diagonal that is still matching: the whole warp goes on, 128 symbols per round
                 uint32_t pending = __ballot_sync(FULL, more);
@@ -213,6 +227,8 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
                 a.dist[job.out_index] = static_cast<double>(a.t + 1u);
                 a.dist_hi[job.out_index] = static_cast<double>(longer);
             }
+            if (a.profile)
+                a.profile[job_id] = make_uint4(la, lb, static_cast<uint32_t>(waves) | (static_cast<uint32_t>(a.stage) << 16), static_cast<uint32_t>(clock64() - clock_begin));
         }
     }
 }
@@ -229,6 +245,14 @@ int launch_wfa(svb_ctx* ctx, WfaArgs a) {
         SVB_CUDA(ctx, cudaFuncSetAttribute(wfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(big)));
         ctx->wfa_attr_set = true;
     }
+    // profiling aid: SVB_WFA_PROFILE=<file> dumps one uint4 per job of the launch (the count must be known: only tools use it)
+    const char* profile_path = getenv("SVB_WFA_PROFILE");
+    a.profile = nullptr;
+    if (profile_path && a.big_cap) {
+        SVB_CUDA(ctx, cudaMallocAsync(&a.profile, sizeof(uint4) * a.big_cap, ctx->stream));
+        SVB_CUDA(ctx, cudaMemsetAsync(a.profile, 0, sizeof(uint4) * a.big_cap, ctx->stream));
+    }
+    {
     KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
     a.stage = 0;
     a.cap_chars = static_cast<uint32_t>(small - fixed);
@@ -237,6 +261,17 @@ int launch_wfa(svb_ctx* ctx, WfaArgs a) {
     a.cap_chars = static_cast<uint32_t>(big - fixed);
     wfa_kernel<<<static_cast<unsigned>(ctx->sm_count), WFA_THREADS, big, ctx->stream>>>(a);
     ctx->launches += 2;
+    }
     SVB_CUDA(ctx, cudaGetLastError());
+    if (a.profile) {
+        std::vector<uint4> h(a.big_cap);
+        SVB_CUDA(ctx, cudaMemcpyAsync(h.data(), a.profile, sizeof(uint4) * a.big_cap, cudaMemcpyDeviceToHost, ctx->stream));
+        SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (FILE* f = fopen(profile_path, "wb")) {
+            fwrite(h.data(), sizeof(uint4), a.big_cap, f);
+            fclose(f);
+        }
+        cudaFreeAsync(a.profile, ctx->stream);
+    }
     return SVB_OK;
 }

@@ -16,7 +16,7 @@
 #include "linkage.cuh"   // SVB_HD
 
 constexpr int WFA_NEG = -(1 << 29);              // "diagonal not reached"
-constexpr uint32_t WFA_PAD = 8;                  // sentinel bytes behind each string (word-wise extension reads ahead)
+constexpr uint32_t WFA_PAD = 12;                 // sentinel bytes behind each string (word-wise extension reads ahead)
 constexpr uint8_t WFA_END_A = 0xFD, WFA_END_B = 0xFC, WFA_NOCLASS_A = 0xFB, WFA_NOCLASS_B = 0xFA;
 constexpr uint32_t WFA_MAX_T = 1024;             // thresholds above this take the exact kernel (t^2 work stops paying)
 
@@ -77,6 +77,25 @@ SVB_HD uint32_t wfa_extend(const uint32_t* A, const uint32_t* B, uint32_t i, uin
     return run;
 }
 
+// The same for exactly 8 symbols with every load issued at once (one shared-memory latency instead of two dependent
+// rounds): what a thread of the kernel does before the whole warp takes over a diagonal that keeps matching.
+SVB_HD uint32_t wfa_extend8(const uint32_t* A, const uint32_t* B, uint32_t i, uint32_t j, bool* more) {
+    const uint32_t ia = i >> 2, sa = (i & 3u) * 8u, ib = j >> 2, sb = (j & 3u) * 8u;
+    const uint32_t a0 = A[ia], a1 = A[ia + 1u], a2 = A[ia + 2u], b0 = B[ib], b1 = B[ib + 1u], b2 = B[ib + 2u];
+#ifdef __CUDA_ARCH__
+    const uint32_t x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+    const uint32_t x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+#else
+    const uint32_t x0 = (sa ? (a0 >> sa) | (a1 << (32u - sa)) : a0) ^ (sb ? (b0 >> sb) | (b1 << (32u - sb)) : b0);
+    const uint32_t x1 = (sa ? (a1 >> sa) | (a2 << (32u - sa)) : a1) ^ (sb ? (b1 >> sb) | (b2 << (32u - sb)) : b1);
+#endif
+    *more = false;
+    if (x0) return wfa_first_diff(x0);
+    if (x1) return 4u + wfa_first_diff(x1);
+    *more = true;
+    return 8u;
+}
+
 // Serial driver (host check, and the specification of what the kernel computes): the distance if it is <= t, else -1.
 // A, B: word-aligned class bytes with sentinels; F0, F1: 2 t + 7 ints each.
 SVB_HD long long wfa_distance_serial(const uint32_t* A, int la, const uint32_t* B, int lb, int t, int* F0, int* F1) {
@@ -92,6 +111,7 @@ SVB_HD long long wfa_distance_serial(const uint32_t* A, int la, const uint32_t* 
             int v = s == 0 ? 0 : wfa_next(prev[mid + k - 1], prev[mid + k], prev[mid + k + 1], k, la, lb);
             if (v > WFA_NEG / 2) {
                 bool more = true;
+                v += static_cast<int>(wfa_extend8(A, B, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), &more));
                 while (more) v += static_cast<int>(wfa_extend(A, B, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), 32u, &more));
             }
             cur[mid + k] = v;

@@ -35,6 +35,23 @@ print("pair x5: K8 (wavefront x2 + resolve + exact kernel) %.3f ms per call, sor
 print("pair stats: %(partitions)d partitions, %(pairs)d cross-haplotype pairs, %(exact_pairs)d needed the exact kernel, "
       "%(table_cells).3g full-table cells" % stats)
 print("K8: %.3g equivalent cell updates per second" % (stats["table_cells"] / (t["edit_distance"][0] / 5 * 1e-3)))
+wpath = "/tmp/wfa_profile.bin"
+os.environ["SVB_WFA_PROFILE"] = wpath
+eng.pair(tabs[0], tabs[1], recs[0], recs[1], ref, params)
+del os.environ["SVB_WFA_PROFILE"]
+w = np.fromfile(wpath, dtype=np.uint32).reshape(-1, 4)
+w = w[w[:, 3] > 0]
+cyc = w[:, 3].astype(np.float64)
+waves = w[:, 2] & 0xFFFF
+trimmed = waves == 0xFFFF
+print("wavefront kernel: %d jobs profiled, sum of job cycles %.3g, max %.3g (%.3f ms at 1.9 GHz); settled by trimming / length: %d (cycles sum %.3g, max %.3g)"
+      % (w.shape[0], cyc.sum(), cyc.max(), cyc.max() / 1.9e6, trimmed.sum(), cyc[trimmed].sum(), cyc[trimmed].max() if trimmed.any() else 0))
+print("     la     lb  waves stage   cycles")
+for i in np.argsort(-cyc)[:20]:
+    print("%7d %6d %6s %5d %8d" % (w[i, 0], w[i, 1], "-" if trimmed[i] else str(int(waves[i])), int(w[i, 2] >> 16) if not trimmed[i] else 0, w[i, 3]))
+ran = ~trimmed
+if ran.any():
+    print("jobs that ran waves: %d, mean cycles %.3g, mean waves %.1f" % (ran.sum(), cyc[ran].mean(), waves[ran].mean()))
 path = "/tmp/ed_profile.bin"
 os.environ["SVB_ED_PROFILE"] = path
 eng.timing_reset()
