@@ -243,7 +243,8 @@ def b200_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from svim_asm_b200 import sharded
-        return sharded.bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block, build_reference)
+        return sharded.bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block, build_reference,
+                                     parity_tools=(cpu_sample, run_cpu_pipeline, parity_check))
     torch.cuda.set_device(local)
     cfg, rb1, rb2, bases, off = build_workload(args.scale)
     h1, h2 = pinned_host(HostBatch.from_record_batch(rb1)), pinned_host(HostBatch.from_record_batch(rb2))

@@ -240,7 +240,23 @@ int svb_exchange_pack(svb_ctx* ctx, const svb_table* t1, const svb_table* t2, vo
  * (host).  The result keeps the rows whose key contig (Candidate.get_key, SVCandidate.py:17-19) belongs to `rank`. */
 int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, const uint64_t* sizes, int world, int hap,
                         const int32_t* owner, int n_contig, int rank, svb_table** out);
-const void* svb_table_device_rows(const svb_table* t);            /* device pointer of the rows (all-gather of paired rows) */
+const void* svb_table_device_rows(const svb_table* t);
+/* The same exchange over PEER MEMORY, without a collective library (one process per GPU, CUDA IPC): every rank owns a
+ * window in its HBM with one slot per rank; svb_exchange_share stores this rank's packed tables straight into its slot of
+ * every peer's window (one kernel, NVLink stores), raises a flag there, waits on the flags of its own window (a one-warp
+ * kernel on the library's stream) and unpacks; svb_exchange_gather_paired does the same for the paired rows and puts them
+ * into pair_candidates' order (type, then contig by python string order) on the device.  Set-up: create, exchange the
+ * 64-byte handles between the processes (any transport), open.  Both calls are collective: every rank makes them once
+ * per step, in the same order. */
+typedef struct svb_exchange svb_exchange;
+int svb_exchange_create(svb_ctx* ctx, int world, int rank, uint64_t slot_bytes, uint64_t result_bytes, svb_exchange** out);
+int svb_exchange_handle(svb_ctx* ctx, const svb_exchange* x, uint8_t handle_out[64]);
+int svb_exchange_open(svb_ctx* ctx, svb_exchange* x, const uint8_t* handles /* world x 64 bytes, rank order */);
+void svb_exchange_destroy(svb_ctx* ctx, svb_exchange* x);
+int svb_exchange_share(svb_ctx* ctx, svb_exchange* x, const svb_table* t1, const svb_table* t2, const int32_t* owner, int n_contig,
+                       svb_table** u1, svb_table** u2);
+int svb_exchange_gather_paired(svb_ctx* ctx, svb_exchange* x, const svb_table* paired, const int32_t* contig_lexrank, int n_contig,
+                               svb_table** out);            /* device pointer of the rows (all-gather of paired rows) */
 
 /* ---- VCF body: the text of write_final_vcf's record lines (SVIM_COMBINE.py:428-475) and of
  * Candidate*.get_vcf_entry* (SVCandidate.py:53-78,99-125,151-176,203-261,296-347,389-443), assembled on the device: REF /

@@ -112,6 +112,12 @@ SIGNATURES = {
     "svb_exchange_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_u64]),
     "svb_exchange_unpack": (c_int, [c_void_p, c_void_p, c_u64, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "svb_table_device_rows": (c_void_p, [c_void_p]),
+    "svb_exchange_create": (c_int, [c_void_p, c_int, c_int, c_u64, c_u64, P(c_void_p)]),
+    "svb_exchange_handle": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_exchange_open": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "svb_exchange_destroy": (None, [c_void_p, c_void_p]),
+    "svb_exchange_share": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, P(c_void_p), P(c_void_p)]),
+    "svb_exchange_gather_paired": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, P(c_void_p)]),
     "svb_table_set_pool_from_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, c_void_p]),
 }
 

@@ -74,6 +74,7 @@ static int check_device_status(svb_ctx* ctx) {
         return svb_fail(ctx, SVB_ERR_ASSERT, "candidate end is smaller than its start (reference assertion, SVCandidate.py)");
     if (st & DEV_ERR_NOSEQ)
         return svb_fail(ctx, SVB_ERR_ARG, "insertion candidates need the query sequences: call svb_records_set_sequences first");
+    if (st & DEV_ERR_EXCHANGE) return svb_fail(ctx, SVB_ERR_CUDA, "multi-GPU exchange: a peer did not arrive in time");
     return svb_fail(ctx, SVB_ERR_CAPACITY, "per-read scratch capacity exceeded");
 }
 

@@ -94,6 +94,7 @@ enum : uint32_t {
     DEV_ERR_ASSERT = 2u,         // reference assert end >= start would fire
     DEV_ERR_CAPACITY = 4u,       // per-read scratch exceeded (inversion run > 32, ...)
     DEV_ERR_NOSEQ = 8u,          // an insertion needs query bases that were not uploaded
+    DEV_ERR_EXCHANGE = 16u,      // a peer's flag did not arrive within the exchange time-out (exchange.cu)
 };
 
 int svb_fail(svb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess);

@@ -10,6 +10,9 @@
 // a W-way merge: a row's position is the sum over the runs of "rows before me" (binary search), counted over owned
 // rows only through an exclusive scan of the ownership flags.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
 #include <vector>
 
 #include "pairing.cuh"
@@ -243,5 +246,352 @@ int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, c
 }
 
 const void* svb_table_device_rows(const svb_table* t) { return t ? t->d_rows : nullptr; }
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Exchange window over peer memory (SURVEY.md 8e, C1 "fused after K5"): the all-gatherv of the candidate tables and of the
+// paired rows WITHOUT a collective library and without host-visible sizes in between.
+//
+// Every rank owns a window in its HBM (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by every peer):
+//     in slot [world]   one packed pair of haplotype tables per rank: 64-byte header {sizes[4], payload bytes} + svb_exchange_pack layout
+//     result slot [world]  one run of paired rows per rank: 64-byte header {rows} + rows
+//     flags             one 32-bit epoch per (kind, writer rank), 128 bytes apart
+// `put` is ONE kernel: it stores this rank's payload straight into its slot of EVERY peer's window over NVLink (16-byte
+// stores, grid-stride), and the last block to finish raises this rank's flag in every window (system-scope fences on both
+// sides).  `wait` is a one-warp kernel on the consumer's stream that spins on the flags of its own window; what follows on
+// that stream reads the gathered data in place.  Epochs only grow, so nothing is reset between steps; a rank overwrites a
+// peer's slot for step s + 1 only after it has seen that peer's result flag of step s, which the peer raises after it
+// has read everything of step s.
+namespace {
+
+constexpr uint32_t XW_HEADER = 64;
+constexpr uint32_t XW_FLAG_STRIDE = 128;
+constexpr int XW_MAX_PIECES = 8;
+
+struct PutPiece {
+    const uint8_t* src;
+    uint64_t bytes;
+    uint64_t dst_off;                // offset inside the destination slot
+};
+struct PutArgs {
+    uint8_t* peer_slot[EXCH_MAX_WORLD];          // this rank's slot in every rank's window (own window included)
+    uint32_t* peer_flag[EXCH_MAX_WORLD];         // this rank's flag in every rank's window
+    PutPiece piece[XW_MAX_PIECES];
+    uint64_t header[8];                          // written to offset 0 of every slot
+    int world, n_pieces;
+    uint32_t epoch;
+    unsigned int* done;                          // device counter of finished blocks (zeroed by the caller)
+};
+
+__global__ void __launch_bounds__(256) exchange_put_kernel(const __grid_constant__ PutArgs a) {
+    const uint64_t tid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x, stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (int p = 0; p < a.world; ++p) {
+        uint8_t* slot = a.peer_slot[p];
+        if (tid < 8) reinterpret_cast<uint64_t*>(slot)[tid] = a.header[tid];
+        for (int k = 0; k < a.n_pieces; ++k) {
+            const PutPiece pc = a.piece[k];
+            const uint4* s4 = reinterpret_cast<const uint4*>(pc.src);
+            uint4* d4 = reinterpret_cast<uint4*>(slot + pc.dst_off);
+            const uint64_t n16 = pc.bytes / 16;
+            for (uint64_t i = tid; i < n16; i += stride) d4[i] = s4[i];
+            for (uint64_t i = n16 * 16 + tid; i < pc.bytes; i += stride) slot[pc.dst_off + i] = pc.src[i];
+        }
+    }
+    // every store of this block is visible system-wide before the block counts itself done; the last block raises the flags
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (last && threadIdx.x < static_cast<unsigned>(a.world)) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(a.peer_flag[threadIdx.x]) = a.epoch;
+        __threadfence_system();
+    }
+}
+
+// spin until every writer's flag in OUR window has reached `epoch` (or give up after `timeout_ns`: a peer died)
+__global__ void exchange_wait_kernel(const uint32_t* flags, int world, uint32_t epoch, unsigned long long timeout_ns, uint32_t* dev_status) {
+    const int p = threadIdx.x;
+    if (p < world) {
+        const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(reinterpret_cast<const uint8_t*>(flags) + static_cast<size_t>(p) * XW_FLAG_STRIDE);
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (static_cast<int32_t>(*f - epoch) < 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) {
+                atomicOr(dev_status, DEV_ERR_EXCHANGE);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+// final order of pair_candidates' output over the ranks' runs: type, then key contig in python string order; every (type,
+// contig) group comes from ONE rank (the owner of the contig), already in partition / label order, so a row's position is
+// its index in its own run plus the rows of the other runs with a smaller key
+struct ResRuns {
+    const svb_row* rows[EXCH_MAX_WORLD];
+    uint32_t n[EXCH_MAX_WORLD], base[EXCH_MAX_WORLD];
+    int world;
+    uint32_t total;
+};
+__device__ __forceinline__ unsigned long long order_key(const svb_row& r, const int32_t* lexrank, int n_contig) {
+    const int32_t tid = key_contig(r);
+    const uint32_t rank = (tid >= 0 && tid < n_contig) ? static_cast<uint32_t>(lexrank[tid]) : 0xFFFFFFFFu;
+    return (static_cast<unsigned long long>(r.type) << 32) | rank;
+}
+__global__ void order_runs_kernel(const __grid_constant__ ResRuns rs, const int32_t* __restrict__ lexrank, int n_contig, svb_row* __restrict__ out) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= rs.total) return;
+    int r = 0;
+    while (r + 1 < rs.world && x >= rs.base[r + 1]) ++r;
+    const uint32_t i = x - rs.base[r];
+    svb_row row = rs.rows[r][i];
+    const unsigned long long key = order_key(row, lexrank, n_contig);
+    uint32_t pos = i;
+    for (int q = 0; q < rs.world; ++q) {
+        if (q == r) continue;
+        uint32_t lo = 0, hi = rs.n[q];
+        // rows of run q that come first: smaller key; equal keys cannot occur across runs (one owner per contig) but are
+        // ordered by rank for determinism
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const unsigned long long k = order_key(rs.rows[q][mid], lexrank, n_contig);
+            if (k < key || (k == key && q < r)) lo = mid + 1; else hi = mid;
+        }
+        pos += lo;
+    }
+    row.ordinal = pos;
+    out[pos] = row;
+}
+
+}  // namespace
+
+struct svb_exchange {
+    int device = 0, world = 1, rank = 0;
+    uint64_t slot_bytes = 0, res_bytes = 0, window_bytes = 0;
+    uint8_t* window = nullptr;                   // own window
+    uint8_t* peer[EXCH_MAX_WORLD] = {};          // every rank's window as mapped here (peer[rank] == window)
+    bool opened[EXCH_MAX_WORLD] = {};
+    unsigned int* d_done = nullptr;              // block counters of the put kernels
+    uint32_t epoch = 0;
+    uint64_t timeout_ns = 20000000000ull;
+    uint64_t in_off(int r) const { return static_cast<uint64_t>(r) * slot_bytes; }
+    uint64_t res_off(int r) const { return static_cast<uint64_t>(world) * slot_bytes + static_cast<uint64_t>(r) * res_bytes; }
+    uint64_t flag_off(int kind, int r) const {
+        return static_cast<uint64_t>(world) * (slot_bytes + res_bytes) + (static_cast<uint64_t>(kind) * EXCH_MAX_WORLD + r) * XW_FLAG_STRIDE;
+    }
+};
+
+static int exchange_put(svb_ctx* ctx, svb_exchange* x, int kind, const PutPiece* pieces, int n_pieces, const uint64_t header[8]) {
+    PutArgs a;
+    memset(&a, 0, sizeof a);
+    a.world = x->world;
+    a.n_pieces = n_pieces;
+    a.epoch = x->epoch;
+    uint64_t total = 0;
+    for (int k = 0; k < n_pieces; ++k) { a.piece[k] = pieces[k]; total += pieces[k].bytes; }
+    for (int k = 0; k < 8; ++k) a.header[k] = header[k];
+    for (int p = 0; p < x->world; ++p) {
+        a.peer_slot[p] = x->peer[p] + (kind == 0 ? x->in_off(x->rank) : x->res_off(x->rank));
+        a.peer_flag[p] = reinterpret_cast<uint32_t*>(x->peer[p] + x->flag_off(kind, x->rank));
+    }
+    a.done = x->d_done + kind;
+    SVB_CUDA(ctx, cudaMemsetAsync(a.done, 0, sizeof(unsigned int), ctx->stream));
+    const unsigned blocks = static_cast<unsigned>(std::min<uint64_t>(std::max<uint64_t>(total / (256 * 64), 1), static_cast<uint64_t>(ctx->sm_count)));
+    exchange_put_kernel<<<blocks, 256, 0, ctx->stream>>>(a);
+    ctx->launches += 1;
+    SVB_CUDA(ctx, cudaGetLastError());
+    return SVB_OK;
+}
+
+static int exchange_wait(svb_ctx* ctx, svb_exchange* x, int kind) {
+    exchange_wait_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(x->window + x->flag_off(kind, 0)), x->world, x->epoch,
+                                                    x->timeout_ns, ctx->d_status);
+    ctx->launches += 1;
+    SVB_CUDA(ctx, cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" {
+
+int svb_exchange_create(svb_ctx* ctx, int world, int rank, uint64_t slot_bytes, uint64_t result_bytes, svb_exchange** out) {
+    if (!ctx || !out || world < 1 || world > EXCH_MAX_WORLD || rank < 0 || rank >= world)
+        return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_create") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    svb_exchange* x = new (std::nothrow) svb_exchange();
+    if (!x) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_exchange_create");
+    x->device = ctx->device;
+    x->world = world;
+    x->rank = rank;
+    x->slot_bytes = (std::max<uint64_t>(slot_bytes, 4096) + 255) & ~255ull;
+    x->res_bytes = (std::max<uint64_t>(result_bytes, 4096) + 255) & ~255ull;
+    x->window_bytes = x->flag_off(2, 0);
+    cudaError_t e = cudaMalloc(&x->window, x->window_bytes);          // cudaMalloc, not the stream-ordered pool: IPC needs it
+    if (e == cudaSuccess) e = cudaMemset(x->window, 0, x->window_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&x->d_done, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        svb_exchange_destroy(ctx, x);
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_create", e);
+    }
+    x->peer[rank] = x->window;
+    if (const char* env = getenv("SVB_EXCHANGE_TIMEOUT_S")) {
+        const long long v = atoll(env);
+        if (v > 0) x->timeout_ns = static_cast<uint64_t>(v) * 1000000000ull;
+    }
+    *out = x;
+    return SVB_OK;
+}
+
+int svb_exchange_handle(svb_ctx* ctx, const svb_exchange* x, uint8_t handle_out[64]) {
+    if (!ctx || !x || !handle_out) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_handle") : SVB_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaSetDevice(ctx->device);
+    cudaIpcMemHandle_t h;
+    SVB_CUDA(ctx, cudaIpcGetMemHandle(&h, x->window));
+    memcpy(handle_out, &h, 64);
+    return SVB_OK;
+}
+
+int svb_exchange_open(svb_ctx* ctx, svb_exchange* x, const uint8_t* handles) {
+    if (!ctx || !x || !handles) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_open") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    for (int p = 0; p < x->world; ++p) {
+        if (p == x->rank || x->opened[p]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * static_cast<size_t>(p), 64);
+        void* ptr = nullptr;
+        SVB_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer[p] = static_cast<uint8_t*>(ptr);
+        x->opened[p] = true;
+    }
+    return SVB_OK;
+}
+
+void svb_exchange_destroy(svb_ctx* ctx, svb_exchange* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int p = 0; p < x->world; ++p)
+        if (x->opened[p] && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
+    if (x->window) cudaFree(x->window);
+    if (x->d_done) cudaFree(x->d_done);
+    delete x;
+}
+
+// All-gatherv of both haplotype tables over the windows, then "all ranks' rows in append order, restricted to the key
+// contigs this rank owns" (svb_exchange_unpack) for both haplotypes.  Collective: every rank calls it once per step.
+int svb_exchange_share(svb_ctx* ctx, svb_exchange* x, const svb_table* t1, const svb_table* t2, const int32_t* owner, int n_contig,
+                       svb_table** u1, svb_table** u2) {
+    if (!ctx || !x || !t1 || !t2 || !owner || !u1 || !u2) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_share") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    *u1 = *u2 = nullptr;
+    x->epoch += 1;
+    uint64_t sizes[4];
+    svb_exchange_sizes(t1, t2, sizes);
+    const Layout l = layout_of(sizes);
+    if (XW_HEADER + l.total > x->slot_bytes) return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_exchange_share: tables larger than the window slot");
+    const svb_table* t[2] = {t1, t2};
+    for (int h = 0; h < 2; ++h)
+        if (t[h]->n && !t[h]->d_pool_off) return svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_share: gather the tables' sequences first (svb_table_gather_sequences)");
+    PutPiece pieces[XW_MAX_PIECES];
+    int np = 0;
+    for (int h = 0; h < 2; ++h) {
+        if (t[h]->n) pieces[np++] = PutPiece{reinterpret_cast<const uint8_t*>(t[h]->d_rows), sizeof(svb_row) * t[h]->n, XW_HEADER + l.rows[h]};
+        if (t[h]->d_pool_off && t[h]->n) pieces[np++] = PutPiece{reinterpret_cast<const uint8_t*>(t[h]->d_pool_off), sizeof(uint64_t) * t[h]->n, XW_HEADER + l.off[h]};
+        if (t[h]->d_pool_off && t[h]->pool_bytes) pieces[np++] = PutPiece{t[h]->d_pool, t[h]->pool_bytes, XW_HEADER + l.pool[h]};
+    }
+    uint64_t header[8] = {sizes[0], sizes[1], sizes[2], sizes[3], l.total, x->epoch, 0, 0};
+    int rc = exchange_put(ctx, x, 0, pieces, np, header);
+    if (rc == SVB_OK) rc = exchange_wait(ctx, x, 0);
+    if (rc != SVB_OK) return rc;
+    // the sizes of every rank's tables: 64 bytes per slot header, one strided copy, one synchronisation
+    std::vector<uint64_t> headers(static_cast<size_t>(x->world) * 8);
+    SVB_CUDA(ctx, cudaMemcpy2DAsync(headers.data(), XW_HEADER, x->window, x->slot_bytes, XW_HEADER, x->world, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t h_status = 0;
+    SVB_CUDA(ctx, cudaMemcpyAsync(&h_status, ctx->d_status, sizeof h_status, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_status & DEV_ERR_EXCHANGE) {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_share: a peer did not deliver its tables in time");
+    }
+    std::vector<uint64_t> all_sizes(static_cast<size_t>(x->world) * 4);
+    for (int r = 0; r < x->world; ++r) {
+        for (int k = 0; k < 4; ++k) all_sizes[4 * r + k] = headers[8 * r + k];
+        if (headers[8 * r + 5] != x->epoch) return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_share: ranks are out of step");
+    }
+    // tables that did not bring a pool pack no offsets: unpack reads zeros there (the slot was cleared at creation and pools
+    // never shrink to "absent" between steps of one run)
+    rc = svb_exchange_unpack(ctx, x->window + XW_HEADER, x->slot_bytes, all_sizes.data(), x->world, 1, owner, n_contig, x->rank, u1);
+    if (rc == SVB_OK) rc = svb_exchange_unpack(ctx, x->window + XW_HEADER, x->slot_bytes, all_sizes.data(), x->world, 2, owner, n_contig, x->rank, u2);
+    if (rc != SVB_OK && *u1) { svb_table_free(*u1); *u1 = nullptr; }
+    return rc;
+}
+
+// All-gatherv of the paired rows of every rank, put into pair_candidates' order (type, contig by python string order).
+// Collective.  contig_lexrank: host array, rank of every contig name.
+int svb_exchange_gather_paired(svb_ctx* ctx, svb_exchange* x, const svb_table* paired, const int32_t* contig_lexrank, int n_contig,
+                               svb_table** out) {
+    if (!ctx || !x || !paired || !out || (n_contig && !contig_lexrank)) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_gather_paired") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    if (XW_HEADER + sizeof(svb_row) * paired->n > x->res_bytes) return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_exchange_gather_paired: rows exceed the result slot");
+    PutPiece piece{reinterpret_cast<const uint8_t*>(paired->d_rows), sizeof(svb_row) * paired->n, XW_HEADER};
+    uint64_t header[8] = {paired->n, x->epoch, 0, 0, 0, 0, 0, 0};
+    int rc = exchange_put(ctx, x, 1, &piece, paired->n ? 1 : 0, header);
+    if (rc == SVB_OK) rc = exchange_wait(ctx, x, 1);
+    if (rc != SVB_OK) return rc;
+    std::vector<uint64_t> headers(static_cast<size_t>(x->world) * 8);
+    SVB_CUDA(ctx, cudaMemcpy2DAsync(headers.data(), XW_HEADER, x->window + x->res_off(0), x->res_bytes, XW_HEADER, x->world, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t h_status = 0;
+    SVB_CUDA(ctx, cudaMemcpyAsync(&h_status, ctx->d_status, sizeof h_status, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_status & DEV_ERR_EXCHANGE) {
+        cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_gather_paired: a peer did not deliver its rows in time");
+    }
+    ResRuns rs;
+    memset(&rs, 0, sizeof rs);
+    rs.world = x->world;
+    uint64_t total = 0;
+    for (int r = 0; r < x->world; ++r) {
+        if (headers[8 * r + 1] != x->epoch) return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_gather_paired: ranks are out of step");
+        rs.rows[r] = reinterpret_cast<const svb_row*>(x->window + x->res_off(r) + XW_HEADER);
+        rs.n[r] = static_cast<uint32_t>(headers[8 * r]);
+        rs.base[r] = static_cast<uint32_t>(total);
+        total += headers[8 * r];
+    }
+    if (total >= 0xFFFFFFF0ull) return svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_gather_paired: too many rows");
+    rs.total = static_cast<uint32_t>(total);
+    svb_table* t = new (std::nothrow) svb_table();
+    if (!t) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_exchange_gather_paired");
+    t->device = ctx->device;
+    t->stream = ctx->stream;
+    t->cap = std::max<uint64_t>(total, 1);
+    t->n = total;
+    int32_t* d_lex = nullptr;
+    cudaError_t e = cudaMallocAsync(&t->d_rows, sizeof(svb_row) * t->cap, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_lex, sizeof(int32_t) * std::max(n_contig, 1), ctx->stream);
+    if (e == cudaSuccess && n_contig) e = cudaMemcpyAsync(d_lex, contig_lexrank, sizeof(int32_t) * n_contig, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && total) {
+        order_runs_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(rs, d_lex, n_contig, t->d_rows);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (d_lex) cudaFreeAsync(d_lex, ctx->stream);
+    if (e != cudaSuccess) {
+        svb_table_free(t);
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_gather_paired", e);
+    }
+    *out = t;
+    return SVB_OK;
+}
 
 }  // extern "C"

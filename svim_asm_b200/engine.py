@@ -375,6 +375,51 @@ class DeviceBuffer(DeviceView):
             self.ptr = 0
 
 
+class ExchangeWindow(object):
+    """One rank's window of the peer-memory exchange (csrc/exchange.cu): `handle` is the 64-byte CUDA IPC handle the other
+    processes need; after open(handles of all ranks) share() / gather_paired() are the two collective calls of a step."""
+
+    def __init__(self, engine, world, rank, slot_bytes, result_bytes):
+        self.engine, self.world, self.rank = engine, int(world), int(rank)
+        out = ctypes.c_void_p()
+        engine._check(lib.svb_exchange_create(engine.handle, self.world, self.rank, int(slot_bytes), int(result_bytes), ctypes.byref(out)))
+        self.ptr = out
+        buf = np.zeros(64, dtype=np.uint8)
+        engine._check(lib.svb_exchange_handle(engine.handle, self.ptr, _lib.ptr(buf)))
+        self.handle = buf.tobytes()
+
+    def open(self, handles):
+        blob = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        assert blob.shape[0] == 64 * self.world
+        self.engine._check(lib.svb_exchange_open(self.engine.handle, self.ptr, _lib.ptr(blob)))
+
+    def share(self, table1, table2, owner):
+        owner = np.ascontiguousarray(owner, dtype=np.int32)
+        u1, u2 = ctypes.c_void_p(), ctypes.c_void_p()
+        self.engine._check(lib.svb_exchange_share(self.engine.handle, self.ptr, table1.handle, table2.handle, _lib.ptr(owner),
+                                                  owner.shape[0], ctypes.byref(u1), ctypes.byref(u2)))
+        return Table(self.engine, u1), Table(self.engine, u2)
+
+    def gather_paired(self, paired, contig_lexrank):
+        ranks = np.ascontiguousarray(contig_lexrank, dtype=np.int32)
+        out = ctypes.c_void_p()
+        self.engine._check(lib.svb_exchange_gather_paired(self.engine.handle, self.ptr, paired.handle, _lib.ptr(ranks), ranks.shape[0],
+                                                          ctypes.byref(out)))
+        return Table(self.engine, out)
+
+    def close(self):
+        if self.ptr:
+            if getattr(self.engine, "handle", None):
+                lib.svb_exchange_destroy(self.engine.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine(object):
     """One GPU context (svb_ctx*).  Not thread-safe, like the reference."""
 
@@ -559,6 +604,10 @@ class Engine(object):
         self._check(lib.svb_exchange_unpack(self.handle, ctypes.c_void_p(int(device_ptr)), int(stride), _lib.ptr(sizes),
                                             sizes.shape[0], int(hap), _lib.ptr(owner), owner.shape[0], int(rank), ctypes.byref(out)))
         return Table(self, out)
+
+    def exchange_window(self, world, rank, slot_bytes, result_bytes):
+        """Peer-memory exchange window of this rank (svb_exchange_create); see ExchangeWindow."""
+        return ExchangeWindow(self, world, rank, slot_bytes, result_bytes)
 
     def device_alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)

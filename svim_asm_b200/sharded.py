@@ -295,10 +295,61 @@ def sharded_step_device(stage, rank, world, owner, lexrank, device, row_dtype):
     return out
 
 
+def sharded_step_window(stage, window, owner, lexrank):
+    """One step on one rank over the peer-memory exchange window (csrc/exchange.cu: svb_exchange_share /
+    svb_exchange_gather_paired): no collective library and no torch in the step.  The tables go from this rank's HBM
+    straight into every peer's window (one kernel of NVLink stores + a flag), the consumer waits on the device, the paired
+    rows travel the same way and are put into pair_candidates' order on the device; one download at the end.
+    Returns the complete paired table (identical on every rank)."""
+    eng = stage.eng
+    t1, t2 = stage.collect(1), stage.collect(2)
+    u1, u2 = window.share(t1, t2, owner)
+    t1.free()
+    t2.free()
+    paired = eng.pair(u1, u2, stage.records[0], stage.records[1], stage.ref, stage.params)
+    everything = window.gather_paired(paired, lexrank)
+    out = everything.to_numpy()
+    for t in (u1, u2, paired, everything):
+        t.free()
+    stage.done()
+    return out
+
+
+def open_window(eng, rank, world, slot_bytes=None, result_bytes=None):
+    """Create this rank's exchange window and map every peer's (handles travel through torch.distributed once, at set-up).
+    Returns None when CUDA IPC is not available between the ranks (all ranks agree): the caller falls back to NCCL."""
+    import torch
+    import torch.distributed as dist
+    slot_bytes = slot_bytes or int(os.environ.get("SVB_EXCHANGE_SLOT_MB", "64")) << 20
+    result_bytes = result_bytes or int(os.environ.get("SVB_EXCHANGE_RESULT_MB", "16")) << 20
+    window, ok = None, 1
+    try:
+        window = eng.exchange_window(world, rank, slot_bytes, result_bytes)
+        handles = [None] * world
+        dist.all_gather_object(handles, window.handle)
+    except RuntimeError:
+        handles, ok = None, 0
+        junk = [None] * world
+        dist.all_gather_object(junk, b"")
+    if ok:
+        try:
+            window.open(handles)
+        except RuntimeError as exc:
+            print("[sharded] peer-memory window unavailable on rank %d (%s): falling back to NCCL" % (rank, exc), file=sys.stderr)
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", eng.device))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if window is not None:
+            window.close()
+        return None
+    return window
+
+
 _PROFILE = {}
 
 
-def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block, build_reference):
+def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler, cpu_baseline_block, build_reference, parity_tools=None):
     """bench.py for WORLD_SIZE > 1 (launched by torchrun): strong scaling, max over ranks."""
     import json
     import torch
@@ -318,6 +369,8 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     s1, g1 = shard_records(rb1, owner, rank)
     s2, g2 = shard_records(rb2, owner, rank)
     n_aln_total, n_ops_total = rb1.n_aln + rb2.n_aln, rb1.n_ops + rb2.n_ops
+    # rank 0 keeps the bounded CPU sample (a few contigs, closed under SA tags) for the parity check of the gathered table
+    sample = parity_tools[0](rb1, rb2, cfg) if (parity_tools and rank == 0) else None
     del rb1, rb2
     hosts = [pinned_host(HostBatch.from_record_batch(s1)), pinned_host(HostBatch.from_record_batch(s2))]
     del s1, s2
@@ -328,15 +381,24 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         if turn == rank:
             bases, off = build_reference(cfg)
             ref = eng.load_reference(bases, off)           # every rank keeps the whole reference in HBM (3.1 GB of 180 GB)
-            del bases
+            if sample is None:
+                del bases
         dist.barrier()
     resident = [eng.load_records(h, with_sequences=True) for h in hosts]
     for rec, g in zip(resident, (g1, g2)):
         eng.set_global_index(rec, g)
 
+    window = None if os.environ.get("SVB_EXCHANGE", "window") == "nccl" else open_window(eng, rank, world)
+    exchange = "nccl all-gather (torch.distributed)" if window is None else "peer-memory window (CUDA IPC, NVLink stores + device flags)"
+
+    def one_step(stage):
+        if window is not None:
+            return sharded_step_window(stage, window, owner, ranks)
+        return sharded_step_device(stage, rank, world, owner, ranks, device, _lib.ROW_DTYPE)
+
     def timed(stage_factory, steps, warmup):
         for _ in range(warmup):
-            table = sharded_step_device(stage_factory(), rank, world, owner, ranks, device, _lib.ROW_DTYPE)
+            table = one_step(stage_factory())
         dist.barrier()
         torch.cuda.synchronize()
         eng.synchronize()
@@ -345,7 +407,7 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         _PROFILE.clear()
         eng.mark(2)
         for _ in range(steps):
-            table = sharded_step_device(stage_factory(), rank, world, owner, ranks, device, _lib.ROW_DTYPE)
+            table = one_step(stage_factory())
         eng.mark(3)
         eng.synchronize()
         torch.cuda.synchronize()
@@ -378,22 +440,42 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     h2d = torch.tensor([float(stages[-1].h2d)], dtype=torch.float64, device=device)
     dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
     assert table.shape[0] == table2.shape[0]
+    parity = None
+    if sample is not None:
+        # the gathered, ordered table of the sharded run against the oracle on the CPU sample (outside the timed region)
+        s1, s2, tids, idx1, idx2 = sample
+        _dt, _na, _no, want = parity_tools[1](s1, s2, bases, off)
+        parity = parity_tools[2](table2, (want, tids, idx1, idx2))
+        del bases
     if rank == 0:
         peak, peak_src = peak_hbm()
         local_ops, local_aln = hosts[0].n_ops + hosts[1].n_ops, hosts[0].n_aln + hosts[1].n_aln
         scan_avg = scan_ms / max(scan_launches, 1)
         alg = (4.0 * local_ops + 32.0 * local_aln) / 2.0
         achieved = alg / (scan_avg * 1e-3) / 1e9 if scan_avg > 0 else 0.0
+        # DRAM bytes per launch: the ncu capture of the full-size launch (profiles/) measured 1.016 x the algorithmic bytes;
+        # a shard runs the same kernel on fewer units, so the shard's figure is that ratio times its algorithmic bytes
+        traffic, traffic_src = None, None
+        try:
+            cap = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_cigar_scan_traffic.json")))
+            ratio = cap["cigar_scan_dram_bytes_per_launch"] / (4.0 * cap["n_ops"] + 32.0 * cap.get("n_aln", 0) + 64.0 * cap.get("n_rows", 0))
+            traffic = ratio * alg
+            traffic_src = "profiles/r1_cigar_scan_traffic.json: measured DRAM bytes / algorithmic bytes of the full-size launch (%.3f) x this shard's algorithmic bytes" % ratio
+        except Exception:
+            pass
         print(json.dumps({
             "metric": "alignments_per_sec", "value": n_aln_total / sec, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "cigar_ops_per_sec": n_ops_total / sec,
             "config": workload_config(cfg, args, paired_rows=int(table.shape[0]),
-                                      shard="rank 0 holds %d of %d alignments" % (local_aln, n_aln_total)),
+                                      shard="rank 0 holds %d of %d alignments" % (local_aln, n_aln_total), exchange=exchange),
             "roofline": {"kernel": "cigar_scan (rank 0 shard)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launch_ms": scan_avg},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "launch_ms": scan_avg, "algorithmic_bytes_per_launch": alg},
             "e2e": {"value": n_aln_total / e2e_sec, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d.item()),
                     "d2h_bytes_per_step": int(table.nbytes), "ms_per_step": e2e_sec * 1e3},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": parity, "gpu_launches": int(launches), "clocks": clocks,
         }), flush=True)
+    if window is not None:
+        window.close()
     dist.destroy_process_group()
