@@ -258,8 +258,7 @@ def b200_arm(args):
     rec1, rec2 = eng.load_records(h1, with_sequences=True), eng.load_records(h2, with_sequences=True)
 
     def step_resident():
-        t1 = eng.collect(rec1, params, hap=1)
-        t2 = eng.collect(rec2, params, hap=2)
+        t1, t2 = eng.collect2(rec1, rec2, params)        # both haplotypes, one host synchronisation
         paired = eng.pair(t1, t2, rec1, rec2, ref, params)
         n = len(paired), len(t1), len(t2)
         t1.free(), t2.free(), paired.free()
@@ -306,10 +305,9 @@ def b200_arm(args):
     # ---- e2e: host buffers in, paired table out, every step
     def step_e2e():
         r1, r2 = eng.load_records(h1), eng.load_records(h2)
-        t1 = eng.collect(r1, params, hap=1)
-        t2 = eng.collect(r2, params, hap=2)
-        t1.attach_sequences_host(h1)          # only the inserted bases cross PCIe, not the 2 x 0.65 GB of query sequence
-        t2.attach_sequences_host(h2)
+        eng.map_sequences_host(r1)            # the query sequences stay in pinned host memory: only the inserted bases cross
+        eng.map_sequences_host(r2)            # PCIe (gathered in place into the tables' pools), not 2 x 0.65 GB
+        t1, t2 = eng.collect2(r1, r2, params, with_pools=True)
         paired = eng.pair(t1, t2, r1, r2, ref, params)
         rows = paired.to_numpy()
         for obj in (t1, t2, paired, r1, r2):

@@ -170,9 +170,22 @@ void svb_records_free(svb_records* rec);
  * SVIM_COMBINE.py:65-76).  seq_off has n_aln + 1 byte offsets. */
 int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq4, const uint64_t* seq_off);
 
+/* The same without the upload: the sequences stay in PINNED host memory of the caller (which must outlive the records) and
+ * the device reads the inserted bases it needs in place over PCIe. */
+int svb_records_map_sequences_host(svb_ctx* ctx, svb_records* rec, const uint8_t* seq4_pinned, const uint64_t* seq_off_pinned);
+
 /* K2 cigar_scan + K4 segment_walk + K5 ordered merge.  hap = 0 (haploid), 1 or 2.
  * Rows come out in the reference's emission order (SVIM_COLLECT.py:74,79-80). */
 int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_table** out);
+
+/* Both haplotypes of a diploid run (svim-asm:97,114: two analyze_alignment_file_coordsorted calls) with ONE host
+ * synchronisation: the scans, finalize passes and walk counts of both are enqueued, the host reads all counts at once, the
+ * walk rows are written and merged without waiting again.  hap = 1 for rec1, 2 for rec2.  with_pools != 0 also copies the
+ * inserted bases of the INS rows next to each table (svb_table_gather_sequences) -- their size is summed on the device
+ * before the synchronisation, so this adds no wait either; the records need their sequences (svb_records_set_sequences
+ * or svb_records_map_sequences_host). */
+int svb_collect2(svb_ctx* ctx, const svb_records* rec1, const svb_records* rec2, const svb_params* p, int with_pools,
+                 svb_table** out1, svb_table** out2);
 
 /* analyze_cigar_indel (SVIM_intra.py:8-30) on one op list: rows of (pos_ref, pos_read, length, is_del). */
 int svb_cigar_indel(svb_ctx* ctx, const uint32_t* packed_ops, uint32_t n_ops, int32_t min_length,

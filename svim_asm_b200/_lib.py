@@ -80,6 +80,8 @@ SIGNATURES = {
                                  c_void_p, c_i32, P(c_void_p)]),
     "svb_records_free": (None, [c_void_p]),
     "svb_records_set_sequences": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "svb_collect2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, P(c_void_p), P(c_void_p)]),
+    "svb_records_map_sequences_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "svb_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_int, P(c_void_p)]),
     "svb_cigar_indel": (c_int, [c_void_p, c_void_p, c_u32, c_i32, c_void_p, c_u32, P(c_u32)]),
     "svb_ref_load": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, P(c_void_p)]),

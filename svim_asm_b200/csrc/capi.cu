@@ -227,6 +227,7 @@ static void free_async(void* p, cudaStream_t st) {
 void svb_records_free(svb_records* r) {
     if (!r) return;
     cudaSetDevice(r->device);
+    if (r->seq_borrowed) { r->d_seq4 = nullptr; r->d_seq_off = nullptr; }      // pinned host memory of the caller, not ours
     void* ptrs[] = {r->d_hdr, r->d_cigar, r->d_off4, r->d_chunk_first, r->d_seg, r->d_sa_count, r->d_contig_len,
                     r->d_contig_lexrank, r->d_aln_sum, r->d_prim_list, r->d_seq4, r->d_seq_off, r->d_global_idx};
     for (void* q : ptrs) free_async(q, r->stream);
@@ -334,8 +335,11 @@ int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq
     if (!ctx || !rec || !seq_off) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_records_set_sequences") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
     const uint64_t bytes = seq_off[rec->n_aln];
-    free_async(rec->d_seq4, ctx->stream);
-    free_async(rec->d_seq_off, ctx->stream);
+    if (!rec->seq_borrowed) {
+        free_async(rec->d_seq4, ctx->stream);
+        free_async(rec->d_seq_off, ctx->stream);
+    }
+    rec->seq_borrowed = false;
     rec->d_seq4 = nullptr;
     rec->d_seq_off = nullptr;
     SVB_CUDA(ctx, cudaMallocAsync(&rec->d_seq_off, sizeof(uint64_t) * (static_cast<size_t>(rec->n_aln) + 1), ctx->stream));
@@ -347,6 +351,34 @@ int svb_records_set_sequences(svb_ctx* ctx, svb_records* rec, const uint8_t* seq
     }
     rec->seq_bytes = bytes;
     SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SVB_OK;
+}
+
+// The query sequences stay where they are -- in PINNED host memory of the caller -- and the device reads the few MB of
+// inserted bases it needs in place over PCIe (sequence pools of svb_collect2 / svb_table_gather_sequences) instead of the
+// 0.65 GB of a whole assembly being uploaded.  The buffers must outlive the records.
+int svb_records_map_sequences_host(svb_ctx* ctx, svb_records* rec, const uint8_t* seq4_pinned, const uint64_t* seq_off_pinned) {
+    if (!ctx || !rec || !seq_off_pinned) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_records_map_sequences_host") : SVB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    auto view = [](const void* p) -> void* {
+        cudaPointerAttributes attr;
+        if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged) ? attr.devicePointer : nullptr;
+    };
+    void* d_off = view(seq_off_pinned);
+    void* d_seq = seq4_pinned ? view(seq4_pinned) : nullptr;
+    if (!d_off || (seq4_pinned && !d_seq)) return svb_fail(ctx, SVB_ERR_ARG, "svb_records_map_sequences_host: the buffers are not pinned host memory");
+    if (!rec->seq_borrowed) {
+        free_async(rec->d_seq4, ctx->stream);
+        free_async(rec->d_seq_off, ctx->stream);
+    }
+    rec->d_seq4 = static_cast<uint8_t*>(d_seq);
+    rec->d_seq_off = static_cast<uint64_t*>(d_off);
+    rec->seq_bytes = 0;
+    rec->seq_borrowed = true;
     return SVB_OK;
 }
 
@@ -433,89 +465,195 @@ int svb_table_import(svb_ctx* ctx, const void* device_src, uint64_t n_rows, svb_
 
 // ---- collect -----------------------------------------------------------------------------------
 
+// ---- collect: enqueue (K2 + finalize + K4 count), ONE synchronisation for the counts, finish (K4 write + K5 merge) ----
+// A collect is split so that the two haplotypes of a diploid run share the synchronisation (svb_collect2): everything up to
+// the counts of both is enqueued, the host waits once, then the walk rows are written and merged without waiting again.
+// Device counters of a pending collect (base = 0 or 16): [base] indel rows, [base + 1] walk rows, [base + 2] 4-bit bytes of
+// the walk's inserted sequences, [base + 3] those of the indel rows.
+namespace {
+
+struct CollectPending {
+    const svb_records* rec = nullptr;
+    int hap = 0, base = 0;
+    svb_table* indel = nullptr;
+    WalkPending* walk = nullptr;
+};
+
+__global__ void ins_bytes_kernel(const svb_row* __restrict__ rows, const unsigned long long* __restrict__ n_dev, unsigned long long cap,
+                                 unsigned long long* __restrict__ total) {
+    const unsigned long long n = min(*n_dev, cap);
+    unsigned long long mine = 0;
+    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+        if (rows[i].type == SVB_INS) mine += (rows[i].seq_len + 1u) / 2u;
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(total, mine);
+}
+
+void collect_drop(svb_ctx* ctx, CollectPending& c) {
+    if (c.indel) svb_table_free(c.indel);
+    walk_discard(ctx, c.walk);
+    c.indel = nullptr;
+    c.walk = nullptr;
+}
+
+int collect_begin(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, int base, uint64_t cap, bool with_walk, CollectPending* c) {
+    c->rec = rec;
+    c->hap = hap;
+    c->base = base;
+    c->indel = table_alloc(ctx, cap);
+    if (!c->indel) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: indel table");
+    ScanOutput so{c->indel->d_rows, c->indel->cap, ctx->d_counters + base};
+    int rc = launch_cigar_scan(ctx, rec, p, hap, so);
+    if (rc == SVB_OK) {
+        cudaError_t e = cudaMemsetAsync(ctx->d_counters + base + 3, 0, sizeof(unsigned long long), ctx->stream);
+        if (e == cudaSuccess) {
+            ins_bytes_kernel<<<static_cast<unsigned>(std::min<uint64_t>((cap + 255) / 256, 2048)), 256, 0, ctx->stream>>>(
+                c->indel->d_rows, ctx->d_counters + base, c->indel->cap, ctx->d_counters + base + 3);
+            ctx->launches += 1;
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: inserted bytes", e);
+    }
+    if (rc == SVB_OK && with_walk) rc = walk_count_async(ctx, rec, p, hap, ctx->d_counters + base + 1, &c->walk);
+    if (rc != SVB_OK) collect_drop(ctx, *c);
+    return rc;
+}
+
+// the counts of the pending collects + the device status, one wait
+int collect_sync(svb_ctx* ctx, CollectPending* list, int n) {
+    uint32_t* h_status = reinterpret_cast<uint32_t*>(ctx->h_pinned + 12);
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < n && e == cudaSuccess; ++k)
+        e = cudaMemcpyAsync(ctx->h_pinned + list[k].base, ctx->d_counters + list[k].base, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: cigar_scan", e);
+    if (*h_status) return check_device_status(ctx);          // the kernels flagged something the reference would have raised on
+    return SVB_OK;
+}
+
+// after collect_sync: K4 write pass, K5 merge, optionally the sequence pool -- all stream ordered, no further wait
+int collect_end(svb_ctx* ctx, CollectPending& c, const svb_params* p, bool with_pool, svb_table** out) {
+    *out = nullptr;
+    const unsigned long long n_indel = ctx->h_pinned[c.base], n_walk = c.walk ? ctx->h_pinned[c.base + 1] : 0ull;
+    const unsigned long long pool_bytes = ctx->h_pinned[c.base + 3] + (c.walk ? ctx->h_pinned[c.base + 2] : 0ull);
+    if (n_indel > c.indel->cap) {
+        // the capacity guess (1 row per 512 ops) was too small: scan once more with the exact size (the walk's count pass is
+        // still valid: it reads the per-alignment sums, not the rows)
+        svb_table_free(c.indel);
+        c.indel = nullptr;
+        CollectPending again;
+        int rc = collect_begin(ctx, c.rec, p, c.hap, c.base, n_indel, false, &again);
+        if (rc == SVB_OK) {
+            again.walk = nullptr;
+            rc = collect_sync(ctx, &again, 1);
+        }
+        if (rc != SVB_OK) {
+            collect_drop(ctx, again);
+            collect_drop(ctx, c);
+            return rc;
+        }
+        c.indel = again.indel;
+        if (ctx->h_pinned[c.base] > c.indel->cap) {
+            collect_drop(ctx, c);
+            return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_collect: indel table overflow");
+        }
+    }
+    svb_table* indel = c.indel;
+    c.indel = nullptr;
+    indel->n = ctx->h_pinned[c.base];
+    // K4: split-alignment walk rows (own table, emission order per primary)
+    svb_row* d_walk = nullptr;
+    int rc = walk_write_async(ctx, c.walk, n_walk, &d_walk);
+    c.walk = nullptr;
+    if (rc != SVB_OK) {
+        svb_table_free(indel);
+        return rc;
+    }
+    svb_table* result = indel;
+    if (n_walk) {
+        // K5: order-preserving merge by ordinal (record order; indels of a record before its walk rows)
+        svb_table* merged = table_alloc(ctx, indel->n + n_walk);
+        if (!merged) {
+            svb_table_free(indel);
+            free_async(d_walk, ctx->stream);
+            return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: merged table");
+        }
+        rc = launch_merge_tables(ctx, indel->d_rows, indel->n, d_walk, n_walk, merged->d_rows);     // stream ordered: no wait
+        merged->n = indel->n + n_walk;
+        svb_table_free(indel);
+        free_async(d_walk, ctx->stream);
+        if (rc != SVB_OK) {
+            svb_table_free(merged);
+            return rc;
+        }
+        result = merged;
+    }
+    if (with_pool) {
+        if (!c.rec->d_seq_off) {
+            svb_table_free(result);
+            return svb_fail(ctx, SVB_ERR_ARG, "svb_collect2: sequence pools need the query sequences (svb_records_set_sequences)");
+        }
+        rc = gather_pool_known(ctx, result, c.rec->d_seq4, c.rec->d_seq_off, pool_bytes);
+        if (rc != SVB_OK) {
+            svb_table_free(result);
+            return rc;
+        }
+    }
+    *out = result;
+    return SVB_OK;
+}
+
+uint64_t collect_cap_guess(const svb_records* rec) {
+    // K2's row capacity is a guess (1 row per 512 ops; human assemblies have about 1 per 20,000); an overflow is detected from
+    // the exact count and that scan is repeated once with the right size
+    return std::max<uint64_t>(4096, rec->n_ops / 512);
+}
+
+}  // namespace
+
 int svb_collect(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, svb_table** out) {
     if (!ctx || !rec || !p || !out || hap < 0 || hap > 2) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_collect") : SVB_ERR_ARG;
     if (rec->device != ctx->device) return svb_fail(ctx, SVB_ERR_ARG, "svb_collect: records live on another device");
     cudaSetDevice(ctx->device);
     *out = nullptr;
-
-    // K2: indel rows.  Capacity is a guess (1 row per 512 ops; human assemblies have about 1 per 20,000); an
-    // overflow is detected from the exact count and the scan is repeated once with the right size.
-    // K4's count pass is enqueued right behind the scan (it needs the scan's per-alignment sums, not its rows), so
-    // that both counts and the device status come back with a single synchronisation.
-    uint64_t cap = std::max<uint64_t>(4096, rec->n_ops / 512);
-    svb_table* indel = nullptr;
-    WalkPending* walk = nullptr;
-    unsigned long long n_indel = 0, n_walk = 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        indel = table_alloc(ctx, cap);
-        if (!indel) {
-            walk_discard(ctx, walk);
-            return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: indel table");
-        }
-        ScanOutput so{indel->d_rows, indel->cap, ctx->d_counters};
-        int rc = launch_cigar_scan(ctx, rec, p, hap, so);
-        if (rc == SVB_OK && attempt == 0) rc = walk_count_async(ctx, rec, p, hap, &walk);
-        if (rc != SVB_OK) {
-            svb_table_free(indel);
-            walk_discard(ctx, walk);
-            return rc;
-        }
-        uint32_t* h_status = reinterpret_cast<uint32_t*>(ctx->h_pinned + 12);
-        cudaError_t e = cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) {
-            svb_table_free(indel);
-            walk_discard(ctx, walk);
-            return svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: cigar_scan", e);
-        }
-        if (*h_status) {                  // the kernels flagged something the reference would have raised on
-            svb_table_free(indel);
-            walk_discard(ctx, walk);
-            return check_device_status(ctx);
-        }
-        n_indel = ctx->h_pinned[0];
-        if (attempt == 0) n_walk = ctx->h_pinned[1];
-        if (n_indel <= indel->cap) break;
-        svb_table_free(indel);
-        indel = nullptr;
-        cap = n_indel;
-    }
-    if (!indel) {
-        walk_discard(ctx, walk);
-        return svb_fail(ctx, SVB_ERR_CAPACITY, "svb_collect: indel table overflow");
-    }
-    indel->n = n_indel;
-
-    // K4: split-alignment walk rows (own table, emission order per primary)
-    svb_row* d_walk = nullptr;
-    int rc = walk_write_async(ctx, walk, n_walk, &d_walk);
+    CollectPending c;
+    int rc = collect_begin(ctx, rec, p, hap, 0, collect_cap_guess(rec), true, &c);
+    if (rc != SVB_OK) return rc;
+    rc = collect_sync(ctx, &c, 1);
     if (rc != SVB_OK) {
-        svb_table_free(indel);
+        collect_drop(ctx, c);
         return rc;
     }
-    if (n_walk == 0) {
-        *out = indel;
-        return SVB_OK;
-    }
-    // K5: order-preserving merge by ordinal (record order; indels of a record before its walk rows)
-    svb_table* merged = table_alloc(ctx, n_indel + n_walk);
-    if (!merged) {
-        svb_table_free(indel);
-        free_async(d_walk, ctx->stream);
-        return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: merged table");
-    }
-    rc = launch_merge_tables(ctx, indel->d_rows, n_indel, d_walk, n_walk, merged->d_rows);     // stream ordered: no wait
-    svb_table_free(indel);
-    free_async(d_walk, ctx->stream);
+    return collect_end(ctx, c, p, false, out);
+}
+
+int svb_collect2(svb_ctx* ctx, const svb_records* rec1, const svb_records* rec2, const svb_params* p, int with_pools, svb_table** out1,
+                 svb_table** out2) {
+    if (!ctx || !rec1 || !rec2 || !p || !out1 || !out2) return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_collect2") : SVB_ERR_ARG;
+    if (rec1->device != ctx->device || rec2->device != ctx->device) return svb_fail(ctx, SVB_ERR_ARG, "svb_collect2: records live on another device");
+    cudaSetDevice(ctx->device);
+    *out1 = *out2 = nullptr;
+    CollectPending c[2];
+    int rc = collect_begin(ctx, rec1, p, 1, 0, collect_cap_guess(rec1), true, &c[0]);
+    if (rc != SVB_OK) return rc;
+    rc = collect_begin(ctx, rec2, p, 2, 16, collect_cap_guess(rec2), true, &c[1]);
+    if (rc == SVB_OK) rc = collect_sync(ctx, c, 2);
     if (rc != SVB_OK) {
-        svb_table_free(merged);
+        collect_drop(ctx, c[0]);
+        collect_drop(ctx, c[1]);
         return rc;
     }
-    merged->n = n_indel + n_walk;
-    *out = merged;
-    return SVB_OK;
+    rc = collect_end(ctx, c[0], p, with_pools != 0, out1);
+    if (rc == SVB_OK) rc = collect_end(ctx, c[1], p, with_pools != 0, out2);
+    if (rc != SVB_OK) {
+        collect_drop(ctx, c[0]);
+        collect_drop(ctx, c[1]);
+        if (*out1) { svb_table_free(*out1); *out1 = nullptr; }
+        if (*out2) { svb_table_free(*out2); *out2 = nullptr; }
+    }
+    return rc;
 }
 
 int svb_cigar_indel(svb_ctx* ctx, const uint32_t* packed_ops, uint32_t n_ops, int32_t min_length, int64_t* out4,

@@ -33,6 +33,7 @@ struct svb_records {
     uint64_t* d_seq_off = nullptr;    // [n_aln + 1]
     uint32_t* d_global_idx = nullptr; // optional [n_aln]: index of each record in the unsharded batch (exchange.cu)
     uint64_t seq_bytes = 0;
+    bool seq_borrowed = false;        // d_seq4 / d_seq_off are device views of the caller's pinned host buffers
     std::vector<int32_t> h_contig_len; // host copy of the contig table (svb_pair checks that both haplotypes share it)
 };
 
@@ -128,9 +129,10 @@ uint64_t cigar_padded_n4(uint64_t n4);   // uint4 capacity d_cigar must be alloc
 int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec);
 int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out);
 struct WalkPending;   // a walk whose count pass is in flight (segment_walk.cu)
-int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, WalkPending** out);   // total -> d_counters[1]
+int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, unsigned long long* totals, WalkPending** out);   // totals[0] rows, [1] inserted bytes
 int walk_write_async(svb_ctx* ctx, WalkPending* w, uint64_t n_rows, svb_row** d_rows_out);                     // consumes w
 void walk_discard(svb_ctx* ctx, WalkPending* w);
+int gather_pool_known(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off, uint64_t pool_bytes);   // seqpool.cu
 int launch_merge_tables(svb_ctx* ctx, const svb_row* a, uint64_t na, const svb_row* b, uint64_t nb, svb_row* out);
 int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
                 const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);

@@ -179,12 +179,15 @@ int svb_exchange_pack(svb_ctx* ctx, const svb_table* t1, const svb_table* t2, vo
     return SVB_OK;
 }
 
-int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, const uint64_t* sizes, int world, int hap,
-                        const int32_t* owner, int n_contig, int rank, svb_table** out) {
+// enqueue only: the number of rows kept lands in h_pinned[13 + hap - 1] once the stream has run (the caller synchronises once
+// for both haplotypes and then sets the tables' sizes)
+static int exchange_unpack_enqueue(svb_ctx* ctx, const void* d_gathered, uint64_t stride, const uint64_t* sizes, int world, int hap,
+                                   const int32_t* owner, int n_contig, int rank, svb_table** out) {
     if (!ctx || !d_gathered || !sizes || !owner || !out || world < 1 || world > EXCH_MAX_WORLD || hap < 1 || hap > 2)
         return ctx ? svb_fail(ctx, SVB_ERR_ARG, "svb_exchange_unpack") : SVB_ERR_ARG;
     cudaSetDevice(ctx->device);
     *out = nullptr;
+    const int slot = 13 + hap - 1;               // device counter / pinned word of this haplotype ([12] is the status word)
     const int h = hap - 1;
     const uint8_t* base = static_cast<const uint8_t*>(d_gathered);
     Runs rs;
@@ -228,20 +231,31 @@ int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, c
     const unsigned blocks = static_cast<unsigned>((rows_total + 1 + 255) / 256);
     owned_flags_kernel<<<blocks, 256, 0, ctx->stream>>>(rs, d_owner, n_contig, rank, d_flags);
     ctx->launches += 1;
-    int rc = launch_scan_u32(ctx, d_flags, static_cast<uint32_t>(rows_total + 1), ctx->d_counters + 11);
+    int rc = launch_scan_u32(ctx, d_flags, static_cast<uint32_t>(rows_total + 1), ctx->d_counters + slot);
     if (rc != SVB_OK) return fail(rc);
     if (rows_total) {
         place_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(rs, d_flags, t->d_rows, t->d_pool_off);
         ctx->launches += 1;
     }
     EX_CUDA(cudaGetLastError());
-    EX_CUDA(cudaMemcpyAsync(ctx->h_pinned + 11, ctx->d_counters + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    EX_CUDA(cudaStreamSynchronize(ctx->stream));
+    EX_CUDA(cudaMemcpyAsync(ctx->h_pinned + slot, ctx->d_counters + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 #undef EX_CUDA
-    t->n = ctx->h_pinned[11];
     cudaFreeAsync(d_owner, ctx->stream);
     cudaFreeAsync(d_flags, ctx->stream);
     *out = t;
+    return SVB_OK;
+}
+
+int svb_exchange_unpack(svb_ctx* ctx, const void* d_gathered, uint64_t stride, const uint64_t* sizes, int world, int hap,
+                        const int32_t* owner, int n_contig, int rank, svb_table** out) {
+    int rc = exchange_unpack_enqueue(ctx, d_gathered, stride, sizes, world, hap, owner, n_contig, rank, out);
+    if (rc != SVB_OK) return rc;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        svb_table_free(*out);
+        *out = nullptr;
+        return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_unpack");
+    }
+    (*out)->n = ctx->h_pinned[13 + hap - 1];
     return SVB_OK;
 }
 
@@ -529,10 +543,17 @@ int svb_exchange_share(svb_ctx* ctx, svb_exchange* x, const svb_table* t1, const
     }
     // tables that did not bring a pool pack no offsets: unpack reads zeros there (the slot was cleared at creation and pools
     // never shrink to "absent" between steps of one run)
-    rc = svb_exchange_unpack(ctx, x->window + XW_HEADER, x->slot_bytes, all_sizes.data(), x->world, 1, owner, n_contig, x->rank, u1);
-    if (rc == SVB_OK) rc = svb_exchange_unpack(ctx, x->window + XW_HEADER, x->slot_bytes, all_sizes.data(), x->world, 2, owner, n_contig, x->rank, u2);
-    if (rc != SVB_OK && *u1) { svb_table_free(*u1); *u1 = nullptr; }
-    return rc;
+    rc = exchange_unpack_enqueue(ctx, x->window + XW_HEADER, x->slot_bytes, all_sizes.data(), x->world, 1, owner, n_contig, x->rank, u1);
+    if (rc == SVB_OK) rc = exchange_unpack_enqueue(ctx, x->window + XW_HEADER, x->slot_bytes, all_sizes.data(), x->world, 2, owner, n_contig, x->rank, u2);
+    if (rc == SVB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_share: unpack");
+    if (rc != SVB_OK) {
+        if (*u1) { svb_table_free(*u1); *u1 = nullptr; }
+        if (*u2) { svb_table_free(*u2); *u2 = nullptr; }
+        return rc;
+    }
+    (*u1)->n = ctx->h_pinned[13];
+    (*u2)->n = ctx->h_pinned[14];
+    return SVB_OK;
 }
 
 // All-gatherv of the paired rows of every rank, put into pair_candidates' order (type, contig by python string order).

@@ -11,6 +11,7 @@
 //       label order -> linkage.cuh, one thread per partition; then the genotype / merge rules of :184-365.
 // Output rows appear in the reference's order: type by type, partition by partition, label by label.
 #include <algorithm>
+#include <cstdlib>
 
 #include "pairing.cuh"
 #include "walk.cuh"
@@ -19,7 +20,7 @@
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ROUNDS = 8;
+constexpr int RS_ROUNDS = 2;          // 512 keys per tile: a whole-genome diploid sample (18,000 keys) spreads over 37 CTAs
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
 
 struct PairArgs {
@@ -230,17 +231,15 @@ __device__ void make_desc(const svb_row& r, long long lo, long long hi, const Pa
 
 // one thread per partition: the cross-haplotype pairs that need an edit distance
 // (launched before the host knows the number of partitions: the bound is read from the device)
-__global__ void enumerate_jobs_kernel(const PairArgs a, const unsigned long long* __restrict__ n_parts_dev) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= static_cast<uint32_t>(*n_parts_dev)) return;
-    const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
+__device__ void enumerate_partition(const PairArgs& a, uint32_t p) {
+    const uint32_t first = __ldcg(a.part_start + p), n = __ldcg(a.part_start + p + 1) - first;
     if (n < 2u || n > static_cast<uint32_t>(PAIR_MAX)) return;
-    const svb_row r0 = a.rows[a.order[first]];
+    const svb_row r0 = a.rows[__ldcg(a.order + first)];
     if (r0.type == SVB_BND) return;
     for (uint32_t i = 0; i + 1 < n; ++i) {
-        const svb_row ri = a.rows[a.order[first + i]];
+        const svb_row ri = a.rows[__ldcg(a.order + first + i)];
         for (uint32_t j = i + 1; j < n; ++j) {
-            const svb_row rj = a.rows[a.order[first + j]];
+            const svb_row rj = a.rows[__ldcg(a.order + first + j)];
             if (ri.hap == rj.hap) continue;
             const bool by_source = ri.type == SVB_DEL || ri.type == SVB_INV || ri.type == SVB_DUP_TAN;
             const int32_t tid = by_source ? ri.src_tid : ri.dst_tid;
@@ -266,6 +265,226 @@ __global__ void enumerate_jobs_kernel(const PairArgs a, const unsigned long long
                 static_cast<uint32_t>(slot);
         }
     }
+}
+
+__global__ void enumerate_jobs_kernel(const PairArgs a, const unsigned long long* __restrict__ n_parts_dev) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= static_cast<uint32_t>(*n_parts_dev)) return;
+    enumerate_partition(a, p);
+}
+
+// ---- K6 + K7 + job enumeration in ONE launch ---------------------------------------------------------------------------
+// For a diploid human sample the pairing front is latency, not work: 18,000 keys, 40 key bits, and until round 2 a chain of
+// 22 launches (keys, 5 x (histogram, scan, scatter), heads, scan, partition starts, jobs: 0.14 ms of launch gaps and 6 us
+// kernels).  Here a handful of co-resident CTAs (cooperative launch; one per 512-key tile, at most FRONT_MAX_TILES) run the
+// same phases back to back, separated by a grid barrier: a counter in global memory that every CTA bumps once per phase.
+// The per-tile histograms live in global memory as before (digit-major); instead of a separate scan launch every CTA
+// rebuilds the offsets of its own tile from them (256 x tiles words, read from L2).
+constexpr uint32_t FRONT_MAX_TILES = 148;
+
+struct FrontArgs {
+    const svb_row* h1; const svb_row* h2; uint32_t n1, n2;
+    const uint64_t* pool_off1; const uint64_t* pool_off2; const uint64_t* seq_off1; const uint64_t* seq_off2;
+    uint32_t rank_bits, key_bits, n_tiles;
+    long long max_distance;
+    svb_row* rows;
+    unsigned long long* keys[2];
+    uint32_t* vals[2];
+    uint32_t* hist;                  // [256][n_tiles]
+    uint32_t* tile_heads;            // [n_tiles]
+    uint32_t* part_start;
+    unsigned long long* n_parts_dev;
+    unsigned int* barrier;           // zeroed by the host
+    PairArgs pa;                     // pa.order must point at the buffer the LAST pass writes
+};
+
+__device__ __forceinline__ void front_barrier(unsigned int* counter, unsigned int& phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++phase;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned int target = phase * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RS_THREADS) pair_front_kernel(const __grid_constant__ FrontArgs f) {
+    __shared__ uint32_t s_hist[256], s_base[256], s_running[256], s_scan[256];
+    __shared__ uint32_t s_wc[RS_THREADS / 32][256];
+    __shared__ uint32_t s_tile_off[FRONT_MAX_TILES + 1];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n = f.n1 + f.n2;
+    unsigned int phase = 0;
+
+    // ---- keys (concat_keys_kernel)
+    for (uint32_t i = blockIdx.x * RS_THREADS + tid; i < n; i += gridDim.x * RS_THREADS) {
+        svb_row r = i < f.n1 ? f.h1[i] : f.h2[i - f.n1];
+        r.hap = i < f.n1 ? 1 : 2;
+        r.reserved0 = ~0ull;
+        if (r.type == SVB_INS) {
+            const uint64_t* pool_off = i < f.n1 ? f.pool_off1 : f.pool_off2;
+            const uint64_t* seq_off = i < f.n1 ? f.seq_off1 : f.seq_off2;
+            if (pool_off) r.reserved0 = pool_off[i < f.n1 ? i : i - f.n1] * 2ull;
+            else if (seq_off) r.reserved0 = seq_off[r.aln_idx] * 2ull + r.seq_pos;
+            else atomicOr(f.pa.dev_status, DEV_ERR_NOSEQ);
+        }
+        f.rows[i] = r;
+        int32_t ktid, pos;
+        key_of(r, ktid, pos);
+        uint32_t rank = 0;
+        if (ktid < 0 || ktid >= f.pa.n_contig) atomicOr(f.pa.dev_status, DEV_ERR_BAD_TID);
+        else rank = static_cast<uint32_t>(f.pa.contig_lexrank[ktid]);
+        f.keys[0][i] = (static_cast<unsigned long long>(r.type) << (32u + f.rank_bits)) | (static_cast<unsigned long long>(rank) << 32) |
+                       static_cast<uint32_t>(pos);
+        f.vals[0][i] = i;
+    }
+    front_barrier(f.barrier, phase);
+
+    // ---- stable LSD radix sort, 8 bits per pass
+    int cur = 0;
+    for (uint32_t shift = 0; shift < f.key_bits; shift += 8) {
+        const unsigned long long* kin = f.keys[cur];
+        const uint32_t* vin = f.vals[cur];
+        unsigned long long* kout = f.keys[cur ^ 1];
+        uint32_t* vout = f.vals[cur ^ 1];
+        for (uint32_t t = blockIdx.x; t < f.n_tiles; t += gridDim.x) {          // histogram of every tile of this CTA
+            s_hist[tid] = 0;
+            __syncthreads();
+            const uint32_t base = t * RS_TILE;
+            for (int r = 0; r < RS_ROUNDS; ++r) {
+                const uint32_t i = base + r * RS_THREADS + tid;
+                if (i < n) atomicAdd(&s_hist[(__ldcg(kin + i) >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            f.hist[tid * f.n_tiles + t] = s_hist[tid];
+            __syncthreads();
+        }
+        front_barrier(f.barrier, phase);
+        for (uint32_t t = blockIdx.x; t < f.n_tiles; t += gridDim.x) {
+            // offsets of tile t: keys with a smaller digit (all tiles) + keys with this digit in earlier tiles
+            uint32_t total = 0, before = 0;
+            for (uint32_t q = 0; q < f.n_tiles; ++q) {
+                const uint32_t c = __ldcg(f.hist + tid * f.n_tiles + q);
+                total += c;
+                if (q < t) before += c;
+            }
+            // exclusive scan of `total` over the 256 digits (one per thread)
+            uint32_t inc = total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+                if (static_cast<int>(lane) >= d) inc += y;
+            }
+            if (lane == 31u) s_scan[warp] = inc;
+            __syncthreads();
+            uint32_t warp_before = 0;
+            for (uint32_t w = 0; w < warp; ++w) warp_before += s_scan[w];
+            s_base[tid] = warp_before + inc - total + before;
+            s_running[tid] = 0;
+            __syncthreads();
+            const uint32_t base = t * RS_TILE;
+            for (int r = 0; r < RS_ROUNDS; ++r) {                                 // radix_scatter_kernel's rounds
+#pragma unroll
+                for (int w = 0; w < RS_THREADS / 32; ++w) s_wc[w][tid] = 0;
+                __syncthreads();
+                const uint32_t i = base + r * RS_THREADS + tid;
+                const bool valid = i < n;
+                unsigned long long key = 0;
+                uint32_t val = 0, d = 0x100u | lane;                              // invalid lanes match nobody
+                if (valid) {
+                    key = __ldcg(kin + i);
+                    val = __ldcg(vin + i);
+                    d = static_cast<uint32_t>(key >> shift) & 255u;
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+                if (valid && rank_in_warp == 0u) s_wc[warp][d] = __popc(peers);
+                __syncthreads();
+                if (valid) {
+                    uint32_t ahead = 0;
+                    for (uint32_t w = 0; w < warp; ++w) ahead += s_wc[w][d];
+                    const uint32_t dst = s_base[d] + s_running[d] + ahead + rank_in_warp;      // stable: round, warp, lane order
+                    kout[dst] = key;
+                    vout[dst] = val;
+                }
+                __syncthreads();
+                uint32_t add = 0;
+#pragma unroll
+                for (int w = 0; w < RS_THREADS / 32; ++w) add += s_wc[w][tid];
+                s_running[tid] += add;
+                __syncthreads();
+            }
+        }
+        front_barrier(f.barrier, phase);
+        cur ^= 1;
+    }
+    const unsigned long long* keys = f.keys[cur];
+
+    // ---- partition heads (heads_kernel): count per tile, offsets, starts
+    auto is_head = [&](uint32_t i) -> uint32_t {
+        if (i == 0) return 1u;
+        const unsigned long long a = __ldcg(keys + i - 1), b = __ldcg(keys + i);
+        const long long pa = static_cast<int32_t>(static_cast<uint32_t>(a)), pb = static_cast<int32_t>(static_cast<uint32_t>(b));
+        const long long gap = pa > pb ? pa - pb : pb - pa;
+        return ((a >> 32) != (b >> 32) || gap > f.max_distance) ? 1u : 0u;
+    };
+    for (uint32_t t = blockIdx.x; t < f.n_tiles; t += gridDim.x) {
+        uint32_t mine = 0;
+        for (int r = 0; r < RS_ROUNDS; ++r) {
+            const uint32_t i = t * RS_TILE + r * RS_THREADS + tid;
+            if (i < n) mine += is_head(i);
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0) s_scan[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t sum = 0;
+            for (int w = 0; w < RS_THREADS / 32; ++w) sum += s_scan[w];
+            f.tile_heads[t] = sum;
+        }
+        __syncthreads();
+    }
+    front_barrier(f.barrier, phase);
+    if (tid == 0) {
+        uint32_t sum = 0;
+        for (uint32_t q = 0; q < f.n_tiles; ++q) {
+            s_tile_off[q] = sum;
+            sum += __ldcg(f.tile_heads + q);
+        }
+        s_tile_off[f.n_tiles] = sum;
+        if (blockIdx.x == 0) {
+            *f.n_parts_dev = sum;
+            f.part_start[sum] = n;
+        }
+    }
+    __syncthreads();
+    for (uint32_t t = blockIdx.x; t < f.n_tiles; t += gridDim.x) {
+        uint32_t running = s_tile_off[t];
+        for (int r = 0; r < RS_ROUNDS; ++r) {                 // rows of a tile in order: round, then thread
+            const uint32_t i = t * RS_TILE + r * RS_THREADS + tid;
+            const uint32_t h = i < n ? is_head(i) : 0u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, h != 0u);
+            if (lane == 0) s_scan[warp] = __popc(bal);
+            __syncthreads();
+            uint32_t ahead = 0, round_total = 0;
+            for (uint32_t w = 0; w < RS_THREADS / 32; ++w) {
+                if (w < warp) ahead += s_scan[w];
+                round_total += s_scan[w];
+            }
+            if (h) f.part_start[running + ahead + __popc(bal & ((1u << lane) - 1u))] = i;
+            running += round_total;
+            __syncthreads();
+        }
+    }
+    front_barrier(f.barrier, phase);
+
+    // ---- the cross-haplotype pairs of every partition (enumerate_jobs_kernel)
+    const uint32_t n_parts = static_cast<uint32_t>(*reinterpret_cast<volatile unsigned long long*>(f.n_parts_dev));
+    for (uint32_t p = blockIdx.x * RS_THREADS + tid; p < n_parts; p += gridDim.x * RS_THREADS) enumerate_partition(f.pa, p);
 }
 
 // Which pairs need their EXACT distance?  The wavefront kernel (wfa.cu) left, for every cross-haplotype pair, either the
@@ -491,33 +710,13 @@ static int run_pairing_once(svb_ctx* ctx, const svb_table* h1, const svb_table* 
     // [6] longest text the exact kernel could not park, [7..8] the wavefront kernel's three 32-bit counters
     unsigned long long* cnt = ctx->d_counters;
     PAIR_CUDA(cudaMemsetAsync(cnt + 2, 0, 9 * sizeof(unsigned long long), ctx->stream));      // [9] radix scan total, [10] table cells
-    int cur_buf = 0;
-    {
-        KernelTimer timer(ctx, SVB_K_SORT);
-        concat_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h1->d_rows, n1, h2->d_rows, n2, h1->d_pool_off, h2->d_pool_off,
-                                                                     h1->d_pool_off ? nullptr : rec1->d_seq_off,
-                                                                     h2->d_pool_off ? nullptr : rec2->d_seq_off, rec->d_contig_lexrank, rec->n_contig,
-                                                                     rank_bits, rows, keys[0], vals[0], ctx->d_status);
-        ctx->launches += 1;
-        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
-            radix_hist_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], n, shift, hist, n_blocks);
-            int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, cnt + 9);
-            if (rc != SVB_OK) return fail(rc);
-            radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], vals[cur_buf], keys[cur_buf ^ 1], vals[cur_buf ^ 1], n,
-                                                                           shift, hist, n_blocks);
-            cur_buf ^= 1;
-            ctx->launches += 2;
-        }
-        heads_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], n, p->partition_max_distance, head);
-        ctx->launches += 1;
-        int rc = launch_scan_u32(ctx, head, n, cnt + 2);
-        if (rc != SVB_OK) return fail(rc);
-    }
-    PAIR_CUDA(cudaGetLastError());
+    const uint32_t n_passes = (key_bits + 7u) / 8u;
+    const bool fused_front = n_blocks <= FRONT_MAX_TILES && !getenv("SVB_PAIR_UNFUSED");
+    int cur_buf = fused_front ? static_cast<int>(n_passes & 1u) : 0;
 
     PairArgs a;
     a.rows = rows;
-    a.order = vals[cur_buf];
+    a.order = vals[cur_buf];          // (the unfused path sets it again once its passes are enqueued)
     a.part_start = part_start;
     a.n_parts_dev = cnt + 2;
     a.n_rows = n;
@@ -539,11 +738,57 @@ static int run_pairing_once(svb_ctx* ctx, const svb_table* h1, const svb_table* 
     a.counts = counts;
     a.out = nullptr;
     a.dev_status = ctx->d_status;
-    {
+    if (fused_front) {
+        // keys, radix passes, partition starts and the job list in ONE cooperative launch (pair_front_kernel)
+        FrontArgs f;
+        f.h1 = h1->d_rows; f.h2 = h2->d_rows; f.n1 = n1; f.n2 = n2;
+        f.pool_off1 = h1->d_pool_off; f.pool_off2 = h2->d_pool_off;
+        f.seq_off1 = h1->d_pool_off ? nullptr : rec1->d_seq_off;
+        f.seq_off2 = h2->d_pool_off ? nullptr : rec2->d_seq_off;
+        f.rank_bits = rank_bits; f.key_bits = key_bits; f.n_tiles = n_blocks;
+        f.max_distance = p->partition_max_distance;
+        f.rows = rows;
+        f.keys[0] = keys[0]; f.keys[1] = keys[1]; f.vals[0] = vals[0]; f.vals[1] = vals[1];
+        f.hist = hist;
+        f.tile_heads = head;
+        f.part_start = part_start;
+        f.n_parts_dev = cnt + 2;
+        f.barrier = reinterpret_cast<unsigned int*>(cnt + 9);          // zeroed with the other counters above
+        f.pa = a;
+        void* kargs[] = {&f};
         KernelTimer timer(ctx, SVB_K_SORT);
-        part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start, cnt + 2);
-        enumerate_jobs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, cnt + 2);
-        ctx->launches += 2;
+        PAIR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(pair_front_kernel), dim3(n_blocks), dim3(RS_THREADS), kargs, 0, ctx->stream));
+        ctx->launches += 1;
+    } else {
+        {
+            KernelTimer timer(ctx, SVB_K_SORT);
+            concat_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(h1->d_rows, n1, h2->d_rows, n2, h1->d_pool_off, h2->d_pool_off,
+                                                                         h1->d_pool_off ? nullptr : rec1->d_seq_off,
+                                                                         h2->d_pool_off ? nullptr : rec2->d_seq_off, rec->d_contig_lexrank, rec->n_contig,
+                                                                         rank_bits, rows, keys[0], vals[0], ctx->d_status);
+            ctx->launches += 1;
+            for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+                radix_hist_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], n, shift, hist, n_blocks);
+                int rc = launch_scan_u32(ctx, hist, 256u * n_blocks, cnt + 9);
+                if (rc != SVB_OK) return fail(rc);
+                radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(keys[cur_buf], vals[cur_buf], keys[cur_buf ^ 1], vals[cur_buf ^ 1], n,
+                                                                               shift, hist, n_blocks);
+                cur_buf ^= 1;
+                ctx->launches += 2;
+            }
+            heads_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], n, p->partition_max_distance, head);
+            ctx->launches += 1;
+            int rc = launch_scan_u32(ctx, head, n, cnt + 2);
+            if (rc != SVB_OK) return fail(rc);
+        }
+        PAIR_CUDA(cudaGetLastError());
+        a.order = vals[cur_buf];
+        {
+            KernelTimer timer(ctx, SVB_K_SORT);
+            part_start_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(keys[cur_buf], head, n, p->partition_max_distance, part_start, cnt + 2);
+            enumerate_jobs_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, cnt + 2);
+            ctx->launches += 2;
+        }
     }
     PAIR_CUDA(cudaGetLastError());
     // K8: thresholded wavefronts for every pair, then the exact kernel for the few pairs whose exact value can matter

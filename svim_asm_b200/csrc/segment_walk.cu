@@ -34,25 +34,59 @@ struct WalkArgs {
     WalkScratch* scratch;
     uint32_t* counts;             // [n_prim + 1]  pass 1: counts; after the scan: exclusive offsets
     svb_row* rows;                // pass 2 destination
+    svb_row* stage;               // [n_prim][WALK_STAGE_ROWS] rows kept by the count pass
     uint32_t* dev_status;
+    unsigned long long* totals;   // [0] rows of the walk, [1] 4-bit bytes of their inserted sequences (count pass)
+    unsigned int* done;           // CTAs of the count pass that have finished
 };
 
+constexpr int WALK_THREADS = 32;          // one warp per CTA ...
+constexpr int WALK_PER_CTA = 8;           // ... of which 8 lanes carry a primary: the walk is serial, divergent code (ncu: 8 of 32
+                                          // lanes active on average, 13 cycles per issued instruction), so its duration is the
+                                          // number of DIFFERENT paths a warp has to serialise; few primaries per warp and many
+                                          // CTAs (one per SM for a human assembly) shorten it, idle lanes cost nothing
+constexpr int WALK_SMEM_SLOTS = 8;        // segments (primary + SA entries) whose scratch lives in shared memory
+constexpr uint32_t WALK_STAGE_ROWS = 8;   // rows per primary the count pass keeps, so that the write pass only moves them
+
+// The walk is a chain of dependent reads and writes of a read's scratch slots (sort, three lists, their passes): in global
+// memory every step costs an L2 round trip (31 us per pass measured for 850 primaries); reads with up to WALK_SMEM_SLOTS
+// segments -- nearly all -- keep them in shared memory, the rest falls back to the global slots.
+// WRITE = false: count pass.  Also sums the 4-bit bytes of the inserted sequences (they size the table's sequence pool
+// without another round trip to the host), and the LAST CTA to finish turns the counts into exclusive offsets and
+// publishes the totals (no separate scan launch).
 template <bool WRITE>
-__global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
-    const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= a.n_prim) return;
-    const uint32_t aln = a.prim_list[pi];
-    const svb_aln_hdr h = a.hdr[aln];
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs a) {
+    __shared__ WalkScratch s_sc[WALK_PER_CTA * WALK_SMEM_SLOTS];
+    const uint32_t pi = blockIdx.x * WALK_PER_CTA + threadIdx.x;
     WalkOut o;
-    o.rows = WRITE ? a.rows + a.counts[pi] : nullptr;
+    o.rows = nullptr;
+    o.cap = 0xFFFFFFFFu;
     o.n = 0;
     o.err = 0;
+    o.ins_bytes = 0;
+    if (threadIdx.x < static_cast<unsigned>(WALK_PER_CTA) && pi < a.n_prim) {
+    if (WRITE) {
+        // the count pass left up to WALK_STAGE_ROWS finished rows per primary: nearly every primary only moves them
+        const uint32_t first = a.counts[pi], c = a.counts[pi + 1] - first;
+        if (c <= WALK_STAGE_ROWS) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.stage + static_cast<size_t>(pi) * WALK_STAGE_ROWS);
+            uint4* dst = reinterpret_cast<uint4*>(a.rows + first);
+            for (uint32_t q = 0; q < 4u * c; ++q) dst[q] = src[q];
+            return;
+        }
+    }
+    const uint32_t aln = a.prim_list[pi];
+    const svb_aln_hdr h = a.hdr[aln];
+    o.rows = WRITE ? a.rows + a.counts[pi] : a.stage + static_cast<size_t>(pi) * WALK_STAGE_ROWS;
+    if (!WRITE) o.cap = WALK_STAGE_ROWS;
     const uint4 sums = a.aln_sum[aln];
     // SVIM_COLLECT.py:71 (filter), :73 (supplementary records get no walk), :11-12 (hard clips -> no SA)
     const bool eligible = !(h.flag & 0x4) && !(h.flag & 0x100) && static_cast<int32_t>(h.mapq) >= a.p.min_mapq &&
                           !(h.flag & 0x800) && sums.w == 0u && h.n_cigar > 0u;
     if (eligible) {
-        WalkScratch* sc = a.scratch + (static_cast<size_t>(h.sa_first) + pi);
+        const uint32_t n_sa = a.sa_count[aln];
+        WalkScratch* sc = (n_sa + 1u <= static_cast<uint32_t>(WALK_SMEM_SLOTS)) ? s_sc + threadIdx.x * WALK_SMEM_SLOTS
+                                                                                 : a.scratch + (static_cast<size_t>(h.sa_first) + pi);
         const uint32_t* ops = a.cigar + h.cigar_off;
         // query_alignment_start: leading S (H skipped)                       [pysam getQueryStart]
         long long qas = 0;
@@ -87,7 +121,6 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
         prim.rev = rev;
         sc[0].seg = prim;
         uint32_t k = 1;
-        const uint32_t n_sa = a.sa_count[aln];
         for (uint32_t s = 0; s < n_sa; ++s) {
             const svb_segment g = a.seg[h.sa_first + s];
             if (static_cast<int32_t>(g.mapq) < a.p.min_mapq) continue;                 // SVIM_COLLECT.py:77
@@ -120,6 +153,36 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkArgs a) {
         if (o.err & (WALK_ERR_ASSERT | WALK_ERR_NOSEQ)) st |= DEV_ERR_ASSERT;
         if (o.err & WALK_ERR_CAPACITY) st |= DEV_ERR_CAPACITY;
         atomicOr(a.dev_status, st);
+    }
+    }
+    if (WRITE) return;
+    // ---- count pass only: inserted bytes, then the last CTA scans the counts
+    const uint32_t bytes = __reduce_add_sync(0xffffffffu, o.ins_bytes);
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        if (bytes) atomicAdd(a.totals + 1, static_cast<unsigned long long>(bytes));
+        __threadfence();
+        s_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+    }
+    __syncwarp();
+    if (!s_last) return;
+    __threadfence();
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < a.n_prim; base += 32u) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t x = i < a.n_prim ? __ldcg(a.counts + i) : 0u;
+        uint32_t inc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (static_cast<int>(threadIdx.x) >= d) inc += y;
+        }
+        if (i < a.n_prim) a.counts[i] = carry + inc - x;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (threadIdx.x == 0) {
+        a.counts[a.n_prim] = carry;
+        a.totals[0] = carry;
     }
 }
 
@@ -194,17 +257,19 @@ struct WalkPending {
     unsigned blocks = 0;
 };
 
-int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, WalkPending** out) {
+// `totals`: two device words that receive the number of walk rows and the 4-bit bytes of their inserted sequences
+int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, unsigned long long* totals, WalkPending** out) {
     *out = nullptr;
-    SVB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 1, 0, sizeof(unsigned long long), ctx->stream));
+    SVB_CUDA(ctx, cudaMemsetAsync(totals, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (rec->n_prim == 0) return SVB_OK;
     const size_t scratch_entries = static_cast<size_t>(rec->n_seg) + rec->n_prim;
-    const size_t counts_bytes = (static_cast<size_t>(rec->n_prim) + 2) * sizeof(uint32_t);
+    const size_t counts_bytes = (static_cast<size_t>(rec->n_prim) + 2) * sizeof(uint32_t) + 16;
     const size_t counts_pad = (counts_bytes + 255) & ~static_cast<size_t>(255);
     WalkPending* w = new (std::nothrow) WalkPending();
     if (!w) return svb_fail(ctx, SVB_ERR_NOMEM, "segment_walk");
     // own allocation (the shared scratch is in use by cigar_scan's unit states on the same stream)
-    cudaError_t e = cudaMallocAsync(&w->base, counts_pad + scratch_entries * sizeof(WalkScratch), ctx->stream);
+    const size_t scratch_bytes = (scratch_entries * sizeof(WalkScratch) + 255) & ~static_cast<size_t>(255);
+    cudaError_t e = cudaMallocAsync(&w->base, counts_pad + scratch_bytes + static_cast<size_t>(rec->n_prim) * WALK_STAGE_ROWS * sizeof(svb_row), ctx->stream);
     if (e != cudaSuccess) {
         delete w;
         return svb_fail(ctx, SVB_ERR_NOMEM, "segment_walk scratch", e);
@@ -229,17 +294,20 @@ int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, 
     a.p.rot = p->reference_overlap_tolerance;
     a.hap = static_cast<uint32_t>(hap);
     a.counts = reinterpret_cast<uint32_t*>(w->base);
+    a.done = reinterpret_cast<unsigned int*>(w->base + (static_cast<size_t>(rec->n_prim) + 2) * sizeof(uint32_t));
     a.scratch = reinterpret_cast<WalkScratch*>(w->base + counts_pad);
+    a.stage = reinterpret_cast<svb_row*>(w->base + counts_pad + scratch_bytes);
     a.rows = nullptr;
     a.dev_status = ctx->d_status;
-    w->blocks = (rec->n_prim + 127u) / 128u;
-    {
+    a.totals = totals;
+    w->blocks = (rec->n_prim + WALK_PER_CTA - 1u) / WALK_PER_CTA;
+    e = cudaMemsetAsync(a.done, 0, sizeof(unsigned int), ctx->stream);
+    if (e == cudaSuccess) {
         KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
-        walk_kernel<false><<<w->blocks, 128, 0, ctx->stream>>>(a);
-        scan_u32_kernel<<<1, 1024, 0, ctx->stream>>>(a.counts, rec->n_prim, ctx->d_counters + 1);
-        ctx->launches += 2;
+        walk_kernel<false><<<w->blocks, WALK_THREADS, 0, ctx->stream>>>(a);       // count + scan + totals in one launch
+        ctx->launches += 1;
+        e = cudaGetLastError();
     }
-    e = cudaGetLastError();
     if (e != cudaSuccess) {
         cudaFreeAsync(w->base, ctx->stream);
         delete w;
@@ -269,7 +337,7 @@ int walk_write_async(svb_ctx* ctx, WalkPending* w, uint64_t n_rows, svb_row** d_
             w->a.rows = rows;
             {
                 KernelTimer timer(ctx, SVB_K_SEGMENT_WALK);
-                walk_kernel<true><<<w->blocks, 128, 0, ctx->stream>>>(w->a);
+                walk_kernel<true><<<w->blocks, WALK_THREADS, 0, ctx->stream>>>(w->a);
                 ctx->launches += 1;
             }
             e = cudaGetLastError();

@@ -81,6 +81,42 @@ static int gather_pool(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const ui
     return SVB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+__global__ void pool_check_kernel(const uint32_t* __restrict__ off32, uint32_t n, unsigned long long expected, uint32_t* dev_status) {
+    if (off32[n] != expected) atomicOr(dev_status, DEV_ERR_CAPACITY);
+}
+}  // namespace
+
+// The same gather when the pool's size is already known (svb_collect2 sums the inserted bytes on the device before its one
+// synchronisation): nothing waits.  A total that disagrees with the rows raises the device status word.
+int gather_pool_known(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off, uint64_t pool_bytes) {
+    table_drop_pool(t);
+    const uint32_t n = static_cast<uint32_t>(t->n);
+    uint32_t* off32 = nullptr;
+    SVB_CUDA(ctx, cudaMallocAsync(&off32, sizeof(uint32_t) * (static_cast<size_t>(n) + 2), ctx->stream));
+    SVB_CUDA(ctx, cudaMallocAsync(&t->d_pool_off, sizeof(uint64_t) * (static_cast<size_t>(n) + 1), ctx->stream));
+    SVB_CUDA(ctx, cudaMallocAsync(&t->d_pool, std::max<uint64_t>(pool_bytes, 1), ctx->stream));
+    t->pool_bytes = pool_bytes;
+    if (n) {
+        pool_sizes_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(t->d_rows, n, off32);
+        ctx->launches += 1;
+    }
+    int rc = launch_scan_u32(ctx, off32, n, ctx->d_counters + 10);
+    if (rc != SVB_OK) return rc;
+    pool_check_kernel<<<1, 1, 0, ctx->stream>>>(off32, n, pool_bytes, ctx->d_status);
+    const uint64_t threads = (static_cast<uint64_t>(n) + 1) * 32;
+    pool_gather_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(t->d_rows, n, off32, seq4, seq_off,
+                                                                                              t->d_pool, t->d_pool_off);
+    ctx->launches += 2;
+    SVB_CUDA(ctx, cudaGetLastError());
+    SVB_CUDA(ctx, cudaFreeAsync(off32, ctx->stream));
+    return SVB_OK;
+}
+
+extern "C" {
+
 // device address of a host pointer the GPU can read in place (pinned / registered memory), else nullptr
 static const void* device_view_of_host(const void* p) {
     cudaPointerAttributes attr;

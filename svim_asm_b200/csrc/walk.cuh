@@ -50,8 +50,10 @@ enum : uint32_t { WALK_ERR_BAD_TID = 1u, WALK_ERR_ASSERT = 2u, WALK_ERR_CAPACITY
 
 struct WalkOut {
     svb_row* rows;           // nullptr: count only
+    uint32_t cap;            // rows beyond `cap` are counted but not stored
     uint32_t n;
     uint32_t err;
+    uint32_t ins_bytes;      // 4-bit packed bytes of the inserted sequences emitted so far (sizes the table's sequence pool)
 };
 
 SVB_HD int32_t wk_max(int32_t a, int32_t b) { return a > b ? a : b; }
@@ -73,7 +75,7 @@ SVB_HD void wk_blank(svb_row& r, const WalkRead& rd, uint32_t local) {
 }
 
 SVB_HD void wk_push(WalkOut& o, const svb_row& r) {
-    if (o.rows) o.rows[o.n] = r;
+    if (o.rows && o.n < o.cap) o.rows[o.n] = r;
     ++o.n;
 }
 
@@ -105,6 +107,7 @@ SVB_HD void wk_emit_ins(WalkOut& o, const WalkRead& rd, int32_t tid, long long s
     r.dst_start = static_cast<int32_t>(start < 0 ? 0 : start);                  // :134
     r.dst_end = static_cast<int32_t>(end < rd.contig_len[tid] ? end : rd.contig_len[tid]);   // :136
     wk_pyslice(seq_start, seq_stop, rd.l_seq, r.seq_pos, r.seq_len);
+    o.ins_bytes += (r.seq_len + 1u) / 2u;
     wk_push(o, r);
 }
 SVB_HD void wk_emit_inv(WalkOut& o, const WalkRead& rd, int32_t tid, long long start, long long end, bool complete) {

@@ -497,6 +497,20 @@ class Engine(object):
         self._check(lib.svb_collect(self.handle, rec.handle, _lib.ptr(params), int(hap), ctypes.byref(out)))
         return Table(self, out)
 
+    def collect2(self, rec1, rec2, params, with_pools=False):
+        """Both haplotypes of a diploid run with one host synchronisation (svb_collect2); with_pools also copies the inserted
+        bases of the INS rows next to each table."""
+        o1, o2 = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(lib.svb_collect2(self.handle, rec1.handle, rec2.handle, _lib.ptr(params), 1 if with_pools else 0,
+                                     ctypes.byref(o1), ctypes.byref(o2)))
+        return Table(self, o1), Table(self, o2)
+
+    def map_sequences_host(self, rec):
+        """The record image reads its query sequences in place from the host batch's PINNED buffers (no upload)."""
+        host = rec.host
+        self._check(lib.svb_records_map_sequences_host(self.handle, rec.handle, _lib.ptr(host.seq4), _lib.ptr(host.seq_off)))
+        rec.has_sequences = True
+
     def pair(self, table1, table2, rec1, rec2, reference, params):
         out = ctypes.c_void_p()
         self._check(lib.svb_pair(self.handle, table1.handle, table2.handle, rec1.handle, rec2.handle,

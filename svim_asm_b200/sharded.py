@@ -223,6 +223,20 @@ class DeviceStage(object):
         table.remap_records(self.records[k])
         return table
 
+    def collect_both(self):
+        """Both haplotypes with one host synchronisation (svb_collect2), their sequence pools and global record indices."""
+        if self.resident is None:                      # end-to-end leg: this step's records come from pinned host memory
+            for k in range(2):
+                h = self.hosts[k]
+                self.records[k] = self.eng.load_records(h)
+                self.eng.set_global_index(self.records[k], self.global_idx[k])
+                self.eng.map_sequences_host(self.records[k])
+                self.h2d += sum(getattr(h, n).nbytes for n in ("hdr", "cigar", "seg", "sa_count")) + 4 * h.n_aln
+        t1, t2 = self.eng.collect2(self.records[0], self.records[1], self.params, with_pools=True)
+        t1.remap_records(self.records[0])
+        t2.remap_records(self.records[1])
+        return t1, t2
+
     def done(self):
         if self.resident is None:
             for r in self.records:
@@ -302,16 +316,32 @@ def sharded_step_window(stage, window, owner, lexrank):
     rows travel the same way and are put into pair_candidates' order on the device; one download at the end.
     Returns the complete paired table (identical on every rank)."""
     eng = stage.eng
-    t1, t2 = stage.collect(1), stage.collect(2)
+    prof = _PROFILE if os.environ.get("SVB_SHARD_PROFILE") else None
+
+    def tick(name):
+        if prof is not None:              # profiling aid: synchronised phase times (host clock)
+            eng.synchronize()
+            now = time.perf_counter()
+            prof[name] = prof.get(name, 0.0) + now - prof["_t"]
+            prof["_t"] = now
+    if prof is not None:
+        eng.synchronize()
+        prof["_t"] = time.perf_counter()
+    t1, t2 = stage.collect_both()
+    tick("collect x2 (+ pool, remap)")
     u1, u2 = window.share(t1, t2, owner)
+    tick("share (put, wait, unpack x2)")
     t1.free()
     t2.free()
     paired = eng.pair(u1, u2, stage.records[0], stage.records[1], stage.ref, stage.params)
+    tick("pair")
     everything = window.gather_paired(paired, lexrank)
+    tick("gather paired (put, wait, order)")
     out = everything.to_numpy()
     for t in (u1, u2, paired, everything):
         t.free()
     stage.done()
+    tick("download + free")
     return out
 
 

@@ -36,7 +36,7 @@ extern "C" int hc_walk(const int32_t* segs, int k, int32_t read_len, uint32_t l_
     WalkParams p{params[0], params[1], params[2], params[3], params[4], params[5], params[6]};
     WalkRead rd{aln_idx, hap, read_len, l_seq, contig_len, lexrank, n_contig};
     std::vector<svb_row> rows(static_cast<size_t>(k) * k + 8);
-    WalkOut o{rows.data(), 0, 0};
+    WalkOut o{rows.data(), static_cast<uint32_t>(rows.size()), 0, 0, 0};
     walk_read(rd, p, sc.data(), static_cast<uint32_t>(k), o);
     if (o.err) return -static_cast<int>(o.err);
     for (uint32_t i = 0; i < o.n && static_cast<int>(i) < cap; ++i) rows_out[i] = rows[i];

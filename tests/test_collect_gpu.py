@@ -164,3 +164,70 @@ def test_very_long_ops_do_not_overflow_packed_sums(engine):
     want = port.collect(host, port.Params())
     assert util.rows_equal(got, want) is None, util.rows_equal(got, want)
     assert got.shape[0] == 2
+
+
+def test_collect2_equals_two_collects(engine):
+    """svb_collect2 (both haplotypes, one host synchronisation, sequence pools sized on the device) against two svb_collect
+    calls + svb_table_gather_sequences: same rows, same pools; also with the query sequences read in place from pinned host
+    memory (svb_records_map_sequences_host) instead of uploaded."""
+    from svim_asm_b200.bench_util import pinned_host
+    cfg = synth.SynthConfig(["chr1", "chr10", "chr2"], [400000, 300000, 350000], 110, 7e4, 808, sv_per_event=7e-3,
+                            split_fraction=0.5, sv_max=2500)
+    rb1, rb2 = synth.make_diploid(cfg)
+    h1, h2 = pinned_host(HostBatch.from_record_batch(rb1)), pinned_host(HostBatch.from_record_batch(rb2))
+    params = make_params()
+    r1, r2 = engine.load_records(h1, with_sequences=True), engine.load_records(h2, with_sequences=True)
+    want = []
+    for k, r in ((1, r1), (2, r2)):
+        t = engine.collect(r, params, hap=k)
+        t.gather_sequences(r)
+        want.append((t.to_numpy(), t.pool_to_numpy()))
+    assert want[0][0].shape[0] > 60 and np.any(want[0][0]["ordinal"] & np.uint64(0x80000000)) and want[0][1][0].shape[0] > 500
+    for mapped in (False, True):
+        if mapped:
+            r1, r2 = engine.load_records(h1), engine.load_records(h2)
+            engine.map_sequences_host(r1)
+            engine.map_sequences_host(r2)
+        for with_pools in (False, True):
+            t1, t2 = engine.collect2(r1, r2, params, with_pools=with_pools)
+            for t, (rows, (pool, off)) in zip((t1, t2), want):
+                assert t.to_numpy().tobytes() == rows.tobytes()
+                if with_pools:
+                    got_pool, got_off = t.pool_to_numpy()
+                    assert got_pool.tobytes() == pool.tobytes() and np.array_equal(got_off, off)
+    # an empty haplotype next to a full one
+    empty = HostBatch.from_record_batch(rb1.subset(np.zeros(0, dtype=np.int64)))
+    re_ = engine.load_records(empty, with_sequences=True)
+    t1, t2 = engine.collect2(r1, re_, params, with_pools=True)
+    assert len(t2) == 0 and t1.to_numpy().tobytes() == want[0][0].tobytes()
+
+
+def test_walk_with_many_segments_per_read(engine):
+    """Reads split into many segments: more walk rows per primary than the count pass stages (the write pass recomputes
+    those), more segments than the shared-memory scratch holds (global scratch), next to ordinary two-segment reads."""
+    names, lengths = ["chr1", "chr2"], [3_000_000, 2_000_000]
+    records = []
+
+    def chain(name, n_seg, start, seg=10000, gap=500):
+        # n_seg forward segments, each `gap` further along the reference than the read: n_seg - 1 deletions (App. D "DEL fwd")
+        L = n_seg * seg
+        segs = [(i * seg, (i + 1) * seg, start + i * (seg + gap)) for i in range(n_seg)]
+
+        def cigar(q0, q1):
+            ops = ([(4, q0)] if q0 else []) + [(7, q1 - q0)] + ([(4, L - q1)] if L - q1 else [])
+            return ops
+        sa = ";".join("chr1,%d,+,%s,60,0" % (p + 1, "".join("%d%s" % (ln, "MIDNSHP=X"[op]) for op, ln in cigar(q0, q1)))
+                      for q0, q1, p in segs[1:]) + ";"
+        records.append(dict(tid=0, pos=segs[0][2], cigar=cigar(*segs[0][:2]), sa=sa, name=name))
+    chain("two", 2, 100000)
+    chain("twelve", 12, 400000)          # 11 rows > the 8 staged ones, 12 segments > the 8 shared-memory slots
+    chain("nine", 9, 900000)             # 8 rows: exactly the staged capacity, 9 segments > 8 slots
+    chain("five", 5, 1500000)
+    records.sort(key=lambda r: r["pos"])
+    rb = util.batch_from_records(names, lengths, records)
+    host = HostBatch.from_record_batch(rb)
+    rec = engine.load_records(host, with_sequences=True)
+    got = engine.collect(rec, make_params()).to_numpy()
+    want = port.collect(host, port.Params())
+    assert util.rows_equal(got, want) is None, util.rows_equal(got, want)
+    assert want.shape[0] == 1 + 11 + 8 + 4 and set(want["type"].tolist()) == {0}

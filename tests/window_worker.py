@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def main(rank, world, device, out_dir, seed):
     sys.path.insert(0, ROOT)
     from svim_asm_b200 import sharded, synth
+    from svim_asm_b200.bench_util import pinned_host
     from svim_asm_b200.engine import Engine, HostBatch, lexrank, make_params
     names = ["chr1", "chr10", "chr2", "chr3", "chrX"]
     cfg = synth.SynthConfig(names, [300000, 200000, 250000, 150000, 100000], 120, 5e4, seed, sv_per_event=6e-3,
@@ -30,7 +31,7 @@ def main(rank, world, device, out_dir, seed):
     hosts, gidx = [], []
     for k in range(2):
         sub, g = sharded.shard_records(rb[k], owner, rank)
-        hosts.append(HostBatch.from_record_batch(sub))
+        hosts.append(pinned_host(HostBatch.from_record_batch(sub)))        # the upload-per-step leg reads the sequences in place
         gidx.append(g)
     resident = [eng.load_records(h, with_sequences=True) for h in hosts]
     for rec, g in zip(resident, gidx):
