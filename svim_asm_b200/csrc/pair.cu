@@ -565,6 +565,71 @@ __device__ void emit_cluster(const svb_row& first, const svb_row* second, const 
     out[slot] = r;
 }
 
+// pair_haplotypes / pair_haplotypes_breakends for one partition (SVIM_COMBINE.py:120-161): flat-cluster labels in scipy's
+// numbering.  Returns the number of clusters; labels[i] in 1 .. clusters.
+__device__ int partition_labels(const PairArgs& a, uint32_t p, uint32_t first, uint32_t n, int* labels) {
+    const bool bnd = a.rows[a.order[first]].type == SVB_BND;
+    const double threshold = bnd ? 0.3 : a.max_edit_distance;
+    double D[PAIR_DIST_STRIDE];
+    int m = 0;
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+        const svb_row& ri = a.rows[a.order[first + i]];
+        for (uint32_t j = i + 1; j < n; ++j, ++m) {
+            const svb_row& rj = a.rows[a.order[first + j]];
+            double d;
+            if (bnd) {                                                                 // :105-117 (dest contig never compared)
+                const bool same_dirs = ((ri.flags ^ rj.flags) & (SVB_F_SRC_FWD | SVB_F_DST_FWD)) == 0;
+                if (ri.hap != rj.hap && same_dirs) {
+                    const long long d1 = static_cast<long long>(ri.src_start) - rj.src_start;
+                    const long long d2 = static_cast<long long>(ri.dst_start) - rj.dst_start;
+                    d = static_cast<double>((d1 < 0 ? -d1 : d1) + (d2 < 0 ? -d2 : d2)) / 3000.0;
+                } else {
+                    d = 99999.0;
+                }
+            } else if (ri.hap == rj.hap) {
+                d = 1000000000.0;                                                      // :40-41
+            } else {
+                d = a.dist[a.job_slot[static_cast<size_t>(p) * PAIR_DIST_STRIDE + m]];
+            }
+            D[m] = d;
+        }
+    }
+    if (n == 2u) {          // one merge at D[0]: a single cluster when it is within the cut, else the two leaves left to right
+        labels[0] = 1;
+        labels[1] = D[0] <= threshold ? 1 : 2;
+        return labels[1];
+    }
+    return link_complete_fcluster(static_cast<int>(n), D, threshold, labels);
+}
+
+// clusters of 1 or 2 members become rows (other sizes: logged, skipped, :204-205); WRITE = false only counts them
+template <bool WRITE>
+__device__ uint32_t partition_rows(const PairArgs& a, uint32_t first, uint32_t n, const int* labels, int n_clusters, uint32_t slot) {
+    uint32_t produced = 0;
+    for (int c = 1; c <= n_clusters; ++c) {
+        int members = 0, i0 = -1, i1 = -1;
+        for (uint32_t i = 0; i < n; ++i)
+            if (labels[i] == c) {
+                if (members == 0) i0 = static_cast<int>(i);
+                else if (members == 1) i1 = static_cast<int>(i);
+                ++members;
+            }
+        if (members == 1 || members == 2) {
+            if (WRITE) {
+                const svb_row f = a.rows[a.order[first + i0]];
+                if (members == 2) {
+                    const svb_row s = a.rows[a.order[first + i1]];
+                    emit_cluster(f, &s, a, a.out, slot + produced);
+                } else {
+                    emit_cluster(f, nullptr, a, a.out, slot + produced);
+                }
+            }
+            ++produced;
+        }
+    }
+    return produced;
+}
+
 template <bool WRITE>
 __global__ void __launch_bounds__(64) cluster_kernel(const PairArgs a) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -573,62 +638,98 @@ __global__ void __launch_bounds__(64) cluster_kernel(const PairArgs a) {
         return;
     }
     const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
-    uint32_t slot = WRITE ? a.counts[p] : 0u;
+    const uint32_t slot = WRITE ? a.counts[p] : 0u;
     uint32_t produced = 0;
     if (n == 1u) {
         if (WRITE) emit_cluster(a.rows[a.order[first]], nullptr, a, a.out, slot);
         produced = 1;
     } else if (n <= static_cast<uint32_t>(PAIR_MAX)) {
-        double D[PAIR_DIST_STRIDE];
         int labels[PAIR_MAX];
-        const bool bnd = a.rows[a.order[first]].type == SVB_BND;
-        int m = 0;
-        for (uint32_t i = 0; i + 1 < n; ++i) {
-            const svb_row& ri = a.rows[a.order[first + i]];
-            for (uint32_t j = i + 1; j < n; ++j, ++m) {
-                const svb_row& rj = a.rows[a.order[first + j]];
-                double d;
-                if (bnd) {                                                                 // :105-117 (dest contig never compared)
-                    const bool same_dirs = ((ri.flags ^ rj.flags) & (SVB_F_SRC_FWD | SVB_F_DST_FWD)) == 0;
-                    if (ri.hap != rj.hap && same_dirs) {
-                        const long long d1 = static_cast<long long>(ri.src_start) - rj.src_start;
-                        const long long d2 = static_cast<long long>(ri.dst_start) - rj.dst_start;
-                        d = static_cast<double>((d1 < 0 ? -d1 : d1) + (d2 < 0 ? -d2 : d2)) / 3000.0;
-                    } else {
-                        d = 99999.0;
-                    }
-                } else if (ri.hap == rj.hap) {
-                    d = 1000000000.0;                                                      // :40-41
-                } else {
-                    d = a.dist[a.job_slot[static_cast<size_t>(p) * PAIR_DIST_STRIDE + m]];
-                }
-                D[m] = d;
-            }
-        }
-        const int n_clusters = link_complete_fcluster(static_cast<int>(n), D, bnd ? 0.3 : a.max_edit_distance, labels);
-        for (int c = 1; c <= n_clusters; ++c) {
-            int members = 0, i0 = -1, i1 = -1;
-            for (uint32_t i = 0; i < n; ++i)
-                if (labels[i] == c) {
-                    if (members == 0) i0 = static_cast<int>(i);
-                    else if (members == 1) i1 = static_cast<int>(i);
-                    ++members;
-                }
-            if (members == 1 || members == 2) {                                            // other sizes: logged, skipped (:204-205)
-                if (WRITE) {
-                    const svb_row f = a.rows[a.order[first + i0]];
-                    if (members == 2) {
-                        const svb_row s = a.rows[a.order[first + i1]];
-                        emit_cluster(f, &s, a, a.out, slot + produced);
-                    } else {
-                        emit_cluster(f, nullptr, a, a.out, slot + produced);
-                    }
-                }
-                ++produced;
-            }
-        }
+        const int n_clusters = partition_labels(a, p, first, n, labels);
+        produced = partition_rows<WRITE>(a, first, n, labels, n_clusters, slot);
     }
     if (!WRITE) a.counts[p] = produced;
+}
+
+// ---- K9 in ONE launch: labels, row counts, their prefix over the partitions, rows ---------------------------------------
+// (count pass + scan launch + write pass until round 2: the linkage of every partition ran twice and the row offsets made
+// a round trip through a single-CTA scan).  Cooperative launch: tile = 64 partitions; phase 1 computes the labels of a
+// partition once and keeps them packed (4 bits per member) next to its row count; one grid barrier; phase 2 derives the
+// tile's first row from the tile sums and writes the rows.
+struct ClusterFusedArgs {
+    PairArgs pa;
+    unsigned long long* packed;      // [n_rows] labels (4 bits each), clusters << 40, rows << 48
+    uint32_t* tile_sum;              // [ceil(n_rows / 64)]
+    unsigned int* barrier;
+    unsigned long long* total;       // rows written
+};
+
+__global__ void __launch_bounds__(64) cluster_fused_kernel(const __grid_constant__ ClusterFusedArgs c) {
+    const PairArgs& a = c.pa;
+    __shared__ uint32_t s_w[2];
+    __shared__ uint32_t s_base;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_parts = static_cast<uint32_t>(*a.n_parts_dev), n_tiles = (n_parts + 63u) / 64u;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t p = t * 64u + tid;
+        uint32_t produced = 0;
+        if (p < n_parts) {
+            const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
+            unsigned long long pk = 0;
+            if (n == 1u) {
+                produced = 1;
+            } else if (n <= static_cast<uint32_t>(PAIR_MAX)) {
+                int labels[PAIR_MAX];
+                const int n_clusters = partition_labels(a, p, first, n, labels);
+                produced = partition_rows<false>(a, first, n, labels, n_clusters, 0u);
+                for (uint32_t i = 0; i < n; ++i) pk |= static_cast<unsigned long long>(labels[i]) << (4u * i);
+                pk |= static_cast<unsigned long long>(n_clusters) << 40;
+            }
+            c.packed[p] = pk | (static_cast<unsigned long long>(produced) << 48);
+        }
+        const uint32_t wsum = __reduce_add_sync(0xffffffffu, produced);
+        if (lane == 0) s_w[warp] = wsum;
+        __syncthreads();
+        if (tid == 0) c.tile_sum[t] = s_w[0] + s_w[1];
+        __syncthreads();
+    }
+    unsigned int phase = 0;
+    front_barrier(c.barrier, phase);
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint32_t before = 0;
+        for (uint32_t q = tid; q < t; q += 64u) before += __ldcg(c.tile_sum + q);
+        before = __reduce_add_sync(0xffffffffu, before);
+        if (lane == 0) s_w[warp] = before;
+        __syncthreads();
+        if (tid == 0) s_base = s_w[0] + s_w[1];
+        __syncthreads();
+        const uint32_t base = s_base;
+        const uint32_t p = t * 64u + tid;
+        const unsigned long long pk = p < n_parts ? c.packed[p] : 0ull;
+        const uint32_t produced = static_cast<uint32_t>(pk >> 48);
+        uint32_t inc = produced;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (static_cast<int>(lane) >= d) inc += y;
+        }
+        if (lane == 31u) s_w[warp] = inc;
+        __syncthreads();
+        const uint32_t slot = base + (warp ? s_w[0] : 0u) + inc - produced;
+        if (p < n_parts) {
+            const uint32_t first = a.part_start[p], n = a.part_start[p + 1] - first;
+            if (n == 1u) {
+                emit_cluster(a.rows[a.order[first]], nullptr, a, a.out, slot);
+            } else if (n <= static_cast<uint32_t>(PAIR_MAX)) {
+                int labels[PAIR_MAX];
+                for (uint32_t i = 0; i < n; ++i) labels[i] = static_cast<int>((pk >> (4u * i)) & 15ull);
+                partition_rows<true>(a, first, n, labels, static_cast<int>((pk >> 40) & 255ull), slot);
+            }
+        }
+        if (t == n_tiles - 1u && tid == 63u) *c.total = static_cast<unsigned long long>(slot) + produced;
+        __syncthreads();
+    }
+    if (n_tiles == 0u && blockIdx.x == 0 && tid == 0) *c.total = 0ull;
 }
 
 }  // namespace
@@ -812,23 +913,37 @@ static int run_pairing_once(svb_ctx* ctx, const svb_table* h1, const svb_table* 
         int rc = launch_edit_distance(ctx, jobs, exact_list, cnt + 4, max_jobs, ref->d_bases, seq_a, seq_b, ref->d_class_map, dist, dist_hi, cnt + 6);
         if (rc != SVB_OK) return fail(rc);
     }
-    {
-        KernelTimer timer(ctx, SVB_K_CLUSTER);
-        cluster_kernel<false><<<(n + 64) / 64, 64, 0, ctx->stream>>>(a);
-        ctx->launches += 1;
-        int rc = launch_scan_u32(ctx, counts, n, cnt + 5);
-        if (rc != SVB_OK) return fail(rc);
-    }
-    PAIR_CUDA(cudaGetLastError());
     // pairing never makes rows (every output row is one input row or the merge of two): the table is allocated for n
-    // rows and the write pass runs without waiting for the exact count, which comes back with the final synchronisation
+    // rows and written without waiting for the exact count, which comes back with the final synchronisation
     result->cap = std::max<uint64_t>(n, 1);
     PAIR_CUDA(cudaMallocAsync(&result->d_rows, sizeof(svb_row) * result->cap, ctx->stream));
     a.out = result->d_rows;
-    {
+    const unsigned cluster_tiles = (n + 63u) / 64u;
+    if (cluster_tiles <= static_cast<unsigned>(ctx->sm_count) * 8u && !getenv("SVB_PAIR_UNFUSED")) {
+        ClusterFusedArgs cf;
+        cf.pa = a;
+        cf.packed = reinterpret_cast<unsigned long long*>(keys[cur_buf ^ 1]);        // the sort's spare key buffer: n words, free by now
+        cf.tile_sum = head;                                                       // free since the partition starts exist
+        cf.barrier = reinterpret_cast<unsigned int*>(cnt + 9) + 1;                 // second word of the barrier slot (zeroed above)
+        cf.total = cnt + 5;
+        void* kargs[] = {&cf};
         KernelTimer timer(ctx, SVB_K_CLUSTER);
-        cluster_kernel<true><<<(n + 64) / 64, 64, 0, ctx->stream>>>(a);
+        PAIR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(cluster_fused_kernel), dim3(cluster_tiles), dim3(64), kargs, 0, ctx->stream));
         ctx->launches += 1;
+    } else {
+        {
+            KernelTimer timer(ctx, SVB_K_CLUSTER);
+            cluster_kernel<false><<<(n + 64) / 64, 64, 0, ctx->stream>>>(a);
+            ctx->launches += 1;
+            int rc = launch_scan_u32(ctx, counts, n, cnt + 5);
+            if (rc != SVB_OK) return fail(rc);
+        }
+        PAIR_CUDA(cudaGetLastError());
+        {
+            KernelTimer timer(ctx, SVB_K_CLUSTER);
+            cluster_kernel<true><<<(n + 64) / 64, 64, 0, ctx->stream>>>(a);
+            ctx->launches += 1;
+        }
     }
     PAIR_CUDA(cudaGetLastError());
     PAIR_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, cnt + 2, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
