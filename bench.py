@@ -230,6 +230,52 @@ def workload_config(cfg, args, **extra):
     return c
 
 
+def file_to_vcf_block(cfg, rb1, rb2, bases, off, runs=3):
+    """SURVEY.md 8d's third scope: BAM files + FASTA -> variants.vcf through the drop-in CLI (`svim-asm diploid`): device
+    ingest (BGZF inflate + record split on the GPU), COLLECT, PAIR, VCF body assembled on the device.  The files are written
+    once (page cache / tmpfs), the best of `runs` is reported, and the VCF is compared with the python writer's."""
+    import shutil
+    from svim_asm_b200 import bamio, cli
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    tmp = tempfile.mkdtemp(prefix="svb_bench_", dir=base)
+    try:
+        t0 = time.time()
+        p1, p2, pf = os.path.join(tmp, "h1.bam"), os.path.join(tmp, "h2.bam"), os.path.join(tmp, "ref.fa")
+        bamio.write_bam(p1, rb1, level=1)
+        bamio.write_bam(p2, rb2, level=1)
+        ref = {n: bases[int(off[t]):int(off[t + 1])] for t, n in enumerate(cfg.contig_names)}
+        bamio.write_fasta(pf, ref, cfg.contig_names)
+        bytes_in = sum(os.path.getsize(p) for p in (p1, p2, pf))
+        log("file -> VCF inputs: 2 BAM + FASTA, %.2f GB, written in %.0fs" % (bytes_in / 1e9, time.time() - t0))
+        import logging
+        logging.disable(logging.CRITICAL)                 # the CLI logs like the reference; keep the bench's stderr readable
+
+        def masked(path):
+            return [ln for ln in open(path).read().split("\n") if not ln.startswith("##fileDate")]
+        times = []
+        for run in range(runs):
+            out = os.path.join(tmp, "out%d" % run)
+            t0 = time.perf_counter()
+            cli.main(["diploid", out, p1, p2, pf])
+            times.append((time.perf_counter() - t0) * 1e3)
+        vcf = os.path.join(tmp, "out%d" % (runs - 1), "variants.vcf")
+        os.environ["SVIM_ASM_B200_VCF"] = "host"
+        try:
+            cli.main(["diploid", os.path.join(tmp, "out_host"), p1, p2, pf])
+        finally:
+            del os.environ["SVIM_ASM_B200_VCF"]
+            logging.disable(logging.NOTSET)
+        same = masked(vcf) == masked(os.path.join(tmp, "out_host", "variants.vcf"))
+        if not same:
+            raise SystemExit("bench.py: the device-assembled variants.vcf differs from the python writer's")
+        n_rec = sum(1 for ln in open(vcf) if not ln.startswith("#"))
+        return {"ms": min(times), "runs_ms": times, "bytes_in": int(bytes_in), "vcf_records": int(n_rec), "vcf_bytes": os.path.getsize(vcf),
+                "vcf_equal_python_writer": True,
+                "scope": "svim-asm diploid h1.bam h2.bam ref.fa -> variants.vcf, files in the page cache; first run includes CUDA / pinned-buffer set-up"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
 
@@ -278,6 +324,7 @@ def b200_arm(args):
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
     timing = eng.timing()
+    pair_stats = eng.pair_stats()
     ms_step = ms_total / args.steps
     value = n_aln / (ms_step / 1e3)
 
@@ -328,12 +375,20 @@ def b200_arm(args):
 
     cpu, material = cpu_baseline_block(rb1, rb2, bases, off, cfg)
     parity = parity_check(rows, material)
+    # K8 is latency / compute bound, not bandwidth bound: reported as pairs and as the full-table cells an exhaustive aligner
+    # (edlib, what the reference calls) would have to fill for the same pairs, per second of K8 time
+    k8_ms = timing["edit_distance"][0] / args.steps
+    k8 = {"ms_per_step": k8_ms, "pairs": pair_stats["pairs"], "pairs_needing_exact_kernel": pair_stats["exact_pairs"],
+          "full_table_cells": pair_stats["table_cells"], "equivalent_cell_updates_per_s": pair_stats["table_cells"] / (k8_ms * 1e-3) if k8_ms else None,
+          "partitions": pair_stats["partitions"]}
+    ftv = None if args.no_file_leg else file_to_vcf_block(cfg, rb1, rb2, bases, off)
     print(json.dumps({
         "metric": "alignments_per_sec", "value": value, "unit": "alignments/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic", "cigar_ops_per_sec": n_ops / (ms_step / 1e3),
         "config": workload_config(cfg, args, paired_rows=int(n_out[0]), candidates=[int(n_out[1]), int(n_out[2])]),
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_check": parity, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_check": parity, "k8": k8, "file_to_vcf": ftv,
+        "gpu_launches": int(launches),
         "clocks": clocks,
     }), flush=True)
 
@@ -345,6 +400,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the whole-genome workload (testing only)")
+    ap.add_argument("--no-file-leg", dest="no_file_leg", action="store_true", help="skip the file -> variants.vcf measurement")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: python's sys.stdout keeps the original descriptor, descriptor 1 itself is
     # pointed at stderr so that anything a native library prints there (NCCL's version banner ...) cannot get in front

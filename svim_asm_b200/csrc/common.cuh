@@ -82,6 +82,8 @@ struct svb_ctx {
     unsigned long long* h_pinned = nullptr;     // 64-word pinned readback area
     uint8_t* h_text = nullptr;        // grow-only pinned buffer the VCF body is returned in (vcf_device.cu)
     size_t h_text_cap = 0;
+    void* h_stage = nullptr;          // grow-only pinned staging buffer of svb_table_to_host
+    size_t h_stage_cap = 0;
     bool wfa_attr_set = false;        // cudaFuncSetAttribute is per device: one flag per context, not per process
     bool scan_attr_set[8] = {};
     uint64_t ed_stride = 512u * 1024u; // bytes per worker warp for parked bottom-row deltas of the exact edit-distance kernel (grows on demand)

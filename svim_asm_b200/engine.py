@@ -213,7 +213,7 @@ class Table(object):
 
     def to_numpy(self):
         n = len(self)
-        rows = np.zeros(n, dtype=_lib.ROW_DTYPE)
+        rows = np.empty(n, dtype=_lib.ROW_DTYPE)
         got = ctypes.c_uint64()
         self.engine._check(lib.svb_table_to_host(self.engine.handle, self.handle, _lib.ptr(rows), n, ctypes.byref(got)))
         return rows
