@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -39,7 +40,8 @@ namespace {
 enum : uint32_t {
     ING_ERR_INFLATE = 1u,       // a member did not inflate to its ISIZE
     ING_ERR_RECORD = 2u,        // truncated / malformed BAM record
-    ING_ERR_TAG = 4u            // malformed auxiliary field
+    ING_ERR_TAG = 4u,           // malformed auxiliary field
+    ING_ERR_INDEX = 8u          // the .bai offsets do not lie on the record chain (stale index): serial walk instead
 };
 
 struct DevMember {
@@ -57,6 +59,7 @@ struct InfTables {
     uint8_t lengths[320];
     // direct lookup on the next bits of the stream (entries of inflate_core.cuh: literal, or base + extra-bit count)
     uint32_t fast_len[1 << INF_LEN_BITS], fast_dist[1 << INF_DIST_BITS];
+    InfQueue queue;              // matches decoded by lane 0, resolved by the whole warp
 };
 
 // One warp, one member.  Lane 0 runs the serial part (block headers, the symbol loop of inflate_core.cuh: literals and
@@ -99,24 +102,24 @@ __device__ int inflate_member_warp(const uint8_t* __restrict__ src, uint32_t src
         inf_fill_table(T.distcnt, T.distsym, T.fast_dist, INF_DIST_BITS, true, lane, 32u);
         __syncwarp();
         while (true) {
-            uint32_t event = INF_EV_EOB, ev_len = 0, ev_dist = 0;
-            if (lane == 0) err = inf_run(b, lencode, distcode, T.fast_len, T.fast_dist, o, &event, &ev_len, &ev_dist);
-            err = __shfl_sync(FULLM, err, 0);
+            // lane 0 decodes a batch: literals into the ring, matches into the queue; then the warp resolves the matches
+            uint32_t event = INF_EV_EOB, n_queued = 0;
+            if (lane == 0) err = inf_run_queued(b, lencode, distcode, T.fast_len, T.fast_dist, o, T.queue, &n_queued, &event);
+            // one shuffle carries the error, the event and the queue length; another the position
+            const uint32_t word = __shfl_sync(FULLM, static_cast<uint32_t>(err) | (event << 8) | (n_queued << 16), 0);
+            err = static_cast<int>(word & 255u);
             if (err) return err;
-            event = __shfl_sync(FULLM, event, 0);
+            event = (word >> 8) & 255u;
+            n_queued = word >> 16;
             o.pos = __shfl_sync(FULLM, o.pos, 0);
+            __syncwarp();                               // lane 0's ring and queue stores before the other lanes read them
+            inf_resolve(o, T.queue, n_queued, lane, 32u);
             if (event == INF_EV_EOB) break;
-            __syncwarp();                               // lane 0's ring stores before the other lanes read the ring
             if (event == INF_EV_FLUSH) {
                 inf_flush(o, o.pos, lane, 32u);
                 o.flushed = o.pos;
-            } else {
-                ev_len = __shfl_sync(FULLM, ev_len, 0);
-                ev_dist = __shfl_sync(FULLM, ev_dist, 0);
-                inf_copy_long(o, ev_len, ev_dist, lane, 32u);
-                o.pos += ev_len;
+                __syncwarp();
             }
-            __syncwarp();
         }
     } while (!last);
     __syncwarp();
@@ -169,6 +172,32 @@ __global__ void bam_chase_kernel(const uint8_t* __restrict__ data, uint64_t star
         p += 4 + static_cast<uint64_t>(block);
     }
     *n_rec = n;
+}
+
+// The same walk in parallel.  A BAM file comes with an index (the reference insists on it: svim-asm:66-72 check_index), and the
+// index names record starts: every chunk begin of every bin and every linear-index entry is the virtual offset of a record.
+// For genome-genome alignments (records of hundreds of kilobases) that is nearly every record.  Thread i walks from known
+// start i to known start i + 1 and MUST land on it exactly; anything else (a stale or foreign index) raises ING_ERR_INDEX and
+// the host falls back to the serial walk.  WRITE = false counts the records of every segment, WRITE = true writes their
+// offsets at the scanned positions.
+template <bool WRITE>
+__global__ void bam_chase_indexed_kernel(const uint8_t* __restrict__ data, const uint64_t* __restrict__ starts, uint32_t n_seg,
+                                         uint32_t* __restrict__ counts, uint64_t* __restrict__ rec_off, uint32_t* status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    uint64_t p = starts[i];
+    const uint64_t end = starts[i + 1];
+    uint32_t n = 0;
+    const uint32_t base = WRITE ? counts[i] : 0u;
+    while (p < end) {
+        if (p + 4 > end) { atomicOr(status, ING_ERR_INDEX); break; }
+        const int32_t block = static_cast<int32_t>(ld_u32(data + p));
+        if (block < 32 || p + 4 + static_cast<uint64_t>(block) > end) { atomicOr(status, ING_ERR_INDEX); break; }
+        if (WRITE) rec_off[base + n] = p + 4;
+        ++n;
+        p += 4 + static_cast<uint64_t>(block);
+    }
+    if (!WRITE) counts[i] = n;
 }
 
 struct RecInfo {                 // where the variable-length parts of one record sit in the inflated stream
@@ -311,6 +340,68 @@ struct Cleanup {                 // frees whatever was allocated when the functi
 
 extern "C" {
 
+// Record starts named by <path>.bai as offsets into the inflated stream, sorted, unique, inside (first_record, total_out).
+// Empty when there is no usable index (the caller then walks the chain serially).
+static std::vector<uint64_t> bai_record_starts(const std::string& bai_path, const std::vector<BgzfMember>& members, uint64_t first_record,
+                                               uint64_t total_out) {
+    std::vector<uint64_t> out;
+    FILE* f = fopen(bai_path.c_str(), "rb");
+    if (!f) return out;
+    std::vector<uint8_t> buf;
+    {
+        fseek(f, 0, SEEK_END);
+        const long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (n > 8 && n < (1l << 30)) {
+            buf.resize(static_cast<size_t>(n));
+            if (fread(buf.data(), 1, buf.size(), f) != buf.size()) buf.clear();
+        }
+        fclose(f);
+    }
+    if (buf.size() < 8 || memcmp(buf.data(), "BAI\1", 4) != 0) return out;
+    const uint8_t* p = buf.data() + 4;
+    const uint8_t* const end = buf.data() + buf.size();
+    auto rd32 = [&](uint32_t* v) { if (end - p < 4) return false; memcpy(v, p, 4); p += 4; return true; };
+    auto rd64 = [&](uint64_t* v) { if (end - p < 8) return false; memcpy(v, p, 8); p += 8; return true; };
+    std::vector<uint64_t> voff;
+    uint32_t n_ref = 0;
+    if (!rd32(&n_ref)) return out;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        uint32_t n_bin = 0;
+        if (!rd32(&n_bin)) return out;
+        for (uint32_t b = 0; b < n_bin; ++b) {
+            uint32_t bin = 0, n_chunk = 0;
+            if (!rd32(&bin) || !rd32(&n_chunk)) return out;
+            for (uint32_t c = 0; c < n_chunk; ++c) {
+                uint64_t beg = 0, fin = 0;
+                if (!rd64(&beg) || !rd64(&fin)) return out;
+                if (bin != 37450u) voff.push_back(beg);          // 37450: the metadata pseudo-bin, not offsets of records
+            }
+        }
+        uint32_t n_intv = 0;
+        if (!rd32(&n_intv)) return out;
+        for (uint32_t k = 0; k < n_intv; ++k) {
+            uint64_t io = 0;
+            if (!rd64(&io)) return out;
+            if (io) voff.push_back(io);
+        }
+    }
+    std::sort(voff.begin(), voff.end());
+    voff.erase(std::unique(voff.begin(), voff.end()), voff.end());
+    size_t m = 0;                                                // members are in file order: one forward scan serves all offsets
+    for (uint64_t v : voff) {
+        const uint64_t coff = v >> 16, uoff = v & 0xFFFFull;
+        while (m < members.size() && members[m].file_off < coff) ++m;
+        if (m == members.size()) break;
+        if (members[m].file_off != coff || uoff >= members[m].out_len) continue;
+        const uint64_t at = members[m].out_off + uoff;
+        if (at > first_record && at < total_out) out.push_back(at);
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+    return out;
+}
+
 // timings of the last svb_bam_open_device call (ms): read file, H2D, inflate, chase, fields + copy, host parse, total
 // (kept per context: two contexts ingesting at the same time do not share a buffer)
 int svb_bam_device_timings(svb_ctx* ctx, double out[12]) {
@@ -448,7 +539,42 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     uint64_t* d_rec_off = nullptr;
     uint32_t n_rec = 0;
     cudaEventRecord(ev[3], st);
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    bool chased = false;
+    if (!getenv("SVB_INGEST_SERIAL_CHASE")) {
+        // record starts from the index: the walk becomes one short segment per thread (bam_chase_indexed_kernel)
+        std::vector<uint64_t> starts = bai_record_starts(std::string(path) + ".bai", members, first_record, total_out);
+        if (starts.size() >= 64) {
+            starts.insert(starts.begin(), first_record);
+            starts.push_back(total_out);
+            const uint32_t n_seg = static_cast<uint32_t>(starts.size() - 1);
+            uint64_t* d_starts = nullptr;
+            uint32_t* d_counts = nullptr;
+            ING_CUDA(cudaMallocAsync(&d_starts, sizeof(uint64_t) * starts.size(), st));
+            gc.dev.push_back(d_starts);
+            ING_CUDA(cudaMallocAsync(&d_counts, sizeof(uint32_t) * (static_cast<size_t>(n_seg) + 2), st));
+            gc.dev.push_back(d_counts);
+            ING_CUDA(cudaMemcpyAsync(d_starts, starts.data(), sizeof(uint64_t) * starts.size(), cudaMemcpyHostToDevice, st));
+            bam_chase_indexed_kernel<false><<<(n_seg + 127) / 128, 128, 0, st>>>(d_data, d_starts, n_seg, d_counts, nullptr, d_status);
+            ctx->launches += 1;
+            if (launch_scan_u32(ctx, d_counts, n_seg, ctx->d_counters + 15) != SVB_OK) return fail(SVB_ERR_CUDA, svb_last_error(ctx));
+            uint32_t h2[4] = {0, 0, 0, 0};
+            unsigned long long total = 0;
+            ING_CUDA(cudaMemcpyAsync(h2, d_status, sizeof h2, cudaMemcpyDeviceToHost, st));
+            ING_CUDA(cudaMemcpyAsync(&total, ctx->d_counters + 15, sizeof total, cudaMemcpyDeviceToHost, st));
+            ING_CUDA(cudaStreamSynchronize(st));
+            if (!(h2[0] & (ING_ERR_INDEX | ING_ERR_RECORD)) && total > 0 && total < 0x7fffffffull) {
+                n_rec = static_cast<uint32_t>(total);
+                inflate_cycles = static_cast<unsigned long long>(h2[2]) | (static_cast<unsigned long long>(h2[3]) << 32);
+                ING_CUDA(cudaMallocAsync(&d_rec_off, sizeof(uint64_t) * n_rec, st));
+                bam_chase_indexed_kernel<true><<<(n_seg + 127) / 128, 128, 0, st>>>(d_data, d_starts, n_seg, d_counts, d_rec_off, d_status);
+                ctx->launches += 1;
+                chased = true;
+            } else {                     // the index does not describe this file: forget it
+                ING_CUDA(cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
+            }
+        }
+    }
+    for (int attempt = 0; attempt < 2 && !chased; ++attempt) {
         ING_CUDA(cudaMallocAsync(&d_rec_off, sizeof(uint64_t) * cap, st));
         bam_chase_kernel<<<1, 32, 0, st>>>(d_data, first_record, total_out, d_rec_off, cap, d_status + 1, d_status);
         ctx->launches += 1;

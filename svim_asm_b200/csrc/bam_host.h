@@ -28,6 +28,7 @@ struct svb_bam {
 // one BGZF member (an independent raw-deflate stream): where its payload sits in the file, where its bytes go
 struct BgzfMember {
     uint64_t in_off, in_len, out_off, out_len;
+    uint64_t file_off;               // where the member (its gzip header) starts in the file: the `coffset` of BAI virtual offsets
 };
 // members with ISIZE 0 (the EOF marker) are skipped; false + *why on a malformed file
 bool bgzf_member_table(const uint8_t* raw, uint64_t size, std::vector<BgzfMember>* blocks, uint64_t* total_out, std::string* why);

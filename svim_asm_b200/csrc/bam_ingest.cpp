@@ -146,6 +146,7 @@ bool bgzf_member_table(const uint8_t* raw, uint64_t size, std::vector<BgzfMember
         const uint64_t hdr_len = 12ull + xlen;
         BgzfMember b;
         b.in_off = in + hdr_len;
+        b.file_off = in;
         b.in_len = bsize - hdr_len - 8;
         b.out_len = rd32(raw + in + bsize - 4);
         b.out_off = total_out;

@@ -135,6 +135,7 @@ int walk_count_async(svb_ctx* ctx, const svb_records* rec, const svb_params* p, 
 int walk_write_async(svb_ctx* ctx, WalkPending* w, uint64_t n_rows, svb_row** d_rows_out);                     // consumes w
 void walk_discard(svb_ctx* ctx, WalkPending* w);
 int gather_pool_known(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uint64_t* seq_off, uint64_t pool_bytes);   // seqpool.cu
+int launch_scan_u32(svb_ctx* ctx, uint32_t* v, uint32_t n, unsigned long long* d_total);   // exclusive scan in place, v[n] = total (segment_walk.cu)
 int launch_merge_tables(svb_ctx* ctx, const svb_row* a, uint64_t na, const svb_row* b, uint64_t nb, svb_row* out);
 int run_pairing(svb_ctx* ctx, const svb_table* h1, const svb_table* h2, const svb_records* rec1,
                 const svb_records* rec2, const svb_ref* ref, const svb_params* p, svb_table** out);

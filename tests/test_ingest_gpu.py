@@ -159,3 +159,26 @@ def test_device_ingest_tag_types_unmapped_and_empty_files(engine, tmp_path):
         HostBatch.from_bam_device(engine, bad)
     with pytest.raises((RuntimeError, IOError)):
         HostBatch.from_bam(bad)
+
+
+def test_record_chase_from_the_index_and_without(engine, tmp_path, monkeypatch):
+    """Record boundaries: in parallel from the record starts the .bai names (every segment must land on the next start),
+    serially without an index, and serially again when the index belongs to another file (stale index -> fall-back)."""
+    cfg = synth.SynthConfig(["chr1", "chr10", "chr2"], [900000, 700000, 800000], 700, 2.5e5, 97, sv_per_event=3e-3,
+                            split_fraction=0.3, sv_max=800)
+    rb = synth.make_haploid(cfg)
+    path = str(tmp_path / "a.bam")
+    bamio.write_bam(path, rb, level=1)
+    want = _compare(engine, path)                              # with a.bam.bai: the indexed walk
+    assert want.n_aln > 500
+    monkeypatch.setenv("SVB_INGEST_SERIAL_CHASE", "1")
+    _compare(engine, path)                                     # forced serial walk
+    monkeypatch.delenv("SVB_INGEST_SERIAL_CHASE")
+    import os
+    os.remove(path + ".bai")
+    _compare(engine, path)                                     # no index at all
+    other = synth.make_haploid(synth.SynthConfig(["chr1", "chr10", "chr2"], [900000, 700000, 800000], 650, 2.4e5, 98, sv_per_event=3e-3,
+                                                 split_fraction=0.3, sv_max=800))
+    bamio.write_bam(str(tmp_path / "b.bam"), other, level=1)
+    os.replace(str(tmp_path / "b.bam.bai"), path + ".bai")     # an index of another file
+    _compare(engine, path)
