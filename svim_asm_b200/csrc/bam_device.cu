@@ -59,7 +59,6 @@ struct InfTables {
     uint8_t lengths[320];
     // direct lookup on the next bits of the stream (entries of inflate_core.cuh: literal, or base + extra-bit count)
     uint32_t fast_len[1 << INF_LEN_BITS], fast_dist[1 << INF_DIST_BITS];
-    InfQueue queue;              // matches decoded by lane 0, resolved by the whole warp
 };
 
 // One warp, one member.  Lane 0 runs the serial part (block headers, the symbol loop of inflate_core.cuh: literals and
@@ -102,24 +101,24 @@ __device__ int inflate_member_warp(const uint8_t* __restrict__ src, uint32_t src
         inf_fill_table(T.distcnt, T.distsym, T.fast_dist, INF_DIST_BITS, true, lane, 32u);
         __syncwarp();
         while (true) {
-            // lane 0 decodes a batch: literals into the ring, matches into the queue; then the warp resolves the matches
-            uint32_t event = INF_EV_EOB, n_queued = 0;
-            if (lane == 0) err = inf_run_queued(b, lencode, distcode, T.fast_len, T.fast_dist, o, T.queue, &n_queued, &event);
-            // one shuffle carries the error, the event and the queue length; another the position
-            const uint32_t word = __shfl_sync(FULLM, static_cast<uint32_t>(err) | (event << 8) | (n_queued << 16), 0);
-            err = static_cast<int>(word & 255u);
+            uint32_t event = INF_EV_EOB, ev_len = 0, ev_dist = 0;
+            if (lane == 0) err = inf_run(b, lencode, distcode, T.fast_len, T.fast_dist, o, &event, &ev_len, &ev_dist);
+            err = __shfl_sync(FULLM, err, 0);
             if (err) return err;
-            event = (word >> 8) & 255u;
-            n_queued = word >> 16;
+            event = __shfl_sync(FULLM, event, 0);
             o.pos = __shfl_sync(FULLM, o.pos, 0);
-            __syncwarp();                               // lane 0's ring and queue stores before the other lanes read them
-            inf_resolve(o, T.queue, n_queued, lane, 32u);
             if (event == INF_EV_EOB) break;
+            __syncwarp();                               // lane 0's ring stores before the other lanes read the ring
             if (event == INF_EV_FLUSH) {
                 inf_flush(o, o.pos, lane, 32u);
                 o.flushed = o.pos;
-                __syncwarp();
+            } else {
+                ev_len = __shfl_sync(FULLM, ev_len, 0);
+                ev_dist = __shfl_sync(FULLM, ev_dist, 0);
+                inf_copy_long(o, ev_len, ev_dist, lane, 32u);
+                o.pos += ev_len;
             }
+            __syncwarp();
         }
     } while (!last);
     __syncwarp();

@@ -299,7 +299,7 @@ SVB_HD void inf_refill(InfBits& b) {
 // INF_RING) reads global memory: that range has been flushed, because at most INF_FLUSH_AT + 258 bytes are ever unflushed.
 // (Measured on B200: the symbol loop is bound by dependent-instruction latency, about 5 cycles per instruction per warp, so
 // the sizes are chosen for 7 CTAs = 28 decoding warps per SM rather than for the largest window.)
-constexpr uint32_t INF_RING = 2048, INF_FLUSH_AT = 512, INF_RMASK = INF_RING - 1u;
+constexpr uint32_t INF_RING = 2048, INF_FLUSH_AT = 1024, INF_RMASK = INF_RING - 1u;
 struct InfOut {
     uint8_t* ring;
     uint8_t* data;          // where the member's first byte goes in global memory
@@ -440,115 +440,6 @@ SVB_HD int inf_run(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, 
             for (uint32_t i = 0; i < len; ++i) o.ring[(w + i) & INF_RMASK] = o.ring[(w - dist + i) & INF_RMASK];
         }
         o.pos += len;
-    }
-}
-
-// ---- decode and copy decoupled (round 2) ------------------------------------------------------------------------------
-// The kernel is bound by instruction ISSUE (24 decoding warps per SM, one active lane each, 110 instructions per symbol
-// measured), and most of those instructions were the decoding lane copying short matches byte by byte.  Here the decoding
-// lane only DECODES: literals go straight to their place in the ring (the lane knows every symbol's output position),
-// matches are queued as {position, length, distance}; when the queue is full, a flush is due or the block ends, the whole
-// warp resolves the queued matches in order -- one step of up to 32 bytes per match instead of 5 instructions per byte.
-// A literal written ahead of an unresolved match is harmless as long as it does not wrap onto that match's source in the
-// ring (see the end of the loop); in-order resolution keeps matches that copy from earlier matches correct.
-constexpr uint32_t INF_QUEUE = 32;
-enum : uint32_t { INF_EV_QUEUE = 3 };
-struct InfQueue {
-    uint32_t at[INF_QUEUE];       // output position | length << 16 (a member holds at most 65,536 bytes)
-    uint32_t dist[INF_QUEUE];
-};
-
-// Symbols of the current block, run by the decoding lane, until the block ends (INF_EV_EOB), INF_FLUSH_AT bytes wait in the
-// ring (INF_EV_FLUSH) or the queue is full (INF_EV_QUEUE).  *n_queued matches are left in `q`; o.pos is behind the last symbol.
-SVB_HD int inf_run_queued(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, const uint32_t* tlen, const uint32_t* tdist,
-                          InfOut& o, InfQueue& q, uint32_t* n_queued, uint32_t* event) {
-    uint32_t nq = 0;
-    *n_queued = 0;
-    while (true) {
-        if (o.pos - o.flushed >= INF_FLUSH_AT) {
-            *event = INF_EV_FLUSH;
-            break;
-        }
-        if (nq == INF_QUEUE) {
-            *event = INF_EV_QUEUE;
-            break;
-        }
-        if (b.cnt < 32) inf_refill(b);
-        uint32_t e = tlen[static_cast<uint32_t>(b.buf) & ((1u << INF_LEN_BITS) - 1u)];
-        if ((e & 15u) == 0u) {                                   // code longer than the table
-            const int sym = inf_decode(b, lencode);
-            if (sym < 0) return INF_ERR_CODE;
-            e = inf_len_entry(static_cast<uint32_t>(sym), 0u);
-        } else {
-            b.buf >>= (e & 15u);
-            b.cnt -= static_cast<int>(e & 15u);
-        }
-        const uint32_t kind = e & INF_K_MASK;
-        if (kind == INF_K_LIT) {
-            if (o.pos >= o.out_len) return INF_ERR_OUTPUT;
-            o.ring[(o.rbase + o.pos) & INF_RMASK] = static_cast<uint8_t>(e >> 16);
-            ++o.pos;
-            continue;
-        }
-        if (kind != INF_K_LEN) {
-            if (kind == INF_K_BAD) return INF_ERR_CODE;
-            if (inf_overrun(b)) return INF_ERR_INPUT;
-            *event = INF_EV_EOB;
-            break;
-        }
-        const uint32_t xl = (e >> 8) & 15u;
-        const uint32_t len = (e >> 16) + (static_cast<uint32_t>(b.buf) & ((1u << xl) - 1u));
-        b.buf >>= xl;
-        b.cnt -= static_cast<int>(xl);
-        if (b.cnt < 32) inf_refill(b);
-        uint32_t d = tdist[static_cast<uint32_t>(b.buf) & ((1u << INF_DIST_BITS) - 1u)];
-        if ((d & 15u) == 0u) {
-            const int dsym = inf_decode(b, distcode);
-            if (dsym < 0) return INF_ERR_CODE;
-            d = inf_dist_entry(static_cast<uint32_t>(dsym), 0u);
-        } else {
-            b.buf >>= (d & 15u);
-            b.cnt -= static_cast<int>(d & 15u);
-        }
-        if ((d & INF_K_MASK) == INF_K_BAD) return INF_ERR_CODE;
-        const uint32_t xd = (d >> 8) & 15u;
-        const uint32_t dist = (d >> 16) + (static_cast<uint32_t>(b.buf) & ((1u << xd) - 1u));
-        b.buf >>= xd;
-        b.cnt -= static_cast<int>(xd);
-        if (dist > o.pos) return INF_ERR_CODE;
-        if (o.pos + len > o.out_len) return INF_ERR_OUTPUT;
-        if (inf_overrun(b)) return INF_ERR_INPUT;
-        q.at[nq] = o.pos | (len << 16);
-        q.dist[nq] = dist;
-        ++nq;
-        o.pos += len;
-        // What is written AHEAD of an unresolved match must not wrap onto its source in the ring.  Until the batch ends at
-        // most INF_FLUSH_AT + 258 further bytes are produced, so a source within INF_RING - (INF_FLUSH_AT + 258) is safe;
-        // a match that reaches further back ends the batch and is resolved before anything else is written.
-        if (dist + len > INF_RING - (INF_FLUSH_AT + 258u)) {
-            *event = INF_EV_QUEUE;
-            break;
-        }
-    }
-    *n_queued = nq;
-    return INF_OK;
-}
-
-// The queued matches, in order, every one copied by n_lanes lanes at once (the caller synchronises the lanes before and after).
-// An overlapping run (dist < len) repeats its last `dist` bytes, so byte i comes from source byte i mod dist: only bytes that
-// existed before the match are read, and the lanes need no order among themselves.
-SVB_HD void inf_resolve(const InfOut& o, const InfQueue& q, uint32_t n_queued, uint32_t lane, uint32_t n_lanes) {
-    for (uint32_t k = 0; k < n_queued; ++k) {
-        const uint32_t at = q.at[k], dist = q.dist[k];
-        const uint32_t pos = at & 0xFFFFu, len = at >> 16, w = o.rbase + pos;
-        const bool in_ring = dist + len <= INF_RING;
-        for (uint32_t i = lane; i < len; i += n_lanes) {
-            const uint32_t j = dist >= len ? i : (dist == 1u ? 0u : i % dist);
-            o.ring[(w + i) & INF_RMASK] = in_ring ? o.ring[(w - dist + j) & INF_RMASK] : o.data[pos - dist + j];
-        }
-#ifdef __CUDA_ARCH__
-        __syncwarp();                                           // the next match may read what this one wrote
-#endif
     }
 }
 

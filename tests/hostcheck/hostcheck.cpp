@@ -191,20 +191,17 @@ extern "C" int hc_inflate_fast(const uint8_t* src_in, unsigned src_len, uint8_t*
             inf_fill_table(lencnt, lensym, tlen.data(), INF_LEN_BITS, false, lane, 32u);
             inf_fill_table(distcnt, distsym, tdist.data(), INF_DIST_BITS, true, lane, 32u);
         }
-        while (true) {                                      // decode a batch (lane 0), resolve its matches (all lanes), as bam_device.cu
-            uint32_t event = 0, n_queued = 0;
-            InfQueue queue;
-            err = inf_run_queued(b, lencode, distcode, tlen.data(), tdist.data(), o, queue, &n_queued, &event);
+        while (true) {
+            uint32_t event = 0, ev_len = 0, ev_dist = 0;
+            err = inf_run(b, lencode, distcode, tlen.data(), tdist.data(), o, &event, &ev_len, &ev_dist);
             if (err) return err;
-            // the lanes of one match run in any order (here: descending), the matches in order
-            for (uint32_t k = 0; k < n_queued; ++k) {
-                InfQueue one;
-                one.at[0] = queue.at[k];
-                one.dist[0] = queue.dist[k];
-                for (uint32_t lane = 32u; lane-- > 0u;) inf_resolve(o, one, 1u, lane, 32u);
-            }
             if (event == INF_EV_EOB) break;
-            if (event == INF_EV_FLUSH) flush();
+            if (event == INF_EV_FLUSH) {
+                flush();
+                continue;
+            }
+            for (uint32_t lane = 0; lane < 32u; ++lane) inf_copy_long(o, ev_len, ev_dist, lane, 32u);
+            o.pos += ev_len;
         }
     } while (!last);
     flush();
