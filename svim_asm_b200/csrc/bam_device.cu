@@ -506,6 +506,10 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     ctx->launches += 1;
     cudaEventRecord(ev[2], st);
 
+    // while the GPU inflates: the record starts the index names (host work, hidden behind the inflate kernel)
+    std::vector<uint64_t> index_starts;
+    if (!getenv("SVB_INGEST_SERIAL_CHASE")) index_starts = bai_record_starts(std::string(path) + ".bai", members, 0, total_out);
+
     // ---- BAM header: host parse of the first bytes of the inflated stream
     std::unique_ptr<svb_bam> bam_owner(new (std::nothrow) svb_bam());
     svb_bam* bam = bam_owner.get();
@@ -539,11 +543,14 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     uint32_t n_rec = 0;
     cudaEventRecord(ev[3], st);
     bool chased = false;
-    if (!getenv("SVB_INGEST_SERIAL_CHASE")) {
+    {
         // record starts from the index: the walk becomes one short segment per thread (bam_chase_indexed_kernel)
-        std::vector<uint64_t> starts = bai_record_starts(std::string(path) + ".bai", members, first_record, total_out);
+        std::vector<uint64_t> starts;
+        starts.reserve(index_starts.size() + 2);
+        starts.push_back(first_record);
+        for (uint64_t at : index_starts)
+            if (at > first_record) starts.push_back(at);
         if (starts.size() >= 64) {
-            starts.insert(starts.begin(), first_record);
             starts.push_back(total_out);
             const uint32_t n_seg = static_cast<uint32_t>(starts.size() - 1);
             uint64_t* d_starts = nullptr;

@@ -97,6 +97,10 @@ int svb_create(int device, svb_ctx** out) {
     }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    ctx->main_stream = ctx->stream;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_counters, 64 * sizeof(unsigned long long));
@@ -137,7 +141,10 @@ void svb_destroy(svb_ctx* ctx) {
     if (ctx->h_text) cudaFreeHost(ctx->h_text);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     upload_release(ctx);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     delete ctx;
 }
 
@@ -588,6 +595,7 @@ int collect_end(svb_ctx* ctx, CollectPending& c, const svb_params* p, bool with_
     svb_table* indel = c.indel;
     c.indel = nullptr;
     indel->n = ctx->h_pinned[c.base];
+    indel->stream = ctx->stream;          // its last readers (merge, pool gather) run on the stream this finish is enqueued on
     // K4: split-alignment walk rows (own table, emission order per primary)
     svb_row* d_walk = nullptr;
     int rc = walk_write_async(ctx, c.walk, n_walk, &d_walk);
@@ -660,18 +668,41 @@ int svb_collect2(svb_ctx* ctx, const svb_records* rec1, const svb_records* rec2,
     if (rec1->device != ctx->device || rec2->device != ctx->device) return svb_fail(ctx, SVB_ERR_ARG, "svb_collect2: records live on another device");
     cudaSetDevice(ctx->device);
     *out1 = *out2 = nullptr;
+    // The scans are bandwidth-bound and fill the GPU; the walk is a few dozen latency-bound warps.  Haplotype 1's walk
+    // count runs on the side stream while haplotype 2 is scanned, and after the one synchronisation the two finishing chains
+    // (walk write, merge, pool) run side by side.
+    const bool overlap = !getenv("SVB_COLLECT_ONE_STREAM");
     CollectPending c[2];
-    int rc = collect_begin(ctx, rec1, p, 1, 0, collect_cap_guess(rec1), true, &c[0]);
+    int rc = collect_begin(ctx, rec1, p, 1, 0, collect_cap_guess(rec1), !overlap, &c[0]);
     if (rc != SVB_OK) return rc;
-    rc = collect_begin(ctx, rec2, p, 2, 16, collect_cap_guess(rec2), true, &c[1]);
+    if (overlap) {
+        SideStream side(ctx);
+        rc = walk_count_async(ctx, rec1, p, 1, ctx->d_counters + 1, &c[0].walk);
+    }
+    if (rc == SVB_OK) rc = collect_begin(ctx, rec2, p, 2, 16, collect_cap_guess(rec2), true, &c[1]);
+    if (overlap) SideStream::join(ctx);
     if (rc == SVB_OK) rc = collect_sync(ctx, c, 2);
     if (rc != SVB_OK) {
         collect_drop(ctx, c[0]);
         collect_drop(ctx, c[1]);
         return rc;
     }
-    rc = collect_end(ctx, c[0], p, with_pools != 0, out1);
-    if (rc == SVB_OK) rc = collect_end(ctx, c[1], p, with_pools != 0, out2);
+    int rc2 = SVB_OK;
+    if (overlap) {
+        {
+            SideStream side(ctx);
+            rc2 = collect_end(ctx, c[1], p, with_pools != 0, out2);
+            if (rc2 == SVB_OK) {            // allocated on the side stream, used and freed on the main one from now on
+                (*out2)->stream = ctx->main_stream;
+            }
+        }
+        rc = collect_end(ctx, c[0], p, with_pools != 0, out1);
+        SideStream::join(ctx);
+    } else {
+        rc = collect_end(ctx, c[0], p, with_pools != 0, out1);
+        if (rc == SVB_OK) rc2 = collect_end(ctx, c[1], p, with_pools != 0, out2);
+    }
+    if (rc == SVB_OK) rc = rc2;
     if (rc != SVB_OK) {
         collect_drop(ctx, c[0]);
         collect_drop(ctx, c[1]);

@@ -66,6 +66,9 @@ struct TimedSpan {
 struct svb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t main_stream = nullptr;   // `stream` outside a SideStream scope
+    cudaStream_t side = nullptr;          // second stream: independent halves of a diploid collect overlap (svb_collect2)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int scan_variant = 0;             // 0 per-warp TMA bulk-copy ring (default: measured faster, profiles/), 1 LDG.128.nc
     int sm_count = 148;
@@ -107,6 +110,23 @@ int svb_fail(svb_ctx* ctx, int code, const char* what, cudaError_t e = cudaSucce
         cudaError_t e__ = (call);                                                   \
         if (e__ != cudaSuccess) return svb_fail((ctx), SVB_ERR_CUDA, #call, e__);   \
     } while (0)
+
+// While one of these is alive everything the library enqueues through ctx->stream goes to the SIDE stream, ordered after what
+// the main stream held when the scope began (fork); join() makes the main stream wait for it.  Used where two chains of
+// small, latency-bound kernels are independent (the two haplotypes of svb_collect2).
+struct SideStream {
+    svb_ctx* c;
+    explicit SideStream(svb_ctx* ctx) : c(ctx) {
+        cudaEventRecord(c->ev_fork, c->main_stream);
+        cudaStreamWaitEvent(c->side, c->ev_fork, 0);
+        c->stream = c->side;
+    }
+    ~SideStream() { c->stream = c->main_stream; }
+    static void join(svb_ctx* ctx) {
+        cudaEventRecord(ctx->ev_join, ctx->side);
+        cudaStreamWaitEvent(ctx->main_stream, ctx->ev_join, 0);
+    }
+};
 
 // scoped kernel timer: records start/stop events on ctx->stream for kernel class `k`
 struct KernelTimer {

@@ -103,7 +103,7 @@ int gather_pool_known(svb_ctx* ctx, svb_table* t, const uint8_t* seq4, const uin
         pool_sizes_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(t->d_rows, n, off32);
         ctx->launches += 1;
     }
-    int rc = launch_scan_u32(ctx, off32, n, ctx->d_counters + 10);
+    int rc = launch_scan_u32(ctx, off32, n, ctx->d_counters + (ctx->stream == ctx->side ? 26 : 10));     // (two gathers may run side by side)
     if (rc != SVB_OK) return rc;
     pool_check_kernel<<<1, 1, 0, ctx->stream>>>(off32, n, pool_bytes, ctx->d_status);
     const uint64_t threads = (static_cast<uint64_t>(n) + 1) * 32;
