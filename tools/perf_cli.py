@@ -45,6 +45,8 @@ for run in range(args.runs):
     n_lines = sum(1 for ln in open(os.path.join(out, "variants.vcf")) if not ln.startswith("#"))
     print("run %d: %.3f s wall, %d VCF records" % (run, wall, n_lines), flush=True)
     if run == args.runs - 1:
+        from svim_asm_b200.runtime import get_engine
+        print("stages of the last device ingest (ms):", {k: round(v, 2) for k, v in get_engine().ingest_timings().items()}, flush=True)
         s = io.StringIO()
         pstats.Stats(prof, stream=s).sort_stats("cumulative").print_stats(28)
         print("\n".join(s.getvalue().split("\n")[:60]))
