@@ -29,21 +29,22 @@
 namespace {
 using namespace edstr;
 
-constexpr int WFA_THREADS = 128;
+constexpr int WFA_THREADS = 256;         // 8 warps: 4 per direction of the bidirectional wavefront
+constexpr int WFA_SIDE = WFA_THREADS / 2;
+constexpr int WFA_ILP = 1;                        // diagonals per thread and round (4 independent chains were measured slower: the loop is bound by issue slots shared with the other resident CTAs, not by the latency of one chain)
 constexpr uint32_t WFA_SLACK = 160;               // readable bytes behind the second string (warp-wide extension reads ahead)
 
 struct WfaControl {
     uint32_t job;
     uint32_t trim[2];
-    uint32_t pad;
+    uint32_t hit;              // bit 0: the waves met at total 2 r - 1, bit 1: at 2 r
 };
 
 __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
     extern __shared__ uint32_t smem_w[];
     const int t = static_cast<int>(a.t), W = 2 * t + 7, mid = t + 3;
-    int* F0 = reinterpret_cast<int*>(smem_w);
-    int* F1 = F0 + W;
-    uint8_t* cls2 = reinterpret_cast<uint8_t*>(F1 + W);
+    int* const Fw = reinterpret_cast<int*>(smem_w);          // [side][wave parity][W]: forward 0 / 1, backward 0 / 1
+    uint8_t* cls2 = reinterpret_cast<uint8_t*>(Fw + 4 * W);
     WfaControl* ctl = reinterpret_cast<WfaControl*>(cls2 + 512);
     uint32_t* Aw = reinterpret_cast<uint32_t*>(ctl + 1);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
             }
             continue;
         }
-        const uint32_t a_bytes = (la + WFA_PAD + 3u) & ~3u, b_bytes = (lb + WFA_PAD + 3u) & ~3u;
+        const uint32_t a_bytes = (WFA_FRONT + la + WFA_PAD + 3u) & ~3u, b_bytes = (WFA_FRONT + lb + WFA_PAD + 3u) & ~3u;
         if (a_bytes + b_bytes + WFA_SLACK > a.cap_chars) {
             if (tid == 0) {
                 bool queued = false;
@@ -152,73 +153,134 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
                 const uint32_t i = i0 + u * WFA_THREADS + tid;
                 if (i < la) {
                     const uint32_t c = tok_class(cls2, ba[u], ma[u]);
-                    As[i] = c < ED_NOCLASS ? static_cast<uint8_t>(c) : WFA_NOCLASS_A;
+                    As[WFA_FRONT + i] = c < ED_NOCLASS ? static_cast<uint8_t>(c) : WFA_NOCLASS_A;
                 }
                 if (i < lb) {
                     const uint32_t c = tok_class(cls2, bb[u], mb[u]);
-                    Bs[i] = c < ED_NOCLASS ? static_cast<uint8_t>(c) : WFA_NOCLASS_B;
+                    Bs[WFA_FRONT + i] = c < ED_NOCLASS ? static_cast<uint8_t>(c) : WFA_NOCLASS_B;
                 }
             }
         }
-        for (uint32_t i = la + tid; i < a_bytes; i += WFA_THREADS) As[i] = WFA_END_A;
-        for (uint32_t i = lb + tid; i < b_bytes + WFA_SLACK; i += WFA_THREADS) Bs[i] = WFA_END_B;
-        for (int x = static_cast<int>(tid); x < 2 * W; x += WFA_THREADS) F0[x] = WFA_NEG;
+        if (tid < WFA_FRONT) { As[tid] = WFA_FRONT_A; Bs[tid] = WFA_FRONT_B; }
+        for (uint32_t i = WFA_FRONT + la + tid; i < a_bytes; i += WFA_THREADS) As[i] = WFA_END_A;
+        for (uint32_t i = WFA_FRONT + lb + tid; i < b_bytes + WFA_SLACK; i += WFA_THREADS) Bs[i] = WFA_END_B;
+        for (int x = static_cast<int>(tid); x < 4 * W; x += WFA_THREADS) Fw[x] = WFA_NEG;
+        if (tid == 0) ctl->hit = 0u;
         __syncthreads();
 
-        // ---- waves
+        // ---- waves, from both ends at once (wfa_core.cuh: bidirectional wavefronts).  Warps 0-3 advance the forward wave, warps
+        // 4-7 the backward one (the same recurrence on the reversed strings); after every round the two are checked for an
+        // overlap at the totals 2 r - 1 (forward r, backward r - 1) and 2 r.  A pair that differs by more than t is settled
+        // after t / 2 rounds instead of t waves.
         const int ila = static_cast<int>(la), ilb = static_cast<int>(lb), kd = ilb - ila;
-        int* prev = F0;
-        int* cur = F1;
+        const bool backward = tid >= static_cast<uint32_t>(WFA_SIDE);
+        const uint32_t st = tid & static_cast<uint32_t>(WFA_SIDE - 1);       // thread within its side
+        int* const mine = Fw + (backward ? 2 * W : 0);          // this side's two arrays
         int result = -1, waves = 0;
-        for (int s = 0; s <= t; ++s) {
-            waves = s + 1;
+        for (int r = 0;; ++r) {
+            waves = r + 1;
+            const int* prev = mine + ((r & 1) ^ 1) * W;
+            int* cur = mine + (r & 1) * W;
             int klo, khi;
-            wfa_range(s, t, kd, ila, ilb, klo, khi);
-            int found = 0;
-            for (int base = klo; base <= khi; base += WFA_THREADS) {
-                const int k = base + static_cast<int>(tid);
-                const bool active = k <= khi;
-                int v = WFA_NEG;
-                bool more = false;
-                if (active) {
-                    v = s == 0 ? 0 : wfa_next(prev[mid + k - 1], prev[mid + k], prev[mid + k + 1], k, ila, ilb);
-                    if (v > WFA_NEG / 2) v += static_cast<int>(wfa_extend8(Aw, Bw, static_cast<uint32_t>(v), static_cast<uint32_t>(v + k), &more));
+            wfa_range(r, t, kd, ila, ilb, klo, khi);
+            // Every thread carries WFA_ILP diagonals through the round as independent, branch-free chains (the loop is bound by
+            // the latency of ONE chain -- three shared-memory reads, the recurrence, six reads, funnel shifts, compare -- with most
+            // issue slots idle): WFA_SIDE threads x WFA_ILP diagonals per pass.
+            for (int base = klo; base <= khi; base += WFA_SIDE * WFA_ILP) {
+                int k[WFA_ILP], v[WFA_ILP];
+                bool more[WFA_ILP];
+#pragma unroll
+                for (int u = 0; u < WFA_ILP; ++u) {
+                    k[u] = base + static_cast<int>(st) + WFA_SIDE * u;
+                    const bool active = k[u] <= khi;
+                    const int kk = active ? k[u] : klo;                       // a safe diagonal for the lanes beyond the range
+                    int x = r == 0 ? 0 : wfa_next_closed(prev[mid + kk - 1], prev[mid + kk], prev[mid + kk + 1], kk, ila, ilb);
+                    const bool valid = active && x > WFA_NEG / 2;
+                    const int xs = valid ? x : 0;                             // safe offsets for the loads below
+                    const uint32_t oa = backward ? WFA_FRONT + static_cast<uint32_t>(ila - 1 - xs) : WFA_FRONT + static_cast<uint32_t>(xs);
+                    const int jb = valid ? xs + kk : 0;
+                    const uint32_t ob = backward ? WFA_FRONT + static_cast<uint32_t>(ilb - 1 - jb) : WFA_FRONT + static_cast<uint32_t>(jb);
+                    uint32_t x0, x1;
+                    if (!backward) {
+                        x0 = wfa_load4(Aw, oa) ^ wfa_load4(Bw, ob);
+                        x1 = wfa_load4(Aw, oa + 4u) ^ wfa_load4(Bw, ob + 4u);
+                    } else {
+                        x0 = wfa_load4(Aw, oa - 3u) ^ wfa_load4(Bw, ob - 3u);
+                        x1 = wfa_load4(Aw, oa - 7u) ^ wfa_load4(Bw, ob - 7u);
+                    }
+                    const uint32_t n0 = backward ? static_cast<uint32_t>(__clz(static_cast<int>(x0 | 1u))) >> 3 : (static_cast<uint32_t>(__ffs(static_cast<int>(x0 | 0x80000000u))) - 1u) >> 3;
+                    const uint32_t n1 = backward ? static_cast<uint32_t>(__clz(static_cast<int>(x1 | 1u))) >> 3 : (static_cast<uint32_t>(__ffs(static_cast<int>(x1 | 0x80000000u))) - 1u) >> 3;
+                    const uint32_t run = x0 ? n0 : 4u + (x1 ? n1 : 4u);
+                    more[u] = valid && x0 == 0u && x1 == 0u;
+                    v[u] = valid ? x + static_cast<int>(run) : (active ? x : WFA_NEG);
                 }
                 // a diagonal that is still matching: the whole warp goes on, 128 symbols per round
-                uint32_t pending = __ballot_sync(FULL, more);
-                while (pending) {
-                    const int src = __ffs(static_cast<int>(pending)) - 1;
-                    pending &= pending - 1u;
-                    const uint32_t i0 = static_cast<uint32_t>(__shfl_sync(FULL, v, src));
-                    const uint32_t j0 = i0 + static_cast<uint32_t>(__shfl_sync(FULL, k, src));
-                    uint32_t run = 0;
-                    while (true) {
-                        const uint32_t x = wfa_load4(Aw, i0 + run + 4u * lane) ^ wfa_load4(Bw, j0 + run + 4u * lane);
-                        const uint32_t bal = __ballot_sync(FULL, x != 0u);
-                        if (bal) {
-                            const int f = __ffs(static_cast<int>(bal)) - 1;
-                            const uint32_t xf = __shfl_sync(FULL, x, f);
-                            run += 4u * static_cast<uint32_t>(f) + wfa_first_diff(xf);
-                            break;
+#pragma unroll
+                for (int u = 0; u < WFA_ILP; ++u) {
+                    uint32_t pending = __ballot_sync(FULL, more[u]);
+                    while (pending) {
+                        const int src = __ffs(static_cast<int>(pending)) - 1;
+                        pending &= pending - 1u;
+                        const int v0 = __shfl_sync(FULL, v[u], src), k0 = __shfl_sync(FULL, k[u], src);
+                        uint32_t run = 0;
+                        while (true) {
+                            uint32_t x;
+                            if (!backward) {
+                                const uint32_t ia = WFA_FRONT + static_cast<uint32_t>(v0) + run + 4u * lane;
+                                x = wfa_load4(Aw, ia) ^ wfa_load4(Bw, ia + static_cast<uint32_t>(k0));
+                            } else {
+                                const int pa = static_cast<int>(WFA_FRONT) + ila - 1 - v0 - 3 - static_cast<int>(run) - 4 * static_cast<int>(lane);
+                                x = wfa_load4s(Aw, pa) ^ wfa_load4s(Bw, pa + kd - k0);     // pb = FRONT + lb - 1 - (v0 + k0) = pa + kd - k0
+                            }
+                            const uint32_t bal = __ballot_sync(FULL, x != 0u);
+                            if (bal) {
+                                const int f = __ffs(static_cast<int>(bal)) - 1;
+                                const uint32_t xf = __shfl_sync(FULL, x, f);
+                                run += 4u * static_cast<uint32_t>(f) + (backward ? wfa_last_diff(xf) : wfa_first_diff(xf));
+                                break;
+                            }
+                            run += 128u;
                         }
-                        run += 128u;
+                        if (static_cast<int>(lane) == src) v[u] = v0 + static_cast<int>(run);
                     }
-                    if (static_cast<int>(lane) == src) v = static_cast<int>(i0 + run);
                 }
-                if (active) {
-                    cur[mid + k] = v;
-                    if (k == kd && v >= ila) found = 1;
-                }
+#pragma unroll
+                for (int u = 0; u < WFA_ILP; ++u)
+                    if (k[u] <= khi) cur[mid + k[u]] = v[u];
             }
-            if (tid == 0) {            // the next wave reads one diagonal beyond this range on either side
+            if (st == 0) {             // the next wave reads one diagonal beyond this range on either side
                 cur[mid + klo - 1] = cur[mid + klo - 2] = WFA_NEG;
                 cur[mid + khi + 1] = cur[mid + khi + 2] = WFA_NEG;
             }
-            if (__syncthreads_or(found)) {
-                result = s;
-                break;
+            __syncthreads();
+            // ---- do the waves overlap?  forward wave r against backward wave r - 1 (total 2 r - 1) and r (total 2 r)
+            {
+                const int* F = Fw + (r & 1) * W;
+                const int* Gc = Fw + 2 * W + (r & 1) * W;
+                const int* Gp = Fw + 2 * W + ((r & 1) ^ 1) * W;
+                int glo = 0, ghi = -1, plo = 0, phi = -1;
+                wfa_range(r, t, kd, ila, ilb, glo, ghi);
+                if (r > 0) wfa_range(r - 1, t, kd, ila, ilb, plo, phi);
+                uint32_t hit = 0;
+                for (int k = klo + static_cast<int>(tid); k <= khi; k += WFA_THREADS) {
+                    const int f = F[mid + k], kb = kd - k;
+                    if (f <= WFA_NEG / 2) continue;
+                    if (kb >= plo && kb <= phi) {
+                        const int g = Gp[mid + kb];
+                        if (g > WFA_NEG / 2 && f + g >= ila) hit |= 1u;
+                    }
+                    if (kb >= glo && kb <= ghi) {
+                        const int g = Gc[mid + kb];
+                        if (g > WFA_NEG / 2 && f + g >= ila) hit |= 2u;
+                    }
+                }
+                if (hit) atomicOr(&ctl->hit, hit);
             }
-            int* tmp = prev; prev = cur; cur = tmp;
+            __syncthreads();
+            const uint32_t h = ctl->hit;
+            if (h & 1u) { result = 2 * r - 1; break; }
+            if (h & 2u) { result = 2 * r <= t ? 2 * r : -1; break; }
+            if (2 * r + 1 > t) break;                           // every total up to t has been tested
         }
         if (tid == 0) {
             if (result >= 0) {
@@ -238,7 +300,7 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
 // counters: [0] next job of stage 0, [1] size of the queue for stage 1, [2] next job of stage 1 (zeroed by the caller)
 int launch_wfa(svb_ctx* ctx, WfaArgs a) {
     if (a.t > WFA_MAX_T) return svb_fail(ctx, SVB_ERR_ARG, "launch_wfa: threshold too large");
-    const size_t fixed = sizeof(int) * 2u * (2u * a.t + 7u) + 512u + sizeof(WfaControl);
+    const size_t fixed = sizeof(int) * 4u * (2u * a.t + 7u) + 512u + sizeof(WfaControl);
     const size_t small = fixed + 24u * 1024u;          // pairs of up to about 12,000 trimmed symbols each: 7-8 CTAs per SM
     const size_t big = 227u * 1024u - 1024u;           // the rest, one CTA per SM
     if (!ctx->wfa_attr_set) {                          // per context = per device (function attributes are per device)
@@ -256,7 +318,7 @@ int launch_wfa(svb_ctx* ctx, WfaArgs a) {
     KernelTimer timer(ctx, SVB_K_EDIT_DISTANCE);
     a.stage = 0;
     a.cap_chars = static_cast<uint32_t>(small - fixed);
-    wfa_kernel<<<static_cast<unsigned>(ctx->sm_count) * 7u, WFA_THREADS, small, ctx->stream>>>(a);
+    wfa_kernel<<<static_cast<unsigned>(ctx->sm_count) * 4u, WFA_THREADS, small, ctx->stream>>>(a);
     a.stage = 1;
     a.cap_chars = static_cast<uint32_t>(big - fixed);
     wfa_kernel<<<static_cast<unsigned>(ctx->sm_count), WFA_THREADS, big, ctx->stream>>>(a);

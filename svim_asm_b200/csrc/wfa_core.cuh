@@ -124,3 +124,121 @@ SVB_HD long long wfa_distance_serial(const uint32_t* A, int la, const uint32_t* 
     }
     return -1;
 }
+
+// ---- bidirectional wavefronts ------------------------------------------------------------------------------------------
+// A forward wavefront from (0, 0) and a backward one from (la, lb) (the same recurrence on the reversed strings) meet in the
+// middle: with F[s][k] = the furthest row on diagonal k whose prefix distance is <= s and G[s][k'] the same for the reversed
+// strings (k' = kd - k in forward terms), d <= sf + sb exactly when some diagonal has F[sf][k] + G[sb][kd - k] >= la
+// (prefix distances do not decrease along a diagonal, so the backward point is reachable forward with <= sf edits once the
+// forward reach is at or beyond it).  Testing the totals 0, 1, 2, ... in order gives d, and "more than t" after t: the same
+// answer as the one-sided run in half as many DEPENDENT waves, because the two sides advance at the same time.
+// Strings carry WFA_FRONT sentinel bytes in front as well (the backward extension runs off the beginning).
+constexpr uint32_t WFA_FRONT = 12;
+constexpr uint8_t WFA_FRONT_A = 0xF9, WFA_FRONT_B = 0xF8;
+
+SVB_HD uint32_t wfa_last_diff(uint32_t x) {      // number of equal bytes from the TOP of the word down (x != 0)
+#ifdef __CUDA_ARCH__
+    return static_cast<uint32_t>(__clz(static_cast<int>(x))) >> 3;
+#else
+    uint32_t n = 0;
+    while (!(x & 0xFF000000u)) { x <<= 8; ++n; }
+    return n;
+#endif
+}
+
+// Backward match extension: the bytes at offsets pa, pa - 1, ... of A against pb, pb - 1, ... of B (byte offsets into the
+// buffers, sentinels included), at most `limit` (a multiple of 4).
+SVB_HD uint32_t wfa_rextend(const uint32_t* A, const uint32_t* B, uint32_t pa, uint32_t pb, uint32_t limit, bool* more) {
+    uint32_t run = 0;
+    *more = false;
+    while (run < limit) {
+        const uint32_t x = wfa_load4(A, pa - 3u - run) ^ wfa_load4(B, pb - 3u - run);
+        if (x) return run + wfa_last_diff(x);
+        run += 4u;
+    }
+    *more = true;
+    return run;
+}
+
+// four bytes at a byte offset that may be NEGATIVE (the warp-wide backward extension looks up to 128 bytes before the front
+// sentinels: the caller guarantees that much readable memory in front of the buffer)
+SVB_HD uint32_t wfa_load4s(const uint32_t* w, int off) {
+    const int idx = off >> 2;
+    const uint32_t sh = (static_cast<uint32_t>(off) & 3u) * 8u;
+    const uint32_t lo = w[idx], hi = w[idx + 1];
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+
+// the backward twin of wfa_extend8: 8 symbols ending at pa / pb, every load issued at once
+SVB_HD uint32_t wfa_rextend8(const uint32_t* A, const uint32_t* B, uint32_t pa, uint32_t pb, bool* more) {
+    const uint32_t x0 = wfa_load4(A, pa - 3u) ^ wfa_load4(B, pb - 3u);
+    const uint32_t x1 = wfa_load4(A, pa - 7u) ^ wfa_load4(B, pb - 7u);
+    *more = false;
+    if (x0) return wfa_last_diff(x0);
+    if (x1) return 4u + wfa_last_diff(x1);
+    *more = true;
+    return 8u;
+}
+
+// monotone closure of wfa_next: a diagonal keeps what it had reached with fewer edits (F[s][k] = max row with distance <= s)
+SVB_HD int wfa_next_closed(int fm1, int f0, int fp1, int k, int la, int lb) {
+    return wfa_imax(wfa_next(fm1, f0, fp1, k, la, lb), f0);
+}
+
+// Serial driver of the bidirectional run: the distance if it is <= t, else -1.  A, B: word-aligned buffers, WFA_FRONT front
+// sentinels + symbols + WFA_PAD back sentinels; Ff / Fb: two arrays of 2 t + 7 ints each.
+SVB_HD long long wfa_bidir_serial(const uint32_t* A, int la, const uint32_t* B, int lb, int t, int* Ff0, int* Ff1, int* Fb0, int* Fb1) {
+    const int kd = lb - la, W = 2 * t + 7, mid = t + 3;
+    if ((kd < 0 ? -kd : kd) > t) return -1;
+    for (int x = 0; x < W; ++x) Ff0[x] = Ff1[x] = Fb0[x] = Fb1[x] = WFA_NEG;
+    int* fprev = Ff0; int* fcur = Ff1; int* bprev = Fb0; int* bcur = Fb1;
+    auto wave = [&](bool backward, int s, const int* prev, int* cur) {
+        int klo, khi;
+        wfa_range(s, t, kd, la, lb, klo, khi);
+        for (int k = klo; k <= khi; ++k) {
+            int v = s == 0 ? 0 : wfa_next_closed(prev[mid + k - 1], prev[mid + k], prev[mid + k + 1], k, la, lb);
+            if (v > WFA_NEG / 2) {
+                bool more = true;
+                while (more) {
+                    if (!backward) v += static_cast<int>(wfa_extend(A, B, WFA_FRONT + static_cast<uint32_t>(v), WFA_FRONT + static_cast<uint32_t>(v + k), 32u, &more));
+                    else v += static_cast<int>(wfa_rextend8(A, B, WFA_FRONT + static_cast<uint32_t>(la - 1 - v), WFA_FRONT + static_cast<uint32_t>(lb - 1 - (v + k)), &more));
+                }
+            }
+            cur[mid + k] = v;
+        }
+        cur[mid + klo - 1] = cur[mid + klo - 2] = WFA_NEG;
+        cur[mid + khi + 1] = cur[mid + khi + 2] = WFA_NEG;
+    };
+    auto overlap = [&](int sf, const int* F, int sb, const int* G) {
+        int klo, khi, glo, ghi;
+        wfa_range(sf, t, kd, la, lb, klo, khi);
+        wfa_range(sb, t, kd, la, lb, glo, ghi);
+        for (int k = klo; k <= khi; ++k) {
+            const int kb = kd - k;
+            if (kb < glo || kb > ghi) continue;
+            const int f = F[mid + k], g = G[mid + kb];
+            if (f > WFA_NEG / 2 && g > WFA_NEG / 2 && f + g >= la) return true;
+        }
+        return false;
+    };
+    wave(false, 0, fprev, fcur);
+    wave(true, 0, bprev, bcur);
+    if (overlap(0, fcur, 0, bcur)) return 0;
+    int sf = 0, sb = 0;
+    while (sf + sb < t) {
+        { int* x = fprev; fprev = fcur; fcur = x; }
+        ++sf;
+        wave(false, sf, fprev, fcur);
+        if (overlap(sf, fcur, sb, bcur)) return sf + sb;
+        if (sf + sb >= t) break;
+        { int* x = bprev; bprev = bcur; bcur = x; }
+        ++sb;
+        wave(true, sb, bprev, bcur);
+        if (overlap(sf, fcur, sb, bcur)) return sf + sb;
+    }
+    return -1;
+}

@@ -144,6 +144,20 @@ extern "C" long long hc_wfa(const uint8_t* a, long long la, const uint8_t* b, lo
     return wfa_distance_serial(A.data(), static_cast<int>(la), B.data(), static_cast<int>(lb), t, F0.data(), F1.data());
 }
 
+// the bidirectional run (two wavefronts meeting in the middle), strings with front and back sentinels
+extern "C" long long hc_wfa_bidir(const uint8_t* a, long long la, const uint8_t* b, long long lb, int t) {
+    std::vector<uint32_t> A((static_cast<size_t>(la) + WFA_FRONT + WFA_PAD + 7) / 4 + 1, 0u), B((static_cast<size_t>(lb) + WFA_FRONT + WFA_PAD + 7) / 4 + 1, 0u);
+    uint8_t* pa = reinterpret_cast<uint8_t*>(A.data());
+    uint8_t* pb = reinterpret_cast<uint8_t*>(B.data());
+    for (uint32_t i = 0; i < WFA_FRONT; ++i) { pa[i] = WFA_FRONT_A; pb[i] = WFA_FRONT_B; }
+    for (long long i = 0; i < la; ++i) pa[WFA_FRONT + i] = a[i];
+    for (long long i = 0; i < lb; ++i) pb[WFA_FRONT + i] = b[i];
+    for (uint32_t i = 0; i < WFA_PAD; ++i) { pa[WFA_FRONT + la + i] = WFA_END_A; pb[WFA_FRONT + lb + i] = WFA_END_B; }
+    const size_t W = 2 * static_cast<size_t>(t) + 7;
+    std::vector<int> F0(W), F1(W), G0(W), G1(W);
+    return wfa_bidir_serial(A.data(), static_cast<int>(la), B.data(), static_cast<int>(lb), t, F0.data(), F1.data(), G0.data(), G1.data());
+}
+
 extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return win_kmax(m, n, bw); }
 
 #include "../../svim_asm_b200/csrc/inflate_core.cuh"
