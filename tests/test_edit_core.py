@@ -154,11 +154,14 @@ def test_wavefront_threshold_core_matches_plain_dp():
                 del b[pos % len(b)]
         return bytes(b)
     cases = [(b"A" * 500, b"A" * 490 + b"C" * 10, 20), (b"AC" * 300, b"CA" * 300, 5), (b"ACGT" * 100, b"ACGT" * 99, 4),
-             (b"A" * 100, b"A" * 100, 0), (b"", b"", 0), (b"", b"AAA", 3), (b"", b"AAA", 2), (b"AAA", b"", 3)]
+             (b"A" * 100, b"A" * 100, 0), (b"", b"", 0), (b"", b"AAA", 3), (b"", b"AAA", 2), (b"AAA", b"", 3), (b"A", b"C", 1), (b"A", b"C", 0),
+             (b"ACGTACGTAC", b"ACGTACGTAC", 0), (b"ACGTACGTAC", b"TACGTACGTA", 2), (b"ACGTACGTAC", b"TACGTACGTA", 1)]
     for _ in range(1500):
         a = bytes(rng.choice(alphabet, int(rng.integers(0, 400))).tolist())
         b = mutate(a, int(rng.integers(0, 60))) if rng.random() < 0.7 else bytes(rng.choice(alphabet, int(rng.integers(0, 400))).tolist())
-        cases.append((a, b, int(rng.choice([0, 1, 5, 10, 30, 200]))))
+        cases.append((a, b, int(rng.choice([0, 1, 2, 3, 5, 10, 30, 31, 200]))))
     for a, b, t in cases:
         d = port.edit_distance(a, b)
         assert lib.hc_wfa(a, len(a), b, len(b), t) == (d if d <= t else -1), (len(a), len(b), t, d)
+        # the bidirectional run (forward and backward waves meeting in the middle: what the kernel does)
+        assert lib.hc_wfa_bidir(a, len(a), b, len(b), t) == (d if d <= t else -1), ("bidirectional", len(a), len(b), t, d)
