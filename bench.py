@@ -230,6 +230,32 @@ def workload_config(cfg, args, **extra):
     return c
 
 
+def file_leg_child(tmp, runs):
+    """Child process of file_to_vcf_block: `runs` x cli.main on the files in `tmp`, then once with the python writer."""
+    import logging
+    from svim_asm_b200 import cli
+    logging.disable(logging.CRITICAL)                     # the CLI logs like the reference; keep the bench's output clean
+    p1, p2, pf = os.path.join(tmp, "h1.bam"), os.path.join(tmp, "h2.bam"), os.path.join(tmp, "ref.fa")
+
+    def masked(path):
+        return [ln for ln in open(path).read().split("\n") if not ln.startswith("##fileDate")]
+    times = []
+    for run in range(runs):
+        out = os.path.join(tmp, "out%d" % run)
+        t0 = time.perf_counter()
+        cli.main(["diploid", out, p1, p2, pf])
+        times.append((time.perf_counter() - t0) * 1e3)
+    from svim_asm_b200.runtime import get_engine
+    stages = {k: round(v, 2) for k, v in get_engine().ingest_timings().items()}
+    vcf = os.path.join(tmp, "out%d" % (runs - 1), "variants.vcf")
+    os.environ["SVIM_ASM_B200_VCF"] = "host"
+    cli.main(["diploid", os.path.join(tmp, "out_host"), p1, p2, pf])
+    same = masked(vcf) == masked(os.path.join(tmp, "out_host", "variants.vcf"))
+    n_rec = sum(1 for ln in open(vcf) if not ln.startswith("#"))
+    print(json.dumps({"ms": min(times), "runs_ms": times, "vcf_records": int(n_rec), "vcf_bytes": os.path.getsize(vcf),
+                      "vcf_equal_python_writer": bool(same), "last_ingest_stages_ms": stages}), flush=True)
+
+
 def file_to_vcf_block(cfg, rb1, rb2, bases, off, runs=3):
     """SURVEY.md 8d's third scope: BAM files + FASTA -> variants.vcf through the drop-in CLI (`svim-asm diploid`): device
     ingest (BGZF inflate + record split on the GPU), COLLECT, PAIR, VCF body assembled on the device.  The files are written
@@ -247,31 +273,19 @@ def file_to_vcf_block(cfg, rb1, rb2, bases, off, runs=3):
         bamio.write_fasta(pf, ref, cfg.contig_names)
         bytes_in = sum(os.path.getsize(p) for p in (p1, p2, pf))
         log("file -> VCF inputs: 2 BAM + FASTA, %.2f GB, written in %.0fs" % (bytes_in / 1e9, time.time() - t0))
-        import logging
-        logging.disable(logging.CRITICAL)                 # the CLI logs like the reference; keep the bench's stderr readable
-
-        def masked(path):
-            return [ln for ln in open(path).read().split("\n") if not ln.startswith("##fileDate")]
-        times = []
-        for run in range(runs):
-            out = os.path.join(tmp, "out%d" % run)
-            t0 = time.perf_counter()
-            cli.main(["diploid", out, p1, p2, pf])
-            times.append((time.perf_counter() - t0) * 1e3)
-        vcf = os.path.join(tmp, "out%d" % (runs - 1), "variants.vcf")
-        os.environ["SVIM_ASM_B200_VCF"] = "host"
-        try:
-            cli.main(["diploid", os.path.join(tmp, "out_host"), p1, p2, pf])
-        finally:
-            del os.environ["SVIM_ASM_B200_VCF"]
-            logging.disable(logging.NOTSET)
-        same = masked(vcf) == masked(os.path.join(tmp, "out_host", "variants.vcf"))
-        if not same:
+        # the runs happen in a process of their own, like a user's `svim-asm diploid ...` (this process still holds the record
+        # images, pinned buffers and memory pools of the legs above); it reports its wall times and compares the two writers
+        child = subprocess.run([sys.executable, os.path.abspath(__file__), "--file-leg-child", tmp, "--steps", str(runs)],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
+        if child.returncode != 0 or not child.stdout.strip():
+            raise SystemExit("bench.py: the file -> VCF leg failed (exit %d)" % child.returncode)
+        res = json.loads(child.stdout.strip().split("\n")[-1])
+        if not res.get("vcf_equal_python_writer"):
             raise SystemExit("bench.py: the device-assembled variants.vcf differs from the python writer's")
-        n_rec = sum(1 for ln in open(vcf) if not ln.startswith("#"))
-        return {"ms": min(times), "runs_ms": times, "bytes_in": int(bytes_in), "vcf_records": int(n_rec), "vcf_bytes": os.path.getsize(vcf),
-                "vcf_equal_python_writer": True,
-                "scope": "svim-asm diploid h1.bam h2.bam ref.fa -> variants.vcf, files in the page cache; first run includes CUDA / pinned-buffer set-up"}
+        res["bytes_in"] = int(bytes_in)
+        res["scope"] = ("svim-asm diploid h1.bam h2.bam ref.fa -> variants.vcf in a fresh process, files in the page cache; `ms` = best of "
+                        "%d runs, the first one includes CUDA start-up and the pinned-buffer set-up" % runs)
+        return res
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -401,7 +415,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the whole-genome workload (testing only)")
     ap.add_argument("--no-file-leg", dest="no_file_leg", action="store_true", help="skip the file -> variants.vcf measurement")
+    ap.add_argument("--file-leg-child", dest="file_leg_child", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.file_leg_child:
+        return file_leg_child(args.file_leg_child, args.steps)
     # stdout carries exactly ONE JSON line: python's sys.stdout keeps the original descriptor, descriptor 1 itself is
     # pointed at stderr so that anything a native library prints there (NCCL's version banner ...) cannot get in front
     sys.stdout.flush()
