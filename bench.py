@@ -239,10 +239,12 @@ def file_leg_child(tmp, runs):
 
     def masked(path):
         return [ln for ln in open(path).read().split("\n") if not ln.startswith("##fileDate")]
+    import gc
     times = []
     for run in range(runs):
         out = os.path.join(tmp, "out%d" % run)
-        t0 = time.perf_counter()
+        gc.collect()                                      # the previous run's record images go back to the memory pool before
+        t0 = time.perf_counter()                          # this one allocates (else the pool grows by gigabytes: 0.4 s of cuMemCreate)
         cli.main(["diploid", out, p1, p2, pf])
         times.append((time.perf_counter() - t0) * 1e3)
     from svim_asm_b200.runtime import get_engine
@@ -252,11 +254,11 @@ def file_leg_child(tmp, runs):
     cli.main(["diploid", os.path.join(tmp, "out_host"), p1, p2, pf])
     same = masked(vcf) == masked(os.path.join(tmp, "out_host", "variants.vcf"))
     n_rec = sum(1 for ln in open(vcf) if not ln.startswith("#"))
-    print(json.dumps({"ms": min(times), "runs_ms": times, "vcf_records": int(n_rec), "vcf_bytes": os.path.getsize(vcf),
+    print(json.dumps({"ms": min(times), "median_ms": float(np.median(times[1:])) if len(times) > 1 else times[0], "runs_ms": times, "vcf_records": int(n_rec), "vcf_bytes": os.path.getsize(vcf),
                       "vcf_equal_python_writer": bool(same), "last_ingest_stages_ms": stages}), flush=True)
 
 
-def file_to_vcf_block(cfg, rb1, rb2, bases, off, runs=3):
+def file_to_vcf_block(cfg, rb1, rb2, bases, off, runs=5):
     """SURVEY.md 8d's third scope: BAM files + FASTA -> variants.vcf through the drop-in CLI (`svim-asm diploid`): device
     ingest (BGZF inflate + record split on the GPU), COLLECT, PAIR, VCF body assembled on the device.  The files are written
     once (page cache / tmpfs), the best of `runs` is reported, and the VCF is compared with the python writer's."""

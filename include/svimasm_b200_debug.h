@@ -30,7 +30,8 @@ int svb_mark(svb_ctx* ctx, int slot);
 int svb_elapsed_ms(svb_ctx* ctx, int slot_begin, int slot_end, double* ms);
 /* ms of the context's last svb_bam_open_device call: [0] file read, [1] H2D, [2] inflate kernel, [3] record chase,
  * [4] field + copy kernels, [5] host SA parse + record image, [6] total wall, [7] inflated bytes,
- * [8] resident inflate CTAs per SM, [9] mean clock cycles per BGZF member, [10] members */
+ * [8] resident inflate CTAs per SM, [9] mean clock cycles per BGZF member, [10] members, [11] segments of the index-driven
+ * record walk (0: the serial walk ran) */
 int svb_bam_device_timings(svb_ctx* ctx, double out[12]);
 /* the resident reference back on the host: bases (may be NULL), their count, the 256-entry symbol-class map */
 int svb_ref_to_host(svb_ctx* ctx, const svb_ref* ref, uint8_t* bases_dst, uint64_t cap, uint64_t* n_bases, uint8_t* class_map256_dst);

@@ -543,6 +543,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     uint32_t n_rec = 0;
     cudaEventRecord(ev[3], st);
     bool chased = false;
+    ctx->ingest_ms[11] = 0.0;
     {
         // record starts from the index: the walk becomes one short segment per thread (bam_chase_indexed_kernel)
         std::vector<uint64_t> starts;
@@ -575,6 +576,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
                 bam_chase_indexed_kernel<true><<<(n_seg + 127) / 128, 128, 0, st>>>(d_data, d_starts, n_seg, d_counts, d_rec_off, d_status);
                 ctx->launches += 1;
                 chased = true;
+                ctx->ingest_ms[11] = static_cast<double>(n_seg);      // segments of the indexed walk (0: serial walk)
             } else {                     // the index does not describe this file: forget it
                 ING_CUDA(cudaMemsetAsync(d_status, 0, sizeof(uint32_t), st));
             }

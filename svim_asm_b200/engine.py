@@ -479,7 +479,7 @@ class Engine(object):
         v = np.zeros(12, dtype=np.float64)
         self._check(lib.svb_bam_device_timings(self.handle, _lib.ptr(v)))
         keys = ("read_file", "h2d", "inflate", "chase", "fields_copy", "host_parse", "total", "inflated_bytes",
-                "inflate_ctas_per_sm", "inflate_cycles_per_member", "members")
+                "inflate_ctas_per_sm", "inflate_cycles_per_member", "members", "indexed_chase_segments")
         return dict(zip(keys, (float(x) for x in v)))
 
     def load_reference(self, bases, contig_off):

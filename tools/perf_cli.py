@@ -18,6 +18,7 @@ from svim_asm_b200 import bamio, cli, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=0.1)
 ap.add_argument("--runs", type=int, default=2)
+ap.add_argument("--dir", default=None, help="where the input files are written (default: the system temp directory)")
 args = ap.parse_args()
 
 lengths = [max(100000, int(x * args.scale)) for x in synth.HG38_LENGTHS]
@@ -26,7 +27,7 @@ cfg = synth.SynthConfig(list(synth.HG38_NAMES), lengths, max(24, int(40000 * arg
 t0 = time.time()
 rb1, rb2 = synth.make_diploid(cfg)
 ref = synth.random_reference(cfg)
-tmp = tempfile.mkdtemp()
+tmp = tempfile.mkdtemp(dir=args.dir)
 p1, p2, pf = os.path.join(tmp, "h1.bam"), os.path.join(tmp, "h2.bam"), os.path.join(tmp, "ref.fa")
 bamio.write_bam(p1, rb1, level=1)
 bamio.write_bam(p2, rb2, level=1)
