@@ -352,7 +352,7 @@ def b200_arm(args):
     achieved = alg_bytes / (scan_avg * 1e-3) / 1e9
     traffic = None
     try:      # DRAM bytes of one launch from the committed ncu capture (profiles/), valid for the full-size workload only
-        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_cigar_scan_traffic.json")))
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r2_cigar_scan_traffic.json")))
         if abs(cap["n_ops"] - n_ops / 2.0) < 0.02 * cap["n_ops"]:
             traffic = cap["cigar_scan_dram_bytes_per_launch"]
     except Exception:

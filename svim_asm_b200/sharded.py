@@ -487,10 +487,10 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         # a shard runs the same kernel on fewer units, so the shard's figure is that ratio times its algorithmic bytes
         traffic, traffic_src = None, None
         try:
-            cap = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_cigar_scan_traffic.json")))
+            cap = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_cigar_scan_traffic.json")))
             ratio = cap["cigar_scan_dram_bytes_per_launch"] / (4.0 * cap["n_ops"] + 32.0 * cap.get("n_aln", 0) + 64.0 * cap.get("n_rows", 0))
             traffic = ratio * alg
-            traffic_src = "profiles/r1_cigar_scan_traffic.json: measured DRAM bytes / algorithmic bytes of the full-size launch (%.3f) x this shard's algorithmic bytes" % ratio
+            traffic_src = "profiles/r2_cigar_scan_traffic.json: measured DRAM bytes / algorithmic bytes of the full-size launch (%.3f) x this shard's algorithmic bytes" % ratio
         except Exception:
             pass
         print(json.dumps({
