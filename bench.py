@@ -277,8 +277,10 @@ def file_to_vcf_block(cfg, rb1, rb2, bases, off, runs=5):
         log("file -> VCF inputs: 2 BAM + FASTA, %.2f GB, written in %.0fs" % (bytes_in / 1e9, time.time() - t0))
         # the runs happen in a process of their own, like a user's `svim-asm diploid ...` (this process still holds the record
         # images, pinned buffers and memory pools of the legs above); it reports its wall times and compares the two writers
-        child = subprocess.run([sys.executable, os.path.abspath(__file__), "--file-leg-child", tmp, "--steps", str(runs)],
-                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
+        child_log = os.environ.get("SVB_BENCH_CHILD_LOG")             # where the child's stderr goes (e.g. with SVB_INGEST_TRACE=1)
+        with (open(child_log, "w") if child_log else open(os.devnull, "w")) as child_err:
+            child = subprocess.run([sys.executable, os.path.abspath(__file__), "--file-leg-child", tmp, "--steps", str(runs)],
+                                   stdout=subprocess.PIPE, stderr=child_err, text=True, timeout=900)
         if child.returncode != 0 or not child.stdout.strip():
             raise SystemExit("bench.py: the file -> VCF leg failed (exit %d)" % child.returncode)
         res = json.loads(child.stdout.strip().split("\n")[-1])

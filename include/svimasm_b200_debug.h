@@ -37,6 +37,9 @@ int svb_bam_device_timings(svb_ctx* ctx, double out[12]);
 int svb_ref_to_host(svb_ctx* ctx, const svb_ref* ref, uint8_t* bases_dst, uint64_t cap, uint64_t* n_bases, uint8_t* class_map256_dst);
 /* the context's last svb_pair: [0] partitions, [1] cross-haplotype pairs (edit-distance jobs), [2] pairs that needed the
  * exact kernel after the thresholded wavefront pass, [3] sum of len(h1) x len(h2) over the pairs (full-table cells) */
+/* The BGZF member table of a file built by n_threads host threads (csrc/bam_ingest.cpp: the parallel walk of the device ingest
+ * against the serial one); out = {members, inflated bytes, checksum over every member's offsets and sizes}. */
+int svb_bgzf_member_table_check(const char* path, int n_threads, uint64_t out[3]);
 int svb_pair_stats(svb_ctx* ctx, uint64_t out[4]);
 
 #ifdef __cplusplus

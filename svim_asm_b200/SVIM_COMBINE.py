@@ -54,6 +54,10 @@ class ReferencePrefetch(threading.Thread):
             self.result = None
 
 
+def prefetch_pending(fasta_path, contig_names):
+    return (os.path.abspath(fasta_path), tuple(contig_names)) in _PREFETCH
+
+
 def drop_prefetches():
     """Wait for background loads nobody picked up and release what they produced."""
     while _PREFETCH:

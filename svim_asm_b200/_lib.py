@@ -93,6 +93,7 @@ SIGNATURES = {
     "svb_edit_distance_bounded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_u32, c_i64, c_void_p]),
     "svb_form_partitions": (c_int, [c_void_p, c_void_p, c_u32, c_i64, c_void_p, c_void_p, P(c_u32)]),
     "svb_pair_stats": (c_int, [c_void_p, c_void_p]),
+    "svb_bgzf_member_table_check": (c_int, [c_char_p, c_int, c_void_p]),
     "svb_cluster_labels": (c_int, [c_void_p, c_void_p, c_void_p, c_u32, c_double, c_void_p]),
     "svb_table_size": (c_i64, [c_void_p]),
     "svb_table_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_u64, P(c_u64)]),

@@ -2,8 +2,9 @@
 
 `write_bam` serialises a `synth.RecordBatch` as a real BGZF BAM plus a `.bai`
 index, `write_fasta` a FASTA plus `.fai`.  Reading BAM files is NOT done here:
-the product path reads them with the multi-threaded C++ ingest inside
-`libsvimasm_b200.so` (`svb_bam_open`, csrc/bam_ingest.cpp).
+the product path reads them with the device ingest / the multi-threaded C++ ingest inside
+`libsvimasm_b200.so` (`svb_bam_open_device`, `svb_bam_open`); `read_reference_names` only peeks at
+the contig names of a header so that the CLI can start loading the FASTA before the ingest is through.
 """
 import os
 import struct
@@ -169,3 +170,45 @@ def write_fasta(path, reference, names, line_width=60):
             if n % line_width:
                 out.write(seq[full * line_width:].tobytes() + b"\n")
             fai.write("%s\t%d\t%d\t%d\t%d\n" % (name, n, offset, line_width, line_width + 1))
+
+
+def read_reference_names(path, limit=64 << 20):
+    """Contig names of a BAM header, in header order, from the first BGZF members of the file (a few kilobytes for a
+    human genome); None when the file does not look like a BAM.  The CLI uses it to start the FASTA -> HBM load while
+    the first BAM is still being ingested; the ingest itself reads the header again, on its own."""
+    try:
+        with open(path, "rb") as f:
+            data = bytearray()
+
+            def need(n):
+                while len(data) < n:
+                    head = f.read(18)
+                    if len(head) < 18 or head[:4] != b"\x1f\x8b\x08\x04" or head[12:14] != b"BC" or len(data) > limit:
+                        return False
+                    xlen = struct.unpack("<H", head[10:12])[0]
+                    bsize = struct.unpack("<H", head[16:18])[0] + 1
+                    rest = f.read(bsize - 18)
+                    if len(rest) != bsize - 18:
+                        return False
+                    data.extend(zlib.decompress(rest[xlen - 6:-8], -15))
+                return True
+            if not need(12) or data[:4] != b"BAM\x01":
+                return None
+            l_text = struct.unpack_from("<i", data, 4)[0]
+            at = 8 + l_text
+            if l_text < 0 or not need(at + 4):
+                return None
+            n_ref = struct.unpack_from("<i", data, at)[0]
+            at += 4
+            names = []
+            for _ in range(n_ref):
+                if not need(at + 4):
+                    return None
+                l_name = struct.unpack_from("<i", data, at)[0]
+                if l_name <= 0 or not need(at + 4 + l_name + 4):
+                    return None
+                names.append(bytes(data[at + 4:at + 4 + l_name - 1]).decode("ascii"))
+                at += 4 + l_name + 4
+            return names
+    except (OSError, ValueError, zlib.error, struct.error, UnicodeDecodeError):
+        return None

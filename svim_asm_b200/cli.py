@@ -7,7 +7,6 @@ from time import localtime, strftime
 
 __version__ = "1.0.3"
 
-
 def _open_sorted_bam(path, which):
     """svim-asm:63-80 / 85-120: header must say SO:coordinate and an index must sit next to the file."""
     from .bamfile import AlignmentFile
@@ -59,13 +58,19 @@ def main(argv=None):
             h.close()
 
 
-def _prefetch_reference(options, bam):
-    """Start the FASTA -> HBM load in the background (needed by PAIR and by the VCF alleles) once the contigs are known."""
-    if os.environ.get("SVIM_ASM_B200_PREFETCH", "1") == "0":
+def _prefetching():
+    return os.environ.get("SVIM_ASM_B200_PREFETCH", "1") != "0" and os.environ.get("SVIM_ASM_B200_INGEST", "device") != "host"
+
+
+def _prefetch_reference(options, contig_names):
+    """Start the FASTA -> HBM load in the background (needed by PAIR and by the VCF alleles) once the contigs are known:
+    before the first ingest when the header's contig names can be peeked at, else right after it."""
+    if not _prefetching() or not contig_names:
         return
-    if os.path.exists(options.genome) and os.path.exists(options.genome + ".fai") and getattr(bam, "records", None) is not None:
-        from .SVIM_COMBINE import ReferencePrefetch
-        ReferencePrefetch(options.genome, bam.references)
+    if os.path.exists(options.genome) and os.path.exists(options.genome + ".fai"):
+        from .SVIM_COMBINE import ReferencePrefetch, prefetch_pending
+        if not prefetch_pending(options.genome, contig_names):
+            ReferencePrefetch(options.genome, contig_names)
 
 
 def _run(options):
@@ -82,20 +87,28 @@ def _run(options):
     if options.sub == "haploid":
         logging.info("MODE: haploid")
         logging.info("INPUT: {0}".format(os.path.abspath(options.bam_file)))
+        if _prefetching():
+            from .bamio import read_reference_names
+            _prefetch_reference(options, read_reference_names(options.bam_file))
         aln_file1 = _open_sorted_bam(options.bam_file, None)
         if aln_file1 is None:
             return
-        _prefetch_reference(options, aln_file1)
+        if aln_file1.records is not None:
+            _prefetch_reference(options, aln_file1.references)
         options._haplotype = 0
         sv_candidates = analyze_alignment_file_coordsorted(aln_file1, options)
     else:
         logging.info("MODE: diploid")
         logging.info("INPUT1: {0}".format(os.path.abspath(options.bam_file1)))
         logging.info("INPUT2: {0}".format(os.path.abspath(options.bam_file2)))
+        if _prefetching():                 # the FASTA starts moving now, next to the first ingest
+            from .bamio import read_reference_names
+            _prefetch_reference(options, read_reference_names(options.bam_file1))
         aln_file1 = _open_sorted_bam(options.bam_file1, 1)
         if aln_file1 is None:
             return
-        _prefetch_reference(options, aln_file1)
+        if aln_file1.records is not None:
+            _prefetch_reference(options, aln_file1.references)
         options._haplotype = 1
         sv_candidates1 = analyze_alignment_file_coordsorted(aln_file1, options)
         aln_file2 = _open_sorted_bam(options.bam_file2, 2)

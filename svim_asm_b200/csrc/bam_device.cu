@@ -25,6 +25,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bam_host.h"
@@ -50,35 +51,51 @@ struct DevMember {
 };
 
 // One WARP per member.  A thread per member would put 32 unrelated decoder states into one warp: they diverge at every
-// branch and the warp runs them one after the other (measured: 2.5 GB/s).  Here lane 0 decodes (Huffman tables in shared
-// memory, canonical count/symbol form of inflate_core.cuh) and writes the literals; at every match and stored block all
-// 32 lanes copy together; the other lanes wait at the broadcast.  Members of one CTA never interact.
+// branch and the warp runs them one after the other (measured: 2.5 GB/s).  A warp whose lane 0 decodes while the others
+// wait for matches to copy executes 110 instructions per symbol, most of them the decoding lane's byte loops (35 GB/s).
+// Here EVERY lane decodes the SAME member in lock step (inflate_core.cuh: inf_run_lanes) -- the same instruction stream
+// costs a warp the same whether one lane or all 32 execute it -- so every lane knows every symbol without a broadcast and
+// the bytes of a match are copied by the lanes side by side.  Lane 0 alone parses the block headers (they build the code
+// arrays in shared memory) and stores the literals.  Members of one CTA never interact.
 constexpr int INF_WARPS = 4;
+#ifndef INF_MIN_CTAS
+#define INF_MIN_CTAS 9          // resident CTAs per SM the kernel is compiled for (registers <= 65536 / (INF_MIN_CTAS * 128))
+#endif
+// 5.8 KB per warp: 9 CTAs of 4 warps fit the SM's 227 KB.  The scratch array of the block header (code lengths, 320 bytes) lives
+// in the distance table: the tables are built after the header has been parsed.
 struct InfTables {
     uint16_t lencnt[16], lensym[288], distcnt[16], distsym[32];
-    uint8_t lengths[320];
     // direct lookup on the next bits of the stream (entries of inflate_core.cuh: literal, or base + extra-bit count)
-    uint32_t fast_len[1 << INF_LEN_BITS], fast_dist[1 << INF_DIST_BITS];
+    inf_len_t fast_len[1 << INF_LEN_BITS];
+    uint32_t fast_dist[1 << INF_DIST_BITS];
 };
+static_assert(sizeof(uint32_t) * (1 << INF_DIST_BITS) >= 320, "the header's scratch array must fit the distance table");
 
-// One warp, one member.  Lane 0 runs the serial part (block headers, the symbol loop of inflate_core.cuh: literals and
-// short matches go into the warp's output ring in shared memory); all lanes build the direct tables, copy stored blocks
-// and long matches, and flush the ring to global memory in 16-byte vectors.
+// One warp, one member: block headers by lane 0 (the reader's state is handed to every lane afterwards), the direct tables
+// filled by all lanes, then the symbol loop in lock step; stored blocks go through the ring in pieces.
 __device__ int inflate_member_warp(const uint8_t* __restrict__ src, uint32_t src_len, uint8_t* dst, uint32_t out_len, InfTables& T,
                                    uint8_t* ring, uint32_t lane) {
     constexpr uint32_t FULLM = 0xffffffffu;
     InfHuff lencode{T.lencnt, T.lensym}, distcode{T.distcnt, T.distsym};
-    InfBits b{src, src + src_len, 0ull, 0, 0};          // lane 0's
-    InfOut o = inf_out(ring, dst, out_len);             // pos / flushed are warp-uniform wherever the lanes meet
+    InfBits b{src, src + src_len, 0ull, 0, 0};          // the same on every lane
+    InfOut o = inf_out(ring, dst, out_len);             // the same on every lane
     int last = 0;
     do {
         int err = 0;
         uint32_t type = 0, st_off = 0, st_len = 0;
-        if (lane == 0) err = inf_block_header(b, src, o.pos, out_len, lencode, distcode, T.lengths, &last, &type, &st_off, &st_len);
+        if (lane == 0) err = inf_block_header(b, src, o.pos, out_len, lencode, distcode, reinterpret_cast<uint8_t*>(T.fast_dist), &last, &type, &st_off, &st_len);
         err = __shfl_sync(FULLM, err, 0);
         if (err) return err;
         type = __shfl_sync(FULLM, type, 0);
         last = __shfl_sync(FULLM, last, 0);
+        {                                               // lane 0's reader, to every lane
+            const uint32_t at = __shfl_sync(FULLM, static_cast<uint32_t>(b.p - src), 0);
+            const uint32_t lo = __shfl_sync(FULLM, static_cast<uint32_t>(b.buf), 0), hi = __shfl_sync(FULLM, static_cast<uint32_t>(b.buf >> 32), 0);
+            b.p = src + at;
+            b.buf = (static_cast<uint64_t>(hi) << 32) | lo;
+            b.cnt = __shfl_sync(FULLM, b.cnt, 0);
+            b.virt = __shfl_sync(FULLM, b.virt, 0);
+        }
         if (type == 0u) {                               // stored block: through the ring in pieces (later matches may point into it)
             st_off = __shfl_sync(FULLM, st_off, 0);
             st_len = __shfl_sync(FULLM, st_len, 0);
@@ -100,27 +117,11 @@ __device__ int inflate_member_warp(const uint8_t* __restrict__ src, uint32_t src
         inf_fill_table(T.lencnt, T.lensym, T.fast_len, INF_LEN_BITS, false, lane, 32u);
         inf_fill_table(T.distcnt, T.distsym, T.fast_dist, INF_DIST_BITS, true, lane, 32u);
         __syncwarp();
-        while (true) {
-            uint32_t event = INF_EV_EOB, ev_len = 0, ev_dist = 0;
-            if (lane == 0) err = inf_run(b, lencode, distcode, T.fast_len, T.fast_dist, o, &event, &ev_len, &ev_dist);
-            err = __shfl_sync(FULLM, err, 0);
-            if (err) return err;
-            event = __shfl_sync(FULLM, event, 0);
-            o.pos = __shfl_sync(FULLM, o.pos, 0);
-            if (event == INF_EV_EOB) break;
-            __syncwarp();                               // lane 0's ring stores before the other lanes read the ring
-            if (event == INF_EV_FLUSH) {
-                inf_flush(o, o.pos, lane, 32u);
-                o.flushed = o.pos;
-            } else {
-                ev_len = __shfl_sync(FULLM, ev_len, 0);
-                ev_dist = __shfl_sync(FULLM, ev_dist, 0);
-                inf_copy_long(o, ev_len, ev_dist, lane, 32u);
-                o.pos += ev_len;
-            }
-            __syncwarp();
-        }
+        err = inf_run_lanes(b, lencode, distcode, T.fast_len, T.fast_dist, o, lane, 32u);
+        if (err) return err;                            // the same on every lane
+        __syncwarp();                                   // the block's last stores, before lane 0 rebuilds the tables
     } while (!last);
+    if (o.pos > out_len) return INF_ERR_OUTPUT;
     __syncwarp();
     inf_flush(o, o.pos, lane, 32u);
     return o.pos == out_len ? INF_OK : INF_ERR_SIZE;
@@ -128,8 +129,11 @@ __device__ int inflate_member_warp(const uint8_t* __restrict__ src, uint32_t src
 
 // Persistent warps: every warp claims the next member from a counter until none is left, so a slow member never holds
 // the other three warps of its CTA (and the SM's slot) idle.  status[2..3]: sum of member cycles, status[4]: the counter.
-__global__ void __launch_bounds__(INF_WARPS * 32, 7) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const DevMember* __restrict__ members,
-                                                                         uint32_t n, uint8_t* out, uint32_t* status) {
+// (A variant that was launched before the upload and waited, member by member, for "chunk landed" flags written by the copy
+// streams overlapped the two -- and hung for minutes when another host thread made a device-synchronising call while the
+// kernel was spinning: a kernel must not depend on host progress.  The upload now overlaps the host's member table instead.)
+__global__ void __launch_bounds__(INF_WARPS * 32, INF_MIN_CTAS) bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const DevMember* __restrict__ members,
+                                                                                    uint32_t n, uint8_t* out, uint32_t* status) {
     __shared__ InfTables tables[INF_WARPS];
     __shared__ __align__(16) uint8_t rings[INF_WARPS][INF_RING];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -427,6 +431,14 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         return svb_fail(ctx, code, msg.c_str());
     };
     const auto wall0 = std::chrono::steady_clock::now();
+    // SVB_INGEST_TRACE=1: host wall clock at every phase boundary, to stderr (where does the time between the kernels go?)
+    const bool trace = getenv("SVB_INGEST_TRACE") != nullptr;
+    auto mark = [&](const char* what) {
+        if (trace) {
+            const char* base = strrchr(path, '/');
+            fprintf(stderr, "[ingest %s] %8.2f ms  %s\n", base ? base + 1 : path, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(), what);
+        }
+    };
 
     // ---- the file: mapped, not read.  The only full pass over its bytes is the driver's copy to the device (the member
     // table touches 18 bytes per 64 KB); pinning gigabytes first would cost more than it saves.
@@ -456,14 +468,46 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     const uint8_t* raw = static_cast<const uint8_t*>(mapping.p);
     const auto wall_read = std::chrono::steady_clock::now();
 
+#define ING_CUDA(call)                                                             \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return fail(SVB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+    // ---- the upload starts at once, on a thread of its own (upload_file_range: parallel pread + pinned staging); it needs the
+    // file's size only.  The host builds the member table meanwhile.
+    uint8_t *d_comp = nullptr, *d_data = nullptr;
+    DevMember* d_members = nullptr;
+    uint32_t* d_status = nullptr;      // [0] error bits, [1] record count
+    ING_CUDA(cudaMallocAsync(&d_comp, static_cast<size_t>(fsize), st));
+    gc.dev.push_back(d_comp);
+    ING_CUDA(cudaStreamSynchronize(st));                                   // (the upload's streams are not ordered behind `st`)
+    struct Upload {
+        std::thread worker;
+        int rc = SVB_OK;
+        double ms = 0.0;
+        ~Upload() {
+            if (worker.joinable()) worker.join();
+        }
+    } upload;
+    upload.worker = std::thread([&upload, ctx, fd, fsize, d_comp]() {
+        cudaSetDevice(ctx->device);
+        const auto w0 = std::chrono::steady_clock::now();
+        upload.rc = upload_file_range(ctx, fd, 0, static_cast<uint64_t>(fsize), d_comp, false, false);
+        upload.ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+    });
+
+    // ---- meanwhile: the member table (18 bytes of every member's header through the mapping: 20 ms of page faults for 43,000 members)
     std::vector<BgzfMember> members;
     uint64_t total_out = 0;
     unsigned long long inflate_cycles = 0;
     {
         std::string why;
-        if (!bgzf_member_table(raw, static_cast<uint64_t>(fsize), &members, &total_out, &why)) return fail(SVB_ERR_IO, why);
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (!bgzf_member_table(raw, static_cast<uint64_t>(fsize), &members, &total_out, &why, getenv("SVB_INGEST_SERIAL_TABLE") ? 1 : static_cast<int>(std::min(8u, std::max(1u, hw / 4u)))))
+            return fail(SVB_ERR_IO, why);
     }
     if (members.empty() || members.size() > 0x7fffffffull) return fail(SVB_ERR_IO, "not a BAM file");
+    mark("member table");
     std::vector<DevMember> dm(members.size());
     for (size_t i = 0; i < members.size(); ++i) {
         dm[i].in_off = members[i].in_off;
@@ -471,18 +515,6 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         dm[i].in_len = static_cast<uint32_t>(members[i].in_len);
         dm[i].out_len = static_cast<uint32_t>(members[i].out_len);
     }
-
-    // ---- H2D + inflate
-    uint8_t *d_comp = nullptr, *d_data = nullptr;
-    DevMember* d_members = nullptr;
-    uint32_t* d_status = nullptr;      // [0] error bits, [1] record count
-#define ING_CUDA(call)                                                             \
-    do {                                                                           \
-        cudaError_t e__ = (call);                                                  \
-        if (e__ != cudaSuccess) return fail(SVB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
-    } while (0)
-    ING_CUDA(cudaMallocAsync(&d_comp, static_cast<size_t>(fsize), st));
-    gc.dev.push_back(d_comp);
     ING_CUDA(cudaMallocAsync(&d_data, std::max<uint64_t>(total_out, 1), st));
     gc.dev.push_back(d_data);
     ING_CUDA(cudaMallocAsync(&d_members, sizeof(DevMember) * dm.size(), st));
@@ -490,18 +522,20 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     ING_CUDA(cudaMallocAsync(&d_status, 8 * sizeof(uint32_t), st));      // [2..3]: 64-bit sum of member cycles, [4]: member counter
     gc.dev.push_back(d_status);
     ING_CUDA(cudaMemsetAsync(d_status, 0, 8 * sizeof(uint32_t), st));
-    cudaEventRecord(ev[0], st);
-    const auto wall_h2d = std::chrono::steady_clock::now();
-    if (upload_file_range(ctx, fd, 0, static_cast<uint64_t>(fsize), d_comp) != SVB_OK) return fail(SVB_ERR_IO, svb_last_error(ctx));
-    const double h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_h2d).count();
     ING_CUDA(cudaMemcpyAsync(d_members, dm.data(), sizeof(DevMember) * dm.size(), cudaMemcpyHostToDevice, st));
-    cudaEventRecord(ev[1], st);
+    cudaEventRecord(ev[0], st);
+    mark("allocations");
     const uint32_t n_members = static_cast<uint32_t>(dm.size());
-    // many resident warps hide the decoder's latency: ask for the largest shared-memory carveout (32.5 KB of tables and output rings per CTA)
+    // many resident warps hide the decoder's latency: ask for the largest shared-memory carveout (23 KB of tables and output rings per CTA)
     cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int inflate_ctas_per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&inflate_ctas_per_sm, bgzf_inflate_kernel, INF_WARPS * 32, 0);
     const uint32_t inflate_grid = std::min<uint32_t>((n_members + INF_WARPS - 1) / INF_WARPS, static_cast<uint32_t>(ctx->sm_count * std::max(inflate_ctas_per_sm, 1)));
+    upload.worker.join();
+    const double h2d_ms = upload.ms;
+    if (upload.rc != SVB_OK) return fail(SVB_ERR_IO, "upload_file_range: short read or copy error");
+    mark("upload");
+    cudaEventRecord(ev[1], st);
     bgzf_inflate_kernel<<<inflate_grid, INF_WARPS * 32, 0, st>>>(d_comp, d_members, n_members, d_data, d_status);
     ctx->launches += 1;
     cudaEventRecord(ev[2], st);
@@ -509,6 +543,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     // while the GPU inflates: the record starts the index names (host work, hidden behind the inflate kernel)
     std::vector<uint64_t> index_starts;
     if (!getenv("SVB_INGEST_SERIAL_CHASE")) index_starts = bai_record_starts(std::string(path) + ".bai", members, 0, total_out);
+    mark("index parsed");
 
     // ---- BAM header: host parse of the first bytes of the inflated stream
     std::unique_ptr<svb_bam> bam_owner(new (std::nothrow) svb_bam());
@@ -536,6 +571,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         }
     }
     const int32_t n_ref = static_cast<int32_t>(bam->contig_names.size());
+    mark("inflate done, header parsed");
 
     // ---- record boundaries
     uint32_t cap = static_cast<uint32_t>(std::min<uint64_t>(0x7fffffffull, std::max<uint64_t>(1u << 16, (total_out - first_record) / 2048)));
@@ -602,6 +638,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     }
     gc.dev.push_back(d_rec_off);
     cudaEventRecord(ev[4], st);
+    mark("record chain");
 
     // ---- fixed fields + where the variable parts are
     svb_aln_hdr* d_hdr = nullptr;
@@ -626,6 +663,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         if (h_status & ING_ERR_TAG) return fail(SVB_ERR_IO, "malformed auxiliary field");
     }
 
+    mark("fixed fields");
     // ---- host prefix sums: where everything goes
     std::vector<CopyDst> dst(n_rec);
     bam->seq_off.resize(static_cast<size_t>(n_rec) + 1);
@@ -653,6 +691,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
     bam->name_off[n_rec] = no;
     if (co / 4 >= 0xFFFFFFFFull) return fail(SVB_ERR_ARG, "more than 2^34 CIGAR ops");
 
+    mark("host prefix sums");
     // ---- copies
     CopyDst* d_dst = nullptr;
     uint4* d_cigar = nullptr;
@@ -685,6 +724,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         if (e != cudaSuccess) return fail(SVB_ERR_CUDA, std::string("device ingest: ") + cudaGetErrorString(e));
     }
     const auto wall_dev = std::chrono::steady_clock::now();
+    mark("copies");
 
     // ---- SA tags: the same host parser as the host ingest (retrieve_other_alignments, SVIM_COLLECT.py:8-58)
     std::vector<const char*> name_ptrs;
@@ -702,6 +742,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         bam->sa_count[i] = static_cast<uint32_t>(cnt);
     }
 
+    mark("SA tags");
     // ---- the record image (python string order of the contig names is the caller's: SVCandidate.py:352)
     std::vector<int32_t> lexrank(static_cast<size_t>(std::max(n_ref, 0)));
     if (contig_lexrank_or_null) {
@@ -735,6 +776,7 @@ int svb_bam_open_device(svb_ctx* ctx, const char* path, int keep_sequences, cons
         }
     }
     const auto wall_end = std::chrono::steady_clock::now();
+    mark("record image");
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
     };

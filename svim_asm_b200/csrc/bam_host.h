@@ -31,7 +31,8 @@ struct BgzfMember {
     uint64_t file_off;               // where the member (its gzip header) starts in the file: the `coffset` of BAI virtual offsets
 };
 // members with ISIZE 0 (the EOF marker) are skipped; false + *why on a malformed file
-bool bgzf_member_table(const uint8_t* raw, uint64_t size, std::vector<BgzfMember>* blocks, uint64_t* total_out, std::string* why);
+// (n_threads > 1: the list through the member headers is walked in pieces, see bam_ingest.cpp)
+bool bgzf_member_table(const uint8_t* raw, uint64_t size, std::vector<BgzfMember>* blocks, uint64_t* total_out, std::string* why, int n_threads = 1);
 // magic, @HD SO, reference names / lengths -> bam; returns the bytes consumed (the first record starts there),
 // -1 on a malformed header, -2 when `avail` bytes do not hold the whole header yet
 int64_t bam_parse_header(const uint8_t* p, uint64_t avail, svb_bam* bam, std::string* why);

@@ -137,7 +137,10 @@ struct KernelTimer {
     ~KernelTimer();
 };
 
-int upload_file_range(svb_ctx* ctx, int fd, uint64_t offset, uint64_t n, void* d_dst);   // file bytes -> device, parallel pread + pinned staging
+// file bytes -> device, parallel pread + pinned staging.  wait_for_stream = false: the caller has synchronised ctx->stream itself
+// and calls from a thread of its own (errors are returned, not recorded in the context).  background = true: the upload pauses
+// between chunks while a foreground upload of this process is in flight.
+int upload_file_range(svb_ctx* ctx, int fd, uint64_t offset, uint64_t n, void* d_dst, bool wait_for_stream = true, bool background = false);
 void upload_release(svb_ctx* ctx);
 void* svb_scratch(svb_ctx* ctx, size_t bytes);   // grow-only device scratch (nullptr on failure)
 

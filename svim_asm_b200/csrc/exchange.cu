@@ -393,6 +393,7 @@ struct svb_exchange {
     uint8_t* peer[EXCH_MAX_WORLD] = {};          // every rank's window as mapped here (peer[rank] == window)
     bool opened[EXCH_MAX_WORLD] = {};
     unsigned int* d_done = nullptr;              // block counters of the put kernels
+    uint64_t* h_headers = nullptr;               // pinned: the slot headers of every rank (8 words each) + the status word, downloaded once per exchange
     uint32_t epoch = 0;
     uint64_t timeout_ns = 20000000000ull;
     uint64_t in_off(int r) const { return static_cast<uint64_t>(r) * slot_bytes; }
@@ -450,6 +451,7 @@ int svb_exchange_create(svb_ctx* ctx, int world, int rank, uint64_t slot_bytes, 
     cudaError_t e = cudaMalloc(&x->window, x->window_bytes);          // cudaMalloc, not the stream-ordered pool: IPC needs it
     if (e == cudaSuccess) e = cudaMemset(x->window, 0, x->window_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&x->d_done, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaHostAlloc(&x->h_headers, sizeof(uint64_t) * (8 * EXCH_MAX_WORLD + 1), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         svb_exchange_destroy(ctx, x);
@@ -497,6 +499,7 @@ void svb_exchange_destroy(svb_ctx* ctx, svb_exchange* x) {
         if (x->opened[p] && x->peer[p]) cudaIpcCloseMemHandle(x->peer[p]);
     if (x->window) cudaFree(x->window);
     if (x->d_done) cudaFree(x->d_done);
+    if (x->h_headers) cudaFreeHost(x->h_headers);
     delete x;
 }
 
@@ -527,11 +530,11 @@ int svb_exchange_share(svb_ctx* ctx, svb_exchange* x, const svb_table* t1, const
     if (rc == SVB_OK) rc = exchange_wait(ctx, x, 0);
     if (rc != SVB_OK) return rc;
     // the sizes of every rank's tables: 64 bytes per slot header, one strided copy, one synchronisation
-    std::vector<uint64_t> headers(static_cast<size_t>(x->world) * 8);
-    SVB_CUDA(ctx, cudaMemcpy2DAsync(headers.data(), XW_HEADER, x->window, x->slot_bytes, XW_HEADER, x->world, cudaMemcpyDeviceToHost, ctx->stream));
-    uint32_t h_status = 0;
-    SVB_CUDA(ctx, cudaMemcpyAsync(&h_status, ctx->d_status, sizeof h_status, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t* const headers = x->h_headers;          // pinned: the two copies are asynchronous, one wait
+    SVB_CUDA(ctx, cudaMemcpy2DAsync(headers, XW_HEADER, x->window, x->slot_bytes, XW_HEADER, x->world, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaMemcpyAsync(headers + 8 * EXCH_MAX_WORLD, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t h_status = static_cast<uint32_t>(headers[8 * EXCH_MAX_WORLD]);
     if (h_status & DEV_ERR_EXCHANGE) {
         cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
         return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_share: a peer did not deliver its tables in time");
@@ -569,11 +572,11 @@ int svb_exchange_gather_paired(svb_ctx* ctx, svb_exchange* x, const svb_table* p
     int rc = exchange_put(ctx, x, 1, &piece, paired->n ? 1 : 0, header);
     if (rc == SVB_OK) rc = exchange_wait(ctx, x, 1);
     if (rc != SVB_OK) return rc;
-    std::vector<uint64_t> headers(static_cast<size_t>(x->world) * 8);
-    SVB_CUDA(ctx, cudaMemcpy2DAsync(headers.data(), XW_HEADER, x->window + x->res_off(0), x->res_bytes, XW_HEADER, x->world, cudaMemcpyDeviceToHost, ctx->stream));
-    uint32_t h_status = 0;
-    SVB_CUDA(ctx, cudaMemcpyAsync(&h_status, ctx->d_status, sizeof h_status, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t* const headers = x->h_headers;
+    SVB_CUDA(ctx, cudaMemcpy2DAsync(headers, XW_HEADER, x->window + x->res_off(0), x->res_bytes, XW_HEADER, x->world, cudaMemcpyDeviceToHost, ctx->stream));
+    SVB_CUDA(ctx, cudaMemcpyAsync(headers + 8 * EXCH_MAX_WORLD, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t h_status = static_cast<uint32_t>(headers[8 * EXCH_MAX_WORLD]);
     if (h_status & DEV_ERR_EXCHANGE) {
         cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream);
         return svb_fail(ctx, SVB_ERR_CUDA, "svb_exchange_gather_paired: a peer did not deliver its rows in time");

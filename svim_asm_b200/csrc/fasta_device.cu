@@ -86,7 +86,7 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
     uint32_t* d_seen = nullptr;      // [8] presence bits, [8] status
     uint32_t h_seen[9] = {0};
     cudaError_t e = cudaMalloc(&d_raw, fsize);
-    if (e == cudaSuccess && upload_file_range(ctx, fd, 0, fsize, d_raw) != SVB_OK) {
+    if (e == cudaSuccess && upload_file_range(ctx, fd, 0, fsize, d_raw, true, true) != SVB_OK) {      // gives way to a BAM upload in flight: the ingest is waiting for that one
         close(fd);
         cudaFree(d_raw);
         svb_ref_free(r);

@@ -8,12 +8,18 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
 #include "common.cuh"
 
 namespace {
+
+// Uploads in flight that something is waiting for right now (a BAM file: its inflate kernel cannot start before the bytes are
+// there).  A background upload (the FASTA, needed only when pairing starts) pauses between chunks while this is non-zero: the
+// two would otherwise share the page-cache reads and the link half and half, and the ingest would wait twice as long.
+std::atomic<int> g_urgent_uploads(0);
 
 constexpr int UP_MAX_THREADS = 8;
 constexpr size_t UP_SLOT = 4u << 20;
@@ -62,18 +68,26 @@ void upload_release(svb_ctx* ctx) {
 
 // bytes [offset, offset + n) of the open file -> d_dst.  On return the bytes are in device memory (every worker has
 // synchronised its stream), so work enqueued on ctx->stream afterwards sees them.
-int upload_file_range(svb_ctx* ctx, int fd, uint64_t offset, uint64_t n, void* d_dst) {
+int upload_file_range(svb_ctx* ctx, int fd, uint64_t offset, uint64_t n, void* d_dst, bool wait_for_stream, bool background) {
     if (n == 0) return SVB_OK;
     Uploader* u = uploader_of(ctx);
-    if (!u) return svb_fail(ctx, SVB_ERR_NOMEM, "upload_file_range: staging buffers");
-    SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // d_dst may come from a stream-ordered allocation on ctx->stream
+    if (!u) return wait_for_stream ? svb_fail(ctx, SVB_ERR_NOMEM, "upload_file_range: staging buffers") : SVB_ERR_NOMEM;
+    if (wait_for_stream) SVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // d_dst may come from a stream-ordered allocation on ctx->stream
     const uint64_t n_chunks = (n + UP_SLOT - 1) / UP_SLOT;
     std::atomic<uint64_t> next(0);
     std::atomic<int> failed(0);                                  // 1 read error, 2 CUDA error
     const int device = ctx->device;
+    struct Urgent {
+        bool on;
+        explicit Urgent(bool o) : on(o) { if (on) g_urgent_uploads.fetch_add(1); }
+        ~Urgent() { if (on) g_urgent_uploads.fetch_sub(1); }
+    } urgent(!background);
     auto work = [&](int t) {
         cudaSetDevice(device);
         for (int turn = 0; !failed.load(std::memory_order_relaxed); ++turn) {
+            if (background)
+                for (int waited = 0; g_urgent_uploads.load(std::memory_order_relaxed) > 0 && waited < 20000; ++waited)      // (at most 4 s: never a deadlock)
+                    std::this_thread::sleep_for(std::chrono::microseconds(200));
             const uint64_t c = next.fetch_add(1);
             if (c >= n_chunks) break;
             const int s = turn & 1;
@@ -106,6 +120,7 @@ int upload_file_range(svb_ctx* ctx, int fd, uint64_t offset, uint64_t n, void* d
     for (int t = 1; t < n_workers; ++t) pool.emplace_back(work, t);
     work(0);
     for (auto& th : pool) th.join();
+    if (!wait_for_stream && failed.load()) return failed.load() == 1 ? SVB_ERR_IO : SVB_ERR_CUDA;
     if (failed.load() == 1) return svb_fail(ctx, SVB_ERR_IO, "upload_file_range: short read");
     if (failed.load() == 2) return svb_fail(ctx, SVB_ERR_CUDA, "upload_file_range", cudaGetLastError());
     return SVB_OK;

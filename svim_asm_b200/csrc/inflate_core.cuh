@@ -203,26 +203,30 @@ SVB_HD int inflate_member(const uint8_t* src, uint32_t src_len, uint8_t* dst, ui
     return pos == out_len ? INF_OK : INF_ERR_SIZE;
 }
 
-// ---- the fast symbol loop of the device decoder (bam_device.cu; one WARP per member, this part runs in lane 0) -------------
-// The kernel is bound by instruction issue, not by latency (dozens of warps per SM, one active lane each), so what counts
-// is instructions per symbol:
+// ---- the fast symbol loop of the device decoder (bam_device.cu; one WARP per member, every lane runs this loop in lock step) ----
+// What counts is instructions per symbol and the latency of the chain from one symbol to the next:
 //   * the bit buffer is refilled 32 bits at a time from aligned words (bytewise only at a member's unaligned head and tail),
 //   * the direct tables hold finished entries -- literal value, or length / distance BASE with the number of extra bits --
 //     so that a symbol is one table load plus shifts,
-//   * matches of up to INF_SHORT_MATCH bytes (98 % of those in BAM data: 4-byte CIGAR words, short repeats) are copied by
-//     the decoding lane itself; only longer ones are handed to the whole warp.
+//   * matches are copied by the lanes together, a byte each (98 % of those in BAM data are at most 16 bytes: 4-byte CIGAR
+//     words, short repeats).
 constexpr int INF_LEN_BITS = 10, INF_DIST_BITS = 8;
-constexpr uint32_t INF_SHORT_MATCH = 16;
-// table entry: bits 0-3 code length (0 = code longer than the table: slow path), 4-5 kind, 8-11 extra bits, 16-31 value
+// Literal / length table entry, 16 bits (the table is the largest piece of a warp's shared memory, and the number of resident
+// warps is what hides the decoder's latency): bits 0-3 code length (0 = code longer than the table: slow path), bit 4 set for
+// a length symbol, bits 5-7 its number of extra bits (7 = special: value 0 end of block, value 1 invalid symbol), bits 8-15 the
+// literal byte, or the length base - 3.
+typedef uint16_t inf_len_t;
+enum : uint32_t { INF_L_LEN = 1u << 4, INF_L_SPECIAL = 7u << 5 };
+// Distance table entry, 32 bits: bits 0-3 code length (0 = slow path), 4-5 kind, 8-11 extra bits, 16-31 distance base.
 enum : uint32_t { INF_K_LIT = 0u, INF_K_LEN = 1u << 4, INF_K_EOB = 2u << 4, INF_K_BAD = 3u << 4, INF_K_MASK = 3u << 4 };
 
 SVB_HD uint32_t inf_len_entry(uint32_t sym, uint32_t code_len) {
     static const uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
     static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    if (sym < 256u) return (sym << 16) | INF_K_LIT | code_len;
-    if (sym == 256u) return INF_K_EOB | code_len;
-    if (sym >= 286u) return INF_K_BAD | code_len;
-    return (static_cast<uint32_t>(lbase[sym - 257u]) << 16) | (static_cast<uint32_t>(lext[sym - 257u]) << 8) | INF_K_LEN | code_len;
+    if (sym < 256u) return (sym << 8) | code_len;
+    if (sym == 256u) return INF_L_LEN | INF_L_SPECIAL | code_len;
+    if (sym >= 286u) return (1u << 8) | INF_L_LEN | INF_L_SPECIAL | code_len;
+    return (static_cast<uint32_t>(lbase[sym - 257u] - 3u) << 8) | (static_cast<uint32_t>(lext[sym - 257u]) << 5) | INF_L_LEN | code_len;
 }
 SVB_HD uint32_t inf_dist_entry(uint32_t sym, uint32_t code_len) {
     static const uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -240,7 +244,8 @@ SVB_HD uint32_t inf_bitrev(uint32_t v, int n) {          // the low n bits of v,
 // Direct table of a canonical code: entry for every `bits`-bit window whose leading bits are a code of length <= bits.
 // Lanes split the symbols (lane, n_lanes); the caller has zeroed the table and synchronises afterwards.  Deflate packs codes most
 // significant bit first into a stream read least significant bit first, hence the reversal.
-SVB_HD void inf_fill_table(const uint16_t* count, const uint16_t* symbol, uint32_t* table, int bits, bool dist, uint32_t lane,
+template <typename Entry>
+SVB_HD void inf_fill_table(const uint16_t* count, const uint16_t* symbol, Entry* table, int bits, bool dist, uint32_t lane,
                            uint32_t n_lanes) {
     const uint32_t size = 1u << bits;
     uint32_t total = 0;
@@ -259,7 +264,7 @@ SVB_HD void inf_fill_table(const uint16_t* count, const uint16_t* symbol, uint32
             first_idx += cnt;
         }
         if (L == 0 || L > bits) continue;
-        const uint32_t entry = dist ? inf_dist_entry(symbol[j], static_cast<uint32_t>(L)) : inf_len_entry(symbol[j], static_cast<uint32_t>(L));
+        const Entry entry = static_cast<Entry>(dist ? inf_dist_entry(symbol[j], static_cast<uint32_t>(L)) : inf_len_entry(symbol[j], static_cast<uint32_t>(L)));
         for (uint32_t k = inf_bitrev(code, L); k < size; k += 1u << L) table[k] = entry;
     }
 }
@@ -338,48 +343,49 @@ SVB_HD void inf_flush(const InfOut& o, uint32_t upto, uint32_t lane, uint32_t n_
     for (uint32_t p = a + 16u * n_vec + lane; p < upto; p += n_lanes) o.data[p] = o.ring[(o.rbase + p) & INF_RMASK];
 }
 
-// len <= 4 bytes at offset `at` of a match whose source the destination does not overlap: all loads first, then the stores
-template <bool RING_SOURCE>
-SVB_HD void inf_copy_apart4(const InfOut& o, uint32_t at, uint32_t len, uint32_t dist) {
-    const uint32_t w = o.rbase + o.pos + at;
-    uint8_t t[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (static_cast<uint32_t>(i) < len) t[i] = RING_SOURCE ? o.ring[(w - dist + i) & INF_RMASK] : o.data[o.pos + at - dist + i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (static_cast<uint32_t>(i) < len) o.ring[(w + i) & INF_RMASK] = t[i];
-}
-template <bool RING_SOURCE>
-SVB_HD void inf_copy_apart(const InfOut& o, uint32_t len, uint32_t dist) {
-    for (uint32_t at = 0; at < len; at += 4u) inf_copy_apart4<RING_SOURCE>(o, at, len - at < 4u ? len - at : 4u, dist);
-}
+// The lanes that run the symbol loop meet here: their shared-memory / global stores so far are visible to each other afterwards.
+#ifdef __CUDA_ARCH__
+#define INF_LANES_SYNC() __syncwarp()
+#else
+#define INF_LANES_SYNC() ((void)0)
+#endif
 
-// a match of any length, its bytes split between n_lanes lanes (the long matches of the device decoder: the whole warp)
-SVB_HD void inf_copy_long(const InfOut& o, uint32_t len, uint32_t dist, uint32_t lane, uint32_t n_lanes) {
+// a match of any length, its bytes split between the n_lanes lanes; the caller synchronises the lanes before (the bytes written
+// so far are the source) and after (the next symbols may read or overwrite these)
+SVB_HD void inf_copy_match(const InfOut& o, uint32_t len, uint32_t dist, uint32_t lane, uint32_t n_lanes) {
     const uint32_t w = o.rbase + o.pos;
-    const bool in_ring = dist + len <= INF_RING;
-    for (uint32_t i = lane; i < len; i += n_lanes) {
-        const uint32_t k = dist >= len ? i : (dist == 1u ? 0u : i % dist);     // an overlapping run repeats its last dist bytes
-        o.ring[(w + i) & INF_RMASK] = in_ring ? o.ring[(w - dist + k) & INF_RMASK] : o.data[o.pos - dist + k];
+    const bool in_ring = dist + len <= INF_RING;                  // else the source has left the ring: it is in global memory, flushed
+    // one round for all but the longest matches (n_lanes = 32 on the device); not unrolled: the loop is short and rare, the
+    // unrolled version put twenty instructions of trip-count arithmetic in front of every match
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (uint32_t base = 0; base < len; base += n_lanes) {
+        const uint32_t i = base + lane;
+        if (i < len) {
+            uint32_t k = i;
+            if (dist < len) k = dist == 1u ? 0u : i % dist;       // an overlapping run repeats its last dist bytes
+            o.ring[(w + i) & INF_RMASK] = in_ring ? o.ring[(w - dist + k) & INF_RMASK] : o.data[o.pos - dist + k];
+        }
     }
 }
 
-enum : uint32_t { INF_EV_EOB = 0, INF_EV_MATCH = 1, INF_EV_FLUSH = 2 };
-
-// Symbols of the current block, run by the decoding lane, until one of:
-//   INF_EV_EOB    end of the block
-//   INF_EV_MATCH  a match longer than INF_SHORT_MATCH, NOT copied: the caller runs inf_copy_long, adds *ev_len to o.pos
-//   INF_EV_FLUSH  INF_FLUSH_AT or more bytes are waiting in the ring: the caller flushes and calls again
-// Returns INF_OK or an error.
-SVB_HD int inf_run(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, const uint32_t* tlen, const uint32_t* tdist,
-                   InfOut& o, uint32_t* event, uint32_t* ev_len, uint32_t* ev_dist) {
-    *ev_len = 0;
-    *ev_dist = 0;
+// Symbols of the current block until its end-of-block code, run by ALL n_lanes lanes of a warp IN LOCK STEP: every lane keeps
+// the same reader state and decodes the same symbol (one instruction stream: on a SIMT machine 32 lanes decoding the same
+// symbol cost what one lane costs), so that every lane knows every (length, distance) without a broadcast and a match is
+// copied by as many lanes as it has bytes -- six instructions instead of a byte loop of the decoding lane (measured before:
+// 110 warp instructions per symbol with 1.6 active lanes, the copies of short matches most of them).  Literals are stored by
+// lane 0.  When INF_FLUSH_AT bytes wait in the ring, the lanes flush them together.  On the host: lane 0 of 1.
+// Returns INF_OK or an error (the same on every lane).
+SVB_HD int inf_run_lanes(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, const inf_len_t* tlen, const uint32_t* tdist,
+                         InfOut& o, uint32_t lane, uint32_t n_lanes) {
     while (true) {
         if (o.pos - o.flushed >= INF_FLUSH_AT) {
-            *event = INF_EV_FLUSH;
-            return INF_OK;
+            if (o.pos > o.out_len) return INF_ERR_OUTPUT;        // (literals are not checked one by one: nothing past out_len leaves the ring)
+            INF_LANES_SYNC();
+            inf_flush(o, o.pos, lane, n_lanes);
+            o.flushed = o.pos;
+            INF_LANES_SYNC();
         }
         if (b.cnt < 32) inf_refill(b);
         uint32_t e = tlen[static_cast<uint32_t>(b.buf) & ((1u << INF_LEN_BITS) - 1u)];
@@ -391,20 +397,17 @@ SVB_HD int inf_run(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, 
             b.buf >>= (e & 15u);
             b.cnt -= static_cast<int>(e & 15u);
         }
-        const uint32_t kind = e & INF_K_MASK;
-        if (kind == INF_K_LIT) {
-            if (o.pos >= o.out_len) return INF_ERR_OUTPUT;
-            o.ring[(o.rbase + o.pos) & INF_RMASK] = static_cast<uint8_t>(e >> 16);
+        if ((e & INF_L_LEN) == 0u) {                             // literal
+            if (lane == 0u) o.ring[(o.rbase + o.pos) & INF_RMASK] = static_cast<uint8_t>(e >> 8);
             ++o.pos;
             continue;
         }
-        if (kind != INF_K_LEN) {
-            if (kind == INF_K_BAD) return INF_ERR_CODE;
-            *event = INF_EV_EOB;
-            return inf_overrun(b) ? INF_ERR_INPUT : INF_OK;
+        const uint32_t xl = (e >> 5) & 7u;
+        if (xl == 7u) {
+            if (e >> 8) return INF_ERR_CODE;                     // symbol 286 / 287
+            return inf_overrun(b) ? INF_ERR_INPUT : INF_OK;      // end of block
         }
-        const uint32_t xl = (e >> 8) & 15u;
-        const uint32_t len = (e >> 16) + (static_cast<uint32_t>(b.buf) & ((1u << xl) - 1u));
+        const uint32_t len = (e >> 8) + 3u + (static_cast<uint32_t>(b.buf) & ((1u << xl) - 1u));
         b.buf >>= xl;
         b.cnt -= static_cast<int>(xl);
         if (b.cnt < 32) inf_refill(b);
@@ -424,21 +427,9 @@ SVB_HD int inf_run(InfBits& b, const InfHuff& lencode, const InfHuff& distcode, 
         b.cnt -= static_cast<int>(xd);
         if (dist > o.pos) return INF_ERR_CODE;
         if (o.pos + len > o.out_len) return INF_ERR_OUTPUT;
-        if (len > INF_SHORT_MATCH) {
-            if (inf_overrun(b)) return INF_ERR_INPUT;
-            *event = INF_EV_MATCH;
-            *ev_len = len;
-            *ev_dist = dist;
-            return INF_OK;
-        }
-        if (dist + len > INF_RING) {                             // the source has left the ring: it is in global memory
-            inf_copy_apart<false>(o, len, dist);
-        } else if (dist >= len) {
-            inf_copy_apart<true>(o, len, dist);
-        } else {                                                 // overlapping: byte by byte in order
-            const uint32_t w = o.rbase + o.pos;
-            for (uint32_t i = 0; i < len; ++i) o.ring[(w + i) & INF_RMASK] = o.ring[(w - dist + i) & INF_RMASK];
-        }
+        INF_LANES_SYNC();
+        inf_copy_match(o, len, dist, lane, n_lanes);
+        INF_LANES_SYNC();
         o.pos += len;
     }
 }

@@ -31,7 +31,6 @@ using namespace edstr;
 
 constexpr int WFA_THREADS = 256;         // 8 warps: 4 per direction of the bidirectional wavefront
 constexpr int WFA_SIDE = WFA_THREADS / 2;
-constexpr int WFA_ILP = 1;                        // diagonals per thread and round (4 independent chains were measured slower: the loop is bound by issue slots shared with the other resident CTAs, not by the latency of one chain)
 constexpr uint32_t WFA_SLACK = 160;               // readable bytes behind the second string (warp-wide extension reads ahead)
 
 struct WfaControl {
@@ -39,6 +38,78 @@ struct WfaControl {
     uint32_t trim[2];
     uint32_t hit;              // bit 0: the waves met at total 2 r - 1, bit 1: at 2 r
 };
+
+// One diagonal of a wave, one thread.  `prev` is this side's previous wave, `other` the OTHER side's previous wave (both
+// complete since the last barrier), `cur` this side's new wave.  Everything is branch-free sentinel arithmetic: a diagonal
+// that was not reached holds WFA_NEG, and WFA_NEG + anything stays far below every real row, so
+//     v = min(max(prev[k] + 1, prev[k - 1], prev[k + 1] + 1), la, lb - k)          (furthest row with distance <= r on k)
+// needs no validity tests (the clamp keeps the point inside the table: a cell next to a reached cell of the last row or
+// column is within one more edit).  Then eight symbols of match extension with every load issued at once; a diagonal still
+// matching after that is taken on by the whole warp, 128 symbols per step.
+// The forward side also tests for an overlap with the backward wave g = other[kd - k] of the previous round:
+//     prev[k] + g >= la : the waves of round r - 1 had met                      -> total 2 r - 2   (bit 0)
+//     v + g >= la       : this wave meets the backward wave of round r - 1      -> total 2 r - 1   (bit 1)
+// (wfa_core.cuh: F[sf][k] + G[sb][kd - k] >= la  <=>  distance <= sf + sb; every diagonal on which the waves of round r - 1
+// can meet within t edits lies in the range of round r, see the loop below.)
+template <bool BACKWARD>
+__device__ __forceinline__ uint32_t wave_diagonal(const int* prev, const int* other, int* cur, const uint32_t* Aw, const uint32_t* Bw, int k, bool active,
+                                                  int klo, int plo, int phi, int mid, int ila, int ilb, int kd, uint32_t lane) {
+    const int kk = active ? k : klo;                              // a safe diagonal for the threads beyond the range
+    const int fm1 = prev[mid + kk - 1], f0 = prev[mid + kk], fp1 = prev[mid + kk + 1];
+    const int kb = kd - kk;
+    const bool partner = !BACKWARD && active && kb >= plo && kb <= phi;
+    const int g = partner ? other[mid + kb] : WFA_NEG;
+    int x = max(max(f0 + 1, fm1), fp1 + 1);
+    x = min(x, min(ila, ilb - kk));
+    const bool valid = active && x > WFA_NEG / 2;
+    const int xs = valid ? x : 0;                                 // safe offsets for the loads below
+    const int jb = xs + (valid ? kk : 0);
+    uint32_t x0, x1, n0, n1;
+    if (!BACKWARD) {
+        const uint32_t oa = WFA_FRONT + static_cast<uint32_t>(xs), ob = WFA_FRONT + static_cast<uint32_t>(jb);
+        x0 = wfa_load4(Aw, oa) ^ wfa_load4(Bw, ob);
+        x1 = wfa_load4(Aw, oa + 4u) ^ wfa_load4(Bw, ob + 4u);
+        n0 = (static_cast<uint32_t>(__ffs(static_cast<int>(x0 | 0x80000000u))) - 1u) >> 3;
+        n1 = (static_cast<uint32_t>(__ffs(static_cast<int>(x1 | 0x80000000u))) - 1u) >> 3;
+    } else {
+        const uint32_t oa = WFA_FRONT + static_cast<uint32_t>(ila - 1 - xs), ob = WFA_FRONT + static_cast<uint32_t>(ilb - 1 - jb);
+        x0 = wfa_load4(Aw, oa - 3u) ^ wfa_load4(Bw, ob - 3u);
+        x1 = wfa_load4(Aw, oa - 7u) ^ wfa_load4(Bw, ob - 7u);
+        n0 = static_cast<uint32_t>(__clz(static_cast<int>(x0 | 1u))) >> 3;
+        n1 = static_cast<uint32_t>(__clz(static_cast<int>(x1 | 1u))) >> 3;
+    }
+    const uint32_t run8 = x0 ? n0 : 4u + (x1 ? n1 : 4u);
+    int v = valid ? x + static_cast<int>(run8) : WFA_NEG;
+    // a diagonal that is still matching: the whole warp goes on, 128 symbols per step
+    uint32_t pending = __ballot_sync(FULL, valid && (x0 | x1) == 0u);
+    while (pending) {
+        const int src = __ffs(static_cast<int>(pending)) - 1;
+        pending &= pending - 1u;
+        const int v0 = __shfl_sync(FULL, v, src), k0 = __shfl_sync(FULL, kk, src);
+        uint32_t run = 0;
+        while (true) {
+            uint32_t y;
+            if (!BACKWARD) {
+                const uint32_t ia = WFA_FRONT + static_cast<uint32_t>(v0) + run + 4u * lane;
+                y = wfa_load4(Aw, ia) ^ wfa_load4(Bw, ia + static_cast<uint32_t>(k0));
+            } else {
+                const int pa = static_cast<int>(WFA_FRONT) + ila - 1 - v0 - 3 - static_cast<int>(run) - 4 * static_cast<int>(lane);
+                y = wfa_load4s(Aw, pa) ^ wfa_load4s(Bw, pa + kd - k0);     // pb = FRONT + lb - 1 - (v0 + k0) = pa + kd - k0
+            }
+            const uint32_t bal = __ballot_sync(FULL, y != 0u);
+            if (bal) {
+                const int f = __ffs(static_cast<int>(bal)) - 1;
+                const uint32_t yf = __shfl_sync(FULL, y, f);
+                run += 4u * static_cast<uint32_t>(f) + (BACKWARD ? wfa_last_diff(yf) : wfa_first_diff(yf));
+                break;
+            }
+            run += 128u;
+        }
+        if (static_cast<int>(lane) == src) v = v0 + static_cast<int>(run);
+    }
+    if (active) cur[mid + k] = v;
+    return (f0 + g >= ila ? 1u : 0u) | (v + g >= ila ? 2u : 0u);   // (g == WFA_NEG: neither)
+}
 
 __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
     extern __shared__ uint32_t smem_w[];
@@ -164,123 +235,52 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
         if (tid < WFA_FRONT) { As[tid] = WFA_FRONT_A; Bs[tid] = WFA_FRONT_B; }
         for (uint32_t i = WFA_FRONT + la + tid; i < a_bytes; i += WFA_THREADS) As[i] = WFA_END_A;
         for (uint32_t i = WFA_FRONT + lb + tid; i < b_bytes + WFA_SLACK; i += WFA_THREADS) Bs[i] = WFA_END_B;
-        for (int x = static_cast<int>(tid); x < 4 * W; x += WFA_THREADS) Fw[x] = WFA_NEG;
+        for (int x = static_cast<int>(tid); x < 4 * W; x += WFA_THREADS) Fw[x] = (x == W + mid || x == 3 * W + mid) ? -1 : WFA_NEG;      // "wave -1": row -1 on diagonal 0, so that wave 0 starts at row 0
         if (tid == 0) ctl->hit = 0u;
         __syncthreads();
 
         // ---- waves, from both ends at once (wfa_core.cuh: bidirectional wavefronts).  Warps 0-3 advance the forward wave, warps
-        // 4-7 the backward one (the same recurrence on the reversed strings); after every round the two are checked for an
-        // overlap at the totals 2 r - 1 (forward r, backward r - 1) and 2 r.  A pair that differs by more than t is settled
-        // after t / 2 rounds instead of t waves.
+        // 4-7 the backward one (the same recurrence on the reversed strings).  A pair that differs by more than t is settled
+        // after t / 2 rounds instead of t waves.  A round of a long far pair is a chain of dependent instructions of ONE warp
+        // (measured: a 9,748-symbol pair alone on the GPU took 1,800 cycles per round with 220-330 instructions per warp and
+        // round), so the round is kept short: sentinel arithmetic instead of validity branches, the overlap test folded into
+        // the wave (one more shared-memory read), one barrier.
         const int ila = static_cast<int>(la), ilb = static_cast<int>(lb), kd = ilb - ila;
         const bool backward = tid >= static_cast<uint32_t>(WFA_SIDE);
-        const uint32_t st = tid & static_cast<uint32_t>(WFA_SIDE - 1);       // thread within its side
-        int* const mine = Fw + (backward ? 2 * W : 0);          // this side's two arrays
+        const int st = static_cast<int>(tid & static_cast<uint32_t>(WFA_SIDE - 1));       // thread within its side
+        int* const mine = Fw + (backward ? 2 * W : 0);          // this side's two arrays (wave r lives in array r & 1)
+        const int* const theirs = Fw + (backward ? 0 : 2 * W);
         int result = -1, waves = 0;
+        // ONE barrier per round.  Round r: both sides compute wave r from wave r - 1; the forward threads test, on the way, the
+        // totals 2 r - 2 (waves r - 1 of both sides) and 2 r - 1 (their new wave against the backward wave r - 1), so that the
+        // totals 0, 1, 2, ... are tested in order, two per round, and the answer is read after the round's barrier.
+        // Coverage: two waves that meet on diagonal k within t edits have |kd - k| <= sb and sf + sb <= t, hence k passes the
+        // pruning of wfa_range for wave sf + 1 too: every diagonal that matters for the totals of round r is in round r's range.
+        int plo = 0, phi = -1;                                  // the range of the previous round's waves (forward and backward alike)
         for (int r = 0;; ++r) {
             waves = r + 1;
             const int* prev = mine + ((r & 1) ^ 1) * W;
+            const int* other = theirs + ((r & 1) ^ 1) * W;
             int* cur = mine + (r & 1) * W;
             int klo, khi;
             wfa_range(r, t, kd, ila, ilb, klo, khi);
-            // Every thread carries WFA_ILP diagonals through the round as independent, branch-free chains (the loop is bound by
-            // the latency of ONE chain -- three shared-memory reads, the recurrence, six reads, funnel shifts, compare -- with most
-            // issue slots idle): WFA_SIDE threads x WFA_ILP diagonals per pass.
-            for (int base = klo; base <= khi; base += WFA_SIDE * WFA_ILP) {
-                int k[WFA_ILP], v[WFA_ILP];
-                bool more[WFA_ILP];
-#pragma unroll
-                for (int u = 0; u < WFA_ILP; ++u) {
-                    k[u] = base + static_cast<int>(st) + WFA_SIDE * u;
-                    const bool active = k[u] <= khi;
-                    const int kk = active ? k[u] : klo;                       // a safe diagonal for the lanes beyond the range
-                    int x = r == 0 ? 0 : wfa_next_closed(prev[mid + kk - 1], prev[mid + kk], prev[mid + kk + 1], kk, ila, ilb);
-                    const bool valid = active && x > WFA_NEG / 2;
-                    const int xs = valid ? x : 0;                             // safe offsets for the loads below
-                    const uint32_t oa = backward ? WFA_FRONT + static_cast<uint32_t>(ila - 1 - xs) : WFA_FRONT + static_cast<uint32_t>(xs);
-                    const int jb = valid ? xs + kk : 0;
-                    const uint32_t ob = backward ? WFA_FRONT + static_cast<uint32_t>(ilb - 1 - jb) : WFA_FRONT + static_cast<uint32_t>(jb);
-                    uint32_t x0, x1;
-                    if (!backward) {
-                        x0 = wfa_load4(Aw, oa) ^ wfa_load4(Bw, ob);
-                        x1 = wfa_load4(Aw, oa + 4u) ^ wfa_load4(Bw, ob + 4u);
-                    } else {
-                        x0 = wfa_load4(Aw, oa - 3u) ^ wfa_load4(Bw, ob - 3u);
-                        x1 = wfa_load4(Aw, oa - 7u) ^ wfa_load4(Bw, ob - 7u);
-                    }
-                    const uint32_t n0 = backward ? static_cast<uint32_t>(__clz(static_cast<int>(x0 | 1u))) >> 3 : (static_cast<uint32_t>(__ffs(static_cast<int>(x0 | 0x80000000u))) - 1u) >> 3;
-                    const uint32_t n1 = backward ? static_cast<uint32_t>(__clz(static_cast<int>(x1 | 1u))) >> 3 : (static_cast<uint32_t>(__ffs(static_cast<int>(x1 | 0x80000000u))) - 1u) >> 3;
-                    const uint32_t run = x0 ? n0 : 4u + (x1 ? n1 : 4u);
-                    more[u] = valid && x0 == 0u && x1 == 0u;
-                    v[u] = valid ? x + static_cast<int>(run) : (active ? x : WFA_NEG);
-                }
-                // a diagonal that is still matching: the whole warp goes on, 128 symbols per round
-#pragma unroll
-                for (int u = 0; u < WFA_ILP; ++u) {
-                    uint32_t pending = __ballot_sync(FULL, more[u]);
-                    while (pending) {
-                        const int src = __ffs(static_cast<int>(pending)) - 1;
-                        pending &= pending - 1u;
-                        const int v0 = __shfl_sync(FULL, v[u], src), k0 = __shfl_sync(FULL, k[u], src);
-                        uint32_t run = 0;
-                        while (true) {
-                            uint32_t x;
-                            if (!backward) {
-                                const uint32_t ia = WFA_FRONT + static_cast<uint32_t>(v0) + run + 4u * lane;
-                                x = wfa_load4(Aw, ia) ^ wfa_load4(Bw, ia + static_cast<uint32_t>(k0));
-                            } else {
-                                const int pa = static_cast<int>(WFA_FRONT) + ila - 1 - v0 - 3 - static_cast<int>(run) - 4 * static_cast<int>(lane);
-                                x = wfa_load4s(Aw, pa) ^ wfa_load4s(Bw, pa + kd - k0);     // pb = FRONT + lb - 1 - (v0 + k0) = pa + kd - k0
-                            }
-                            const uint32_t bal = __ballot_sync(FULL, x != 0u);
-                            if (bal) {
-                                const int f = __ffs(static_cast<int>(bal)) - 1;
-                                const uint32_t xf = __shfl_sync(FULL, x, f);
-                                run += 4u * static_cast<uint32_t>(f) + (backward ? wfa_last_diff(xf) : wfa_first_diff(xf));
-                                break;
-                            }
-                            run += 128u;
-                        }
-                        if (static_cast<int>(lane) == src) v[u] = v0 + static_cast<int>(run);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < WFA_ILP; ++u)
-                    if (k[u] <= khi) cur[mid + k[u]] = v[u];
+            uint32_t hit = 0;
+            for (int k = klo + st; k <= ((khi - klo) | (WFA_SIDE - 1)) + klo; k += WFA_SIDE) {      // whole warps go round together
+                if (!backward) hit |= wave_diagonal<false>(prev, other, cur, Aw, Bw, k, k <= khi, klo, plo, phi, mid, ila, ilb, kd, lane);
+                else wave_diagonal<true>(prev, other, cur, Aw, Bw, k, k <= khi, klo, plo, phi, mid, ila, ilb, kd, lane);
             }
             if (st == 0) {             // the next wave reads one diagonal beyond this range on either side
                 cur[mid + klo - 1] = cur[mid + klo - 2] = WFA_NEG;
                 cur[mid + khi + 1] = cur[mid + khi + 2] = WFA_NEG;
             }
-            __syncthreads();
-            // ---- do the waves overlap?  forward wave r against backward wave r - 1 (total 2 r - 1) and r (total 2 r)
-            {
-                const int* F = Fw + (r & 1) * W;
-                const int* Gc = Fw + 2 * W + (r & 1) * W;
-                const int* Gp = Fw + 2 * W + ((r & 1) ^ 1) * W;
-                int glo = 0, ghi = -1, plo = 0, phi = -1;
-                wfa_range(r, t, kd, ila, ilb, glo, ghi);
-                if (r > 0) wfa_range(r - 1, t, kd, ila, ilb, plo, phi);
-                uint32_t hit = 0;
-                for (int k = klo + static_cast<int>(tid); k <= khi; k += WFA_THREADS) {
-                    const int f = F[mid + k], kb = kd - k;
-                    if (f <= WFA_NEG / 2) continue;
-                    if (kb >= plo && kb <= phi) {
-                        const int g = Gp[mid + kb];
-                        if (g > WFA_NEG / 2 && f + g >= ila) hit |= 1u;
-                    }
-                    if (kb >= glo && kb <= ghi) {
-                        const int g = Gc[mid + kb];
-                        if (g > WFA_NEG / 2 && f + g >= ila) hit |= 2u;
-                    }
-                }
-                if (hit) atomicOr(&ctl->hit, hit);
-            }
+            if (hit) atomicOr(&ctl->hit, hit);
             __syncthreads();
             const uint32_t h = ctl->hit;
-            if (h & 1u) { result = 2 * r - 1; break; }
-            if (h & 2u) { result = 2 * r <= t ? 2 * r : -1; break; }
-            if (2 * r + 1 > t) break;                           // every total up to t has been tested
+            if (h & 1u) { result = 2 * r - 2; break; }
+            if (h & 2u) { result = 2 * r - 1 <= t ? 2 * r - 1 : -1; break; }
+            if (2 * r - 1 >= t) break;                          // every total up to t has been tested
+            plo = klo;
+            phi = khi;
         }
         if (tid == 0) {
             if (result >= 0) {

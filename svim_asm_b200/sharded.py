@@ -309,12 +309,13 @@ def sharded_step_device(stage, rank, world, owner, lexrank, device, row_dtype):
     return out
 
 
-def sharded_step_window(stage, window, owner, lexrank):
+def sharded_step_window(stage, window, owner, lexrank, download=True):
     """One step on one rank over the peer-memory exchange window (csrc/exchange.cu: svb_exchange_share /
     svb_exchange_gather_paired): no collective library and no torch in the step.  The tables go from this rank's HBM
     straight into every peer's window (one kernel of NVLink stores + a flag), the consumer waits on the device, the paired
     rows travel the same way and are put into pair_candidates' order on the device; one download at the end.
-    Returns the complete paired table (identical on every rank)."""
+    Returns the complete paired table (identical on every rank); with download=False the table stays in HBM, like the
+    result of the one-GPU resident step, and the number of its rows is returned."""
     eng = stage.eng
     prof = _PROFILE if os.environ.get("SVB_SHARD_PROFILE") else None
 
@@ -337,11 +338,11 @@ def sharded_step_window(stage, window, owner, lexrank):
     tick("pair")
     everything = window.gather_paired(paired, lexrank)
     tick("gather paired (put, wait, order)")
-    out = everything.to_numpy()
+    out = everything.to_numpy() if download else len(everything)
     for t in (u1, u2, paired, everything):
         t.free()
     stage.done()
-    tick("download + free")
+    tick("download + free" if download else "free")
     return out
 
 
@@ -421,14 +422,15 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     window = None if os.environ.get("SVB_EXCHANGE", "window") == "nccl" else open_window(eng, rank, world)
     exchange = "nccl all-gather (torch.distributed)" if window is None else "peer-memory window (CUDA IPC, NVLink stores + device flags)"
 
-    def one_step(stage):
+    def one_step(stage, download):
         if window is not None:
-            return sharded_step_window(stage, window, owner, ranks)
+            return sharded_step_window(stage, window, owner, ranks, download=download)
         return sharded_step_device(stage, rank, world, owner, ranks, device, _lib.ROW_DTYPE)
 
-    def timed(stage_factory, steps, warmup):
+    def timed(stage_factory, steps, warmup, download):
+        one = lambda stage: one_step(stage, download)
         for _ in range(warmup):
-            table = one_step(stage_factory())
+            table = one(stage_factory())
         dist.barrier()
         torch.cuda.synchronize()
         eng.synchronize()
@@ -437,7 +439,7 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         _PROFILE.clear()
         eng.mark(2)
         for _ in range(steps):
-            table = one_step(stage_factory())
+            table = one(stage_factory())
         eng.mark(3)
         eng.synchronize()
         torch.cuda.synchronize()
@@ -455,7 +457,10 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
     eng.timing_reset()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    sec, table = timed(lambda: DeviceStage(eng, hosts, [g1, g2], ref, params, resident), args.steps, warm)
+    # `value`: inputs resident, and the gathered, ordered table stays in HBM on every rank (what the one-GPU resident step
+    # leaves behind as well); `e2e`: host buffers in, the table downloaded
+    sec, table = timed(lambda: DeviceStage(eng, hosts, [g1, g2], ref, params, resident), args.steps, warm, window is None)
+    n_rows_resident = int(table) if window is not None else int(table.shape[0])
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count() - launches0
     timing = eng.timing()
@@ -466,10 +471,10 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
         st = DeviceStage(eng, hosts, [g1, g2], ref, params, None)
         stages.append(st)
         return st
-    e2e_sec, table2 = timed(e2e_factory, args.steps, warm)
+    e2e_sec, table2 = timed(e2e_factory, args.steps, warm, True)
     h2d = torch.tensor([float(stages[-1].h2d)], dtype=torch.float64, device=device)
     dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
-    assert table.shape[0] == table2.shape[0]
+    assert n_rows_resident == table2.shape[0]
     parity = None
     if sample is not None:
         # the gathered, ordered table of the sharded run against the oracle on the CPU sample (outside the timed region)
@@ -497,13 +502,13 @@ def bench_sharded(args, build_workload, workload_config, peak_hbm, ClockSampler,
             "metric": "alignments_per_sec", "value": n_aln_total / sec, "unit": "alignments/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "cigar_ops_per_sec": n_ops_total / sec,
-            "config": workload_config(cfg, args, paired_rows=int(table.shape[0]),
+            "config": workload_config(cfg, args, paired_rows=n_rows_resident,
                                       shard="rank 0 holds %d of %d alignments" % (local_aln, n_aln_total), exchange=exchange),
             "roofline": {"kernel": "cigar_scan (rank 0 shard)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "launch_ms": scan_avg, "algorithmic_bytes_per_launch": alg},
             "e2e": {"value": n_aln_total / e2e_sec, "unit": "alignments/s", "h2d_bytes_per_step": int(h2d.item()),
-                    "d2h_bytes_per_step": int(table.nbytes), "ms_per_step": e2e_sec * 1e3},
+                    "d2h_bytes_per_step": int(table2.nbytes), "ms_per_step": e2e_sec * 1e3},
             "parity_check": parity, "gpu_launches": int(launches), "clocks": clocks,
         }), flush=True)
     if window is not None:

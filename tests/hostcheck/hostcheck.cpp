@@ -166,8 +166,8 @@ extern "C" int hc_inflate(const uint8_t* src, unsigned src_len, uint8_t* dst, un
     return inflate_member(src, src_len, dst, out_len);
 }
 
-// The device decoder's flow (bam_device.cu: block header, direct tables, the fast symbol loop of the decoding lane, long
-// matches copied by the whole warp) with one host thread standing in for the warp.  `misalign` shifts the compressed
+// The device decoder's flow (bam_device.cu: block header, direct tables, the symbol loop every lane runs in lock step, matches
+// copied by the lanes side by side) with one host thread standing in for the warp.  `misalign` shifts the compressed
 // bytes inside their buffer: the word refill must cope with any alignment of a member.
 extern "C" int hc_inflate_fast(const uint8_t* src_in, unsigned src_len, uint8_t* dst, unsigned out_len, unsigned misalign) {
     std::vector<uint32_t> backing((src_len + 16) / 4 + 4);
@@ -175,7 +175,8 @@ extern "C" int hc_inflate_fast(const uint8_t* src_in, unsigned src_len, uint8_t*
     memcpy(src, src_in, src_len);
     uint16_t lencnt[16], lensym[288], distcnt[16], distsym[32];
     uint8_t lengths[320];
-    std::vector<uint32_t> tlen(1u << INF_LEN_BITS), tdist(1u << INF_DIST_BITS);
+    std::vector<inf_len_t> tlen(1u << INF_LEN_BITS);
+    std::vector<uint32_t> tdist(1u << INF_DIST_BITS);
     std::vector<uint8_t> ring(INF_RING, 0xEE);
     InfHuff lencode{lencnt, lensym}, distcode{distcnt, distsym};
     InfBits b{src, src + src_len, 0ull, 0, 0};
@@ -199,25 +200,16 @@ extern "C" int hc_inflate_fast(const uint8_t* src_in, unsigned src_len, uint8_t*
             }
             continue;
         }
-        std::fill(tlen.begin(), tlen.end(), 0u);
+        std::fill(tlen.begin(), tlen.end(), static_cast<inf_len_t>(0));
         std::fill(tdist.begin(), tdist.end(), 0u);
         for (uint32_t lane = 0; lane < 32u; ++lane) {
             inf_fill_table(lencnt, lensym, tlen.data(), INF_LEN_BITS, false, lane, 32u);
             inf_fill_table(distcnt, distsym, tdist.data(), INF_DIST_BITS, true, lane, 32u);
         }
-        while (true) {
-            uint32_t event = 0, ev_len = 0, ev_dist = 0;
-            err = inf_run(b, lencode, distcode, tlen.data(), tdist.data(), o, &event, &ev_len, &ev_dist);
-            if (err) return err;
-            if (event == INF_EV_EOB) break;
-            if (event == INF_EV_FLUSH) {
-                flush();
-                continue;
-            }
-            for (uint32_t lane = 0; lane < 32u; ++lane) inf_copy_long(o, ev_len, ev_dist, lane, 32u);
-            o.pos += ev_len;
-        }
+        err = inf_run_lanes(b, lencode, distcode, tlen.data(), tdist.data(), o, 0u, 1u);      // one host thread stands in for the warp
+        if (err) return err;
     } while (!last);
+    if (o.pos > out_len) return INF_ERR_OUTPUT;
     flush();
     return o.pos == out_len ? INF_OK : INF_ERR_SIZE;
 }
