@@ -36,20 +36,19 @@ class ReferencePrefetch(threading.Thread):
         threading.Thread.__init__(self, daemon=True)
         self.key = (os.path.abspath(fasta_path), tuple(contig_names))
         self.path, self.names, self.result = fasta_path, list(contig_names), None
+        self.device = get_engine().device            # (the main context is created here, on the caller's thread)
         _PREFETCH[self.key] = self
         self.start()
 
     def run(self):
         try:
-            from .engine import Engine
             from .fasta import FastaFile
-            from .runtime import get_engine
             fasta = FastaFile(self.path)
             rows = fasta.fai_rows(self.names)
             fasta.close()
-            engine = Engine(get_engine().device)
+            engine = get_engine(self.device, role="loader")
             self.result = engine.load_reference_fasta(self.path, rows)
-            self.result.loader = engine                  # keeps the context alive as long as the reference
+            self.result.loader = engine                  # (the context lives as long as the process)
         except Exception:
             self.result = None
 

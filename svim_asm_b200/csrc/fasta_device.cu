@@ -85,32 +85,37 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
     FaiEntry* d_fai = nullptr;
     uint32_t* d_seen = nullptr;      // [8] presence bits, [8] status
     uint32_t h_seen[9] = {0};
-    cudaError_t e = cudaMalloc(&d_raw, fsize);
+    // Every allocation is stream-ordered (cudaMallocAsync / cudaFreeAsync): this load runs in the background of the BAM ingests,
+    // and a plain cudaFree waits for the whole device -- for the other thread's inflate kernel -- holding up that thread's own
+    // allocations meanwhile (seen as stalls of 50-700 ms in the ingest's allocation phase).
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMallocAsync(&d_raw, fsize, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);                   // (the upload's streams are not ordered behind `st`)
     if (e == cudaSuccess && upload_file_range(ctx, fd, 0, fsize, d_raw, true, true) != SVB_OK) {      // gives way to a BAM upload in flight: the ingest is waiting for that one
         close(fd);
-        cudaFree(d_raw);
+        cudaFreeAsync(d_raw, st);
         svb_ref_free(r);
         return SVB_ERR_IO;
     }
-    if (e == cudaSuccess) e = cudaMalloc(&d_fai, sizeof(FaiEntry) * std::max<size_t>(entries.size(), 1));
-    if (e == cudaSuccess && n_contig) e = cudaMemcpyAsync(d_fai, entries.data(), sizeof(FaiEntry) * entries.size(), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&d_seen, sizeof(uint32_t) * 9);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_seen, 0, sizeof(uint32_t) * 9, ctx->stream);
-    if (e == cudaSuccess) e = cudaMalloc(&r->d_contig_off, sizeof(uint64_t) * contig_off.size());
-    if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_contig_off, contig_off.data(), sizeof(uint64_t) * contig_off.size(), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && r->n_bases) e = cudaMalloc(&r->d_bases, r->n_bases);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_fai, sizeof(FaiEntry) * std::max<size_t>(entries.size(), 1), st);
+    if (e == cudaSuccess && n_contig) e = cudaMemcpyAsync(d_fai, entries.data(), sizeof(FaiEntry) * entries.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_seen, sizeof(uint32_t) * 9, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_seen, 0, sizeof(uint32_t) * 9, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&r->d_contig_off, sizeof(uint64_t) * contig_off.size(), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_contig_off, contig_off.data(), sizeof(uint64_t) * contig_off.size(), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && r->n_bases) e = cudaMallocAsync(&r->d_bases, r->n_bases, st);
     if (e == cudaSuccess && r->n_bases && n_contig) {
         const dim3 grid(static_cast<unsigned>(ctx->sm_count) * 4u, static_cast<unsigned>(n_contig));
-        fasta_compact_kernel<<<grid, 256, 0, ctx->stream>>>(d_raw, fsize, d_fai, r->d_bases, d_seen, d_seen + 8);
+        fasta_compact_kernel<<<grid, 256, 0, st>>>(d_raw, fsize, d_fai, r->d_bases, d_seen, d_seen + 8);
         ctx->launches += 1;
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_seen, d_seen, sizeof h_seen, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_seen, d_seen, sizeof h_seen, cudaMemcpyDeviceToHost, st);
+    if (d_raw) cudaFreeAsync(d_raw, st);
+    if (d_fai) cudaFreeAsync(d_fai, st);
+    if (d_seen) cudaFreeAsync(d_seen, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     close(fd);
-    cudaFree(d_raw);
-    cudaFree(d_fai);
-    cudaFree(d_seen);
     if (e != cudaSuccess) {
         svb_ref_free(r);
         return svb_fail(ctx, SVB_ERR_CUDA, "svb_ref_load_fasta", e);
@@ -127,8 +132,9 @@ int svb_ref_load_fasta(svb_ctx* ctx, const char* path, const uint64_t* fai, int3
         svb_ref_free(r);
         return svb_fail(ctx, SVB_ERR_FORMAT, why.c_str());
     }
-    e = cudaMalloc(&r->d_class_map, 256);
-    if (e == cudaSuccess) e = cudaMemcpy(r->d_class_map, map, 256, cudaMemcpyHostToDevice);
+    e = cudaMallocAsync(&r->d_class_map, 256, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_class_map, map, 256, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         svb_ref_free(r);
         return svb_fail(ctx, SVB_ERR_CUDA, "svb_ref_load_fasta: class map", e);

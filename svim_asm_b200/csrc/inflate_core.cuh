@@ -389,10 +389,12 @@ SVB_HD int inf_run_lanes(InfBits& b, const InfHuff& lencode, const InfHuff& dist
         }
         if (b.cnt < 32) inf_refill(b);
         uint32_t e = tlen[static_cast<uint32_t>(b.buf) & ((1u << INF_LEN_BITS) - 1u)];
+        bool fast = true;
         if ((e & 15u) == 0u) {                                   // code longer than the table
             const int sym = inf_decode(b, lencode);
             if (sym < 0) return INF_ERR_CODE;
             e = inf_len_entry(static_cast<uint32_t>(sym), 0u);
+            fast = false;
         } else {
             b.buf >>= (e & 15u);
             b.cnt -= static_cast<int>(e & 15u);
@@ -400,6 +402,22 @@ SVB_HD int inf_run_lanes(InfBits& b, const InfHuff& lencode, const InfHuff& dist
         if ((e & INF_L_LEN) == 0u) {                             // literal
             if (lane == 0u) o.ring[(o.rbase + o.pos) & INF_RMASK] = static_cast<uint8_t>(e >> 8);
             ++o.pos;
+            // A literal from the table used at most INF_LEN_BITS of at least 32 valid bits: up to two more table literals
+            // can follow without a refill, and three bytes more do not matter to the flush test (literals come in runs:
+            // sequence and quality bytes).
+            if (fast) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+                for (int more = 0; more < 2; ++more) {
+                    const uint32_t e2 = tlen[static_cast<uint32_t>(b.buf) & ((1u << INF_LEN_BITS) - 1u)];
+                    if ((e2 & 15u) == 0u || (e2 & INF_L_LEN) != 0u) break;
+                    b.buf >>= (e2 & 15u);
+                    b.cnt -= static_cast<int>(e2 & 15u);
+                    if (lane == 0u) o.ring[(o.rbase + o.pos) & INF_RMASK] = static_cast<uint8_t>(e2 >> 8);
+                    ++o.pos;
+                }
+            }
             continue;
         }
         const uint32_t xl = (e >> 5) & 7u;
