@@ -511,17 +511,6 @@ struct CollectPending {
     WalkPending* walk = nullptr;
 };
 
-__global__ void ins_bytes_kernel(const svb_row* __restrict__ rows, const unsigned long long* __restrict__ n_dev, unsigned long long cap,
-                                 unsigned long long* __restrict__ total) {
-    const unsigned long long n = min(*n_dev, cap);
-    unsigned long long mine = 0;
-    for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-         i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
-        if (rows[i].type == SVB_INS) mine += (rows[i].seq_len + 1u) / 2u;
-    for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
-    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(total, mine);
-}
-
 void collect_drop(svb_ctx* ctx, CollectPending& c) {
     if (c.indel) svb_table_free(c.indel);
     walk_discard(ctx, c.walk);
@@ -535,18 +524,9 @@ int collect_begin(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int
     c->base = base;
     c->indel = table_alloc(ctx, cap);
     if (!c->indel) return svb_fail(ctx, SVB_ERR_NOMEM, "svb_collect: indel table");
-    ScanOutput so{c->indel->d_rows, c->indel->cap, ctx->d_counters + base};
+    // (the bytes of inserted sequence the rows hold -- the size of the sequence pool -- are summed by the scan's row finalize)
+    ScanOutput so{c->indel->d_rows, c->indel->cap, ctx->d_counters + base, ctx->d_counters + base + 3};
     int rc = launch_cigar_scan(ctx, rec, p, hap, so);
-    if (rc == SVB_OK) {
-        cudaError_t e = cudaMemsetAsync(ctx->d_counters + base + 3, 0, sizeof(unsigned long long), ctx->stream);
-        if (e == cudaSuccess) {
-            ins_bytes_kernel<<<static_cast<unsigned>(std::min<uint64_t>((cap + 255) / 256, 2048)), 256, 0, ctx->stream>>>(
-                c->indel->d_rows, ctx->d_counters + base, c->indel->cap, ctx->d_counters + base + 3);
-            ctx->launches += 1;
-            e = cudaGetLastError();
-        }
-        if (e != cudaSuccess) rc = svb_fail(ctx, SVB_ERR_CUDA, "svb_collect: inserted bytes", e);
-    }
     if (rc == SVB_OK && with_walk) rc = walk_count_async(ctx, rec, p, hap, ctx->d_counters + base + 1, &c->walk);
     if (rc != SVB_OK) collect_drop(ctx, *c);
     return rc;

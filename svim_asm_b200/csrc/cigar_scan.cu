@@ -710,30 +710,39 @@ __global__ void __launch_bounds__(US_THREADS) unit_scan_kernel(const uint4* __re
 __global__ void finalize_rows_kernel(const svb_row* __restrict__ staged, const unsigned long long* __restrict__ n_staged,
                                      unsigned long long cap, const UnitPrefix* __restrict__ prefix,
                                      const svb_aln_hdr* __restrict__ hdr, const int32_t* __restrict__ contig_len, int32_t n_contig,
-                                     svb_row* __restrict__ out) {
+                                     svb_row* __restrict__ out, unsigned long long* __restrict__ ins_bytes) {
     const unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const unsigned long long n = min(*n_staged, cap);
-    if (i >= n) return;
-    svb_row r = staged[i];
-    const UnitPrefix p = prefix[r.mate_aln];
-    const unsigned long long dst = p.base + static_cast<uint32_t>(r.copies);
-    if (r.flags & ROW_NEEDS_CARRY) {
-        const svb_aln_hdr h = hdr[r.aln_idx];
-        const uint32_t pr = static_cast<uint32_t>(r.reserved0) + p.R, len = static_cast<uint32_t>(r.reserved0 >> 32);
-        const uint32_t pq = r.seq_pos + p.Q;
-        const int32_t clen = (h.tid >= 0 && h.tid < n_contig) ? contig_len[h.tid] : 0;
-        const long long start = static_cast<long long>(h.pos) + pr, end = start + len;
-        const int32_t cs = static_cast<int32_t>(max(0ll, start));
-        const int32_t ce = static_cast<int32_t>(min(static_cast<long long>(clen), end));
-        if (r.type == SVB_DEL) { r.src_start = cs; r.src_end = ce; r.seq_len = 0; }
-        else { r.dst_start = cs; r.dst_end = ce; r.seq_len = pq >= h.l_seq ? 0u : min(len, h.l_seq - pq); }
-        r.seq_pos = r.type == SVB_DEL ? pq : min(pq, h.l_seq);
+    unsigned long long mine = 0;                                  // bytes of inserted sequence of this row (the pool's size is their sum)
+    if (i < n) {
+        svb_row r = staged[i];
+        const UnitPrefix p = prefix[r.mate_aln];
+        const unsigned long long dst = p.base + static_cast<uint32_t>(r.copies);
+        if (r.flags & ROW_NEEDS_CARRY) {
+            const svb_aln_hdr h = hdr[r.aln_idx];
+            const uint32_t pr = static_cast<uint32_t>(r.reserved0) + p.R, len = static_cast<uint32_t>(r.reserved0 >> 32);
+            const uint32_t pq = r.seq_pos + p.Q;
+            const int32_t clen = (h.tid >= 0 && h.tid < n_contig) ? contig_len[h.tid] : 0;
+            const long long start = static_cast<long long>(h.pos) + pr, end = start + len;
+            const int32_t cs = static_cast<int32_t>(max(0ll, start));
+            const int32_t ce = static_cast<int32_t>(min(static_cast<long long>(clen), end));
+            if (r.type == SVB_DEL) { r.src_start = cs; r.src_end = ce; r.seq_len = 0; }
+            else { r.dst_start = cs; r.dst_end = ce; r.seq_len = pq >= h.l_seq ? 0u : min(len, h.l_seq - pq); }
+            r.seq_pos = r.type == SVB_DEL ? pq : min(pq, h.l_seq);
+        }
+        r.flags = 0;
+        r.copies = 0;
+        r.mate_aln = 0xFFFFFFFFu;
+        r.reserved0 = 0;
+        if (dst < cap) {
+            out[dst] = r;
+            if (r.type == SVB_INS) mine = (r.seq_len + 1u) / 2u;
+        }
     }
-    r.flags = 0;
-    r.copies = 0;
-    r.mate_aln = 0xFFFFFFFFu;
-    r.reserved0 = 0;
-    if (dst < cap) out[dst] = r;
+    if (ins_bytes) {                                              // (warp-uniform)
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, d);
+        if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(ins_bytes, mine);
+    }
 }
 
 // geometry of every chunk (one thread per chunk, two binary searches over off4)
@@ -793,7 +802,7 @@ int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec) {
 }
 
 template <int G>
-static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_row* final_rows) {
+static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_row* final_rows, unsigned long long* ins_bytes) {
     const uint64_t unit4 = static_cast<uint64_t>(G) * CHUNK4;
     const uint64_t n_units64 = (rec->n4 + unit4 - 1) / unit4;
     if (n_units64 > 0x7fffffffull) return svb_fail(ctx, SVB_ERR_ARG, "too many CIGAR ops for one launch");
@@ -844,7 +853,7 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_r
         unit_scan_kernel<<<us_ctas, us_threads, 0, ctx->stream>>>(a.unit_agg, n_units, prefix, cta_status, cta_ready, ticket);
         const unsigned long long fin_blocks = (a.cap + 255) / 256;
         finalize_rows_kernel<<<static_cast<unsigned>(std::min<unsigned long long>(fin_blocks, 0x7fffffffull)), 256, 0, ctx->stream>>>(
-            a.rows, a.total, a.cap, prefix, rec->d_hdr, rec->d_contig_len, rec->n_contig, final_rows);
+            a.rows, a.total, a.cap, prefix, rec->d_hdr, rec->d_contig_len, rec->n_contig, final_rows, ins_bytes);
     }
     ctx->launches += 3;
     SVB_CUDA(ctx, cudaGetLastError());
@@ -853,6 +862,7 @@ static int launch_scan_g(svb_ctx* ctx, const svb_records* rec, ScanArgs a, svb_r
 
 int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p, int hap, ScanOutput out) {
     SVB_CUDA(ctx, cudaMemsetAsync(out.d_count, 0, sizeof(unsigned long long), ctx->stream));
+    if (out.d_ins_bytes) SVB_CUDA(ctx, cudaMemsetAsync(out.d_ins_bytes, 0, sizeof(unsigned long long), ctx->stream));
     if (rec->n_aln) SVB_CUDA(ctx, cudaMemsetAsync(rec->d_aln_sum, 0, sizeof(uint4) * rec->n_aln, ctx->stream));
     if (rec->n4 == 0) return SVB_OK;
     ScanArgs a;
@@ -881,8 +891,8 @@ int launch_cigar_scan(svb_ctx* ctx, const svb_records* rec, const svb_params* p,
     const uint64_t four_waves = 4ull * 32ull * static_cast<uint64_t>(ctx->sm_count);
     const uint64_t chunks = (rec->n4 + CHUNK4 - 1) / CHUNK4;
     constexpr int S = 8 / ROWS;                      // keep the unit length in ops when chunks are smaller
-    if (chunks / (16 * S) >= four_waves) return launch_scan_g<16 * S>(ctx, rec, a, out.rows);
-    if (chunks / (8 * S) >= four_waves) return launch_scan_g<8 * S>(ctx, rec, a, out.rows);
-    if (chunks / (4 * S) >= four_waves) return launch_scan_g<4 * S>(ctx, rec, a, out.rows);
-    return launch_scan_g<2 * S>(ctx, rec, a, out.rows);
+    if (chunks / (16 * S) >= four_waves) return launch_scan_g<16 * S>(ctx, rec, a, out.rows, out.d_ins_bytes);
+    if (chunks / (8 * S) >= four_waves) return launch_scan_g<8 * S>(ctx, rec, a, out.rows, out.d_ins_bytes);
+    if (chunks / (4 * S) >= four_waves) return launch_scan_g<4 * S>(ctx, rec, a, out.rows, out.d_ins_bytes);
+    return launch_scan_g<2 * S>(ctx, rec, a, out.rows, out.d_ins_bytes);
 }

@@ -149,6 +149,7 @@ struct ScanOutput {
     svb_row* rows;            // capacity `cap`
     uint64_t cap;
     unsigned long long* d_count;   // total number of emitted rows (may exceed cap)
+    unsigned long long* d_ins_bytes = nullptr;   // optional: bytes of 4-bit inserted sequence the INS rows hold (the sequence pool's size)
 };
 uint64_t cigar_padded_n4(uint64_t n4);   // uint4 capacity d_cigar must be allocated with (whole 64 KB units)
 int launch_build_chunk_index(svb_ctx* ctx, svb_records* rec);
