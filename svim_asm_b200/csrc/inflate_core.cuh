@@ -1,12 +1,13 @@
-// DEFLATE (RFC 1951) decoder for ONE BGZF member, written to run as one GPU thread per member.
+// DEFLATE (RFC 1951) decoder for ONE BGZF member.
 //
 // Where it sits: the reference opens its input with pysam.AlignmentFile (svim-asm:63,85-86), i.e. htslib inflates
 // the BGZF blocks of the BAM file on the host [ext].  BGZF members are independent raw-deflate streams of at most
-// 64 KiB each, so a whole-genome BAM is tens of thousands of independent jobs: one thread per member, every member
-// in flight at once.  The decoder keeps its state small (canonical-Huffman count/symbol arrays, 0.7 KB) so that a
-// few hundred threads per SM keep theirs in L1; it reads the compressed stream and writes the output bytewise.
-//
-// The same code compiles for the host (tests/hostcheck) where it is checked against zlib.
+// 64 KiB each, so a whole-genome BAM is tens of thousands of independent jobs.  Two decoders live here:
+//   * inflate_member: the plain one (canonical-Huffman count/symbol arrays, byte-wise I/O), the specification the other is
+//     tested against and the slow path for codes longer than the direct tables;
+//   * the pieces of the device decoder (bam_device.cu: one WARP per member): block header, direct tables, the symbol loop
+//     that every lane of the warp runs in lock step (inf_run_lanes), the output ring and its flush.
+// The same code compiles for the host (tests/hostcheck) where both are checked against zlib.
 #pragma once
 #include <stdint.h>
 
