@@ -9,7 +9,12 @@ edit distances, clustering -> the paired candidate table (what write_final_vcf c
   e2e   : the same step through the C ABI with HOST buffers: every step uploads both record images from pinned
           memory (svb_load_records + sequences) and reads the paired table back.
   N>1   : the records are sharded by reference contig over the ranks (strong scaling, total work fixed); the
-          candidate tables are all-gathered (NCCL) and every rank pairs the contigs it owns.
+          candidate tables travel through a peer-memory window (CUDA IPC, NVLink stores + device flags; NCCL all-gather
+          as fall-back), every rank pairs the contigs it owns and the paired rows are gathered and ordered on the device.
+  file_to_vcf (N=1): `svim-asm diploid h1.bam h2.bam ref.fa` -> variants.vcf through the drop-in CLI in a process of its
+          own (files on tmpfs), device ingest included; the VCF is compared with the python writer's.
+  parity_check: the paired rows of the whole workload against the oracle on a closed sample of four contigs; the run
+          refuses to print a line when they differ.
 `--impl reference` times the reference's own algorithm on the host CPU (1 core: the reference is single threaded)
 through the oracle port on a bounded sample of the same workload.
 """
