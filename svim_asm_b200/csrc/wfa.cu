@@ -59,8 +59,7 @@ __device__ __forceinline__ uint32_t wave_diagonal(const int* prev, const int* ot
     const int kb = kd - kk;
     const bool partner = !BACKWARD && active && kb >= plo && kb <= phi;
     const int g = partner ? other[mid + kb] : WFA_NEG;
-    int x = max(max(f0 + 1, fm1), fp1 + 1);
-    x = min(x, min(ila, ilb - kk));
+    const int x = wfa_next_clamped(fm1, f0, fp1, kk, ila, ilb);
     const bool valid = active && x > WFA_NEG / 2;
     const int xs = valid ? x : 0;                                 // safe offsets for the loads below
     const int jb = xs + (valid ? kk : 0);
@@ -254,8 +253,11 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
         // ONE barrier per round.  Round r: both sides compute wave r from wave r - 1; the forward threads test, on the way, the
         // totals 2 r - 2 (waves r - 1 of both sides) and 2 r - 1 (their new wave against the backward wave r - 1), so that the
         // totals 0, 1, 2, ... are tested in order, two per round, and the answer is read after the round's barrier.
-        // Coverage: two waves that meet on diagonal k within t edits have |kd - k| <= sb and sf + sb <= t, hence k passes the
-        // pruning of wfa_range for wave sf + 1 too: every diagonal that matters for the totals of round r is in round r's range.
+        // Coverage: the waves of round r - 1 can meet within t edits only on a diagonal with |kd - k| <= sb = r - 1, and round r
+        // visits the diagonals with |kd - k| <= (t + 1) - r: the range is pruned as if t + 1 edits were allowed, because
+        // r - 1 <= t + 1 - r is 2 r - 2 <= t, which holds in every round that runs (with the one-sided bound t - r the last round
+        // of an even t lost the outermost diagonal, and with it a distance of exactly t: found by the host statement of these
+        // rounds, wfa_rounds_serial, against a plain DP).
         int plo = 0, phi = -1;                                  // the range of the previous round's waves (forward and backward alike)
         for (int r = 0;; ++r) {
             waves = r + 1;
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
             const int* other = theirs + ((r & 1) ^ 1) * W;
             int* cur = mine + (r & 1) * W;
             int klo, khi;
-            wfa_range(r, t, kd, ila, ilb, klo, khi);
+            wfa_range(r, t + 1, kd, ila, ilb, klo, khi);        // pruned as if one more edit were allowed: see above
             uint32_t hit = 0;
             for (int k = klo + st; k <= ((khi - klo) | (WFA_SIDE - 1)) + klo; k += WFA_SIDE) {      // whole warps go round together
                 if (!backward) hit |= wave_diagonal<false>(prev, other, cur, Aw, Bw, k, k <= khi, klo, plo, phi, mid, ila, ilb, kd, lane);

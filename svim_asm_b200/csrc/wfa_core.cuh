@@ -242,3 +242,57 @@ SVB_HD long long wfa_bidir_serial(const uint32_t* A, int la, const uint32_t* B, 
     }
     return -1;
 }
+
+// ---- the round structure of the kernel (wfa.cu), stated serially --------------------------------------------------------------
+// Branch-free form of the recurrence: an unreached diagonal holds WFA_NEG, which survives the additions, and the clamp keeps the
+// point inside the table (a cell next to a reached cell of the last row or column is within one more edit, so the clamped value
+// is still "the furthest row with distance <= s").
+SVB_HD int wfa_next_clamped(int fm1, int f0, int fp1, int k, int la, int lb) {
+    return wfa_imin(wfa_imax(wfa_imax(f0 + 1, fm1), fp1 + 1), wfa_imin(la, lb - k));
+}
+
+// What one CTA of wfa_kernel computes for a pair with 0 < min(la, lb) and |lb - la| <= t, round by round: both waves advance
+// from "wave -1" (row -1 on diagonal 0); in round r the forward diagonals also test the backward wave g of round r - 1 on their
+// partner diagonal: prev + g >= la (total 2 r - 2), new + g >= la (total 2 r - 1).  Returns the distance if it is <= t, else -1.
+// F: four arrays of 2 t + 7 ints (forward parity 0 / 1, backward parity 0 / 1).
+SVB_HD long long wfa_rounds_serial(const uint32_t* A, int la, const uint32_t* B, int lb, int t, int* F) {
+    const int kd = lb - la, W = 2 * t + 7, mid = t + 3;
+    for (int x = 0; x < 4 * W; ++x) F[x] = (x == W + mid || x == 3 * W + mid) ? -1 : WFA_NEG;
+    int plo = 0, phi = -1;
+    for (int r = 0;; ++r) {
+        int klo, khi;
+        wfa_range(r, t + 1, kd, la, lb, klo, khi);       // one diagonal more than the one-sided pruning: see wfa.cu
+        unsigned hit = 0;
+        for (int side = 0; side < 2; ++side) {
+            const bool backward = side == 1;
+            const int* prev = F + (2 * side + ((r & 1) ^ 1)) * W;
+            const int* other = F + (2 * (1 - side) + ((r & 1) ^ 1)) * W;
+            int* cur = F + (2 * side + (r & 1)) * W;
+            for (int k = klo; k <= khi; ++k) {
+                const int fm1 = prev[mid + k - 1], f0 = prev[mid + k], fp1 = prev[mid + k + 1];
+                const int kb = kd - k;
+                const int g = (!backward && kb >= plo && kb <= phi) ? other[mid + kb] : WFA_NEG;
+                const int x = wfa_next_clamped(fm1, f0, fp1, k, la, lb);
+                int v = WFA_NEG;
+                if (x > WFA_NEG / 2) {
+                    v = x;
+                    bool more = true;
+                    while (more) {
+                        if (!backward) v += static_cast<int>(wfa_extend8(A, B, WFA_FRONT + static_cast<uint32_t>(v), WFA_FRONT + static_cast<uint32_t>(v + k), &more));
+                        else v += static_cast<int>(wfa_rextend8(A, B, WFA_FRONT + static_cast<uint32_t>(la - 1 - v), WFA_FRONT + static_cast<uint32_t>(lb - 1 - (v + k)), &more));
+                    }
+                }
+                cur[mid + k] = v;
+                if (f0 + g >= la) hit |= 1u;
+                if (v + g >= la) hit |= 2u;
+            }
+            cur[mid + klo - 1] = cur[mid + klo - 2] = WFA_NEG;
+            cur[mid + khi + 1] = cur[mid + khi + 2] = WFA_NEG;
+        }
+        if (hit & 1u) return 2 * r - 2;
+        if (hit & 2u) return 2 * r - 1 <= t ? 2 * r - 1 : -1;
+        if (2 * r - 1 >= t) return -1;
+        plo = klo;
+        phi = khi;
+    }
+}

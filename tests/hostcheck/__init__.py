@@ -34,6 +34,8 @@ def load():
     lib.hc_wfa.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_int]
     lib.hc_wfa_bidir.restype = ctypes.c_longlong
     lib.hc_wfa_bidir.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_int]
+    lib.hc_wfa_rounds.restype = ctypes.c_longlong
+    lib.hc_wfa_rounds.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_int]
     lib.hc_inflate.restype = ctypes.c_int
     lib.hc_inflate.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint]
     lib.hc_inflate_fast.restype = ctypes.c_int

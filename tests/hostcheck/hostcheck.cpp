@@ -158,6 +158,23 @@ extern "C" long long hc_wfa_bidir(const uint8_t* a, long long la, const uint8_t*
     return wfa_bidir_serial(A.data(), static_cast<int>(la), B.data(), static_cast<int>(lb), t, F0.data(), F1.data(), G0.data(), G1.data());
 }
 
+// the kernel's own round structure (sentinel recurrence, overlap test folded into the forward wave), stated serially; the
+// cases the kernel settles before its rounds (an empty string, a length difference beyond t) are settled the same way here
+extern "C" long long hc_wfa_rounds(const uint8_t* a, long long la, const uint8_t* b, long long lb, int t) {
+    const long long longer = la > lb ? la : lb, gap = la > lb ? la - lb : lb - la;
+    if (la == 0 || lb == 0) return longer <= t ? longer : -1;
+    if (gap > t) return -1;
+    std::vector<uint32_t> A((WFA_FRONT + static_cast<size_t>(la) + WFA_PAD + 7) / 4 + 1, 0u), B((WFA_FRONT + static_cast<size_t>(lb) + WFA_PAD + 7) / 4 + 1, 0u);
+    uint8_t* pa = reinterpret_cast<uint8_t*>(A.data());
+    uint8_t* pb = reinterpret_cast<uint8_t*>(B.data());
+    for (uint32_t i = 0; i < WFA_FRONT; ++i) { pa[i] = WFA_FRONT_A; pb[i] = WFA_FRONT_B; }
+    for (long long i = 0; i < la; ++i) pa[WFA_FRONT + i] = a[i];
+    for (long long i = 0; i < lb; ++i) pb[WFA_FRONT + i] = b[i];
+    for (uint32_t i = 0; i < WFA_PAD; ++i) { pa[WFA_FRONT + la + i] = WFA_END_A; pb[WFA_FRONT + lb + i] = WFA_END_B; }
+    std::vector<int> F(4 * (2 * static_cast<size_t>(t) + 7));
+    return wfa_rounds_serial(A.data(), static_cast<int>(la), B.data(), static_cast<int>(lb), t, F.data());
+}
+
 extern "C" unsigned hc_win_kmax(unsigned m, unsigned n, unsigned bw) { return win_kmax(m, n, bw); }
 
 #include "../../svim_asm_b200/csrc/inflate_core.cuh"

@@ -160,8 +160,17 @@ def test_wavefront_threshold_core_matches_plain_dp():
         a = bytes(rng.choice(alphabet, int(rng.integers(0, 400))).tolist())
         b = mutate(a, int(rng.integers(0, 60))) if rng.random() < 0.7 else bytes(rng.choice(alphabet, int(rng.integers(0, 400))).tolist())
         cases.append((a, b, int(rng.choice([0, 1, 2, 3, 5, 10, 30, 31, 200]))))
+    # thresholds right at, below and above the distance (the last round of the bidirectional run tests the total t itself)
+    for a, b, _t in list(cases[13:613]):
+        d = port.edit_distance(a, b)
+        for t in (d - 1, d, d + 1):
+            if 0 <= t <= 300:
+                cases.append((a, b, t))
     for a, b, t in cases:
         d = port.edit_distance(a, b)
         assert lib.hc_wfa(a, len(a), b, len(b), t) == (d if d <= t else -1), (len(a), len(b), t, d)
         # the bidirectional run (forward and backward waves meeting in the middle: what the kernel does)
         assert lib.hc_wfa_bidir(a, len(a), b, len(b), t) == (d if d <= t else -1), ("bidirectional", len(a), len(b), t, d)
+        # the kernel's round structure: branch-free clamped recurrence from "wave -1", the overlap tests of the totals 2r - 2
+        # and 2r - 1 folded into the forward wave of round r
+        assert lib.hc_wfa_rounds(a, len(a), b, len(b), t) == (d if d <= t else -1), ("rounds", len(a), len(b), t, d)

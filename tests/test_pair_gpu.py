@@ -101,6 +101,27 @@ def test_edit_distance_bounded_matches_plain_dp(engine, oracle_clib):
     assert len(d199) > 10                        # the cut itself is exercised (200 merges, 201 does not)
 
 
+def test_edit_distance_bounded_at_the_distance_itself(engine, oracle_clib):
+    """Thresholds right at, below and above every pair's distance, even and odd: the last round of the bidirectional run
+    tests the total t itself, on the outermost diagonal the pruning leaves (a one-sided pruning bound lost exactly that
+    diagonal for even t: found by the host statement of the rounds, tests/test_edit_core.py)."""
+    rng = np.random.default_rng(31)
+    alphabet = list(b"ACGT")
+    pairs = [(b"ACGT" * 100, b"ACGT" * 99), (b"ACGT" * 100 + b"T", b"G" + b"ACGT" * 99)]
+    for _ in range(300):
+        m = int(rng.integers(2, 500))
+        a = bytes(rng.choice(alphabet, m).tolist())
+        b = _mutate(rng, a, int(rng.integers(1, 70)), alphabet)
+        if rng.random() < 0.5 and len(b) > 1:                 # ends that differ: nothing to trim, the rounds see the whole pair
+            a = b"A" + a + b"C"
+            b = b"G" + b + b"T"
+        pairs.append((a, b))
+    want = [port.edit_distance(a, b) for a, b in pairs]
+    for t in sorted({x for d in want for x in (d - 1, d, d + 1) if 0 <= x <= 1024}):
+        got = engine.edit_distance(pairs, max_distance=t)
+        assert got.tolist() == [d if d <= t else -1 for d in want], t
+
+
 def test_edit_distance_bounded_long_pairs(engine, oracle_clib):
     """Long haplotype pairs: the whole-warp match extension, the one-CTA-per-SM stage for strings beyond the small
     shared-memory window, and the hand-over to the exact kernel for strings beyond shared memory altogether."""
