@@ -31,6 +31,9 @@ using namespace edstr;
 
 constexpr int WFA_THREADS = 256;         // 8 warps: 4 per direction of the bidirectional wavefront
 constexpr int WFA_SIDE = WFA_THREADS / 2;
+#ifndef WFA_PRUNE_SLACK
+#define WFA_PRUNE_SLACK 1          // (0 rebuilds the one-sided bound that loses a distance of exactly t: tests/test_pair_gpu.py must catch it)
+#endif
 constexpr uint32_t WFA_SLACK = 160;               // readable bytes behind the second string (warp-wide extension reads ahead)
 
 struct WfaControl {
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
             const int* other = theirs + ((r & 1) ^ 1) * W;
             int* cur = mine + (r & 1) * W;
             int klo, khi;
-            wfa_range(r, t + 1, kd, ila, ilb, klo, khi);        // pruned as if one more edit were allowed: see above
+            wfa_range(r, t + WFA_PRUNE_SLACK, kd, ila, ilb, klo, khi);        // pruned as if one more edit were allowed: see above
             uint32_t hit = 0;
             for (int k = klo + st; k <= ((khi - klo) | (WFA_SIDE - 1)) + klo; k += WFA_SIDE) {      // whole warps go round together
                 if (!backward) hit |= wave_diagonal<false>(prev, other, cur, Aw, Bw, k, k <= khi, klo, plo, phi, mid, ila, ilb, kd, lane);
