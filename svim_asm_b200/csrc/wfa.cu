@@ -280,6 +280,8 @@ __global__ void __launch_bounds__(WFA_THREADS) wfa_kernel(const WfaArgs a) {
             }
             if (hit) atomicOr(&ctl->hit, hit);
             __syncthreads();
+            // (every warp reads the word right behind the barrier; the next write to it is a whole wave away, and a hit ends the
+            // pair, so the word is zero whenever a round starts)
             const uint32_t h = ctl->hit;
             if (h & 1u) { result = 2 * r - 2; break; }
             if (h & 2u) { result = 2 * r - 1 <= t ? 2 * r - 1 : -1; break; }
